@@ -1,0 +1,125 @@
+"""Deterministic synthetic inputs for the pressure-Poisson path.
+
+Everything is keyed on GLOBAL cell / face indices, so a field built block by block for any
+decomposition is bit-identical to the same field built on one block: the projected
+velocity u*, v*, w* = smooth sin/cos field + uniform noise in [-0.5, 0.5), with
+wall-normal faces zeroed so that sum(rhs) = 0 (the solvability condition the reference
+enforces in cuda_solvability, src/cuda_bluebottle.cu:2313-2492).
+
+The noise is a counter-based hash (splitmix64 of the global face index) instead of a
+sequential generator so that each rank can fill only its own block.
+"""
+import numpy as np
+
+from .grid import PERIODIC, grid_shape
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def splitmix64(x):
+    """Vectorised splitmix64 finaliser on uint64 arrays."""
+    with np.errstate(over="ignore"):
+        z = x + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return z
+
+
+def hash_uniform(idx, stream):
+    """uniform [-0.5, 0.5) from integer index array `idx` and an integer stream id."""
+    z = splitmix64(idx.astype(np.uint64) + np.uint64(stream) * np.uint64(0x0123456789ABCDEF))
+    return (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0) - 0.5
+
+
+def _axis(dom, DOM, axis, staggered, periodic):
+    """Per-axis helper: for local index l = 0..n+1(+1) returns (coordinate, global index, wall mask).
+
+    Cell centres: x = (l - 0.5) dx + xs (particle_kernel.cu:1677-1679); faces: x = (l - 1) dx + xs.
+    Global 0-based index = G.is - DOM_BUF + (l - 1); periodic face indices wrap modulo N so the
+    two copies of the periodic face (and the duplicated block-boundary faces) agree."""
+    n = getattr(dom, axis + "n")
+    N = getattr(DOM, axis + "n")
+    s = getattr(dom, axis + "s")
+    d = getattr(dom, "d" + axis)
+    gname = {"x": "Gfx", "y": "Gfy", "z": "Gfz"}[axis] if staggered else "Gcc"
+    g0 = getattr(dom, gname).get({"x": "is", "y": "js", "z": "ks"}[axis]) - 1   # global index of local 1
+    nb = n + 2 + (1 if staggered else 0)
+    l = np.arange(nb)
+    gi = g0 + (l - 1)
+    if staggered:
+        coord = (l - 1) * d + s
+        wall = np.zeros(nb, dtype=bool) if periodic else ((gi == 0) | (gi == N))
+        gi = np.where(gi == N, 0, gi) if periodic else gi
+        valid = (l >= 1) & (l <= n + 1)
+    else:
+        coord = (l - 0.5) * d + s
+        wall = np.zeros(nb, dtype=bool)
+        valid = (l >= 1) & (l <= n)
+    return coord, gi.astype(np.int64), wall, valid
+
+
+def velocity_star(dom, DOM, bc, noise=1.0, seed=7):
+    """u*, v*, w* for one block, in the reference's Gfx / Gfy / Gfz storage (ghosted, s3b).
+
+    Returns three float64 arrays shaped grid_shape(dom, G).  Entries PP_rhs does not read
+    (ghost rows, solver_kernel.cu:128-146) are left 0."""
+    px = bc.pW == PERIODIC and bc.pE == PERIODIC
+    py = bc.pS == PERIODIC and bc.pN == PERIODIC
+    pz = bc.pB == PERIODIC and bc.pT == PERIODIC
+    Lx, Ly, Lz = DOM.xe - DOM.xs, DOM.ye - DOM.ys, DOM.ze - DOM.zs
+    Nx, Ny, Nz = DOM.xn, DOM.yn, DOM.zn
+    out = []
+    for comp, grid in enumerate(("Gfx", "Gfy", "Gfz")):
+        sx, sy, sz = (comp == 0), (comp == 1), (comp == 2)
+        X, GI, WX, VX = _axis(dom, DOM, "x", sx, px)
+        Y, GJ, WY, VY = _axis(dom, DOM, "y", sy, py)
+        Z, GK, WZ, VZ = _axis(dom, DOM, "z", sz, pz)
+        ax = 2 * np.pi * (X - DOM.xs) / Lx
+        ay = 2 * np.pi * (Y - DOM.ys) / Ly
+        az = 2 * np.pi * (Z - DOM.zs) / Lz
+        # component-specific smooth part
+        if comp == 0:
+            fx, fy, fz = np.sin(ax), np.cos(ay), np.cos(az)
+        elif comp == 1:
+            fx, fy, fz = np.cos(ax), np.sin(ay), np.cos(az)
+        else:
+            fx, fy, fz = np.cos(ax), np.cos(ay), np.sin(az)
+        # broadcast in [i, j, k] then permute into the grid's storage order
+        sI, sJ, sK = Nx + 1, Ny + 1, Nz + 1
+        lin = (GI[:, None, None] + sI * (GJ[None, :, None] + sJ * GK[None, None, :]))
+        f = fx[:, None, None] * fy[None, :, None] * fz[None, None, :]
+        if noise != 0.0:
+            f = f + noise * hash_uniform(lin, seed * 4 + comp)
+        wall = (WX[:, None, None] if sx else False) | (WY[None, :, None] if sy else False) | \
+               (WZ[None, None, :] if sz else False)
+        valid = VX[:, None, None] & VY[None, :, None] & VZ[None, None, :]
+        f = np.where(valid & ~wall, f, 0.0)
+        if grid == "Gfx":
+            a = f.transpose(0, 2, 1)       # [i, k, j]
+        elif grid == "Gfy":
+            a = f.transpose(1, 0, 2)       # [j, i, k]
+        else:
+            a = f.transpose(2, 1, 0)       # [k, j, i]
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        assert a.shape == grid_shape(dom, grid), (a.shape, grid_shape(dom, grid))
+        out.append(a)
+    return out
+
+
+def random_spheres(DOM, nparts, radius, seed=20240229, max_tries=200000):
+    """Non-overlapping sphere centres by rejection sampling (config C4).
+    Centres keep one radius + 2 cells clear of every domain face so cages never wrap."""
+    rng = np.random.default_rng(seed)
+    lo = np.array([DOM.xs, DOM.ys, DOM.zs]) + radius + 2 * max(DOM.dx, DOM.dy, DOM.dz)
+    hi = np.array([DOM.xe, DOM.ye, DOM.ze]) - radius - 2 * max(DOM.dx, DOM.dy, DOM.dz)
+    pts = np.empty((0, 3))
+    tries = 0
+    while len(pts) < nparts and tries < max_tries:
+        cand = lo + (hi - lo) * rng.random(3)
+        tries += 1
+        if len(pts) == 0 or np.min(np.sum((pts - cand) ** 2, axis=1)) > (2.2 * radius) ** 2:
+            pts = np.vstack([pts, cand])
+    if len(pts) < nparts:
+        raise RuntimeError("could not place %d spheres of radius %g" % (nparts, radius))
+    return pts[:, 0].copy(), pts[:, 1].copy(), pts[:, 2].copy(), np.full(nparts, float(radius))
