@@ -1,0 +1,237 @@
+/* oracle/ref_shim.cu -- single-rank host shim around the reference's OWN hot-path objects
+ * ("O1").  TEST INFRASTRUCTURE: the resulting oracle/_ref/libbbref.so is a
+ * checker and the `--impl reference` arm of bench.py; it is never on the product path.
+ *
+ * What is linked: /root/reference/src/{solver_kernel,cuda_solver,bluebottle_kernel}.cu,
+ * compiled UNMODIFIED where they lie (oracle/Makefile) with -DDOUBLE -DJACOBI for sm_100a.
+ * This file supplies what the rest of the Bluebottle program would: the globals those
+ * objects reference (definitions mirror bluebottle.c:438-576, mpi_comm.c:26-27,
+ * particle.c:27-28, cuda_bluebottle.cu:34-35), a rank-0-of-1 stand-in for MPI
+ * (allreduce = identity, self MPI_Put = device-to-device copy), the launch geometry of
+ * cuda_blocks_init (cuda_bluebottle.cu:523-581, Gcc part) and the host sequence of
+ * mpi_cuda_exchange_Gcc (mpi_comm.c:257-315) driving the reference's own pack/unpack
+ * kernels.  No reference source text is copied into this repository.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cuda_runtime.h>
+
+#include "cuda_solver.h"      /* reference header (from -I $(REF)/src): types + kernel prototypes */
+#include "cuda_bluebottle.h"  /* pack/unpack kernel prototypes */
+
+/* ---- globals the reference objects link against --------------------------------------- */
+__constant__ dom_struct _dom;            /* cuda_bluebottle.cu:34 */
+__constant__ bin_struct _bins;           /* cuda_bluebottle.cu (referenced by bluebottle_kernel.o, unused here) */
+cuda_blocks_struct blocks;               /* cuda_bluebottle.cu:35 */
+dom_struct *dom;  dom_struct DOM;
+int rank = 0, nprocs = 1;
+int NPARTS = 0, nparts = 0;
+real rho_f, dt, pp_residual, ttime;
+int pp_max_iter, stepnum;
+real *_phi, *_rhs_p, *_r_q, *_z_q, *_p_q, *_pb_q, *_Apb_q, *_invM;
+real *_u_star, *_v_star, *_w_star;
+int *_flag_u, *_flag_v, *_flag_w, *_phase, *_phase_shell;
+static real *_send_Gcc[6], *_recv_Gcc[6];   /* e w n s t b */
+
+static int  g_niter = -1;
+static real g_resid = -1., g_etime = 0.;
+
+extern "C" {
+/* MPI, rank 0 of 1 */
+int MPI_Allreduce(const void *, void *, int, MPI_Datatype, MPI_Op, MPI_Comm) { return 0; }  /* IN_PLACE, 1 rank */
+int MPI_Barrier(MPI_Comm) { return 0; }
+
+/* recorder.c:190-221 -- the solver's only output besides _phi */
+void recorder_PP(char *, int niter, real resid, real etime) { g_niter = niter; g_resid = resid; g_etime = etime; }
+void recorder_PP_init_timed(char *) {}
+void recorder_PP_timed(char *, int niter, real resid, real etime, real, real, real, real, real, real, real, real)
+{ g_niter = niter; g_resid = resid; g_etime = etime; }   /* recorder.h:258-270: 8 segment timers */
+
+/* Net effect of cuda_part_BC_p (cuda_particle.cu:1680 -> particle_kernel.cu:1655-1756): the
+ * final statement (:1753) zeroes rhs in solid cells and keeps it in fluid cells. */
+__global__ void shim_part_BC_p_net(real *rhs, const int *phase, const int *phase_shell, int n)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rhs[i] = (real)(phase[i] < 0 && phase_shell[i]) * rhs[i];
+}
+void cuda_part_BC_p(void)
+{
+  int n = dom[rank].Gcc.s3b;
+  shim_part_BC_p_net<<<(n + 255) / 256, 256>>>(_rhs_p, _phase, _phase_shell, n);
+}
+
+/* mpi_cuda_exchange_Gcc, mpi_comm.c:257-315, for one rank: a neighbour is either this rank
+ * (periodic wrap = self put, domain.c:1151-1159) or MPI_PROC_NULL. */
+void mpi_cuda_exchange_Gcc(real *array)
+{
+  const dom_struct *d = &dom[rank];
+  if (d->e != MPI_PROC_NULL) pack_planes_Gcc_east  <<<blocks.Gcc.num_in, blocks.Gcc.dim_in>>>(array, _send_Gcc[0]);
+  if (d->w != MPI_PROC_NULL) pack_planes_Gcc_west  <<<blocks.Gcc.num_in, blocks.Gcc.dim_in>>>(array, _send_Gcc[1]);
+  if (d->n != MPI_PROC_NULL) pack_planes_Gcc_north <<<blocks.Gcc.num_jn, blocks.Gcc.dim_jn>>>(array, _send_Gcc[2]);
+  if (d->s != MPI_PROC_NULL) pack_planes_Gcc_south <<<blocks.Gcc.num_jn, blocks.Gcc.dim_jn>>>(array, _send_Gcc[3]);
+  if (d->t != MPI_PROC_NULL) pack_planes_Gcc_top   <<<blocks.Gcc.num_kn, blocks.Gcc.dim_kn>>>(array, _send_Gcc[4]);
+  if (d->b != MPI_PROC_NULL) pack_planes_Gcc_bottom<<<blocks.Gcc.num_kn, blocks.Gcc.dim_kn>>>(array, _send_Gcc[5]);
+  cudaDeviceSynchronize();
+  /* w -> recv_e, e -> recv_w, s -> recv_n, n -> recv_s, b -> recv_t, t -> recv_b (mpi_comm.c:293-306) */
+  if (d->w == rank) cudaMemcpy(_recv_Gcc[0], _send_Gcc[1], sizeof(real) * d->Gcc.s2_i, cudaMemcpyDeviceToDevice);
+  if (d->e == rank) cudaMemcpy(_recv_Gcc[1], _send_Gcc[0], sizeof(real) * d->Gcc.s2_i, cudaMemcpyDeviceToDevice);
+  if (d->s == rank) cudaMemcpy(_recv_Gcc[2], _send_Gcc[3], sizeof(real) * d->Gcc.s2_j, cudaMemcpyDeviceToDevice);
+  if (d->n == rank) cudaMemcpy(_recv_Gcc[3], _send_Gcc[2], sizeof(real) * d->Gcc.s2_j, cudaMemcpyDeviceToDevice);
+  if (d->b == rank) cudaMemcpy(_recv_Gcc[4], _send_Gcc[5], sizeof(real) * d->Gcc.s2_k, cudaMemcpyDeviceToDevice);
+  if (d->t == rank) cudaMemcpy(_recv_Gcc[5], _send_Gcc[4], sizeof(real) * d->Gcc.s2_k, cudaMemcpyDeviceToDevice);
+  cudaDeviceSynchronize();
+  if (d->e != MPI_PROC_NULL) unpack_planes_Gcc_east  <<<blocks.Gcc.num_in, blocks.Gcc.dim_in>>>(array, _recv_Gcc[0]);
+  if (d->w != MPI_PROC_NULL) unpack_planes_Gcc_west  <<<blocks.Gcc.num_in, blocks.Gcc.dim_in>>>(array, _recv_Gcc[1]);
+  if (d->n != MPI_PROC_NULL) unpack_planes_Gcc_north <<<blocks.Gcc.num_jn, blocks.Gcc.dim_jn>>>(array, _recv_Gcc[2]);
+  if (d->s != MPI_PROC_NULL) unpack_planes_Gcc_south <<<blocks.Gcc.num_jn, blocks.Gcc.dim_jn>>>(array, _recv_Gcc[3]);
+  if (d->t != MPI_PROC_NULL) unpack_planes_Gcc_top   <<<blocks.Gcc.num_kn, blocks.Gcc.dim_kn>>>(array, _recv_Gcc[4]);
+  if (d->b != MPI_PROC_NULL) unpack_planes_Gcc_bottom<<<blocks.Gcc.num_kn, blocks.Gcc.dim_kn>>>(array, _recv_Gcc[5]);
+  cudaDeviceSynchronize();
+}
+} /* extern "C" */
+
+/* launch geometry for the Gcc kernels: cuda_blocks_init, cuda_bluebottle.cu:523-581 */
+static int thr(int n) { return n < MAX_THREADS_DIM ? n : MAX_THREADS_DIM; }
+static int nblk(int n, int t) { return (n + t - 1) / t; }
+static void shim_blocks_init(const dom_struct *d)
+{
+  int tx = thr(d->Gcc.in), ty = thr(d->Gcc.jn), tz = thr(d->Gcc.kn);
+  int bx = nblk(d->Gcc.in, tx), by = nblk(d->Gcc.jn, ty), bz = nblk(d->Gcc.kn, tz);
+  blocks.Gcc.dim_in = dim3(ty, tz); blocks.Gcc.dim_jn = dim3(tz, tx); blocks.Gcc.dim_kn = dim3(tx, ty);
+  blocks.Gcc.num_in = dim3(by, bz); blocks.Gcc.num_jn = dim3(bz, bx); blocks.Gcc.num_kn = dim3(bx, by);
+  tx = thr(d->Gcc.in + 2); ty = thr(d->Gcc.jn + 2); tz = thr(d->Gcc.kn + 2);
+  bx = nblk(d->Gcc.in, tx - 2); by = nblk(d->Gcc.jn, ty - 2); bz = nblk(d->Gcc.kn, tz - 2);
+  blocks.Gcc.dim_in_s = dim3(ty, tz); blocks.Gcc.dim_jn_s = dim3(tz, tx); blocks.Gcc.dim_kn_s = dim3(tx, ty);
+  blocks.Gcc.num_in_s = dim3(by, bz); blocks.Gcc.num_jn_s = dim3(bz, bx); blocks.Gcc.num_kn_s = dim3(bx, by);
+  /* ghost-inclusive shapes used by zero_rhs_ghost_{i,j,k} (cuda_bluebottle.cu:545-560) */
+  tx = thr(d->Gcc.inb); ty = thr(d->Gcc.jnb); tz = thr(d->Gcc.knb);
+  bx = nblk(d->Gcc.inb, tx); by = nblk(d->Gcc.jnb, ty); bz = nblk(d->Gcc.knb, tz);
+  blocks.Gcc.dim_inb = dim3(ty, tz); blocks.Gcc.dim_jnb = dim3(tz, tx); blocks.Gcc.dim_knb = dim3(tx, ty);
+  blocks.Gcc.num_inb = dim3(by, bz); blocks.Gcc.num_jnb = dim3(bz, bx); blocks.Gcc.num_knb = dim3(bx, by);
+}
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "bbref: %s -> %s\n", #x, cudaGetErrorString(e_)); return -1; } } while (0)
+
+extern "C" {
+
+/* One block (rank 0 of 1); `d` must already be filled (domain_fill semantics). */
+int bbref_init(const dom_struct *d, const dom_struct *D)
+{
+  dom = (dom_struct *)malloc(sizeof(dom_struct));
+  memcpy(dom, d, sizeof(dom_struct)); memcpy(&DOM, D, sizeof(dom_struct));
+  rank = 0; nprocs = 1;
+  CK(cudaMemcpyToSymbol(_dom, dom, sizeof(dom_struct)));          /* cuda_bluebottle.cu:148 */
+  shim_blocks_init(dom);
+  size_t s3 = d->Gcc.s3, s3b = d->Gcc.s3b;
+  /* cuda_dom_malloc_dev: cuda_bluebottle.cu:162-166,222-266,308-319,373 */
+  CK(cudaMalloc(&_phi, s3b * sizeof(real)));    CK(cudaMemset(_phi, 0, s3b * sizeof(real)));
+  CK(cudaMalloc(&_rhs_p, s3b * sizeof(real)));  CK(cudaMemset(_rhs_p, 0, s3b * sizeof(real)));
+  CK(cudaMalloc(&_pb_q, s3b * sizeof(real)));   CK(cudaMemset(_pb_q, 0, s3b * sizeof(real)));
+  CK(cudaMalloc(&_r_q, s3 * sizeof(real)));  CK(cudaMalloc(&_z_q, s3 * sizeof(real)));
+  CK(cudaMalloc(&_p_q, s3 * sizeof(real)));  CK(cudaMalloc(&_Apb_q, s3 * sizeof(real)));
+  CK(cudaMalloc(&_invM, s3 * sizeof(real)));
+  CK(cudaMalloc(&_u_star, (size_t)d->Gfx.s3b * sizeof(real)));
+  CK(cudaMalloc(&_v_star, (size_t)d->Gfy.s3b * sizeof(real)));
+  CK(cudaMalloc(&_w_star, (size_t)d->Gfz.s3b * sizeof(real)));
+  CK(cudaMalloc(&_flag_u, (size_t)d->Gfx.s3b * sizeof(int)));
+  CK(cudaMalloc(&_flag_v, (size_t)d->Gfy.s3b * sizeof(int)));
+  CK(cudaMalloc(&_flag_w, (size_t)d->Gfz.s3b * sizeof(int)));
+  CK(cudaMalloc(&_phase, s3b * sizeof(int)));  CK(cudaMalloc(&_phase_shell, s3b * sizeof(int)));
+  for (int f = 0; f < 6; f++) {
+    size_t n = (f < 2) ? d->Gcc.s2_i : (f < 4) ? d->Gcc.s2_j : d->Gcc.s2_k;
+    CK(cudaMalloc(&_send_Gcc[f], n * sizeof(real)));  CK(cudaMalloc(&_recv_Gcc[f], n * sizeof(real)));
+  }
+  return 0;
+}
+
+int bbref_set_inputs(const int *flag_u, const int *flag_v, const int *flag_w, const int *phase,
+                     const int *phase_shell, const real *u, const real *v, const real *w, int n_parts)
+{
+  const dom_struct *d = &dom[rank];
+  CK(cudaMemcpy(_flag_u, flag_u, (size_t)d->Gfx.s3b * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(_flag_v, flag_v, (size_t)d->Gfy.s3b * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(_flag_w, flag_w, (size_t)d->Gfz.s3b * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(_phase, phase, (size_t)d->Gcc.s3b * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(_phase_shell, phase_shell, (size_t)d->Gcc.s3b * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(_u_star, u, (size_t)d->Gfx.s3b * sizeof(real), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(_v_star, v, (size_t)d->Gfy.s3b * sizeof(real), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(_w_star, w, (size_t)d->Gfz.s3b * sizeof(real), cudaMemcpyHostToDevice));
+  NPARTS = nparts = n_parts;
+  return 0;
+}
+
+/* device-resident inputs (bench: inputs generated on the GPU box by the harness) */
+int bbref_set_inputs_dev(const int *flag_u, const int *flag_v, const int *flag_w, const int *phase,
+                         const int *phase_shell, const real *u, const real *v, const real *w, int n_parts)
+{
+  const dom_struct *d = &dom[rank];
+  CK(cudaMemcpy(_flag_u, flag_u, (size_t)d->Gfx.s3b * sizeof(int), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(_flag_v, flag_v, (size_t)d->Gfy.s3b * sizeof(int), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(_flag_w, flag_w, (size_t)d->Gfz.s3b * sizeof(int), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(_phase, phase, (size_t)d->Gcc.s3b * sizeof(int), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(_phase_shell, phase_shell, (size_t)d->Gcc.s3b * sizeof(int), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(_u_star, u, (size_t)d->Gfx.s3b * sizeof(real), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(_v_star, v, (size_t)d->Gfy.s3b * sizeof(real), cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(_w_star, w, (size_t)d->Gfz.s3b * sizeof(real), cudaMemcpyDeviceToDevice));
+  NPARTS = nparts = n_parts;
+  return 0;
+}
+
+/* Runs the reference entry points exactly as bluebottle.c:139 / :228-232 do.
+ * Returns CUDA-event milliseconds of the solve call; niter/resid as given to recorder_PP.
+ * NB: on non-convergence the reference calls exit(EXIT_FAILURE) (cuda_solver.cu:271-279). */
+int bbref_solve(real rho_f_, real dt_, real pp_residual_, int pp_max_iter_, int use_parts,
+                int *niter, real *resid, float *ms)
+{
+  rho_f = rho_f_; dt = dt_; pp_residual = pp_residual_; pp_max_iter = pp_max_iter_;
+  stepnum = 0; ttime = 0.;
+  g_niter = -1; g_resid = -1.;
+  cuda_PP_init_jacobi_preconditioner();
+  CK(cudaDeviceSynchronize());
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, 0));
+  if (use_parts) cuda_PP_cg(); else cuda_PP_cg_noparts();
+  CK(cudaEventRecord(e1, 0));
+  CK(cudaEventSynchronize(e1));
+  CK(cudaGetLastError());
+  if (ms) CK(cudaEventElapsedTime(ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (niter) *niter = g_niter;
+  if (resid) *resid = g_resid;
+  return 0;
+}
+
+int bbref_get(int which, real *host)   /* 0: phi (s3b)  1: rhs_p (s3b)  2: invM (s3)  3: Apb_q (s3)  4: pb_q (s3b) */
+{
+  const dom_struct *d = &dom[rank];
+  const real *src = which == 0 ? _phi : which == 1 ? _rhs_p : which == 2 ? _invM : which == 3 ? _Apb_q : _pb_q;
+  size_t n = (which == 2 || which == 3) ? d->Gcc.s3 : d->Gcc.s3b;
+  CK(cudaMemcpy(host, src, n * sizeof(real), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+/* one reference SpMV on a host-provided ghosted vector (unit parity of the operator) */
+int bbref_spmv(const real *pb_host, int use_parts, real *Ap_host)
+{
+  const dom_struct *d = &dom[rank];
+  CK(cudaMemcpy(_pb_q, pb_host, (size_t)d->Gcc.s3b * sizeof(real), cudaMemcpyHostToDevice));
+  if (use_parts) PP_spmv_shared_load<<<blocks.Gcc.num_kn_s, blocks.Gcc.dim_kn_s>>>(_flag_u, _flag_v, _flag_w, _pb_q, _Apb_q, _phase);
+  else PP_spmv_shared_load_noparts<<<blocks.Gcc.num_kn_s, blocks.Gcc.dim_kn_s>>>(_flag_u, _flag_v, _flag_w, _pb_q, _Apb_q);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(Ap_host, _Apb_q, (size_t)d->Gcc.s3 * sizeof(real), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+/* the reference halo exchange on a host-provided ghosted vector (cuda_BC_test_periodic analogue) */
+int bbref_exchange(real *arr_host)
+{
+  const dom_struct *d = &dom[rank];
+  CK(cudaMemcpy(_pb_q, arr_host, (size_t)d->Gcc.s3b * sizeof(real), cudaMemcpyHostToDevice));
+  mpi_cuda_exchange_Gcc(_pb_q);
+  CK(cudaMemcpy(arr_host, _pb_q, (size_t)d->Gcc.s3b * sizeof(real), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+} /* extern "C" */
