@@ -1,0 +1,95 @@
+"""ctypes declarations of include/bbpcg.h."""
+import ctypes as C
+import os
+
+from .grid import DomStruct, PressureBC
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(os.path.dirname(_HERE), "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libbbpcg.so")
+DROPIN_PATH = os.path.join(LIB_DIR, "libbbpcg_dropin.so")
+
+BLOB_BYTES = 256
+OK = 0
+STATUS = {0: "converged", 1: "tiny_rhs", 2: "max_iter", 3: "nan", 4: "comm_timeout"}
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+class Result(C.Structure):
+    _fields_ = [("status", C.c_int), ("niter", C.c_int), ("resid", C.c_double), ("sp_rhs", C.c_double),
+                ("sp_rq0", C.c_double), ("ms_setup", C.c_double), ("ms_iter", C.c_double),
+                ("ms_total", C.c_double), ("launches", C.c_longlong)]
+
+
+class FlowParams(C.Structure):
+    _fields_ = [("rho_f", C.c_double), ("pp_residual", C.c_double), ("pp_max_iter", C.c_int)]
+
+
+PART_BC_FN = C.CFUNCTYPE(None)
+
+
+class SolveArgs(C.Structure):
+    _fields_ = [("u_star", C.c_void_p), ("v_star", C.c_void_p), ("w_star", C.c_void_p),
+                ("rhs_p", C.c_void_p), ("phi", C.c_void_p), ("phase", C.c_void_p), ("phase_shell", C.c_void_p),
+                ("rho_f", C.c_double), ("dt", C.c_double), ("pp_residual", C.c_double),
+                ("pp_max_iter", C.c_int), ("use_phase", C.c_int), ("fixed_iters", C.c_int),
+                ("part_bc", PART_BC_FN)]
+
+
+# every symbol include/bbpcg.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "bb_domain_read", "bb_domain_fill", "bb_domain_split", "bb_domain_write_decomp", "bb_domain_free",
+    "bbpcg_create", "bbpcg_destroy", "bbpcg_comm_export", "bbpcg_comm_import", "bbpcg_set_coefficients",
+    "bbpcg_solve", "bbpcg_solve_host", "bbpcg_history", "bbpcg_exchange_Gcc", "bbpcg_rhs", "bbpcg_spmv",
+    "bbpcg_set_option", "bbpcg_get_info", "bbpcg_last_error", "bbpcg_version",
+]
+DROPIN_SYMBOLS = ["cuda_PP_init_jacobi_preconditioner", "cuda_PP_cg", "cuda_PP_cg_noparts", "cuda_PP_cg_timed",
+                  "mpi_cuda_exchange_Gcc", "bbpcg_dropin_finalize"]
+
+_lib = None
+
+
+def load_library():
+    """Load libbbpcg.so; raises LibraryMissing (never falls back to anything else)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, ip, dp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)
+    D = C.POINTER(DomStruct)
+    lib.bb_domain_read.argtypes = [C.c_char_p, C.c_char_p, D, C.POINTER(D), C.POINTER(PressureBC), C.POINTER(FlowParams)]
+    lib.bb_domain_fill.argtypes = [D, D, C.POINTER(PressureBC)]
+    lib.bb_domain_split.argtypes = [D, D]
+    lib.bb_domain_write_decomp.argtypes = [C.c_char_p, D, D, C.c_int]
+    lib.bb_domain_free.argtypes = [D]
+    lib.bb_domain_free.restype = None
+    lib.bbpcg_create.argtypes = [C.POINTER(vp), D, D, C.POINTER(PressureBC), C.c_int]
+    lib.bbpcg_destroy.argtypes = [vp]
+    lib.bbpcg_destroy.restype = None
+    lib.bbpcg_comm_export.argtypes = [vp, vp]
+    lib.bbpcg_comm_import.argtypes = [vp, vp, C.c_int]
+    lib.bbpcg_set_coefficients.argtypes = [vp, vp, vp, vp, vp]
+    lib.bbpcg_solve.argtypes = [vp, C.POINTER(SolveArgs), C.POINTER(Result)]
+    lib.bbpcg_solve_host.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(Result)]
+    lib.bbpcg_history.argtypes = [vp, dp, C.c_int]
+    lib.bbpcg_exchange_Gcc.argtypes = [vp, vp]
+    lib.bbpcg_rhs.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp]
+    lib.bbpcg_spmv.argtypes = [vp, vp, vp, C.c_int]
+    lib.bbpcg_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
+    lib.bbpcg_get_info.argtypes = [vp, C.c_char_p]
+    lib.bbpcg_get_info.restype = C.c_longlong
+    lib.bbpcg_last_error.restype = C.c_char_p
+    lib.bbpcg_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != OK:
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, load_library().bbpcg_last_error().decode()))

@@ -1,0 +1,202 @@
+"""Host-side mirror of the reference's operator interface for the pressure-Poisson path.
+
+`Decomposition` = domain_read_input (decomp part) + domain_fill  (src/domain.c:91-160,918-1486)
+`PoissonSolver.init_jacobi_preconditioner` = cuda_PP_init_jacobi_preconditioner (src/cuda_solver.cu:31-36)
+`PoissonSolver.PP_cg / PP_cg_noparts`      = cuda_PP_cg / cuda_PP_cg_noparts (src/cuda_solver.cu:38-300,573-761)
+`PoissonSolver.exchange_Gcc`               = mpi_cuda_exchange_Gcc (src/mpi_comm.c:257-315)
+
+Array arguments are torch CUDA tensors in the reference's ghosted layouts (grid.grid_shape).
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import lib as L
+from .grid import DomStruct, PressureBC, grid_shape
+
+
+@dataclass
+class SolveResult:
+    status: str
+    niter: int
+    resid: float
+    sp_rhs: float
+    sp_rq0: float
+    ms_setup: float
+    ms_iter: float
+    ms_total: float
+    launches: int
+
+
+class Decomposition:
+    """DOM + dom[] for an In x Jn x Kn block decomposition (one block per rank/GPU)."""
+
+    def __init__(self, DOM, doms, bc, params=None):
+        self.DOM, self.doms, self.bc, self.params = DOM, doms, bc, params
+
+    @property
+    def nranks(self):
+        return self.DOM.In * self.DOM.Jn * self.DOM.Kn
+
+    @classmethod
+    def uniform(cls, extent, cells, blocks=(1, 1, 1), bc=(0,) * 6):
+        """Equal splits, as tools/src/decomp_reader.c writes them."""
+        lib = L.load_library()
+        DOM = DomStruct()
+        DOM.xs, DOM.xe, DOM.ys, DOM.ye, DOM.zs, DOM.ze = [float(v) for v in extent]
+        DOM.xn, DOM.yn, DOM.zn = cells
+        DOM.In, DOM.Jn, DOM.Kn = blocks
+        n = blocks[0] * blocks[1] * blocks[2]
+        doms = (DomStruct * n)()
+        pbc = PressureBC(*bc)
+        L.check(lib.bb_domain_split(C.byref(DOM), doms), "bb_domain_split")
+        L.check(lib.bb_domain_fill(C.byref(DOM), doms, C.byref(pbc)), "bb_domain_fill")
+        return cls(DOM, doms, pbc)
+
+    @classmethod
+    def from_files(cls, flow_config, decomp_config):
+        """flow.config + decomp.config, src/domain.c:72-160."""
+        lib = L.load_library()
+        DOM, pbc, fp = DomStruct(), PressureBC(), L.FlowParams()
+        ptr = C.POINTER(DomStruct)()
+        L.check(lib.bb_domain_read(flow_config.encode(), decomp_config.encode(), C.byref(DOM), C.byref(ptr),
+                                   C.byref(pbc), C.byref(fp)), "bb_domain_read")
+        n = DOM.In * DOM.Jn * DOM.Kn
+        doms = (DomStruct * n)()
+        C.memmove(doms, ptr, C.sizeof(DomStruct) * n)
+        lib.bb_domain_free(ptr)
+        return cls(DOM, doms, pbc, {"rho_f": fp.rho_f, "pp_residual": fp.pp_residual, "pp_max_iter": fp.pp_max_iter})
+
+    def write_decomp(self, path, prec=2):
+        L.check(L.load_library().bb_domain_write_decomp(path.encode(), C.byref(self.DOM), self.doms, prec),
+                "bb_domain_write_decomp")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class PoissonSolver:
+    """One rank's solver object (one per GPU)."""
+
+    def __init__(self, decomp, rank=0, device=None):
+        import torch
+        self.torch = torch
+        self.lib = L.load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("bbpcg needs a CUDA device: there is no CPU path")
+        self.decomp, self.rank = decomp, rank
+        self.dom = decomp.doms[rank]
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.h = C.c_void_p()
+        L.check(self.lib.bbpcg_create(C.byref(self.h), C.byref(self.dom), C.byref(decomp.DOM), C.byref(decomp.bc),
+                                      self.device.index), "bbpcg_create")
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bbpcg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- multi-GPU attach ------------------------------------------------------------------
+    def comm_export(self):
+        buf = C.create_string_buffer(L.BLOB_BYTES)
+        L.check(self.lib.bbpcg_comm_export(self.h, buf), "bbpcg_comm_export")
+        return buf.raw
+
+    def comm_import(self, blobs):
+        allb = b"".join(blobs)
+        assert len(allb) == L.BLOB_BYTES * len(blobs)
+        L.check(self.lib.bbpcg_comm_import(self.h, allb, len(blobs)), "bbpcg_comm_import")
+
+    def comm_init_torch(self):
+        """Exchange the attach records through torch.distributed (replaces the MPI window set-up)."""
+        import torch.distributed as dist
+        n = dist.get_world_size()
+        if n == 1:
+            return
+        blobs = [None] * n
+        dist.all_gather_object(blobs, self.comm_export())
+        self.comm_import(blobs)
+        dist.barrier()
+
+    # ---- helpers ---------------------------------------------------------------------------
+    def empty(self, grid, dtype=None):
+        t = self.torch
+        return t.zeros(grid_shape(self.dom, grid), dtype=dtype or t.float64, device=self.device)
+
+    def to_device(self, arr):
+        return self.torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+
+    def set_option(self, key, value):
+        L.check(self.lib.bbpcg_set_option(self.h, key.encode(), int(value)), "bbpcg_set_option")
+
+    def info(self, key):
+        return self.lib.bbpcg_get_info(self.h, key.encode())
+
+    # ---- the reference's entry points ----------------------------------------------------------
+    def init_jacobi_preconditioner(self, flag_u, flag_v, flag_w, phase=None):
+        self.torch.cuda.synchronize(self.device)
+        L.check(self.lib.bbpcg_set_coefficients(self.h, _ptr(flag_u), _ptr(flag_v), _ptr(flag_w), _ptr(phase)),
+                "bbpcg_set_coefficients")
+
+    def _solve(self, u_star, v_star, w_star, rhs_p, phi, rho_f, dt, pp_residual, pp_max_iter, use_phase,
+               phase=None, phase_shell=None, fixed_iters=0):
+        a = L.SolveArgs()
+        a.u_star, a.v_star, a.w_star = u_star.data_ptr(), v_star.data_ptr(), w_star.data_ptr()
+        a.rhs_p, a.phi = rhs_p.data_ptr(), phi.data_ptr()
+        a.phase = phase.data_ptr() if phase is not None else None
+        a.phase_shell = phase_shell.data_ptr() if phase_shell is not None else None
+        a.rho_f, a.dt, a.pp_residual, a.pp_max_iter = rho_f, dt, pp_residual, pp_max_iter
+        a.use_phase, a.fixed_iters = int(use_phase), int(fixed_iters)
+        res = L.Result()
+        self.torch.cuda.synchronize(self.device)
+        L.check(self.lib.bbpcg_solve(self.h, C.byref(a), C.byref(res)), "bbpcg_solve")
+        return SolveResult(L.STATUS.get(res.status, str(res.status)), res.niter, res.resid, res.sp_rhs, res.sp_rq0,
+                           res.ms_setup, res.ms_iter, res.ms_total, res.launches)
+
+    def PP_cg_noparts(self, u_star, v_star, w_star, rhs_p, phi, rho_f=1.0, dt=1e-3, pp_residual=1e-6,
+                      pp_max_iter=2000, fixed_iters=0):
+        return self._solve(u_star, v_star, w_star, rhs_p, phi, rho_f, dt, pp_residual, pp_max_iter, False,
+                           fixed_iters=fixed_iters)
+
+    def PP_cg(self, u_star, v_star, w_star, rhs_p, phi, phase, phase_shell, rho_f=1.0, dt=1e-3, pp_residual=1e-6,
+              pp_max_iter=2000, fixed_iters=0):
+        return self._solve(u_star, v_star, w_star, rhs_p, phi, rho_f, dt, pp_residual, pp_max_iter, True,
+                           phase=phase, phase_shell=phase_shell, fixed_iters=fixed_iters)
+
+    def solve_host(self, u_h, v_h, w_h, phi_h, rho_f=1.0, dt=1e-3, pp_residual=1e-6, pp_max_iter=2000, fixed_iters=0):
+        """Host (pinned) tensors in, phi host tensor out: the end-to-end form."""
+        res = L.Result()
+        L.check(self.lib.bbpcg_solve_host(self.h, _ptr(u_h), _ptr(v_h), _ptr(w_h), _ptr(phi_h), rho_f, dt, pp_residual,
+                                          pp_max_iter, fixed_iters, C.byref(res)), "bbpcg_solve_host")
+        return SolveResult(L.STATUS.get(res.status, str(res.status)), res.niter, res.resid, res.sp_rhs, res.sp_rq0,
+                           res.ms_setup, res.ms_iter, res.ms_total, res.launches)
+
+    def history(self, cap=70000):
+        out = np.zeros(cap)
+        n = self.lib.bbpcg_history(self.h, out.ctypes.data_as(C.POINTER(C.c_double)), cap)
+        return out[:n].copy()
+
+    def exchange_Gcc(self, array):
+        self.torch.cuda.synchronize(self.device)
+        L.check(self.lib.bbpcg_exchange_Gcc(self.h, _ptr(array)), "bbpcg_exchange_Gcc")
+
+    def rhs(self, u_star, v_star, w_star, rhs_p, rho_f=1.0, dt=1e-3):
+        self.torch.cuda.synchronize(self.device)
+        L.check(self.lib.bbpcg_rhs(self.h, _ptr(u_star), _ptr(v_star), _ptr(w_star), rho_f, dt, _ptr(rhs_p)), "bbpcg_rhs")
+
+    def spmv(self, src_s3b, use_phase=False):
+        d = self.dom
+        out = self.torch.zeros((d.Gcc.get("kn"), d.Gcc.get("jn"), d.Gcc.get("in")), dtype=self.torch.float64,
+                               device=self.device)
+        self.torch.cuda.synchronize(self.device)
+        L.check(self.lib.bbpcg_spmv(self.h, _ptr(src_s3b), _ptr(out), int(use_phase)), "bbpcg_spmv")
+        return out

@@ -1,0 +1,113 @@
+/* bbpcg_dropin.cu -- the reference's entry points on top of libbbpcg (see include/bb_dropin.h).
+ * Every function mirrors its reference namesake's observable behaviour: same globals read,
+ * _phi written, recorder_PP called with (niter, resid, elapsed seconds), print + exit on
+ * non-convergence / NaN (src/cuda_solver.cu:245-251, 271-279). */
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <sys/time.h>
+#include <cuda_runtime.h>
+
+#include "../../include/bbpcg.h"
+#include "../../include/bb_dropin.h"
+
+extern "C" {
+/* globals owned by the Bluebottle host program */
+extern dom_struct *dom;                       /* src/bluebottle.h:511 */
+extern dom_struct DOM;                        /* src/bluebottle.h:487 */
+extern int rank, nprocs;                      /* src/mpi_comm.h:218-230 */
+extern struct bb_pressure_bc bc;              /* first six ints of BC, src/bluebottle.h:663-668 */
+extern real rho_f, dt, pp_residual, ttime;    /* src/bluebottle.h:524,560,572,2439 */
+extern int pp_max_iter, stepnum;              /* src/bluebottle.h:2389,2487 */
+extern int NPARTS, nparts;                    /* src/particle.h:319,331 */
+extern real *_u_star, *_v_star, *_w_star, *_rhs_p, *_phi;
+extern int *_flag_u, *_flag_v, *_flag_w, *_phase, *_phase_shell;
+void cuda_part_BC_p(void);                    /* src/cuda_particle.cu:1680 */
+void recorder_PP(char *name, int niter, real resid, real etime);   /* src/recorder.c:190 */
+int bb_dropin_allgather(const void *send, void *recv, int bytes_per_rank) __attribute__((weak));
+}
+
+static bbpcg_solver *g_solver = NULL;
+
+static void die(const char *what)
+{
+  fprintf(stderr, "N%d >> bbpcg: %s: %s\n", rank, what, bbpcg_last_error());
+  exit(EXIT_FAILURE);
+}
+
+static bbpcg_solver *solver(void)
+{
+  if (g_solver) return g_solver;
+  /* the reference selects the device before MPI_Init (src/mpi_comm.c:42-63); use it as is */
+  if (bbpcg_create(&g_solver, &dom[rank], &DOM, &bc, -1)) die("bbpcg_create");
+  if (nprocs > 1) {
+    if (!bb_dropin_allgather) { fprintf(stderr, "N%d >> bbpcg: nprocs = %d but the host program does not define bb_dropin_allgather()\n", rank, nprocs); exit(EXIT_FAILURE); }
+    char mine[BBPCG_BLOB_BYTES];
+    char *all = (char *)malloc((size_t)nprocs * BBPCG_BLOB_BYTES);
+    if (bbpcg_comm_export(g_solver, mine)) die("bbpcg_comm_export");
+    if (bb_dropin_allgather(mine, all, BBPCG_BLOB_BYTES)) { fprintf(stderr, "N%d >> bbpcg: bb_dropin_allgather failed\n", rank); exit(EXIT_FAILURE); }
+    if (bbpcg_comm_import(g_solver, all, nprocs)) die("bbpcg_comm_import");
+    free(all);
+  }
+  return g_solver;
+}
+
+extern "C" void cuda_PP_init_jacobi_preconditioner(void)
+{
+  /* _phase is only meaningful when particles exist (src/cuda_particle.cu:66-69 vs
+   * src/particle_kernel.cu:121-133), so it is digested only then */
+  if (bbpcg_set_coefficients(solver(), _flag_u, _flag_v, _flag_w, NPARTS > 0 ? _phase : NULL)) die("bbpcg_set_coefficients");
+}
+
+static void run(int use_phase)
+{
+  struct timeval ts, te;
+  gettimeofday(&ts, 0);                                     /* src/cuda_solver.cu:42-43 */
+  bbpcg_solve_args a;
+  bbpcg_result res;
+  memset(&a, 0, sizeof(a));
+  a.u_star = _u_star; a.v_star = _v_star; a.w_star = _w_star; a.rhs_p = _rhs_p; a.phi = _phi;
+  a.phase = _phase; a.phase_shell = _phase_shell;
+  a.rho_f = rho_f; a.dt = dt; a.pp_residual = pp_residual; a.pp_max_iter = pp_max_iter;
+  a.use_phase = use_phase;
+  a.part_bc = (use_phase && nparts > 0) ? cuda_part_BC_p : NULL;     /* :130-132 */
+  if (use_phase && nparts <= 0) a.phase_shell = NULL;                /* no patch on particle-free ranks */
+  cudaDeviceSynchronize();          /* the caller's default-stream work on u*, flags is complete */
+  if (bbpcg_solve(solver(), &a, &res)) die("bbpcg_solve");
+  gettimeofday(&te, 0);
+  real etime = (te.tv_sec - ts.tv_sec) + (te.tv_usec - ts.tv_usec) * 1.e-6;
+  char rname[] = "solver_expd.rec";
+  switch (res.status) {
+    case BBPCG_TINY_RHS:                                   /* :178-189 */
+      recorder_PP(rname, 0, 0., etime);
+      if (rank == 0) printf("N%d >> Norm of the rhs is less than %.1e, exiting solver\n", rank, 1.e-8);
+      break;
+    case BBPCG_CONVERGED:                                  /* :235-241 */
+      recorder_PP(rname, res.niter, res.resid, etime);
+      break;
+    case BBPCG_NAN:                                        /* :245-251 */
+      if (rank == 0) {
+        printf("N%d >> The PP equation did not converge.\n", rank);
+        printf("N%d >> The residual at iteration %d is nan (%lf).\n", rank, res.niter, res.resid);
+      }
+      exit(EXIT_FAILURE);
+    default:                                               /* :271-279 */
+      printf("N%d >> The pressure-Poisson equation did not converge.\n", rank);
+      printf("N%d >> (rhs, rhs) is %e\n", rank, res.sp_rhs);
+      printf("N%d >> Residual at iteration %d is %lf\n", rank, res.niter, res.resid);
+      exit(EXIT_FAILURE);
+  }
+}
+
+extern "C" void cuda_PP_cg(void) { run(NPARTS > 0 ? 1 : 0); }          /* the phase-aware operator equals the plain one when phase == -1 everywhere */
+extern "C" void cuda_PP_cg_noparts(void) { run(0); }
+extern "C" void cuda_PP_cg_timed(void) { run(0); }                     /* reference: noparts variant + segment timers, no caller */
+
+extern "C" void mpi_cuda_exchange_Gcc(real *array)
+{
+  cudaDeviceSynchronize();
+  if (bbpcg_exchange_Gcc(solver(), array)) die("bbpcg_exchange_Gcc");
+}
+
+extern "C" void bbpcg_dropin_finalize(void) { bbpcg_destroy(g_solver); g_solver = NULL; }

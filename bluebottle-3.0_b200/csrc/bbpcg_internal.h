@@ -1,0 +1,155 @@
+/* bbpcg_internal.h -- device-side data layout shared by the kernels and the host driver.
+ *
+ * PRIVATE PADDED LAYOUT ("P-layout") of the solver's own vectors (r, p0, p1, q, x) and byte
+ * masks.  Same logical extent as the reference's ghosted Gcc grid -- (in+2)(jn+2)(kn+2), one
+ * ghost layer, interior 1..n (src/domain.c:1262-1289) -- but every x-row is padded so that
+ * interior cell i = 1 starts on a 128-byte boundary:
+ *
+ *     offset(i,j,k) = (i + 15) + j*px + k*ps,   px = roundup(in + 17, 16),  ps = px*(jn+2)
+ *
+ * ghost i = 0 sits at 15, interior at 16..16+in-1, ghost i = in+1 at 16+in.  All five vectors
+ * and the masks share one index, so one offset addresses a cell in every array.
+ */
+#ifndef BBPCG_INTERNAL_H
+#define BBPCG_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include "../../include/bbpcg.h"
+
+#define BB_XOFF 15
+#define BB_MAXR BBPCG_MAX_RANKS
+#define BB_NSLOT 4                 /* mailbox slots (a peer is at most one stage ahead) */
+#define BB_MAXBLOCKS 65536         /* max CTAs of a reducing kernel */
+
+/* coefficient mask bits (fmask): squared face flags, src/solver_kernel.cu:824-829 */
+#define FM_E 1u
+#define FM_W 2u
+#define FM_N 4u
+#define FM_S 8u
+#define FM_T 16u
+#define FM_B 32u
+#define FM_DEAD 64u                /* ghost cell behind an external wall: z := 0 */
+/* particle mask bits (pmask), src/solver_kernel.cu:683-695 */
+#define PM_C 1u                    /* phase[C] > -1 (solid) */
+#define PM_E 2u
+#define PM_W 4u
+#define PM_N 8u
+#define PM_S 16u
+#define PM_T 32u
+#define PM_B 64u
+
+struct Layout {
+  int in, jn, kn;
+  int px;
+  long long ps;
+  long long n;                     /* elements per array = ps*(kn+2) */
+};
+
+static inline __host__ __device__ long long pidx(const Layout &L, int i, int j, int k)
+{
+  return (long long)(i + BB_XOFF) + (long long)j * L.px + (long long)k * L.ps;
+}
+
+static inline Layout make_layout(int in, int jn, int kn)
+{
+  Layout L;
+  L.in = in; L.jn = jn; L.kn = kn;
+  L.px = ((in + 17) + 15) / 16 * 16;
+  L.ps = (long long)L.px * (jn + 2);
+  L.n = L.ps * (kn + 2);
+  return L;
+}
+
+/* byte offsets of everything inside a rank's single device allocation ("arena").  A pure
+ * function of (in,jn,kn), so a peer can address a neighbour's arrays from its dimensions. */
+struct ArenaMap {
+  size_t r, p0, p1, q, x;          /* doubles[L.n] */
+  size_t fmask, pmask;             /* bytes[L.n]   */
+  size_t recv[2][6];               /* doubles, generic exchange staging (double-buffered) */
+  size_t partials;                 /* doubles[2*BB_MAXBLOCKS] */
+  size_t counter;                  /* unsigned[4] */
+  size_t scal;                     /* Scal */
+  size_t mbox_val;                 /* doubles[BB_NSLOT][BB_MAXR][2] */
+  size_t mbox_flag;                /* u64[BB_NSLOT][BB_MAXR] */
+  size_t history;                  /* doubles[hist_cap] */
+  size_t total;
+};
+
+#define BB_HIST_CAP 65536
+
+static inline ArenaMap make_arena_map(const Layout &L)
+{
+  ArenaMap m;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  size_t vec = (size_t)L.n * sizeof(double);
+  m.r = take(vec); m.p0 = take(vec); m.p1 = take(vec); m.q = take(vec); m.x = take(vec);
+  m.fmask = take((size_t)L.n); m.pmask = take((size_t)L.n);
+  size_t fi = (size_t)L.jn * L.kn, fj = (size_t)L.in * L.kn, fk = (size_t)L.in * L.jn;
+  for (int b = 0; b < 2; b++) for (int f = 0; f < 6; f++)
+    m.recv[b][f] = take(sizeof(double) * (f < 2 ? fi : f < 4 ? fj : fk));
+  m.partials = take(sizeof(double) * 2 * BB_MAXBLOCKS);
+  m.counter = take(sizeof(unsigned) * 4);
+  m.scal = take(512);
+  m.mbox_val = take(sizeof(double) * BB_NSLOT * BB_MAXR * 2);
+  m.mbox_flag = take(sizeof(unsigned long long) * BB_NSLOT * BB_MAXR);
+  m.history = take(sizeof(double) * BB_HIST_CAP);
+  m.total = off;
+  return m;
+}
+
+/* Device-resident solver scalars: no per-iteration host round trip (the reference syncs the
+ * host four times per iteration, src/cuda_solver.cu:204-232). */
+struct Scal {
+  double bb;            /* (b,b)                       cuda_solver.cu:151 */
+  double rz;            /* current (r,z) = sp_rq       :169 / :267        */
+  double pAp;           /* DENOM                       :204               */
+  double alpha;         /* step of the iteration in flight                */
+  double alpha_x;       /* step not yet applied to x (lazy phi update)    */
+  double beta;          /* for the next search update  :256               */
+  double resid;         /* sqrt(rz)/sqrt(bb) at exit   :239               */
+  double rz0;           /* initial (r,z)                                  */
+  double tol2;          /* pp_residual^2                                  */
+  int done;             /* 1: every later kernel of this solve is a no-op */
+  int status;           /* BBPCG_CONVERGED ...                            */
+  int q;                /* completed iterations                           */
+  int max_q;            /* pp_max_iter + 1  (loop bound, :192)            */
+  int fixed;            /* benchmark mode: no stop test                   */
+  int comm_timeout;     /* set if a peer never showed up                  */
+  int pad0, pad1;
+  unsigned long long seq;   /* publish counter, never reset               */
+};
+
+/* where this block's boundary values go: the neighbour's (or, for a periodic wrap onto the
+ * same block, this rank's own) arrays.  r == NULL: external wall / no neighbour. */
+struct NbrFace {
+  double *r, *x;
+  unsigned char *fmask;
+  double *recv[2];      /* neighbour's staging buffer for the OPPOSITE face (generic exchange) */
+  Layout L;
+};
+struct Halo { NbrFace f[6]; };     /* 0:E 1:W 2:N 3:S 4:T 5:B */
+
+struct Comm {
+  int rank, nranks;
+  double *mbox_val[BB_MAXR];                  /* rank p's mailbox (mapped) */
+  unsigned long long *mbox_flag[BB_MAXR];
+};
+
+/* everything a kernel needs about this rank, passed by value */
+struct Dev {
+  Layout L;
+  double *r, *P[2], *q, *x;
+  unsigned char *fmask, *pmask;
+  double *recv[2][6];
+  double *partials;
+  unsigned *counter;
+  Scal *sc;
+  double *history;
+  double idx2, idy2, idz2;        /* 1/(dx*dx) ...  (per block, src/solver_kernel.cu:720-722) */
+  double dx2_6, dy2_6, dz2_6;     /* dx*dx/6 ...    (src/solver_kernel.cu:683)                */
+  Halo halo;
+  Comm comm;
+};
+
+#endif

@@ -1,0 +1,740 @@
+/* bbpcg_kernels.cuh -- hand-written sm_100a kernels of the pressure-Poisson PCG path.
+ *
+ * One PCG iteration is TWO kernels (the reference uses 3 kernels + 2 Thrust reductions + 12
+ * pack/unpack kernels + 4 host syncs, src/cuda_solver.cu:196-263):
+ *
+ *   k_search_spmv   p = z + beta p  (z = r*invM recomputed from the 1-byte mask)   [PP_update_search]
+ *                   x += alpha_prev p_prev   (lazy phi update)                      [PP_update_soln_resid, phi part]
+ *                   q = -A p  (7-point, flag^2 / phase coefficients)                [PP_spmv_shared_load(_noparts)]
+ *                   (p,q) partial -> last CTA: rank-ordered all-reduce, alpha        [inner_product + MPI_Allreduce]
+ *   k_resid         r -= alpha q ; (r, r*invM) partial ; boundary r values are stored
+ *                   straight into the neighbour's ghost cells over NVLink peer memory
+ *                   [PP_update_soln_resid r/z part, inner_product, MPI_Allreduce, mpi_cuda_exchange_Gcc]
+ *                   last CTA: all-reduce, stop test, beta.
+ *
+ * Algorithmic traffic: 48 B + 24 B = 72 B per cell per iteration (+2 mask bytes).
+ * All scalars live in device memory (struct Scal); a finished solve turns every later launch
+ * into a no-op through Scal::done.
+ */
+#ifndef BBPCG_KERNELS_CUH
+#define BBPCG_KERNELS_CUH
+
+#include "bbpcg_internal.h"
+
+typedef unsigned char u8;
+
+/* ------------------------------------------------------------------------------------ */
+/* Jacobi diagonal from the 6 flag^2 bits: PP_jacobi_init, src/solver_kernel.cu:73-80.
+ * invM = -1/M, M = -idx2(fE^2+fW^2) - idy2(fN^2+fS^2) - idz2(fT^2+fB^2).  128 entries:
+ * masks with FM_DEAD (ghosts behind walls) give 0 so that z = p = 0 there. */
+__device__ __forceinline__ void fill_invM_table(double *tab, const Dev &d)
+{
+  for (int m = threadIdx.x; m < 128; m += blockDim.x) {
+    double v = 0.;
+    if (!(m & FM_DEAD)) {
+      int e = (m & FM_E) != 0, w = (m & FM_W) != 0, n = (m & FM_N) != 0, s = (m & FM_S) != 0,
+          t = (m & FM_T) != 0, b = (m & FM_B) != 0;
+      double M = -d.idx2 * (double)(e + w) - d.idy2 * (double)(n + s) - d.idz2 * (double)(t + b);
+      v = -1. / M;
+    }
+    tab[m] = v;
+  }
+}
+
+/* -A p at one cell, noparts operator: src/solver_kernel.cu:824-829 (same association) */
+__device__ __forceinline__ double stencil_noparts(const Dev &d, unsigned m, double pC, double pE, double pW,
+                                                  double pN, double pS, double pT, double pB)
+{
+  double fe = (m & FM_E) ? 1. : 0., fw = (m & FM_W) ? 1. : 0., fn = (m & FM_N) ? 1. : 0.,
+         fs = (m & FM_S) ? 1. : 0., ft = (m & FM_T) ? 1. : 0., fb = (m & FM_B) ? 1. : 0.;
+  return -d.idx2 * (fe * (pE - pC) - fw * (pC - pW))
+         - d.idy2 * (fn * (pN - pC) - fs * (pC - pS))
+         - d.idz2 * (ft * (pT - pC) - fb * (pC - pB));
+}
+
+/* -A p at one cell with particle masking: src/solver_kernel.cu:683-707 */
+__device__ __forceinline__ double stencil_parts(const Dev &d, unsigned m, unsigned pm, double pC, double pE,
+                                                double pW, double pN, double pS, double pT, double pB)
+{
+  double fe = (m & FM_E) ? 1. : 0., fw = (m & FM_W) ? 1. : 0., fn = (m & FM_N) ? 1. : 0.,
+         fs = (m & FM_S) ? 1. : 0., ft = (m & FM_T) ? 1. : 0., fb = (m & FM_B) ? 1. : 0.;
+  bool solid = (pm & PM_C) != 0;
+  double pfx = solid ? -d.dx2_6 : 1., pfy = solid ? -d.dy2_6 : 1., pfz = solid ? -d.dz2_6 : 1.;
+  double pfe = (!solid && !(pm & PM_E)) ? 1. : 0., pfw = (!solid && !(pm & PM_W)) ? 1. : 0.;
+  double pfn = (!solid && !(pm & PM_N)) ? 1. : 0., pfs = (!solid && !(pm & PM_S)) ? 1. : 0.;
+  double pft = (!solid && !(pm & PM_T)) ? 1. : 0., pfb = (!solid && !(pm & PM_B)) ? 1. : 0.;
+  double a;
+  a = -d.idx2 * (fe * (pE * pfe - pfx * pC) - fw * (pC * pfx - pfw * pW));
+  a += -d.idy2 * (fn * (pN * pfn - pfy * pC) - fs * (pC * pfy - pfs * pS));
+  a += -d.idz2 * (ft * (pT * pft - pfz * pC) - fb * (pC * pfz - pfb * pB));
+  return a;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Deterministic grid reduction of NV values: warp shuffle tree -> per-warp slots -> CTA
+ * partial in a fixed slot -> the LAST CTA to arrive sums the slots in a fixed order.
+ * Returns true (all threads) only in that last CTA; tot[] valid in thread 0. */
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int NV>
+__device__ __forceinline__ double block_sum(double v, double *sh /*[32]*/)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double s = 0.;
+  if (threadIdx.x == 0) for (int w = 0; w < nw; w++) s += sh[w];
+  return s;
+}
+
+template <int NV>
+__device__ bool grid_reduce(const Dev &d, double (&v)[NV], int bid, int nblocks, double (&tot)[NV], bool peer_stores)
+{
+  __shared__ double sh[32];
+  __shared__ int s_last;
+  double part[NV];
+#pragma unroll
+  for (int n = 0; n < NV; n++) part[n] = block_sum<NV>(v[n], sh);
+  if (peer_stores) __threadfence_system();       /* halo stores visible before we count in */
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int n = 0; n < NV; n++) d.partials[n * BB_MAXBLOCKS + bid] = part[n];
+    __threadfence_system();
+    unsigned t = atomicAdd(d.counter, 1u);
+    s_last = (t == (unsigned)(nblocks - 1));
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+#pragma unroll
+  for (int n = 0; n < NV; n++) {
+    double s = 0.;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) s += __ldcg(&d.partials[n * BB_MAXBLOCKS + i]);
+    tot[n] = block_sum<NV>(s, sh);
+  }
+  if (threadIdx.x == 0) *d.counter = 0u;
+  return true;
+}
+
+/* Rank-ordered all-reduce of up to 2 doubles through peer-mapped mailboxes (replaces
+ * MPI_Allreduce, src/cuda_solver.cu:152,170,205,232).  Called by the last CTA only.  Every
+ * rank writes its partial into every rank's mailbox (one NVLink store each), then waits for
+ * the N slots of its own mailbox and adds them in rank order: the sum is bit-identical on
+ * all ranks and run to run.  nv == 0 makes it a barrier.  Threads 0..nranks-1 take part. */
+__device__ __forceinline__ void rank_allreduce(const Dev &d, double *v /* thread 0's values, in/out */, int nv)
+{
+  const Comm &c = d.comm;
+  if (c.nranks <= 1) return;
+  __shared__ double s_v[2];
+  __shared__ double s_in[BB_MAXR][2];
+  __shared__ unsigned long long s_seq;
+  if (threadIdx.x == 0) { s_v[0] = nv > 0 ? v[0] : 0.; s_v[1] = nv > 1 ? v[1] : 0.; s_seq = ++d.sc->seq; __threadfence_system(); }
+  __syncthreads();
+  const unsigned long long seq = s_seq;
+  const int slot = (int)(seq & (BB_NSLOT - 1));
+  const int t = threadIdx.x;
+  if (t < c.nranks) {
+    double *dst = c.mbox_val[t] + (size_t)(slot * BB_MAXR + c.rank) * 2;
+    dst[0] = s_v[0]; dst[1] = s_v[1];
+    __threadfence_system();
+    *((volatile unsigned long long *)(c.mbox_flag[t] + slot * BB_MAXR + c.rank)) = seq;
+    /* wait for rank t's contribution in my own mailbox */
+    volatile unsigned long long *f = (volatile unsigned long long *)(c.mbox_flag[c.rank] + slot * BB_MAXR + t);
+    long long t0 = clock64();
+    bool ok = true;
+    while (*f != seq) {
+      if (clock64() - t0 > (1ll << 34)) { ok = false; break; }    /* ~8 s: a peer is gone */
+    }
+    __threadfence_system();
+    volatile double *src = (volatile double *)(c.mbox_val[c.rank] + (size_t)(slot * BB_MAXR + t) * 2);
+    s_in[t][0] = src[0]; s_in[t][1] = src[1];
+    if (!ok) d.sc->comm_timeout = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0., b = 0.;
+    for (int p = 0; p < c.nranks; p++) { a += s_in[p][0]; b += s_in[p][1]; }
+    if (nv > 0) v[0] = a;
+    if (nv > 1) v[1] = b;
+  }
+  __syncthreads();
+}
+
+/* store a boundary value into the neighbours' ghost cells (what mpi_cuda_exchange_Gcc's
+ * pack -> MPI_Put -> unpack achieves, src/mpi_comm.c:257-315, faces only).  `which` selects
+ * the neighbour array: 0 r, 1 x.  Returns true if a (possibly remote) store was made. */
+__device__ __forceinline__ bool push_halo(const Dev &d, int which, int i, int j, int k, double val)
+{
+  const Layout &L = d.L;
+  bool any = false;
+#define BB_PUSH(F, COND, II, JJ, KK)                                            \
+  if (COND) {                                                                   \
+    const NbrFace &nf = d.halo.f[F];                                            \
+    double *base = which == 0 ? nf.r : nf.x;                                    \
+    if (base) { base[pidx(nf.L, II, JJ, KK)] = val; any = true; }               \
+  }
+  BB_PUSH(0, i == L.in, 0, j, k)               /* my east face  -> east neighbour's west ghost  */
+  BB_PUSH(1, i == 1, nf.L.in + 1, j, k)        /* my west face  -> west neighbour's east ghost  */
+  BB_PUSH(2, j == L.jn, i, 0, k)
+  BB_PUSH(3, j == 1, i, nf.L.jn + 1, k)
+  BB_PUSH(4, k == L.kn, i, j, 0)
+  BB_PUSH(5, k == 1, i, j, nf.L.kn + 1)
+#undef BB_PUSH
+  return any;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* k_search_spmv: see file header.  CTA tile TX x TY owned cells, marching KC planes in k.
+ * Phase A (plane kk): every thread computes p_new on the halo'd tile (TX+2)x(TY+2) from
+ * r, p_prev and the mask (values prefetched into registers one plane ahead), stores it into
+ * a 4-slot shared-memory ring, writes p_new / updates x for the cells this CTA owns and keeps
+ * the block's ghost copies of p current.  Phase B (plane kk-1): 7-point operator from the
+ * ring, q store, (p,q) partial.  One __syncthreads per plane. */
+struct SearchArgs {
+  int KC;          /* planes per CTA */
+  int nbx, nby, nbz;
+};
+
+template <int TX, int TY, int NT, int MINB, bool PARTS>
+__global__ void __launch_bounds__(NT, MINB) k_search_spmv(const Dev d, const SearchArgs a)
+{
+  Scal *sc = d.sc;
+  if (sc->done) return;
+  constexpr int HX = TX + 2, HY = TY + 2, NITEM = HX * HY;
+  constexpr int IPT = (NITEM + NT - 1) / NT;
+  constexpr int NB = TX * TY;
+  static_assert(NB % NT == 0, "tile must be a multiple of the CTA size");
+  constexpr int BPT = NB / NT;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *sp = reinterpret_cast<double *>(smem_raw);            /* [4][NITEM] */
+  double *tab = sp + 4 * NITEM;                                 /* [128]      */
+  u8 *sm = reinterpret_cast<u8 *>(tab + 128);                   /* [4][NITEM] */
+
+  const Layout L = d.L;
+  const int q = sc->q;
+  const double beta = sc->beta, ax = sc->alpha_x;
+  const double *__restrict__ r = d.r;
+  const double *__restrict__ pprev = d.P[q & 1];
+  double *__restrict__ pnew = d.P[(q + 1) & 1];
+  double *__restrict__ x = d.x;
+  double *__restrict__ qv = d.q;
+  const u8 *__restrict__ fmask = d.fmask;
+
+  fill_invM_table(tab, d);
+
+  const int tid = threadIdx.x;
+  const int i0 = blockIdx.x * TX + 1, j0 = blockIdx.y * TY + 1;
+  const int k0 = blockIdx.z * a.KC + 1;
+  const int k1 = min(k0 + a.KC - 1, L.kn);
+  const int ilast = min(i0 + TX - 1, L.in), jlast = min(j0 + TY - 1, L.jn);
+
+  /* per-thread item geometry, fixed across planes */
+  int goff[IPT];                 /* in-plane offset of the item, -1: not a cell */
+  unsigned role[IPT];            /* bit0 owned (x,y)   bit1 in-plane ghost this CTA maintains */
+#pragma unroll
+  for (int n = 0; n < IPT; n++) {
+    int idx = tid + n * NT;
+    int hx = idx % HX, hy = idx / HX;
+    int i = i0 - 1 + hx, j = j0 - 1 + hy;
+    bool valid = idx < NITEM && i <= L.in + 1 && j <= L.jn + 1;
+    bool ox = i >= i0 && i <= ilast, oy = j >= j0 && j <= jlast;
+    bool gx = (i == 0 || i == L.in + 1), gy = (j == 0 || j == L.jn + 1);
+    /* a ghost in x next to a cell we own (hx = 0 or the column right of ilast), same in y */
+    bool mx = gx && oy && ((i == 0 && i0 == 1) || (i == L.in + 1 && ilast == L.in));
+    bool my = gy && ox && ((j == 0 && j0 == 1) || (j == L.jn + 1 && jlast == L.jn));
+    goff[n] = valid ? (i + BB_XOFF) + j * L.px : -1;
+    role[n] = (ox && oy ? 1u : 0u) | ((mx || my) ? 2u : 0u);
+  }
+
+  double rr[IPT], pp[IPT], xx[IPT];
+  unsigned mm[IPT];
+
+  auto prefetch = [&](int kk) {
+    const long long pb = (long long)kk * L.ps;
+    const bool plane_owned = kk >= k0 && kk <= k1;
+#pragma unroll
+    for (int n = 0; n < IPT; n++) {
+      rr[n] = 0.; pp[n] = 0.; xx[n] = 0.; mm[n] = FM_DEAD;
+      if (goff[n] >= 0) {
+        const long long g = pb + goff[n];
+        rr[n] = __ldg(r + g);
+        pp[n] = __ldg(pprev + g);
+        mm[n] = __ldg(fmask + g);
+        if (plane_owned && (role[n] & 1u)) xx[n] = x[g];
+      }
+    }
+  };
+
+  double dot = 0.;
+  prefetch(k0 - 1);
+  __syncthreads();          /* invM table ready */
+
+  for (int kk = k0 - 1; kk <= k1 + 1; kk++) {
+    const int slot = kk & 3;
+    const long long pb = (long long)kk * L.ps;
+    const bool plane_owned = kk >= k0 && kk <= k1;
+    const bool plane_ghost = (kk == 0 || kk == L.kn + 1);
+    /* ---- phase A: p_new on the halo'd tile of plane kk ---- */
+#pragma unroll
+    for (int n = 0; n < IPT; n++) {
+      int idx = tid + n * NT;
+      if (idx < NITEM) {
+        double z = rr[n] * tab[mm[n] & 127u];
+        double pn = z + beta * pp[n];                     /* PP_update_search, solver_kernel.cu:921 */
+        sp[slot * NITEM + idx] = pn;
+        sm[slot * NITEM + idx] = (u8)mm[n];
+        if (goff[n] >= 0) {
+          const long long g = pb + goff[n];
+          if (plane_owned) {
+            if (role[n] & 1u) { pnew[g] = pn; x[g] = xx[n] + ax * pp[n]; }   /* phi += alpha p, :852 */
+            else if (role[n] & 2u) pnew[g] = pn;
+          } else if (plane_ghost && (role[n] & 1u)) pnew[g] = pn;
+        }
+      }
+    }
+    if (kk + 1 <= k1 + 1) prefetch(kk + 1);
+    __syncthreads();
+    /* ---- phase B: q = -A p on plane kk-1 ---- */
+    const int kc = kk - 1;
+    if (kc >= k0) {
+      const double *S0 = sp + ((kc - 1) & 3) * NITEM, *S1 = sp + (kc & 3) * NITEM, *S2 = sp + ((kc + 1) & 3) * NITEM;
+      const u8 *M1 = sm + (kc & 3) * NITEM;
+      const long long pc = (long long)kc * L.ps;
+#pragma unroll
+      for (int m = 0; m < BPT; m++) {
+        int idx = tid + m * NT;
+        int tx = idx % TX, ty = idx / TX;
+        int i = i0 + tx, j = j0 + ty;
+        if (i <= L.in && j <= L.jn) {
+          int c = (ty + 1) * HX + (tx + 1);
+          double pC = S1[c];
+          const long long g = pc + (i + BB_XOFF) + (long long)j * L.px;
+          double Ap;
+          if (PARTS) Ap = stencil_parts(d, M1[c], __ldg(d.pmask + g), pC, S1[c + 1], S1[c - 1], S1[c + HX], S1[c - HX], S2[c], S0[c]);
+          else Ap = stencil_noparts(d, M1[c], pC, S1[c + 1], S1[c - 1], S1[c + HX], S1[c - HX], S2[c], S0[c]);
+          qv[g] = Ap;
+          dot += pC * Ap;
+        }
+      }
+    }
+  }
+
+  /* ---- (p,q): grid reduction, rank all-reduce, alpha (cuda_solver.cu:204-206) ---- */
+  double v[1] = { dot }, tot[1];
+  const int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  const int nblocks = gridDim.x * gridDim.y * gridDim.z;
+  if (grid_reduce<1>(d, v, bid, nblocks, tot, false)) {
+    rank_allreduce(d, tot, 1);
+    if (threadIdx.x == 0) {
+      sc->pAp = tot[0];
+      sc->alpha = sc->rz / tot[0];
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* k_resid: r -= alpha q; (r, z); halo push of r; stop test + beta in the last CTA.
+ * One CTA-iteration = ROWS x-rows; thread = VEC consecutive cells.
+ * Follows PP_update_soln_resid (r/z part, src/solver_kernel.cu:855-858) and the host logic
+ * of src/cuda_solver.cu:231-267. */
+__device__ __forceinline__ void finish_iteration(const Dev &d, double rz_new, bool refreshed)
+{
+  Scal *sc = d.sc;
+  const int qn = sc->q + 1;
+  sc->q = qn;
+  if (qn < BB_HIST_CAP) d.history[qn] = rz_new;
+  sc->alpha_x = refreshed ? 0. : sc->alpha;
+  if (sc->comm_timeout) { sc->done = 1; sc->status = 4; sc->resid = sqrt(rz_new) / sqrt(sc->bb); return; }
+  if (!sc->fixed && rz_new <= sc->tol2 * sc->bb) {               /* :235 */
+    sc->done = 1; sc->status = BBPCG_CONVERGED; sc->resid = sqrt(rz_new) / sqrt(sc->bb);
+  } else if (!sc->fixed && isnan(rz_new)) {                      /* :245 */
+    sc->done = 1; sc->status = BBPCG_NAN; sc->resid = rz_new;
+  } else if (!sc->fixed && qn >= sc->max_q) {                    /* :192,:271 */
+    sc->done = 1; sc->status = BBPCG_MAXITER; sc->resid = sqrt(rz_new) / sqrt(sc->bb);
+  } else {
+    sc->beta = rz_new / sc->rz;                                  /* :256 */
+    sc->rz = rz_new;                                             /* :267 */
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_resid(const Dev d)
+{
+  Scal *sc = d.sc;
+  if (sc->done) return;
+  __shared__ double tab[128];
+  fill_invM_table(tab, d);
+  __syncthreads();
+  const Layout L = d.L;
+  const double alpha = sc->alpha;
+  double *__restrict__ r = d.r;
+  const double *__restrict__ qv = d.q;
+  const u8 *__restrict__ fmask = d.fmask;
+  const long long nrows = (long long)L.jn * L.kn;
+  const int half = L.in >> 1;
+  double dot = 0.;
+  bool pushed = false;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int j = (int)(row % L.jn) + 1, k = (int)(row / L.jn) + 1;
+    const long long base = pidx(L, 1, j, k);
+    const bool edge_row = (j == 1 || j == L.jn || k == 1 || k == L.kn);
+    for (int h = threadIdx.x; h < half; h += NT) {
+      const long long g = base + 2 * h;
+      double2 rv = *reinterpret_cast<const double2 *>(r + g);
+      const double2 qq = __ldg(reinterpret_cast<const double2 *>(qv + g));
+      const uchar2 mk = __ldg(reinterpret_cast<const uchar2 *>(fmask + g));
+      rv.x -= alpha * qq.x;  rv.y -= alpha * qq.y;                       /* solver_kernel.cu:855 */
+      const double z0 = rv.x * tab[mk.x & 127u], z1 = rv.y * tab[mk.y & 127u];   /* :858 */
+      dot += rv.x * z0;  dot += rv.y * z1;
+      *reinterpret_cast<double2 *>(r + g) = rv;
+      const int i = 2 * h + 1;
+      if (edge_row || i == 1) pushed |= push_halo(d, 0, i, j, k, rv.x);
+      if (edge_row || i + 1 == L.in) pushed |= push_halo(d, 0, i + 1, j, k, rv.y);
+    }
+    if ((L.in & 1) && threadIdx.x == 0) {                                /* odd row length: last cell */
+      const int i = L.in;
+      const long long g = base + (i - 1);
+      double rv = r[g] - alpha * qv[g];
+      const double z = rv * tab[fmask[g] & 127u];
+      dot += rv * z;
+      r[g] = rv;
+      pushed |= push_halo(d, 0, i, j, k, rv);
+    }
+  }
+  double v[1] = { dot }, tot[1];
+  if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) {
+    rank_allreduce(d, tot, 1);
+    if (threadIdx.x == 0) finish_iteration(d, tot[0], false);
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Every-50th-iteration true-residual refresh, src/cuda_solver.cu:209-223:
+ * k_refresh_x : phi += alpha p (PP_update_solution, solver_kernel.cu:864-881) + halo of phi
+ * k_refresh_r : r = b - (-A)phi ; z ; (r,z)  (SpMV + PP_update_residual, :883-904) + halo of r */
+template <int NT>
+__global__ void __launch_bounds__(NT) k_refresh_x(const Dev d)
+{
+  Scal *sc = d.sc;
+  if (sc->done) return;
+  const Layout L = d.L;
+  const double alpha = sc->alpha, ax = sc->alpha_x;
+  const double *__restrict__ pcur = d.P[(sc->q + 1) & 1];     /* p of the iteration in flight */
+  const double *__restrict__ pprev = d.P[sc->q & 1];
+  (void)pprev; (void)ax;
+  double *__restrict__ x = d.x;
+  const long long nrows = (long long)L.jn * L.kn;
+  bool pushed = false;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int j = (int)(row % L.jn) + 1, k = (int)(row / L.jn) + 1;
+    const long long base = pidx(L, 1, j, k);
+    for (int i = threadIdx.x + 1; i <= L.in; i += NT) {
+      const long long g = base + (i - 1);
+      /* x already holds phi_{q-1} (k_search_spmv applied alpha_{q-1} p_{q-1}); add this step */
+      double xv = x[g] + alpha * pcur[g];
+      x[g] = xv;
+      if (j == 1 || j == L.jn || k == 1 || k == L.kn || i == 1 || i == L.in) pushed |= push_halo(d, 1, i, j, k, xv);
+    }
+  }
+  double v[1] = { 0. }, tot[1];
+  if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) rank_allreduce(d, tot, 0);   /* barrier */
+}
+
+template <int NT, bool PARTS>
+__global__ void __launch_bounds__(NT) k_refresh_r(const Dev d, const double *__restrict__ rhs_s3b, int s1b, int s2b)
+{
+  Scal *sc = d.sc;
+  if (sc->done) return;
+  __shared__ double tab[128];
+  fill_invM_table(tab, d);
+  __syncthreads();
+  const Layout L = d.L;
+  const double *__restrict__ x = d.x;
+  double *__restrict__ r = d.r;
+  const long long nrows = (long long)L.jn * L.kn;
+  double dot = 0.;
+  bool pushed = false;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int j = (int)(row % L.jn) + 1, k = (int)(row / L.jn) + 1;
+    const long long base = pidx(L, 1, j, k);
+    for (int i = threadIdx.x + 1; i <= L.in; i += NT) {
+      const long long g = base + (i - 1);
+      const unsigned m = d.fmask[g];
+      double Ap;
+      if (PARTS) Ap = stencil_parts(d, m, d.pmask[g], x[g], x[g + 1], x[g - 1], x[g + L.px], x[g - L.px], x[g + L.ps], x[g - L.ps]);
+      else Ap = stencil_noparts(d, m, x[g], x[g + 1], x[g - 1], x[g + L.px], x[g - L.px], x[g + L.ps], x[g - L.ps]);
+      double rv = rhs_s3b[i + (long long)j * s1b + (long long)k * s2b] - Ap;    /* solver_kernel.cu:897 */
+      double z = rv * tab[m & 127u];
+      dot += rv * z;
+      r[g] = rv;
+      if (j == 1 || j == L.jn || k == 1 || k == L.kn || i == 1 || i == L.in) pushed |= push_halo(d, 0, i, j, k, rv);
+    }
+  }
+  double v[1] = { dot }, tot[1];
+  if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) {
+    rank_allreduce(d, tot, 1);
+    if (threadIdx.x == 0) finish_iteration(d, tot[0], true);
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Set-up: r = b, x = 0, (b,b), (r,z) -- PP_cg_init (src/solver_kernel.cu:258-283) and the two
+ * inner products of src/cuda_solver.cu:151,169.  p buffers are zeroed by the host (memset), so
+ * the first k_search_spmv computes p = z + 0*0. */
+template <int NT>
+__global__ void __launch_bounds__(NT) k_init(const Dev d, const double *__restrict__ rhs_s3b, int s1b, int s2b,
+                                             double tol2, int max_q, int fixed)
+{
+  __shared__ double tab[128];
+  fill_invM_table(tab, d);
+  __syncthreads();
+  const Layout L = d.L;
+  const long long nrows = (long long)L.jn * L.kn;
+  double bb = 0., rz = 0.;
+  bool pushed = false;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int j = (int)(row % L.jn) + 1, k = (int)(row / L.jn) + 1;
+    const long long base = pidx(L, 1, j, k);
+    for (int i = threadIdx.x + 1; i <= L.in; i += NT) {
+      const long long g = base + (i - 1);
+      const double b = rhs_s3b[i + (long long)j * s1b + (long long)k * s2b];
+      const double z = b * tab[d.fmask[g] & 127u];
+      bb += b * b;  rz += b * z;
+      d.r[g] = b;
+      if (j == 1 || j == L.jn || k == 1 || k == L.kn || i == 1 || i == L.in) pushed |= push_halo(d, 0, i, j, k, b);
+    }
+  }
+  double v[2] = { bb, rz }, tot[2];
+  if (grid_reduce<2>(d, v, blockIdx.x, gridDim.x, tot, pushed)) {
+    rank_allreduce(d, tot, 2);
+    if (threadIdx.x == 0) {
+      Scal *sc = d.sc;
+      sc->bb = tot[0]; sc->rz = tot[1]; sc->rz0 = tot[1];
+      sc->alpha = 0.; sc->alpha_x = 0.; sc->beta = 0.; sc->pAp = 0.; sc->resid = 0.;
+      sc->tol2 = tol2; sc->max_q = max_q; sc->fixed = fixed; sc->q = 0;
+      sc->status = BBPCG_CONVERGED;
+      d.history[0] = tot[1];
+      const double RHS_TOL = 1.e-8;                                          /* cuda_solver.cu:176 */
+      if (!fixed && tot[0] < RHS_TOL * RHS_TOL) { sc->done = 1; sc->status = BBPCG_TINY_RHS; }
+      else sc->done = sc->comm_timeout ? 1 : 0;
+      if (sc->comm_timeout) sc->status = 4;
+    }
+  }
+}
+
+/* phi (caller's Gcc s3b array) = x + alpha_x * p  for interior cells */
+template <int NT>
+__global__ void __launch_bounds__(NT) k_finish(const Dev d, double *__restrict__ phi_s3b, int s1b, int s2b)
+{
+  const Scal *sc = d.sc;
+  const Layout L = d.L;
+  const double ax = sc->alpha_x;
+  const double *__restrict__ pcur = d.P[sc->q & 1];
+  const long long nrows = (long long)L.jn * L.kn;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int j = (int)(row % L.jn) + 1, k = (int)(row / L.jn) + 1;
+    const long long base = pidx(L, 1, j, k);
+    for (int i = threadIdx.x + 1; i <= L.in; i += NT) {
+      const long long g = base + (i - 1);
+      phi_s3b[i + (long long)j * s1b + (long long)k * s2b] = d.x[g] + ax * pcur[g];
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* PP_rhs (src/solver_kernel.cu:89-176): rhs = -(((uE-uW) idx + (vN-vS) idy) + (wT-wB) idz) rho/dt
+ * on interior cells, ghosts of rhs zero (the cudaMemset of cuda_solver.cu:122 is done by the
+ * host before this kernel). u*: Gfx (j fastest), v*: Gfy (k fastest), w*: Gfz (i fastest). */
+struct FaceStrides { int us1b, us2b, vs1b, vs2b, ws1b, ws2b, cs1b, cs2b; };
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_rhs(int in, int jn, int kn, FaceStrides st, const double *__restrict__ u,
+                                            const double *__restrict__ v, const double *__restrict__ w,
+                                            double *__restrict__ rhs, double idx, double idy, double idz, double rho_idt)
+{
+  const long long nrows = (long long)jn * kn;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int j = (int)(row % jn) + 1, k = (int)(row / jn) + 1;
+    for (int i = threadIdx.x + 1; i <= in; i += NT) {
+      const double uW = u[j + (long long)k * st.us1b + (long long)i * st.us2b];
+      const double uE = u[j + (long long)k * st.us1b + (long long)(i + 1) * st.us2b];
+      const double vS = v[k + (long long)i * st.vs1b + (long long)j * st.vs2b];
+      const double vN = v[k + (long long)i * st.vs1b + (long long)(j + 1) * st.vs2b];
+      const double wB = w[i + (long long)j * st.ws1b + (long long)k * st.ws2b];
+      const double wT = w[i + (long long)j * st.ws1b + (long long)(k + 1) * st.ws2b];
+      double t = (uE - uW) * idx;
+      t += (vN - vS) * idy;
+      t += (wT - wB) * idz;
+      t *= rho_idt;
+      rhs[i + (long long)j * st.cs1b + (long long)k * st.cs2b] = -t;
+    }
+  }
+}
+
+/* flags (+ phase) -> 1-byte coefficient masks in the private layout, pushed into the
+ * neighbours' ghost masks.  Replaces PP_jacobi_init (the diagonal is recomputed from the mask). */
+template <int NT>
+__global__ void __launch_bounds__(NT) k_masks(const Dev d, FaceStrides st, const int *__restrict__ fu,
+                                              const int *__restrict__ fv, const int *__restrict__ fw,
+                                              const int *__restrict__ phase)
+{
+  const Layout L = d.L;
+  const long long nrows = (long long)L.jn * L.kn;
+  bool pushed = false;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int j = (int)(row % L.jn) + 1, k = (int)(row / L.jn) + 1;
+    for (int i = threadIdx.x + 1; i <= L.in; i += NT) {
+      const int w_ = fu[j + (long long)k * st.us1b + (long long)i * st.us2b];
+      const int e_ = fu[j + (long long)k * st.us1b + (long long)(i + 1) * st.us2b];
+      const int s_ = fv[k + (long long)i * st.vs1b + (long long)j * st.vs2b];
+      const int n_ = fv[k + (long long)i * st.vs1b + (long long)(j + 1) * st.vs2b];
+      const int b_ = fw[i + (long long)j * st.ws1b + (long long)k * st.ws2b];
+      const int t_ = fw[i + (long long)j * st.ws1b + (long long)(k + 1) * st.ws2b];
+      unsigned m = (e_ * e_ ? FM_E : 0u) | (w_ * w_ ? FM_W : 0u) | (n_ * n_ ? FM_N : 0u) | (s_ * s_ ? FM_S : 0u) |
+                   (t_ * t_ ? FM_T : 0u) | (b_ * b_ ? FM_B : 0u);
+      const long long g = pidx(L, i, j, k);
+      d.fmask[g] = (u8)m;
+      if (phase) {
+        const long long C = i + (long long)j * st.cs1b + (long long)k * st.cs2b;
+        unsigned pm = (phase[C] > -1 ? PM_C : 0u) | (phase[C + 1] > -1 ? PM_E : 0u) | (phase[C - 1] > -1 ? PM_W : 0u) |
+                      (phase[C + st.cs1b] > -1 ? PM_N : 0u) | (phase[C - st.cs1b] > -1 ? PM_S : 0u) |
+                      (phase[C + st.cs2b] > -1 ? PM_T : 0u) | (phase[C - st.cs2b] > -1 ? PM_B : 0u);
+        d.pmask[g] = (u8)pm;
+      }
+      /* neighbours need my boundary masks to form z in their ghost copies of my cells */
+#define BB_PUSHM(F, COND, II, JJ, KK) if (COND) { const NbrFace &nf = d.halo.f[F]; if (nf.fmask) { nf.fmask[pidx(nf.L, II, JJ, KK)] = (u8)m; pushed = true; } }
+      BB_PUSHM(0, i == L.in, 0, j, k)  BB_PUSHM(1, i == 1, nf.L.in + 1, j, k)
+      BB_PUSHM(2, j == L.jn, i, 0, k)  BB_PUSHM(3, j == 1, i, nf.L.jn + 1, k)
+      BB_PUSHM(4, k == L.kn, i, j, 0)  BB_PUSHM(5, k == 1, i, j, nf.L.kn + 1)
+#undef BB_PUSHM
+    }
+  }
+  double v[1] = { 0. }, tot[1];
+  if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) rank_allreduce(d, tot, 0);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* particle right-hand-side patch, src/cuda_solver.cu:128-148 */
+__global__ void k_part_rhs_net(double *rhs, const int *phase, const int *phase_shell, long long n)
+{   /* net effect of part_BC_p, src/particle_kernel.cu:1753 */
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) rhs[i] = (double)(phase[i] < 0 && phase_shell[i]) * rhs[i];
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_coeffs_refine(int in, int jn, int kn, int s1b, int s2b, double *rhs,
+                                                      const int *__restrict__ phase, double idx2, double idy2, double idz2)
+{   /* coeffs_refine, src/solver_kernel.cu:212-256 (in place; only solid neighbours contribute
+       and solid cells are never modified, so the in-place update is order independent) */
+  const long long nrows = (long long)jn * kn;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int j = (int)(row % jn) + 1, k = (int)(row / jn) + 1;
+    for (int i = threadIdx.x + 1; i <= in; i += NT) {
+      const long long CC = i + (long long)j * s1b + (long long)k * s2b;
+      const int is_fluid = (phase[CC] == -1);
+      double v = rhs[CC];
+      v += is_fluid * (phase[CC + 1] > -1) * idx2 * (-rhs[CC + 1]);
+      v += is_fluid * (phase[CC - 1] > -1) * idx2 * (-rhs[CC - 1]);
+      v += is_fluid * (phase[CC + s1b] > -1) * idy2 * (-rhs[CC + s1b]);
+      v += is_fluid * (phase[CC - s1b] > -1) * idy2 * (-rhs[CC - s1b]);
+      v += is_fluid * (phase[CC + s2b] > -1) * idz2 * (-rhs[CC + s2b]);
+      v += is_fluid * (phase[CC - s2b] > -1) * idz2 * (-rhs[CC - s2b]);
+      rhs[CC] = v;
+    }
+  }
+}
+
+/* zero_rhs_ghost_{i,j,k}, src/solver_kernel.cu:178-209 */
+__global__ void k_zero_ghosts(double *a, int inb, int jnb, int knb)
+{
+  const long long n = (long long)inb * jnb * knb;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+    int i = (int)(c % inb), j = (int)((c / inb) % jnb), k = (int)(c / ((long long)inb * jnb));
+    if (i == 0 || i == inb - 1 || j == 0 || j == jnb - 1 || k == 0 || k == knb - 1) a[c] = 0.;
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* generic Gcc halo exchange on a caller-owned s3b array: mpi_cuda_exchange_Gcc,
+ * src/mpi_comm.c:257-315.  k_xchg_send reads my interior faces (what pack_planes_Gcc_* read,
+ * src/bluebottle_kernel.cu:684-780) and stores them directly into the neighbour's staging
+ * buffer for the opposite face (that is the MPI_Put, mpi_comm.c:293-306), same buffer layouts
+ * E/W pp=(j-1)+jn(k-1), N/S pp=(k-1)+kn(i-1), T/B pp=(i-1)+in(j-1); the last CTA runs the rank
+ * barrier (the MPI_Win_fence); k_xchg_recv is unpack_planes_Gcc_* (:1083-1177). */
+__global__ void k_xchg_send(const Dev d, const double *__restrict__ a, int s1b, int s2b, int buf)
+{
+  const Layout L = d.L;
+  const long long fi = (long long)L.jn * L.kn, fj = (long long)L.in * L.kn, fk = (long long)L.in * L.jn;
+  const long long total = 2 * (fi + fj + fk);
+  bool pushed = false;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    long long u = t;
+    int f; long long pp;
+    if (u < 2 * fi) { f = (int)(u / fi); pp = u % fi; }
+    else if ((u -= 2 * fi) < 2 * fj) { f = 2 + (int)(u / fj); pp = u % fj; }
+    else { u -= 2 * fj; f = 4 + (int)(u / fk); pp = u % fk; }
+    const NbrFace &nf = d.halo.f[f];
+    if (!nf.recv[buf]) continue;
+    int i, j, k;
+    if (f < 2) { j = (int)(pp % L.jn) + 1; k = (int)(pp / L.jn) + 1; i = (f == 0) ? L.in : 1; }
+    else if (f < 4) { k = (int)(pp % L.kn) + 1; i = (int)(pp / L.kn) + 1; j = (f == 2) ? L.jn : 1; }
+    else { i = (int)(pp % L.in) + 1; j = (int)(pp / L.in) + 1; k = (f == 4) ? L.kn : 1; }
+    nf.recv[buf][pp] = a[i + (long long)j * s1b + (long long)k * s2b];
+    pushed = true;
+  }
+  double v[1] = { 0. }, tot[1];
+  if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) rank_allreduce(d, tot, 0);
+}
+
+__global__ void k_xchg_recv(const Dev d, double *__restrict__ a, int s1b, int s2b, int buf)
+{
+  const Layout L = d.L;
+  const long long fi = (long long)L.jn * L.kn, fj = (long long)L.in * L.kn, fk = (long long)L.in * L.jn;
+  const long long total = 2 * (fi + fj + fk);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    long long u = t;
+    int f; long long pp;
+    if (u < 2 * fi) { f = (int)(u / fi); pp = u % fi; }
+    else if ((u -= 2 * fi) < 2 * fj) { f = 2 + (int)(u / fj); pp = u % fj; }
+    else { u -= 2 * fj; f = 4 + (int)(u / fk); pp = u % fk; }
+    if (!d.halo.f[f].recv[buf]) continue;           /* no neighbour on this side: ghost untouched */
+    int i, j, k;
+    if (f < 2) { j = (int)(pp % L.jn) + 1; k = (int)(pp / L.jn) + 1; i = (f == 0) ? L.in + 1 : 0; }
+    else if (f < 4) { k = (int)(pp % L.kn) + 1; i = (int)(pp / L.kn) + 1; j = (f == 2) ? L.jn + 1 : 0; }
+    else { i = (int)(pp % L.in) + 1; j = (int)(pp / L.in) + 1; k = (f == 4) ? L.kn + 1 : 0; }
+    a[i + (long long)j * s1b + (long long)k * s2b] = d.recv[buf][f][pp];
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* unit entry: Ap (s3) = -A src (s3b, ghosts as given): same operator device functions */
+template <int NT, bool PARTS>
+__global__ void __launch_bounds__(NT) k_spmv_s3b(const Dev d, const double *__restrict__ src, int s1b, int s2b,
+                                                 double *__restrict__ Ap, int s1, int s2)
+{
+  const Layout L = d.L;
+  const long long nrows = (long long)L.jn * L.kn;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int j = (int)(row % L.jn) + 1, k = (int)(row / L.jn) + 1;
+    for (int i = threadIdx.x + 1; i <= L.in; i += NT) {
+      const long long C = i + (long long)j * s1b + (long long)k * s2b;
+      const long long g = pidx(L, i, j, k);
+      const unsigned m = d.fmask[g];
+      double v;
+      if (PARTS) v = stencil_parts(d, m, d.pmask[g], src[C], src[C + 1], src[C - 1], src[C + s1b], src[C - s1b], src[C + s2b], src[C - s2b]);
+      else v = stencil_noparts(d, m, src[C], src[C + 1], src[C - 1], src[C + s1b], src[C - s1b], src[C + s2b], src[C - s2b]);
+      Ap[(i - 1) + (long long)(j - 1) * s1 + (long long)(k - 1) * s2] = v;
+    }
+  }
+}
+
+#endif

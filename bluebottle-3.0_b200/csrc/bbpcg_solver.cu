@@ -1,0 +1,541 @@
+/* bbpcg_solver.cu -- host driver and C ABI of libbbpcg.so (include/bbpcg.h).
+ *
+ * Host control flow of cuda_PP_cg / cuda_PP_cg_noparts (src/cuda_solver.cu:38-300, 573-761)
+ * re-expressed for a device-resident recurrence: the host only enqueues kernels in batches and
+ * polls one `done` word; alpha, beta, the stop test and the iteration count live in device
+ * memory (struct Scal).  There is NO CPU fallback: every entry point needs a CUDA device.
+ */
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <unistd.h>
+
+#include "bbpcg_kernels.cuh"
+
+/* ---- error plumbing ---------------------------------------------------------------------- */
+static thread_local char g_err[512] = "";
+extern "C" void bbpcg_set_error(const char *fmt, ...)
+{
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+extern "C" const char *bbpcg_last_error(void) { return g_err; }
+extern "C" const char *bbpcg_version(void) { return "bbpcg 0.1 (sm_100a)"; }
+
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+  bbpcg_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); return BBPCG_ECUDA; } } while (0)
+
+/* ---- the solver object ------------------------------------------------------------------- */
+struct ExportBlob {                 /* one rank's record for bbpcg_comm_import (<= BBPCG_BLOB_BYTES) */
+  unsigned magic;
+  int rank, in, jn, kn, device;
+  long long pid;
+  unsigned long long arena_ptr;     /* valid inside the exporting process */
+  unsigned long long arena_bytes;
+  cudaIpcMemHandle_t handle;
+};
+static_assert(sizeof(ExportBlob) <= BBPCG_BLOB_BYTES, "blob too large");
+#define BB_MAGIC 0xbb9c6001u
+
+struct bbpcg_solver {
+  dom_struct dom, DOM;
+  bb_pressure_bc bc;
+  int device;
+  cudaStream_t stream;
+  cudaEvent_t ev[4];
+  cudaEvent_t ev_poll[2];
+  char *arena;
+  ArenaMap amap;
+  Dev dev;
+  FaceStrides fst;
+  int nranks;
+  char *peer_arena[BB_MAXR];        /* mapped bases (own arena for self) */
+  bool peer_opened[BB_MAXR];
+  int has_phase;                    /* set_coefficients was given a phase array */
+  int coeffs_set;
+  /* launch configuration */
+  int tile;                         /* k_search_spmv variant */
+  int kc;                           /* planes per CTA */
+  int resid_blocks, stream_blocks;
+  int check_every;                  /* iterations per polling batch */
+  int sm_count;
+  /* pinned poll words + host-mode buffers */
+  int *h_poll;
+  Scal *h_scal;
+  double *hb_u, *hb_v, *hb_w, *hb_rhs, *hb_phi;
+  int *hb_dummy;
+  long long launches;
+  unsigned exchange_count;
+};
+
+static int nbr_rank(const dom_struct &d, int f)
+{
+  switch (f) { case 0: return d.e; case 1: return d.w; case 2: return d.n; case 3: return d.s; case 4: return d.t; default: return d.b; }
+}
+
+static void point_dev_at_arena(bbpcg_solver *s)
+{
+  Dev &d = s->dev;
+  char *a = s->arena;
+  const ArenaMap &m = s->amap;
+  d.r = (double *)(a + m.r); d.P[0] = (double *)(a + m.p0); d.P[1] = (double *)(a + m.p1);
+  d.q = (double *)(a + m.q); d.x = (double *)(a + m.x);
+  d.fmask = (u8 *)(a + m.fmask); d.pmask = (u8 *)(a + m.pmask);
+  for (int b = 0; b < 2; b++) for (int f = 0; f < 6; f++) d.recv[b][f] = (double *)(a + m.recv[b][f]);
+  d.partials = (double *)(a + m.partials); d.counter = (unsigned *)(a + m.counter);
+  d.sc = (Scal *)(a + m.scal); d.history = (double *)(a + m.history);
+}
+
+/* neighbour tables for a set of ranks whose arenas are addressable at peer_arena[] with
+ * interior sizes dims[][3] */
+static void build_halo(bbpcg_solver *s, const int (*dims)[3])
+{
+  static const int opposite[6] = { 1, 0, 3, 2, 5, 4 };
+  Dev &d = s->dev;
+  for (int f = 0; f < 6; f++) {
+    NbrFace &nf = d.halo.f[f];
+    memset(&nf, 0, sizeof(nf));
+    int nb = nbr_rank(s->dom, f);
+    if (nb < 0) continue;
+    char *base = s->peer_arena[nb];
+    if (!base) continue;
+    Layout L = make_layout(dims[nb][0], dims[nb][1], dims[nb][2]);
+    ArenaMap m = make_arena_map(L);
+    nf.L = L;
+    nf.r = (double *)(base + m.r); nf.x = (double *)(base + m.x); nf.fmask = (u8 *)(base + m.fmask);
+    for (int b = 0; b < 2; b++) nf.recv[b] = (double *)(base + m.recv[b][opposite[f]]);
+  }
+  d.comm.rank = s->dom.rank; d.comm.nranks = s->nranks;
+  for (int p = 0; p < BB_MAXR; p++) { d.comm.mbox_val[p] = NULL; d.comm.mbox_flag[p] = NULL; }
+  for (int p = 0; p < s->nranks; p++) {
+    Layout L = make_layout(dims[p][0], dims[p][1], dims[p][2]);
+    ArenaMap m = make_arena_map(L);
+    d.comm.mbox_val[p] = (double *)(s->peer_arena[p] + m.mbox_val);
+    d.comm.mbox_flag[p] = (unsigned long long *)(s->peer_arena[p] + m.mbox_flag);
+  }
+}
+
+extern "C" int bbpcg_create(bbpcg_solver **out, const dom_struct *dom_rank, const dom_struct *DOM,
+                            const bb_pressure_bc *bc, int device)
+{
+  if (!out || !dom_rank || !DOM || !bc) { bbpcg_set_error("bbpcg_create: NULL argument"); return BBPCG_EINVAL; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    bbpcg_set_error("bbpcg_create: no CUDA device (this library has no CPU path)"); return BBPCG_ECUDA;
+  }
+  if (device < 0) CU(cudaGetDevice(&device));
+  CU(cudaSetDevice(device));
+  bbpcg_solver *s = new bbpcg_solver();
+  memset(s, 0, sizeof(*s));
+  s->dom = *dom_rank; s->DOM = *DOM; s->bc = *bc; s->device = device;
+  const grid_info &g = dom_rank->Gcc;
+  if (g.in < 1 || g.jn < 1 || g.kn < 1 || g.s1b != g.in + 2 || g.s2b != g.s1b * (g.jn + 2)) {
+    bbpcg_set_error("bbpcg_create: dom_struct is not filled (run bb_domain_fill)"); delete s; return BBPCG_EINVAL;
+  }
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  s->sm_count = prop.multiProcessorCount;
+  Dev &d = s->dev;
+  d.L = make_layout(g.in, g.jn, g.kn);
+  s->amap = make_arena_map(d.L);
+  if (cudaMalloc(&s->arena, s->amap.total) != cudaSuccess) {
+    bbpcg_set_error("bbpcg_create: cudaMalloc of %zu bytes failed", s->amap.total); cudaGetLastError(); delete s; return BBPCG_ENOMEM;
+  }
+  CU(cudaMemset(s->arena, 0, s->amap.total));
+  point_dev_at_arena(s);
+  CU(cudaMemset(d.fmask, FM_DEAD, (size_t)d.L.n));          /* ghosts behind walls stay dead forever */
+  d.idx2 = 1. / (dom_rank->dx * dom_rank->dx); d.idy2 = 1. / (dom_rank->dy * dom_rank->dy); d.idz2 = 1. / (dom_rank->dz * dom_rank->dz);
+  d.dx2_6 = (dom_rank->dx * dom_rank->dx) / 6.; d.dy2_6 = (dom_rank->dy * dom_rank->dy) / 6.; d.dz2_6 = (dom_rank->dz * dom_rank->dz) / 6.;
+  s->fst.us1b = dom_rank->Gfx.s1b; s->fst.us2b = dom_rank->Gfx.s2b;
+  s->fst.vs1b = dom_rank->Gfy.s1b; s->fst.vs2b = dom_rank->Gfy.s2b;
+  s->fst.ws1b = dom_rank->Gfz.s1b; s->fst.ws2b = dom_rank->Gfz.s2b;
+  s->fst.cs1b = g.s1b; s->fst.cs2b = g.s2b;
+  CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; i++) CU(cudaEventCreate(&s->ev[i]));
+  for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&s->ev_poll[i], cudaEventDisableTiming));
+  CU(cudaHostAlloc(&s->h_poll, 64, cudaHostAllocDefault));
+  CU(cudaHostAlloc(&s->h_scal, sizeof(Scal), cudaHostAllocDefault));
+  /* single rank: neighbours are this block itself (periodic wrap) or nothing */
+  s->nranks = 1;
+  for (int p = 0; p < BB_MAXR; p++) { s->peer_arena[p] = NULL; s->peer_opened[p] = false; }
+  if (DOM->In * DOM->Jn * DOM->Kn == 1) {
+    s->peer_arena[0] = s->arena;
+    int dims[1][3] = { { g.in, g.jn, g.kn } };
+    build_halo(s, dims);
+  } else {
+    memset(&d.halo, 0, sizeof(d.halo));     /* until bbpcg_comm_import */
+    d.comm.rank = dom_rank->rank; d.comm.nranks = 1;
+  }
+  s->tile = 0; s->kc = 0;
+  s->resid_blocks = s->sm_count * 8;
+  s->stream_blocks = s->sm_count * 8;
+  s->check_every = 10;
+  *out = s;
+  return BBPCG_OK;
+}
+
+extern "C" void bbpcg_destroy(bbpcg_solver *s)
+{
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->stream);
+  for (int p = 0; p < BB_MAXR; p++) if (s->peer_opened[p]) cudaIpcCloseMemHandle(s->peer_arena[p]);
+  cudaFree(s->arena);
+  cudaFree(s->hb_u); cudaFree(s->hb_v); cudaFree(s->hb_w); cudaFree(s->hb_rhs); cudaFree(s->hb_phi);
+  cudaFreeHost(s->h_poll); cudaFreeHost(s->h_scal);
+  for (int i = 0; i < 4; i++) cudaEventDestroy(s->ev[i]);
+  for (int i = 0; i < 2; i++) cudaEventDestroy(s->ev_poll[i]);
+  cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+/* ---- multi-GPU attach --------------------------------------------------------------------- */
+extern "C" int bbpcg_comm_export(bbpcg_solver *s, void *blob)
+{
+  if (!s || !blob) { bbpcg_set_error("bbpcg_comm_export: NULL argument"); return BBPCG_EINVAL; }
+  CU(cudaSetDevice(s->device));
+  ExportBlob b;
+  memset(&b, 0, sizeof(b));
+  b.magic = BB_MAGIC; b.rank = s->dom.rank; b.in = s->dev.L.in; b.jn = s->dev.L.jn; b.kn = s->dev.L.kn;
+  b.device = s->device; b.pid = (long long)getpid();
+  b.arena_ptr = (unsigned long long)(uintptr_t)s->arena; b.arena_bytes = s->amap.total;
+  CU(cudaIpcGetMemHandle(&b.handle, s->arena));
+  memset(blob, 0, BBPCG_BLOB_BYTES);
+  memcpy(blob, &b, sizeof(b));
+  return BBPCG_OK;
+}
+
+extern "C" int bbpcg_comm_import(bbpcg_solver *s, const void *all_blobs, int nranks)
+{
+  if (!s || !all_blobs || nranks < 1 || nranks > BB_MAXR) { bbpcg_set_error("bbpcg_comm_import: bad arguments (nranks %d, max %d)", nranks, BB_MAXR); return BBPCG_EINVAL; }
+  if (nranks != s->DOM.In * s->DOM.Jn * s->DOM.Kn) { bbpcg_set_error("bbpcg_comm_import: %d ranks but the decomposition has %d blocks", nranks, s->DOM.In * s->DOM.Jn * s->DOM.Kn); return BBPCG_EINVAL; }
+  CU(cudaSetDevice(s->device));
+  int dims[BB_MAXR][3];
+  const long long mypid = (long long)getpid();
+  for (int p = 0; p < nranks; p++) {
+    ExportBlob b;
+    memcpy(&b, (const char *)all_blobs + (size_t)p * BBPCG_BLOB_BYTES, sizeof(b));
+    if (b.magic != BB_MAGIC || b.rank != p) { bbpcg_set_error("bbpcg_comm_import: record %d is not rank %d's export", p, p); return BBPCG_ECOMM; }
+    dims[p][0] = b.in; dims[p][1] = b.jn; dims[p][2] = b.kn;
+    if (p == s->dom.rank) { s->peer_arena[p] = s->arena; continue; }
+    if (b.pid == mypid) {
+      /* same process (several ranks driven from one process): the pointer is directly usable;
+       * a different device needs peer access */
+      if (b.device != s->device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, s->device, b.device));
+        if (!can) { bbpcg_set_error("device %d cannot access device %d", s->device, b.device); return BBPCG_ECOMM; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { bbpcg_set_error("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); return BBPCG_ECOMM; }
+        cudaGetLastError();
+      }
+      s->peer_arena[p] = (char *)(uintptr_t)b.arena_ptr;
+    } else {
+      void *ptr = NULL;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, b.handle, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) { bbpcg_set_error("cudaIpcOpenMemHandle(rank %d): %s", p, cudaGetErrorString(e)); cudaGetLastError(); return BBPCG_ECOMM; }
+      s->peer_arena[p] = (char *)ptr; s->peer_opened[p] = true;
+    }
+  }
+  s->nranks = nranks;
+  build_halo(s, dims);
+  return BBPCG_OK;
+}
+
+/* ---- launch helpers ------------------------------------------------------------------------ */
+struct TileCfg { int tx, ty, nt; };
+static const TileCfg k_tiles[] = { { 128, 8, 256 }, { 128, 4, 256 }, { 64, 8, 256 }, { 128, 8, 512 }, { 32, 8, 128 }, { 256, 4, 256 } };
+static const int k_ntiles = sizeof(k_tiles) / sizeof(k_tiles[0]);
+
+template <int TX, int TY, int NT, int MINB>
+static int launch_search_t(bbpcg_solver *s, bool parts)
+{
+  const Layout &L = s->dev.L;
+  constexpr int NITEM = (TX + 2) * (TY + 2);
+  const size_t smem = (size_t)(4 * NITEM + 128) * sizeof(double) + 4 * NITEM;
+  SearchArgs a;
+  a.nbx = (L.in + TX - 1) / TX; a.nby = (L.jn + TY - 1) / TY;
+  int kc = s->kc;
+  if (kc <= 0) {
+    /* enough CTAs for ~4 waves of resident blocks, chunks no shorter than 16 planes */
+    long long want = (long long)s->sm_count * 16;
+    long long per = (long long)a.nbx * a.nby;
+    int nz = (int)((want + per - 1) / per);
+    if (nz < 1) nz = 1;
+    kc = (L.kn + nz - 1) / nz;
+    if (kc < 16) kc = L.kn < 16 ? L.kn : 16;
+  }
+  if (kc > L.kn) kc = L.kn;
+  a.KC = kc; a.nbz = (L.kn + kc - 1) / kc;
+  if ((long long)a.nbx * a.nby * a.nbz > BB_MAXBLOCKS) { bbpcg_set_error("grid too large for the reduction workspace"); return BBPCG_EINVAL; }
+  dim3 grid(a.nbx, a.nby, a.nbz);
+  if (parts) {
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_search_spmv<TX, TY, NT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_search_spmv<TX, TY, NT, MINB, true><<<grid, NT, smem, s->stream>>>(s->dev, a);
+  } else {
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_search_spmv<TX, TY, NT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_search_spmv<TX, TY, NT, MINB, false><<<grid, NT, smem, s->stream>>>(s->dev, a);
+  }
+  s->launches++;
+  return BBPCG_OK;
+}
+
+static int launch_search(bbpcg_solver *s, bool parts)
+{
+  switch (s->tile) {
+    case 0: return launch_search_t<128, 8, 256, 2>(s, parts);
+    case 1: return launch_search_t<128, 4, 256, 3>(s, parts);
+    case 2: return launch_search_t<64, 8, 256, 3>(s, parts);
+    case 3: return launch_search_t<128, 8, 512, 2>(s, parts);
+    case 4: return launch_search_t<32, 8, 128, 4>(s, parts);
+    case 5: return launch_search_t<256, 4, 256, 2>(s, parts);
+  }
+  bbpcg_set_error("unknown tile variant %d", s->tile);
+  return BBPCG_EINVAL;
+}
+
+static int clampi(long long v, int lo, int hi) { return (int)(v < lo ? lo : v > hi ? hi : v); }
+
+/* ---- coefficients -------------------------------------------------------------------------- */
+extern "C" int bbpcg_set_coefficients(bbpcg_solver *s, const int *flag_u, const int *flag_v, const int *flag_w, const int *phase)
+{
+  if (!s || !flag_u || !flag_v || !flag_w) { bbpcg_set_error("bbpcg_set_coefficients: NULL flag array"); return BBPCG_EINVAL; }
+  CU(cudaSetDevice(s->device));
+  if (s->nranks == 1 && s->DOM.In * s->DOM.Jn * s->DOM.Kn != 1) { bbpcg_set_error("decomposition has %d blocks: call bbpcg_comm_import first", s->DOM.In * s->DOM.Jn * s->DOM.Kn); return BBPCG_ECOMM; }
+  const long long nrows = (long long)s->dev.L.jn * s->dev.L.kn;
+  k_masks<256><<<clampi(nrows, 1, s->stream_blocks), 256, 0, s->stream>>>(s->dev, s->fst, flag_u, flag_v, flag_w, phase);
+  s->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  s->has_phase = phase != NULL;
+  s->coeffs_set = 1;
+  return BBPCG_OK;
+}
+
+/* ---- right-hand side ----------------------------------------------------------------------- */
+static int enqueue_rhs(bbpcg_solver *s, const real *u, const real *v, const real *w, real rho_f, real dt, real *rhs)
+{
+  const dom_struct &d = s->dom;
+  CU(cudaMemsetAsync(rhs, 0, sizeof(real) * (size_t)d.Gcc.s3b, s->stream));            /* cuda_solver.cu:122 */
+  const long long nrows = (long long)d.Gcc.jn * d.Gcc.kn;
+  k_rhs<256><<<clampi(nrows, 1, s->stream_blocks), 256, 0, s->stream>>>(d.Gcc.in, d.Gcc.jn, d.Gcc.kn, s->fst, u, v, w, rhs,
+                                                                        1. / d.dx, 1. / d.dy, 1. / d.dz, rho_f / dt);
+  s->launches++;
+  return BBPCG_OK;
+}
+
+extern "C" int bbpcg_rhs(bbpcg_solver *s, const real *u, const real *v, const real *w, real rho_f, real dt, real *rhs)
+{
+  if (!s || !u || !v || !w || !rhs) { bbpcg_set_error("bbpcg_rhs: NULL argument"); return BBPCG_EINVAL; }
+  CU(cudaSetDevice(s->device));
+  int rc = enqueue_rhs(s, u, v, w, rho_f, dt, rhs);
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  return BBPCG_OK;
+}
+
+/* ---- halo exchange on caller arrays -------------------------------------------------------- */
+static int enqueue_exchange(bbpcg_solver *s, real *array)
+{
+  const Layout &L = s->dev.L;
+  const long long total = 2ll * ((long long)L.jn * L.kn + (long long)L.in * L.kn + (long long)L.in * L.jn);
+  const int nb = clampi((total + 255) / 256, 1, s->sm_count * 4);
+  const int buf = (int)(s->exchange_count++ & 1u);
+  k_xchg_send<<<nb, 256, 0, s->stream>>>(s->dev, array, s->fst.cs1b, s->fst.cs2b, buf);
+  k_xchg_recv<<<nb, 256, 0, s->stream>>>(s->dev, array, s->fst.cs1b, s->fst.cs2b, buf);
+  s->launches += 2;
+  return BBPCG_OK;
+}
+
+extern "C" int bbpcg_exchange_Gcc(bbpcg_solver *s, real *array)
+{
+  if (!s || !array) { bbpcg_set_error("bbpcg_exchange_Gcc: NULL argument"); return BBPCG_EINVAL; }
+  CU(cudaSetDevice(s->device));
+  int rc = enqueue_exchange(s, array);
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  return BBPCG_OK;
+}
+
+extern "C" int bbpcg_spmv(bbpcg_solver *s, const real *src_s3b, real *Ap_s3, int use_phase)
+{
+  if (!s || !src_s3b || !Ap_s3) { bbpcg_set_error("bbpcg_spmv: NULL argument"); return BBPCG_EINVAL; }
+  if (!s->coeffs_set) { bbpcg_set_error("bbpcg_spmv: call bbpcg_set_coefficients first"); return BBPCG_EINVAL; }
+  if (use_phase && !s->has_phase) { bbpcg_set_error("bbpcg_spmv: use_phase without a phase array in bbpcg_set_coefficients"); return BBPCG_EINVAL; }
+  CU(cudaSetDevice(s->device));
+  const grid_info &g = s->dom.Gcc;
+  const long long nrows = (long long)g.jn * g.kn;
+  const int nb = clampi(nrows, 1, s->stream_blocks);
+  if (use_phase) k_spmv_s3b<256, true><<<nb, 256, 0, s->stream>>>(s->dev, src_s3b, g.s1b, g.s2b, Ap_s3, g.s1, g.s2);
+  else k_spmv_s3b<256, false><<<nb, 256, 0, s->stream>>>(s->dev, src_s3b, g.s1b, g.s2b, Ap_s3, g.s1, g.s2);
+  s->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  return BBPCG_OK;
+}
+
+/* ---- the solve ----------------------------------------------------------------------------- */
+static int enqueue_iteration(bbpcg_solver *s, int it, bool parts, const real *rhs)
+{
+  const long long nrows = (long long)s->dev.L.jn * s->dev.L.kn;
+  int rc = launch_search(s, parts);
+  if (rc) return rc;
+  if (it % 50 == 0) {                                     /* cuda_solver.cu:209-223 */
+    const int nb = clampi(nrows, 1, s->stream_blocks);
+    k_refresh_x<256><<<nb, 256, 0, s->stream>>>(s->dev);
+    if (parts) k_refresh_r<256, true><<<nb, 256, 0, s->stream>>>(s->dev, rhs, s->fst.cs1b, s->fst.cs2b);
+    else k_refresh_r<256, false><<<nb, 256, 0, s->stream>>>(s->dev, rhs, s->fst.cs1b, s->fst.cs2b);
+    s->launches += 2;
+  } else {
+    k_resid<256><<<clampi(nrows, 1, s->resid_blocks), 256, 0, s->stream>>>(s->dev);
+    s->launches++;
+  }
+  return BBPCG_OK;
+}
+
+extern "C" int bbpcg_solve(bbpcg_solver *s, const bbpcg_solve_args *a, bbpcg_result *res)
+{
+  if (!s || !a || !a->u_star || !a->v_star || !a->w_star || !a->rhs_p || !a->phi) { bbpcg_set_error("bbpcg_solve: NULL argument"); return BBPCG_EINVAL; }
+  if (!s->coeffs_set) { bbpcg_set_error("bbpcg_solve: call bbpcg_set_coefficients first (cuda_PP_init_jacobi_preconditioner)"); return BBPCG_EINVAL; }
+  if (a->use_phase && (!s->has_phase || !a->phase)) { bbpcg_set_error("bbpcg_solve: use_phase needs phase arrays"); return BBPCG_EINVAL; }
+  CU(cudaSetDevice(s->device));
+  const dom_struct &d = s->dom;
+  const grid_info &g = d.Gcc;
+  const Layout &L = s->dev.L;
+  const bool parts = a->use_phase != 0;
+  const long long launches0 = s->launches;
+  const long long nrows = (long long)L.jn * L.kn;
+  const int nbs = clampi(nrows, 1, s->stream_blocks);
+
+  CU(cudaEventRecord(s->ev[0], s->stream));
+  /* ---- set-up: cuda_solver.cu:122-170 ---- */
+  int rc = enqueue_rhs(s, a->u_star, a->v_star, a->w_star, a->rho_f, a->dt, a->rhs_p);
+  if (rc) return rc;
+  if (parts) {                                             /* :128-148 */
+    if (a->part_bc) {
+      CU(cudaStreamSynchronize(s->stream));
+      a->part_bc();                                        /* reference code, default stream */
+      CU(cudaDeviceSynchronize());
+    } else if (a->phase_shell) {
+      k_part_rhs_net<<<(unsigned)((g.s3b + 255) / 256), 256, 0, s->stream>>>(a->rhs_p, a->phase, a->phase_shell, g.s3b);
+      s->launches++;
+    }
+    rc = enqueue_exchange(s, a->rhs_p);
+    if (rc) return rc;
+    k_coeffs_refine<256><<<nbs, 256, 0, s->stream>>>(g.in, g.jn, g.kn, g.s1b, g.s2b, a->rhs_p, a->phase, s->dev.idx2, s->dev.idy2, s->dev.idz2);
+    k_zero_ghosts<<<s->sm_count * 4, 256, 0, s->stream>>>(a->rhs_p, g.inb, g.jnb, g.knb);
+    s->launches += 2;
+  }
+  CU(cudaMemsetAsync(s->dev.x, 0, sizeof(double) * (size_t)L.n, s->stream));
+  CU(cudaMemsetAsync(s->dev.P[0], 0, sizeof(double) * (size_t)L.n, s->stream));
+  const int max_q = a->fixed_iters > 0 ? a->fixed_iters : a->pp_max_iter + 1;
+  k_init<256><<<nbs, 256, 0, s->stream>>>(s->dev, a->rhs_p, g.s1b, g.s2b, a->pp_residual * a->pp_residual, max_q, a->fixed_iters > 0 ? 1 : 0);
+  s->launches++;
+  CU(cudaEventRecord(s->ev[1], s->stream));
+
+  /* ---- iteration loop: kernels are enqueued in batches; each batch ends with an async read
+   * of Scal::done.  Two batches stay in flight so the GPU never idles while the host polls;
+   * once done is set the remaining launches are no-ops. ---- */
+  int it = 0, nbatch = 0;
+  bool finished = false;
+  volatile int *poll = s->h_poll;
+  poll[0] = poll[16 / 4] = 0;
+  while (!finished && it < max_q) {
+    const int upto = (it + s->check_every < max_q) ? it + s->check_every : max_q;
+    while (it < upto) { ++it; rc = enqueue_iteration(s, it, parts, a->rhs_p); if (rc) return rc; }
+    const int slot = nbatch & 1;
+    CU(cudaMemcpyAsync((void *)&s->h_poll[slot * 4], &s->dev.sc->done, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaEventRecord(s->ev_poll[slot], s->stream));
+    if (nbatch >= 1) {
+      const int prev = (nbatch - 1) & 1;
+      CU(cudaEventSynchronize(s->ev_poll[prev]));
+      if (poll[prev * 4]) finished = true;
+    }
+    nbatch++;
+  }
+  CU(cudaEventRecord(s->ev[2], s->stream));
+  k_finish<256><<<nbs, 256, 0, s->stream>>>(s->dev, a->phi, g.s1b, g.s2b);
+  s->launches++;
+  CU(cudaMemcpyAsync(s->h_scal, s->dev.sc, sizeof(Scal), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaEventRecord(s->ev[3], s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaGetLastError());
+
+  const Scal &sc = *s->h_scal;
+  if (res) {
+    float ms;
+    res->status = sc.status; res->niter = sc.q; res->resid = sc.resid; res->sp_rhs = sc.bb; res->sp_rq0 = sc.rz0;
+    if (a->fixed_iters <= 0 && !sc.done) res->status = BBPCG_MAXITER;
+    cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]); res->ms_setup = ms;
+    cudaEventElapsedTime(&ms, s->ev[1], s->ev[2]); res->ms_iter = ms;
+    cudaEventElapsedTime(&ms, s->ev[0], s->ev[3]); res->ms_total = ms;
+    res->launches = s->launches - launches0;
+  }
+  if (sc.status == 4) { bbpcg_set_error("bbpcg_solve: a peer rank never arrived (in-kernel all-reduce timed out)"); return BBPCG_ECOMM; }
+  return BBPCG_OK;
+}
+
+extern "C" int bbpcg_solve_host(bbpcg_solver *s, const real *u_h, const real *v_h, const real *w_h, real *phi_h,
+                                real rho_f, real dt, real pp_residual, int pp_max_iter, int fixed_iters, bbpcg_result *res)
+{
+  if (!s || !u_h || !v_h || !w_h || !phi_h) { bbpcg_set_error("bbpcg_solve_host: NULL argument"); return BBPCG_EINVAL; }
+  CU(cudaSetDevice(s->device));
+  const dom_struct &d = s->dom;
+  if (!s->hb_u) {
+    CU(cudaMalloc(&s->hb_u, sizeof(real) * (size_t)d.Gfx.s3b)); CU(cudaMalloc(&s->hb_v, sizeof(real) * (size_t)d.Gfy.s3b));
+    CU(cudaMalloc(&s->hb_w, sizeof(real) * (size_t)d.Gfz.s3b));
+    CU(cudaMalloc(&s->hb_rhs, sizeof(real) * (size_t)d.Gcc.s3b)); CU(cudaMalloc(&s->hb_phi, sizeof(real) * (size_t)d.Gcc.s3b));
+    CU(cudaMemset(s->hb_phi, 0, sizeof(real) * (size_t)d.Gcc.s3b));
+  }
+  CU(cudaMemcpyAsync(s->hb_u, u_h, sizeof(real) * (size_t)d.Gfx.s3b, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->hb_v, v_h, sizeof(real) * (size_t)d.Gfy.s3b, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->hb_w, w_h, sizeof(real) * (size_t)d.Gfz.s3b, cudaMemcpyHostToDevice, s->stream));
+  bbpcg_solve_args a;
+  memset(&a, 0, sizeof(a));
+  a.u_star = s->hb_u; a.v_star = s->hb_v; a.w_star = s->hb_w; a.rhs_p = s->hb_rhs; a.phi = s->hb_phi;
+  a.rho_f = rho_f; a.dt = dt; a.pp_residual = pp_residual; a.pp_max_iter = pp_max_iter; a.fixed_iters = fixed_iters;
+  int rc = bbpcg_solve(s, &a, res);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(phi_h, s->hb_phi, sizeof(real) * (size_t)d.Gcc.s3b, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return BBPCG_OK;
+}
+
+extern "C" int bbpcg_history(bbpcg_solver *s, double *out, int cap)
+{
+  if (!s || !out || cap < 1) return 0;
+  if (cudaSetDevice(s->device) != cudaSuccess) return 0;
+  int n = s->h_scal->q + 1;
+  if (n > cap) n = cap;
+  if (n > BB_HIST_CAP) n = BB_HIST_CAP;
+  if (cudaMemcpy(out, s->dev.history, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" int bbpcg_set_option(bbpcg_solver *s, const char *key, long long value)
+{
+  if (!s || !key) return BBPCG_EINVAL;
+  if (!strcmp(key, "tile")) { if (value < 0 || value >= k_ntiles) { bbpcg_set_error("tile must be 0..%d", k_ntiles - 1); return BBPCG_EINVAL; } s->tile = (int)value; }
+  else if (!strcmp(key, "kc")) s->kc = (int)value;
+  else if (!strcmp(key, "resid_blocks")) s->resid_blocks = clampi(value, 1, BB_MAXBLOCKS);
+  else if (!strcmp(key, "stream_blocks")) s->stream_blocks = clampi(value, 1, BB_MAXBLOCKS);
+  else if (!strcmp(key, "check_every")) s->check_every = clampi(value, 1, 1000);
+  else { bbpcg_set_error("unknown option %s", key); return BBPCG_EINVAL; }
+  return BBPCG_OK;
+}
+
+extern "C" long long bbpcg_get_info(bbpcg_solver *s, const char *key)
+{
+  if (!s || !key) return -1;
+  if (!strcmp(key, "arena_bytes")) return (long long)s->amap.total;
+  if (!strcmp(key, "launches")) return s->launches;
+  if (!strcmp(key, "pitch")) return s->dev.L.px;
+  if (!strcmp(key, "sm_count")) return s->sm_count;
+  if (!strcmp(key, "nranks")) return s->nranks;
+  if (!strcmp(key, "tile_tx")) return k_tiles[s->tile].tx;
+  if (!strcmp(key, "tile_ty")) return k_tiles[s->tile].ty;
+  return -1;
+}

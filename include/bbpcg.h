@@ -1,0 +1,158 @@
+/* bbpcg.h -- C ABI of the B200-native pressure-Poisson PCG library (libbbpcg.so).
+ *
+ * Explicit-argument form of the reference path (all paths relative to /root/reference):
+ *   cuda_PP_init_jacobi_preconditioner   src/cuda_solver.cu:31-36      -> bbpcg_set_coefficients
+ *   cuda_PP_cg / cuda_PP_cg_noparts      src/cuda_solver.cu:38-300,573-761 -> bbpcg_solve
+ *   mpi_cuda_exchange_Gcc                src/mpi_comm.c:257-315         -> bbpcg_exchange_Gcc
+ *   domain_read_input (decomp part) + domain_fill   src/domain.c:91-160,918-1486 -> bb_domain_*
+ * The reference reads everything from globals; the symbols with the reference's own names and
+ * `void f(void)` signatures are exported by the companion drop-in layer (include/bb_dropin.h),
+ * which forwards to the functions below.
+ *
+ * Conventions: plain pointers and sizes, no C++ or torch types.  Every `const real *` /
+ * `const int *` array argument of the solver calls is a DEVICE pointer in the reference's
+ * ghosted layout (include/bb_grid.h); the caller owns it.  All functions return 0 on success,
+ * a negative BBPCG_E* code on failure (bbpcg_last_error() has the text).  There is no CPU
+ * path: without a CUDA device every compute entry point fails with BBPCG_ECUDA.
+ *
+ * Process model (reference: one MPI rank per GPU, src/mpi_comm.c:42-58): one solver object
+ * per rank/GPU; bbpcg_solve, bbpcg_set_coefficients and bbpcg_exchange_Gcc are COLLECTIVE over
+ * the ranks attached with bbpcg_comm_import().  Work is issued on a private non-blocking
+ * stream and is complete (host-synchronised) on return.
+ */
+#ifndef BBPCG_H
+#define BBPCG_H
+
+#include <stddef.h>
+#include "bb_grid.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BBPCG_OK        0
+#define BBPCG_EINVAL   (-1)
+#define BBPCG_ECUDA    (-2)
+#define BBPCG_ENOMEM   (-3)
+#define BBPCG_ECOMM    (-4)
+#define BBPCG_EIO      (-5)
+
+/* solve status, mirrors the exits of cuda_PP_cg (src/cuda_solver.cu:178-189,235-279) */
+#define BBPCG_CONVERGED   0   /* (r,z) <= pp_residual^2 (b,b)                               */
+#define BBPCG_TINY_RHS    1   /* (b,b) < (1e-8)^2: phi = 0, 0 iterations                    */
+#define BBPCG_MAXITER     2   /* pp_max_iter+1 iterations without convergence (reference: exit) */
+#define BBPCG_NAN         3   /* (r,z) is NaN (reference: exit)                             */
+
+#define BBPCG_MAX_RANKS 16
+#define BBPCG_BLOB_BYTES 256  /* size of one rank's bbpcg_comm_export() record */
+
+typedef struct bbpcg_solver bbpcg_solver;
+
+typedef struct bbpcg_result {
+  int    status;     /* BBPCG_CONVERGED ...                                                  */
+  int    niter;      /* q at exit, as passed to recorder_PP (src/cuda_solver.cu:239)         */
+  double resid;      /* sqrt((r,z)) / sqrt((b,b)) at exit                                    */
+  double sp_rhs;     /* (b,b)                                                                */
+  double sp_rq0;     /* initial (r,z)                                                        */
+  double ms_setup;   /* device time: rhs + init (CUDA events)                                */
+  double ms_iter;    /* device time: the iteration loop only                                 */
+  double ms_total;   /* device time: whole call                                              */
+  long long launches;/* kernels launched by this call                                        */
+} bbpcg_result;
+
+/* ---- host-side decomposition contract (no GPU needed) -------------------------------------
+ * bb_domain_read: parse flow.config (the keys this path needs: GLOBAL DOMAIN, (In,Jn,Kn),
+ * rho_f, pp_max_iter, pp_residual, the six bc.p* lines) and decomp.config (record grammar of
+ * src/domain.c:138-159), then fill every index range like domain_fill.  *dom_out is malloc'ed
+ * with DOM_out->S3 entries; free with bb_domain_free. */
+typedef struct bb_flow_params {
+  double rho_f;
+  double pp_residual;
+  int    pp_max_iter;
+} bb_flow_params;
+
+int  bb_domain_read(const char *flow_config, const char *decomp_config, dom_struct *DOM_out,
+                    dom_struct **dom_out, bb_pressure_bc *bc_out, bb_flow_params *params_out);
+/* dom[] entries must carry I,J,K and xs,xe,xn,ys,ye,yn,zs,ze,zn; DOM must carry the global
+ * extents and In,Jn,Kn.  Fills everything else (neighbours from the pressure BCs). */
+int  bb_domain_fill(dom_struct *DOM, dom_struct *dom, const bb_pressure_bc *bc);
+/* equal splits as tools/src/decomp_reader.c:112-129 writes them */
+int  bb_domain_split(dom_struct *DOM, dom_struct *dom);
+int  bb_domain_write_decomp(const char *path, const dom_struct *DOM, const dom_struct *dom, int prec);
+void bb_domain_free(dom_struct *dom);
+
+/* ---- solver object ------------------------------------------------------------------------ */
+/* dom_rank: this rank's filled block; DOM: the global domain; bc: pressure BC types.
+ * device: CUDA ordinal, or -1 for the current device.  Allocates the private workspace
+ * (5 padded vectors + coefficient masks, ~41 B per cell) in ONE device allocation. */
+int  bbpcg_create(bbpcg_solver **out, const dom_struct *dom_rank, const dom_struct *DOM,
+                  const bb_pressure_bc *bc, int device);
+void bbpcg_destroy(bbpcg_solver *s);
+
+/* Multi-GPU attach (replaces mpi_dom_comm_init / create_windows, src/mpi_comm.c:81-251).
+ * Each rank exports BBPCG_BLOB_BYTES describing its workspace (CUDA IPC handle + layout); the
+ * host program all-gathers the records in rank order by whatever means it has (MPI_Allgather
+ * in Bluebottle, torch.distributed in the harness) and hands the concatenation to
+ * bbpcg_comm_import on every rank.  nranks == 1 needs neither call. */
+int  bbpcg_comm_export(bbpcg_solver *s, void *blob /* BBPCG_BLOB_BYTES */);
+int  bbpcg_comm_import(bbpcg_solver *s, const void *all_blobs, int nranks);
+
+/* = cuda_PP_init_jacobi_preconditioner: digest the face flags (Gfx/Gfy/Gfz s3b ints) and,
+ * if phase != NULL, the particle phase (Gcc s3b ints) into the solver's private coefficient
+ * masks (the Jacobi diagonal is recomputed from them on the fly, no invM vector is stored).
+ * Must be called again whenever flags/phase change (src/bluebottle.c:390-395). */
+int  bbpcg_set_coefficients(bbpcg_solver *s, const int *flag_u, const int *flag_v,
+                            const int *flag_w, const int *phase);
+
+/* Optional callback = the reference's cuda_part_BC_p() (src/cuda_particle.cu:1680), invoked
+ * after PP_rhs when use_phase != 0 (src/cuda_solver.cu:128-132).  When NULL and phase_shell !=
+ * NULL the library applies that kernel's net effect on rhs (rhs *= (phase<0 && phase_shell),
+ * src/particle_kernel.cu:1753) itself. */
+typedef void (*bbpcg_part_bc_fn)(void);
+
+typedef struct bbpcg_solve_args {
+  const real *u_star, *v_star, *w_star;   /* Gfx / Gfy / Gfz s3b, device                    */
+  real       *rhs_p;                       /* Gcc s3b scratch, device (reference: _rhs_p)    */
+  real       *phi;                         /* Gcc s3b, device: OUT, interior written        */
+  const int  *phase, *phase_shell;         /* Gcc s3b, device; only read if use_phase        */
+  real        rho_f, dt;
+  real        pp_residual;
+  int         pp_max_iter;
+  int         use_phase;                   /* 0: cuda_PP_cg_noparts   1: cuda_PP_cg, NPARTS>0 */
+  int         fixed_iters;                 /* >0: run exactly this many iterations, no stop
+                                              test (benchmark mode; status CONVERGED)        */
+  bbpcg_part_bc_fn part_bc;                /* may be NULL                                    */
+} bbpcg_solve_args;
+
+int  bbpcg_solve(bbpcg_solver *s, const bbpcg_solve_args *args, bbpcg_result *res);
+
+/* Host-buffer form used by the end-to-end benchmark and by callers without device arrays:
+ * copies u*,v*,w* host->device, solves, copies phi (s3b) device->host.  Same semantics. */
+int  bbpcg_solve_host(bbpcg_solver *s, const real *u_star_h, const real *v_star_h,
+                      const real *w_star_h, real *phi_h, real rho_f, real dt, real pp_residual,
+                      int pp_max_iter, int fixed_iters, bbpcg_result *res);
+
+/* (r,z) after every iteration of the last solve: out[0] = initial, out[q] = iteration q.
+ * Returns the number of entries written (<= cap). */
+int  bbpcg_history(bbpcg_solver *s, double *out, int cap);
+
+/* = mpi_cuda_exchange_Gcc(array): fill the ghost faces of a caller-owned Gcc s3b device array
+ * from the neighbouring blocks (periodic wrap included; faces only, no edges/corners). */
+int  bbpcg_exchange_Gcc(bbpcg_solver *s, real *array);
+
+/* Unit entry points used by the parity tests (same kernels the solve uses). */
+int  bbpcg_rhs(bbpcg_solver *s, const real *u_star, const real *v_star, const real *w_star,
+               real rho_f, real dt, real *rhs_p);
+/* Ap (s3, ghost-free, device) = -A * src (Gcc s3b, device, ghosts as given) */
+int  bbpcg_spmv(bbpcg_solver *s, const real *src_s3b, real *Ap_s3, int use_phase);
+
+/* tuning / introspection */
+int  bbpcg_set_option(bbpcg_solver *s, const char *key, long long value);
+long long bbpcg_get_info(bbpcg_solver *s, const char *key);
+const char *bbpcg_last_error(void);
+const char *bbpcg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBPCG_H */

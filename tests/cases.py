@@ -1,0 +1,69 @@
+"""Shared case builders for the parity tests: the same seeded inputs go to the CPU oracle
+(oracle/binding.py), to the reference's own kernels (oracle/_ref, when built) and to the CUDA
+library through its C ABI."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from bbpcg import synth
+from bbpcg.grid import BC_SETS, DomStruct
+from oracle import binding as ob
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libbbref.so")
+
+
+class Case:
+    """One synthetic problem held in a multi-block oracle state."""
+
+    def __init__(self, cells, blocks=(1, 1, 1), bc="cavity", extent=None, noise=1.0, nparts=0, radius=1.0, omp=False,
+                 seed=7):
+        self.cells, self.blocks, self.bcname = tuple(cells), tuple(blocks), bc
+        self.extent = extent or (0., 12., 0., 12. * cells[1] / cells[0], 0., 12. * cells[2] / cells[0])
+        self.o = ob.Oracle(self.extent, cells, blocks, BC_SETS[bc], omp=omp)
+        self.nparts = nparts
+        if nparts:
+            px, py, pz, pr = synth.random_spheres(self.o.DOM, nparts, radius)
+            self.parts = (px, py, pz, pr)
+            self.o.build_cages(px, py, pz, pr)
+        else:
+            self.o.build_flags_noparts()
+        for r in range(self.o.nblocks):
+            u, v, w = synth.velocity_star(self.o.dom(r), self.o.DOM, self.o.bc, noise=noise, seed=seed)
+            self.o.array(r, ob.U_STAR)[...] = u
+            self.o.array(r, ob.V_STAR)[...] = v
+            self.o.array(r, ob.W_STAR)[...] = w
+        self.o.jacobi_init()
+
+    def inputs(self, rank=0):
+        a = self.o.array
+        return dict(flag_u=a(rank, ob.FLAG_U), flag_v=a(rank, ob.FLAG_V), flag_w=a(rank, ob.FLAG_W),
+                    phase=a(rank, ob.PHASE), phase_shell=a(rank, ob.PHASE_SHELL),
+                    u_star=a(rank, ob.U_STAR), v_star=a(rank, ob.V_STAR), w_star=a(rank, ob.W_STAR))
+
+    def solve_oracle(self, **kw):
+        kw.setdefault("parts", self.nparts > 0)
+        return self.o.solve(**kw)
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+
+
+def load_ref():
+    """The reference's own kernels (O1); None when oracle/_ref was not built."""
+    if not os.path.exists(REF_LIB):
+        return None
+    lib = C.CDLL(REF_LIB)
+    D = C.POINTER(DomStruct)
+    vp = C.c_void_p
+    lib.bbref_init.argtypes = [D, D]
+    lib.bbref_set_inputs.argtypes = [vp] * 8 + [C.c_int]
+    lib.bbref_set_inputs_dev.argtypes = [vp] * 8 + [C.c_int]
+    lib.bbref_solve.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    lib.bbref_get.argtypes = [C.c_int, vp]
+    lib.bbref_spmv.argtypes = [vp, C.c_int, vp]
+    lib.bbref_exchange.argtypes = [vp]
+    return lib
