@@ -128,6 +128,12 @@ class PoissonSolver:
         dist.barrier()
 
     # ---- helpers ---------------------------------------------------------------------------
+    def _sync_caller_stream(self):
+        """The library works on its own stream: the caller's torch work on the arrays must be
+        complete first.  Only the caller's stream is waited for -- a device-wide synchronize would
+        also wait for OTHER ranks' collective kernels when several ranks share one GPU."""
+        self.torch.cuda.current_stream(self.device).synchronize()
+
     def empty(self, grid, dtype=None):
         t = self.torch
         return t.zeros(grid_shape(self.dom, grid), dtype=dtype or t.float64, device=self.device)
@@ -143,7 +149,7 @@ class PoissonSolver:
 
     # ---- the reference's entry points ----------------------------------------------------------
     def init_jacobi_preconditioner(self, flag_u, flag_v, flag_w, phase=None):
-        self.torch.cuda.synchronize(self.device)
+        self._sync_caller_stream()
         L.check(self.lib.bbpcg_set_coefficients(self.h, _ptr(flag_u), _ptr(flag_v), _ptr(flag_w), _ptr(phase)),
                 "bbpcg_set_coefficients")
 
@@ -157,7 +163,7 @@ class PoissonSolver:
         a.rho_f, a.dt, a.pp_residual, a.pp_max_iter = rho_f, dt, pp_residual, pp_max_iter
         a.use_phase, a.fixed_iters = int(use_phase), int(fixed_iters)
         res = L.Result()
-        self.torch.cuda.synchronize(self.device)
+        self._sync_caller_stream()
         L.check(self.lib.bbpcg_solve(self.h, C.byref(a), C.byref(res)), "bbpcg_solve")
         return SolveResult(L.STATUS.get(res.status, str(res.status)), res.niter, res.resid, res.sp_rhs, res.sp_rq0,
                            res.ms_setup, res.ms_iter, res.ms_total, res.launches)
@@ -186,17 +192,17 @@ class PoissonSolver:
         return out[:n].copy()
 
     def exchange_Gcc(self, array):
-        self.torch.cuda.synchronize(self.device)
+        self._sync_caller_stream()
         L.check(self.lib.bbpcg_exchange_Gcc(self.h, _ptr(array)), "bbpcg_exchange_Gcc")
 
     def rhs(self, u_star, v_star, w_star, rhs_p, rho_f=1.0, dt=1e-3):
-        self.torch.cuda.synchronize(self.device)
+        self._sync_caller_stream()
         L.check(self.lib.bbpcg_rhs(self.h, _ptr(u_star), _ptr(v_star), _ptr(w_star), rho_f, dt, _ptr(rhs_p)), "bbpcg_rhs")
 
     def spmv(self, src_s3b, use_phase=False):
         d = self.dom
         out = self.torch.zeros((d.Gcc.get("kn"), d.Gcc.get("jn"), d.Gcc.get("in")), dtype=self.torch.float64,
                                device=self.device)
-        self.torch.cuda.synchronize(self.device)
+        self._sync_caller_stream()
         L.check(self.lib.bbpcg_spmv(self.h, _ptr(src_s3b), _ptr(out), int(use_phase)), "bbpcg_spmv")
         return out

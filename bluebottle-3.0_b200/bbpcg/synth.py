@@ -123,3 +123,103 @@ def random_spheres(DOM, nparts, radius, seed=20240229, max_tries=200000):
     if len(pts) < nparts:
         raise RuntimeError("could not place %d spheres of radius %g" % (nparts, radius))
     return pts[:, 0].copy(), pts[:, 1].copy(), pts[:, 2].copy(), np.full(nparts, float(radius))
+
+
+# ---- the same fields built with torch on any device (bench.py fills 512^3 blocks on the GPU) ----
+def _i64(v):
+    """two's-complement int64 value of an unsigned 64-bit constant"""
+    v &= 0xFFFFFFFFFFFFFFFF
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def _lsr(t, n):
+    """logical right shift of an int64 tensor holding uint64 bits"""
+    return (t >> n) & ((1 << (64 - n)) - 1)
+
+
+def hash_uniform_torch(idx, stream):
+    """hash_uniform on an int64 torch tensor (wrap-around int64 arithmetic == uint64 arithmetic)."""
+    import torch
+    z = idx + _i64(stream * 0x0123456789ABCDEF) + _i64(0x9E3779B97F4A7C15)
+    z = (z ^ _lsr(z, 30)) * _i64(0xBF58476D1CE4E5B9)
+    z = (z ^ _lsr(z, 27)) * _i64(0x94D049BB133111EB)
+    z = z ^ _lsr(z, 31)
+    return _lsr(z, 11).to(torch.float64) * (1.0 / 9007199254740992.0) - 0.5
+
+
+def velocity_star_torch(dom, DOM, bc, device, noise=1.0, seed=7):
+    """velocity_star() evaluated with torch on `device`; bit-identical to the numpy version (the
+    per-axis sin/cos factors are computed on the host in both, the rest is the same sequence of
+    IEEE operations)."""
+    import torch
+    px = bc.pW == PERIODIC and bc.pE == PERIODIC
+    py = bc.pS == PERIODIC and bc.pN == PERIODIC
+    pz = bc.pB == PERIODIC and bc.pT == PERIODIC
+    Lx, Ly, Lz = DOM.xe - DOM.xs, DOM.ye - DOM.ys, DOM.ze - DOM.zs
+    Nx, Ny = DOM.xn, DOM.yn
+    out = []
+    # storage order (slowest..fastest) of each grid expressed as a permutation of (i, j, k)
+    order = {"Gfx": (0, 2, 1), "Gfy": (1, 0, 2), "Gfz": (2, 1, 0)}
+    for comp, grid in enumerate(("Gfx", "Gfy", "Gfz")):
+        sx, sy, sz = (comp == 0), (comp == 1), (comp == 2)
+        X, GI, WX, VX = _axis(dom, DOM, "x", sx, px)
+        Y, GJ, WY, VY = _axis(dom, DOM, "y", sy, py)
+        Z, GK, WZ, VZ = _axis(dom, DOM, "z", sz, pz)
+        ax = 2 * np.pi * (X - DOM.xs) / Lx
+        ay = 2 * np.pi * (Y - DOM.ys) / Ly
+        az = 2 * np.pi * (Z - DOM.zs) / Lz
+        if comp == 0:
+            fx, fy, fz = np.sin(ax), np.cos(ay), np.cos(az)
+        elif comp == 1:
+            fx, fy, fz = np.cos(ax), np.sin(ay), np.cos(az)
+        else:
+            fx, fy, fz = np.cos(ax), np.cos(ay), np.sin(az)
+        perm = order[grid]
+
+        def shaped(v, axis, dtype=None):
+            """1-D per-axis array -> broadcastable tensor in this grid's storage order"""
+            shp = [1, 1, 1]
+            shp[perm.index(axis)] = len(v)
+            t = torch.from_numpy(np.ascontiguousarray(v))
+            if dtype is not None:
+                t = t.to(dtype)
+            return t.to(device).reshape(shp)
+
+        sI, sJ = Nx + 1, Ny + 1
+        f = (shaped(fx, 0) * shaped(fy, 1)) * shaped(fz, 2)
+        if noise != 0.0:
+            lin = shaped(GI, 0) + sI * (shaped(GJ, 1) + sJ * shaped(GK, 2))
+            f = f + noise * hash_uniform_torch(lin, seed * 4 + comp)
+            del lin
+        keep = (shaped(VX & ~(WX if sx else np.zeros_like(WX)), 0) & shaped(VY & ~(WY if sy else np.zeros_like(WY)), 1)
+                & shaped(VZ & ~(WZ if sz else np.zeros_like(WZ)), 2))
+        f = torch.where(keep, f, torch.zeros((), dtype=torch.float64, device=device)).contiguous()
+        assert tuple(f.shape) == grid_shape(dom, grid), (tuple(f.shape), grid_shape(dom, grid))
+        out.append(f)
+    return out
+
+
+def flags_noparts_torch(dom, DOM, bc, device):
+    """flag_u, flag_v, flag_w (int32, Gfx/Gfy/Gfz s3b) for a particle-free block: 1 everywhere, 0 on
+    external wall faces when BOTH sides of that direction are non-periodic and the block touches the
+    wall (cuda_build_cages, src/cuda_particle.cu:1605-1639; kernels src/particle_kernel.cu:542-576)."""
+    import torch
+    fu = torch.ones(grid_shape(dom, "Gfx"), dtype=torch.int32, device=device)   # [i, k, j]
+    fv = torch.ones(grid_shape(dom, "Gfy"), dtype=torch.int32, device=device)   # [j, i, k]
+    fw = torch.ones(grid_shape(dom, "Gfz"), dtype=torch.int32, device=device)   # [k, j, i]
+    if bc.pW != PERIODIC and bc.pE != PERIODIC:
+        if dom.I == DOM.Is:
+            fu[dom.Gfx.get("_is")] = 0
+        if dom.I == DOM.Ie:
+            fu[dom.Gfx.get("_ie")] = 0
+    if bc.pS != PERIODIC and bc.pN != PERIODIC:
+        if dom.J == DOM.Js:
+            fv[dom.Gfy.get("_js")] = 0
+        if dom.J == DOM.Je:
+            fv[dom.Gfy.get("_je")] = 0
+    if bc.pB != PERIODIC and bc.pT != PERIODIC:
+        if dom.K == DOM.Ks:
+            fw[dom.Gfz.get("_ks")] = 0
+        if dom.K == DOM.Ke:
+            fw[dom.Gfz.get("_ke")] = 0
+    return fu, fv, fw

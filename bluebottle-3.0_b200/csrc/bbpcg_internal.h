@@ -132,6 +132,7 @@ struct Halo { NbrFace f[6]; };     /* 0:E 1:W 2:N 3:S 4:T 5:B */
 
 struct Comm {
   int rank, nranks;
+  long long timeout_cycles;                   /* spin limit of the in-kernel all-reduce */
   double *mbox_val[BB_MAXR];                  /* rank p's mailbox (mapped) */
   unsigned long long *mbox_flag[BB_MAXR];
 };

@@ -151,7 +151,7 @@ __device__ __forceinline__ void rank_allreduce(const Dev &d, double *v /* thread
     long long t0 = clock64();
     bool ok = true;
     while (*f != seq) {
-      if (clock64() - t0 > (1ll << 34)) { ok = false; break; }    /* ~8 s: a peer is gone */
+      if (clock64() - t0 > c.timeout_cycles) { ok = false; break; }    /* a peer is gone */
     }
     __threadfence_system();
     volatile double *src = (volatile double *)(c.mbox_val[c.rank] + (size_t)(slot * BB_MAXR + t) * 2);

@@ -67,7 +67,17 @@ struct bbpcg_solver {
   int *hb_dummy;
   long long launches;
   unsigned exchange_count;
+  /* optional per-kernel timing (bench.py's roofline leg): events around every launch of the
+   * iteration loop, on the solver's own stream */
+  int last_search_grid, last_search_kc;
+  int kernel_timing;
+  cudaEvent_t *kev;                 /* [2*BB_KT_CAP+1] */
+  double kt_search_ms, kt_resid_ms, kt_refresh_ms;
+  int kt_search_n, kt_resid_n, kt_refresh_n;
 };
+#define BB_KT_CAP 4096
+
+static int preload_kernels();
 
 static int nbr_rank(const dom_struct &d, int f)
 {
@@ -107,6 +117,7 @@ static void build_halo(bbpcg_solver *s, const int (*dims)[3])
     for (int b = 0; b < 2; b++) nf.recv[b] = (double *)(base + m.recv[b][opposite[f]]);
   }
   d.comm.rank = s->dom.rank; d.comm.nranks = s->nranks;
+  if (d.comm.timeout_cycles <= 0) d.comm.timeout_cycles = 1ll << 34;       /* ~8 s */
   for (int p = 0; p < BB_MAXR; p++) { d.comm.mbox_val[p] = NULL; d.comm.mbox_flag[p] = NULL; }
   for (int p = 0; p < s->nranks; p++) {
     Layout L = make_layout(dims[p][0], dims[p][1], dims[p][2]);
@@ -151,6 +162,7 @@ extern "C" int bbpcg_create(bbpcg_solver **out, const dom_struct *dom_rank, cons
   s->fst.vs1b = dom_rank->Gfy.s1b; s->fst.vs2b = dom_rank->Gfy.s2b;
   s->fst.ws1b = dom_rank->Gfz.s1b; s->fst.ws2b = dom_rank->Gfz.s2b;
   s->fst.cs1b = g.s1b; s->fst.cs2b = g.s2b;
+  { int rc = preload_kernels(); if (rc) { cudaFree(s->arena); delete s; return rc; } }
   CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 4; i++) CU(cudaEventCreate(&s->ev[i]));
   for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&s->ev_poll[i], cudaEventDisableTiming));
@@ -184,6 +196,7 @@ extern "C" void bbpcg_destroy(bbpcg_solver *s)
   cudaFree(s->arena);
   cudaFree(s->hb_u); cudaFree(s->hb_v); cudaFree(s->hb_w); cudaFree(s->hb_rhs); cudaFree(s->hb_phi);
   cudaFreeHost(s->h_poll); cudaFreeHost(s->h_scal);
+  if (s->kev) { for (int i = 0; i <= 2 * BB_KT_CAP; i++) cudaEventDestroy(s->kev[i]); free(s->kev); }
   for (int i = 0; i < 4; i++) cudaEventDestroy(s->ev[i]);
   for (int i = 0; i < 2; i++) cudaEventDestroy(s->ev_poll[i]);
   cudaStreamDestroy(s->stream);
@@ -270,6 +283,7 @@ static int launch_search_t(bbpcg_solver *s, bool parts)
   a.KC = kc; a.nbz = (L.kn + kc - 1) / kc;
   if ((long long)a.nbx * a.nby * a.nbz > BB_MAXBLOCKS) { bbpcg_set_error("grid too large for the reduction workspace"); return BBPCG_EINVAL; }
   dim3 grid(a.nbx, a.nby, a.nbz);
+  s->last_search_grid = a.nbx * a.nby * a.nbz; s->last_search_kc = kc;
   if (parts) {
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_search_spmv<TX, TY, NT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_search_spmv<TX, TY, NT, MINB, true><<<grid, NT, smem, s->stream>>>(s->dev, a);
@@ -293,6 +307,40 @@ static int launch_search(bbpcg_solver *s, bool parts)
   }
   bbpcg_set_error("unknown tile variant %d", s->tile);
   return BBPCG_EINVAL;
+}
+
+/* Load every kernel of the library NOW.  CUDA loads device functions lazily at their first
+ * launch, and that load takes a context-wide lock; when several ranks share one context (the
+ * single-process test harness) a first launch on one rank's host thread would block the other
+ * ranks' launches while a collective kernel already on the device waits for them. */
+template <typename K> static int preload_one(K kernel)
+{
+  cudaFuncAttributes at;
+  CU(cudaFuncGetAttributes(&at, kernel));
+  return BBPCG_OK;
+}
+template <int TX, int TY, int NT, int MINB> static int preload_search()
+{
+  int rc = preload_one(k_search_spmv<TX, TY, NT, MINB, false>);
+  if (!rc) rc = preload_one(k_search_spmv<TX, TY, NT, MINB, true>);
+  return rc;
+}
+static int preload_kernels()
+{
+  int rc = 0;
+#define PL(...) if (!rc) rc = preload_one(__VA_ARGS__)
+  if (!rc) rc = preload_search<128, 8, 256, 2>();
+  if (!rc) rc = preload_search<128, 4, 256, 3>();
+  if (!rc) rc = preload_search<64, 8, 256, 3>();
+  if (!rc) rc = preload_search<128, 8, 512, 2>();
+  if (!rc) rc = preload_search<32, 8, 128, 4>();
+  if (!rc) rc = preload_search<256, 4, 256, 2>();
+  PL(k_resid<256>); PL(k_refresh_x<256>); PL(k_refresh_r<256, false>); PL(k_refresh_r<256, true>);
+  PL(k_init<256>); PL(k_finish<256>); PL(k_rhs<256>); PL(k_masks<256>); PL(k_part_rhs_net);
+  PL(k_coeffs_refine<256>); PL(k_zero_ghosts); PL(k_xchg_send); PL(k_xchg_recv);
+  PL(k_spmv_s3b<256, false>); PL(k_spmv_s3b<256, true>);
+#undef PL
+  return rc;
 }
 
 static int clampi(long long v, int lo, int hi) { return (int)(v < lo ? lo : v > hi ? hi : v); }
@@ -381,8 +429,11 @@ extern "C" int bbpcg_spmv(bbpcg_solver *s, const real *src_s3b, real *Ap_s3, int
 static int enqueue_iteration(bbpcg_solver *s, int it, bool parts, const real *rhs)
 {
   const long long nrows = (long long)s->dev.L.jn * s->dev.L.kn;
+  const bool kt = s->kernel_timing && it <= BB_KT_CAP;
+  if (kt && it == 1) CU(cudaEventRecord(s->kev[0], s->stream));
   int rc = launch_search(s, parts);
   if (rc) return rc;
+  if (kt) CU(cudaEventRecord(s->kev[2 * it - 1], s->stream));
   if (it % 50 == 0) {                                     /* cuda_solver.cu:209-223 */
     const int nb = clampi(nrows, 1, s->stream_blocks);
     k_refresh_x<256><<<nb, 256, 0, s->stream>>>(s->dev);
@@ -393,6 +444,7 @@ static int enqueue_iteration(bbpcg_solver *s, int it, bool parts, const real *rh
     k_resid<256><<<clampi(nrows, 1, s->resid_blocks), 256, 0, s->stream>>>(s->dev);
     s->launches++;
   }
+  if (kt) CU(cudaEventRecord(s->kev[2 * it], s->stream));
   return BBPCG_OK;
 }
 
@@ -465,6 +517,16 @@ extern "C" int bbpcg_solve(bbpcg_solver *s, const bbpcg_solve_args *a, bbpcg_res
   CU(cudaGetLastError());
 
   const Scal &sc = *s->h_scal;
+  if (s->kernel_timing) {
+    s->kt_search_ms = s->kt_resid_ms = s->kt_refresh_ms = 0.; s->kt_search_n = s->kt_resid_n = s->kt_refresh_n = 0;
+    for (int i = 1; i <= sc.q && i <= BB_KT_CAP && i <= it; i++) {
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, s->kev[2 * i - 2], s->kev[2 * i - 1]);
+      cudaEventElapsedTime(&b, s->kev[2 * i - 1], s->kev[2 * i]);
+      s->kt_search_ms += a; s->kt_search_n++;
+      if (i % 50 == 0) { s->kt_refresh_ms += b; s->kt_refresh_n++; } else { s->kt_resid_ms += b; s->kt_resid_n++; }
+    }
+  }
   if (res) {
     float ms;
     res->status = sc.status; res->niter = sc.q; res->resid = sc.resid; res->sp_rhs = sc.bb; res->sp_rq0 = sc.rz0;
@@ -523,6 +585,15 @@ extern "C" int bbpcg_set_option(bbpcg_solver *s, const char *key, long long valu
   else if (!strcmp(key, "resid_blocks")) s->resid_blocks = clampi(value, 1, BB_MAXBLOCKS);
   else if (!strcmp(key, "stream_blocks")) s->stream_blocks = clampi(value, 1, BB_MAXBLOCKS);
   else if (!strcmp(key, "check_every")) s->check_every = clampi(value, 1, 1000);
+  else if (!strcmp(key, "comm_timeout_ms")) s->dev.comm.timeout_cycles = value * 2000000ll;   /* ~2 GHz */
+  else if (!strcmp(key, "kernel_timing")) {
+    s->kernel_timing = value != 0;
+    if (s->kernel_timing && !s->kev) {
+      CU(cudaSetDevice(s->device));
+      s->kev = (cudaEvent_t *)calloc(2 * BB_KT_CAP + 1, sizeof(cudaEvent_t));
+      for (int i = 0; i <= 2 * BB_KT_CAP; i++) CU(cudaEventCreate(&s->kev[i]));
+    }
+  }
   else { bbpcg_set_error("unknown option %s", key); return BBPCG_EINVAL; }
   return BBPCG_OK;
 }
@@ -537,5 +608,14 @@ extern "C" long long bbpcg_get_info(bbpcg_solver *s, const char *key)
   if (!strcmp(key, "nranks")) return s->nranks;
   if (!strcmp(key, "tile_tx")) return k_tiles[s->tile].tx;
   if (!strcmp(key, "tile_ty")) return k_tiles[s->tile].ty;
+  /* per-kernel device time of the last solve (kernel_timing = 1), nanoseconds / launch counts */
+  if (!strcmp(key, "kt_search_ns")) return (long long)(s->kt_search_ms * 1e6);
+  if (!strcmp(key, "kt_resid_ns")) return (long long)(s->kt_resid_ms * 1e6);
+  if (!strcmp(key, "kt_refresh_ns")) return (long long)(s->kt_refresh_ms * 1e6);
+  if (!strcmp(key, "kt_search_n")) return s->kt_search_n;
+  if (!strcmp(key, "kt_resid_n")) return s->kt_resid_n;
+  if (!strcmp(key, "kt_refresh_n")) return s->kt_refresh_n;
+  if (!strcmp(key, "search_grid")) return s->last_search_grid;
+  if (!strcmp(key, "search_kc")) return s->last_search_kc;
   return -1;
 }

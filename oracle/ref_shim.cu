@@ -203,6 +203,28 @@ int bbref_solve(real rho_f_, real dt_, real pp_residual_, int pp_max_iter_, int 
   return 0;
 }
 
+/* end-to-end form for bench.py's reference arm: u*, v*, w* from (pinned) host buffers, phi back
+ * to the host; *ms covers copies + solve (CUDA events on the default stream the reference uses) */
+int bbref_solve_host(const real *u_h, const real *v_h, const real *w_h, real *phi_h, real rho_f_, real dt_,
+                     real pp_residual_, int pp_max_iter_, int use_parts, int *niter, real *resid, float *ms)
+{
+  const dom_struct *d = &dom[rank];
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, 0));
+  CK(cudaMemcpyAsync(_u_star, u_h, (size_t)d->Gfx.s3b * sizeof(real), cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(_v_star, v_h, (size_t)d->Gfy.s3b * sizeof(real), cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(_w_star, w_h, (size_t)d->Gfz.s3b * sizeof(real), cudaMemcpyHostToDevice, 0));
+  float ms_solve = 0.f;
+  if (bbref_solve(rho_f_, dt_, pp_residual_, pp_max_iter_, use_parts, niter, resid, &ms_solve)) return -1;
+  CK(cudaMemcpyAsync(phi_h, _phi, (size_t)d->Gcc.s3b * sizeof(real), cudaMemcpyDeviceToHost, 0));
+  CK(cudaEventRecord(e1, 0));
+  CK(cudaEventSynchronize(e1));
+  if (ms) CK(cudaEventElapsedTime(ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+
 int bbref_get(int which, real *host)   /* 0: phi (s3b)  1: rhs_p (s3b)  2: invM (s3)  3: Apb_q (s3)  4: pb_q (s3b) */
 {
   const dom_struct *d = &dom[rank];
