@@ -151,6 +151,7 @@ struct Dev {
   double dx2_6, dy2_6, dz2_6;     /* dx*dx/6 ...    (src/solver_kernel.cu:683)                */
   Halo halo;
   Comm comm;
+  int any_nbr;                    /* some face has a neighbour (another rank or a periodic self-wrap) */
 };
 
 #endif

@@ -366,11 +366,35 @@ __device__ __forceinline__ void finish_iteration(const Dev &d, double rz_new, bo
   }
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT) k_resid(const Dev d)
+/* 256-bit global accesses (LDG.E.256 / STG.E.256 on sm_100a): one x-row chunk of 4 cells */
+struct d4 { double a, b, c, d; };
+__device__ __forceinline__ d4 ld256(const double *p)
+{
+  d4 v;
+  asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ d4 ld256_stream(const double *p)      /* read once, then dead: do not keep in L1 */
+{
+  d4 v;
+  asm("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st256(double *p, const d4 &v)
+{
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.a), "d"(v.b), "d"(v.c), "d"(v.d) : "memory");
+}
+
+/* CTA = 128 threads = XT chunk columns x YT rows; one pass = YT*UNR rows, every thread holding UNR
+ * independent 4-cell chunks (UNR x (32 B r + 32 B q + 4 B mask) in flight before the first use). */
+struct ResidArgs { int cpr; int npass; };
+
+template <int XT, int UNR>
+__global__ void __launch_bounds__(128, 4) k_resid(const Dev d, const ResidArgs a)
 {
   Scal *sc = d.sc;
   if (sc->done) return;
+  constexpr int NT = 128, YT = NT / XT;
   __shared__ double tab[128];
   fill_invM_table(tab, d);
   __syncthreads();
@@ -379,35 +403,55 @@ __global__ void __launch_bounds__(NT) k_resid(const Dev d)
   double *__restrict__ r = d.r;
   const double *__restrict__ qv = d.q;
   const u8 *__restrict__ fmask = d.fmask;
-  const long long nrows = (long long)L.jn * L.kn;
-  const int half = L.in >> 1;
+  const unsigned nrows = (unsigned)L.jn * (unsigned)L.kn;
+  const int tx = threadIdx.x % XT, ty = threadIdx.x / XT;
+  const bool any_nbr = d.any_nbr != 0;
   double dot = 0.;
   bool pushed = false;
-  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
-    const int j = (int)(row % L.jn) + 1, k = (int)(row / L.jn) + 1;
-    const long long base = pidx(L, 1, j, k);
-    const bool edge_row = (j == 1 || j == L.jn || k == 1 || k == L.kn);
-    for (int h = threadIdx.x; h < half; h += NT) {
-      const long long g = base + 2 * h;
-      double2 rv = *reinterpret_cast<const double2 *>(r + g);
-      const double2 qq = __ldg(reinterpret_cast<const double2 *>(qv + g));
-      const uchar2 mk = __ldg(reinterpret_cast<const uchar2 *>(fmask + g));
-      rv.x -= alpha * qq.x;  rv.y -= alpha * qq.y;                       /* solver_kernel.cu:855 */
-      const double z0 = rv.x * tab[mk.x & 127u], z1 = rv.y * tab[mk.y & 127u];   /* :858 */
-      dot += rv.x * z0;  dot += rv.y * z1;
-      *reinterpret_cast<double2 *>(r + g) = rv;
-      const int i = 2 * h + 1;
-      if (edge_row || i == 1) pushed |= push_halo(d, 0, i, j, k, rv.x);
-      if (edge_row || i + 1 == L.in) pushed |= push_halo(d, 0, i + 1, j, k, rv.y);
-    }
-    if ((L.in & 1) && threadIdx.x == 0) {                                /* odd row length: last cell */
-      const int i = L.in;
-      const long long g = base + (i - 1);
-      double rv = r[g] - alpha * qv[g];
-      const double z = rv * tab[fmask[g] & 127u];
-      dot += rv * z;
-      r[g] = rv;
-      pushed |= push_halo(d, 0, i, j, k, rv);
+  for (int pass = blockIdx.x; pass < a.npass; pass += gridDim.x) {
+    const unsigned row0 = (unsigned)pass * (YT * UNR) + ty;
+    for (int c = tx; c < a.cpr; c += XT) {
+      d4 rv[UNR], qq[UNR];
+      unsigned mk[UNR];
+      long long g[UNR];
+      int jj[UNR], kk[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; u++) {
+        const unsigned row = row0 + u * YT;
+        const unsigned k0 = row / (unsigned)L.jn;
+        jj[u] = (int)(row - k0 * (unsigned)L.jn) + 1; kk[u] = (int)k0 + 1;
+        g[u] = (long long)kk[u] * L.ps + (long long)jj[u] * L.px + (BB_XOFF + 1) + 4 * c;
+        if (row < nrows) {
+          rv[u] = ld256(r + g[u]);
+          qq[u] = ld256_stream(qv + g[u]);
+          mk[u] = __ldg(reinterpret_cast<const unsigned *>(fmask + g[u]));
+        } else { kk[u] = -1; }
+      }
+      const int i0 = 4 * c + 1;
+      const int nv = min(4, L.in - 4 * c);                              /* cells of this chunk inside the block */
+#pragma unroll
+      for (int u = 0; u < UNR; u++) {
+        if (kk[u] < 0) continue;
+        d4 v = rv[u];
+        v.a -= alpha * qq[u].a; v.b -= alpha * qq[u].b; v.c -= alpha * qq[u].c; v.d -= alpha * qq[u].d;   /* solver_kernel.cu:855 */
+        const double za = v.a * tab[mk[u] & 127u], zb = v.b * tab[(mk[u] >> 8) & 127u],
+                     zc = v.c * tab[(mk[u] >> 16) & 127u], zd = v.d * tab[(mk[u] >> 24) & 127u];          /* :858 */
+        if (nv == 4) {
+          dot += v.a * za; dot += v.b * zb; dot += v.c * zc; dot += v.d * zd;
+          st256(r + g[u], v);
+        } else {                                                          /* ragged row end: never touch the E ghost */
+          double *rp = r + g[u];
+          dot += v.a * za; rp[0] = v.a;
+          if (nv > 1) { dot += v.b * zb; rp[1] = v.b; }
+          if (nv > 2) { dot += v.c * zc; rp[2] = v.c; }
+        }
+        if (any_nbr && (c == 0 || 4 * c + 4 >= L.in || jj[u] == 1 || jj[u] == L.jn || kk[u] == 1 || kk[u] == L.kn)) {
+          pushed |= push_halo(d, 0, i0, jj[u], kk[u], v.a);
+          if (nv > 1) pushed |= push_halo(d, 0, i0 + 1, jj[u], kk[u], v.b);
+          if (nv > 2) pushed |= push_halo(d, 0, i0 + 2, jj[u], kk[u], v.c);
+          if (nv > 3) pushed |= push_halo(d, 0, i0 + 3, jj[u], kk[u], v.d);
+        }
+      }
     }
   }
   double v[1] = { dot }, tot[1];

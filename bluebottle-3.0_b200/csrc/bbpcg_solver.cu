@@ -116,6 +116,8 @@ static void build_halo(bbpcg_solver *s, const int (*dims)[3])
     nf.r = (double *)(base + m.r); nf.x = (double *)(base + m.x); nf.fmask = (u8 *)(base + m.fmask);
     for (int b = 0; b < 2; b++) nf.recv[b] = (double *)(base + m.recv[b][opposite[f]]);
   }
+  d.any_nbr = 0;
+  for (int f = 0; f < 6; f++) if (d.halo.f[f].r) d.any_nbr = 1;
   d.comm.rank = s->dom.rank; d.comm.nranks = s->nranks;
   if (d.comm.timeout_cycles <= 0) d.comm.timeout_cycles = 1ll << 34;       /* ~8 s */
   for (int p = 0; p < BB_MAXR; p++) { d.comm.mbox_val[p] = NULL; d.comm.mbox_flag[p] = NULL; }
@@ -180,7 +182,7 @@ extern "C" int bbpcg_create(bbpcg_solver **out, const dom_struct *dom_rank, cons
     d.comm.rank = dom_rank->rank; d.comm.nranks = 1;
   }
   s->tile = 0; s->kc = 0;
-  s->resid_blocks = s->sm_count * 8;
+  s->resid_blocks = s->sm_count * 12;
   s->stream_blocks = s->sm_count * 8;
   s->check_every = 10;
   *out = s;
@@ -335,7 +337,7 @@ static int preload_kernels()
   if (!rc) rc = preload_search<128, 8, 512, 2>();
   if (!rc) rc = preload_search<32, 8, 128, 4>();
   if (!rc) rc = preload_search<256, 4, 256, 2>();
-  PL(k_resid<256>); PL(k_refresh_x<256>); PL(k_refresh_r<256, false>); PL(k_refresh_r<256, true>);
+  PL(k_resid<128, 4>); PL(k_resid<64, 4>); PL(k_resid<32, 4>); PL(k_refresh_x<256>); PL(k_refresh_r<256, false>); PL(k_refresh_r<256, true>);
   PL(k_init<256>); PL(k_finish<256>); PL(k_rhs<256>); PL(k_masks<256>); PL(k_part_rhs_net);
   PL(k_coeffs_refine<256>); PL(k_zero_ghosts); PL(k_xchg_send); PL(k_xchg_recv);
   PL(k_spmv_s3b<256, false>); PL(k_spmv_s3b<256, true>);
@@ -344,6 +346,28 @@ static int preload_kernels()
 }
 
 static int clampi(long long v, int lo, int hi) { return (int)(v < lo ? lo : v > hi ? hi : v); }
+
+template <int XT, int UNR>
+static int launch_resid_t(bbpcg_solver *s)
+{
+  const Layout &L = s->dev.L;
+  constexpr int YT = 128 / XT;
+  ResidArgs a;
+  a.cpr = (L.in + 3) / 4;
+  const long long nrows = (long long)L.jn * L.kn;
+  a.npass = (int)((nrows + YT * UNR - 1) / (YT * UNR));
+  k_resid<XT, UNR><<<clampi(a.npass, 1, s->resid_blocks), 128, 0, s->stream>>>(s->dev, a);
+  s->launches++;
+  return BBPCG_OK;
+}
+
+static int launch_resid(bbpcg_solver *s)
+{
+  const int cpr = (s->dev.L.in + 3) / 4;
+  if (cpr > 64) return launch_resid_t<128, 4>(s);
+  if (cpr > 32) return launch_resid_t<64, 4>(s);
+  return launch_resid_t<32, 4>(s);
+}
 
 /* ---- coefficients -------------------------------------------------------------------------- */
 extern "C" int bbpcg_set_coefficients(bbpcg_solver *s, const int *flag_u, const int *flag_v, const int *flag_w, const int *phase)
@@ -441,8 +465,8 @@ static int enqueue_iteration(bbpcg_solver *s, int it, bool parts, const real *rh
     else k_refresh_r<256, false><<<nb, 256, 0, s->stream>>>(s->dev, rhs, s->fst.cs1b, s->fst.cs2b);
     s->launches += 2;
   } else {
-    k_resid<256><<<clampi(nrows, 1, s->resid_blocks), 256, 0, s->stream>>>(s->dev);
-    s->launches++;
+    rc = launch_resid(s);
+    if (rc) return rc;
   }
   if (kt) CU(cudaEventRecord(s->kev[2 * it], s->stream));
   return BBPCG_OK;

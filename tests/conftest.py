@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# several ranks share ONE GPU in the single-process harness (tests/gpu_util.py): their collective
+# kernels must be able to run concurrently, so give every stream its own hardware queue
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "bluebottle-3.0_b200"), os.path.join(ROOT, "tests")):
     if p not in sys.path:
