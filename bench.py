@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--cpu-sample-grid", type=int, default=256)
     ap.add_argument("--cpu-sample-iters", type=int, default=20)
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "cuda", "port"])
+    ap.add_argument("--opt", action="append", default=[], help="solver tuning option key=value (bbpcg_set_option)")
     return ap.parse_args()
 
 
@@ -232,6 +233,9 @@ def run_bbpcg(args):
     for key, val in (("tile", args.tile), ("kc", args.kc), ("resid_blocks", args.resid_blocks)):
         if val >= 0:
             s.set_option(key, val)
+    for kv in args.opt:
+        key, val = kv.split("=")
+        s.set_option(key, int(val))
     dom = dec.doms[w.rank]
     fu, fv, fw = synth.flags_noparts_torch(dom, dec.DOM, dec.bc, dev)
     u, v, wz = synth.velocity_star_torch(dom, dec.DOM, dec.bc, dev)

@@ -20,6 +20,8 @@
 #define BB_MAXR BBPCG_MAX_RANKS
 #define BB_NSLOT 4                 /* mailbox slots (a peer is at most one stage ahead) */
 #define BB_MAXBLOCKS 65536         /* max CTAs of a reducing kernel */
+#define BB_GROUP 64                /* CTAs per first-level reduction group */
+#define BB_MAXGROUPS (BB_MAXBLOCKS / BB_GROUP)
 
 /* coefficient mask bits (fmask): squared face flags, src/solver_kernel.cu:824-829 */
 #define FM_E 1u
@@ -67,11 +69,13 @@ struct ArenaMap {
   size_t fmask, pmask;             /* bytes[L.n]   */
   size_t recv[2][6];               /* doubles, generic exchange staging (double-buffered) */
   size_t partials;                 /* doubles[2*BB_MAXBLOCKS] */
-  size_t counter;                  /* unsigned[4] */
+  size_t gpartials;                /* doubles[2*BB_MAXGROUPS]: group sums */
+  size_t counter;                  /* unsigned[4 + BB_MAXGROUPS]: [0] groups done, [4+g] CTAs of group g done */
   size_t scal;                     /* Scal */
   size_t mbox_val;                 /* doubles[BB_NSLOT][BB_MAXR][2] */
   size_t mbox_flag;                /* u64[BB_NSLOT][BB_MAXR] */
   size_t history;                  /* doubles[hist_cap] */
+  size_t invM_tab;                 /* doubles[128]: Jacobi diagonal per mask value */
   size_t total;
 };
 
@@ -89,11 +93,13 @@ static inline ArenaMap make_arena_map(const Layout &L)
   for (int b = 0; b < 2; b++) for (int f = 0; f < 6; f++)
     m.recv[b][f] = take(sizeof(double) * (f < 2 ? fi : f < 4 ? fj : fk));
   m.partials = take(sizeof(double) * 2 * BB_MAXBLOCKS);
-  m.counter = take(sizeof(unsigned) * 4);
+  m.gpartials = take(sizeof(double) * 2 * BB_MAXGROUPS);
+  m.counter = take(sizeof(unsigned) * (4 + BB_MAXGROUPS));
   m.scal = take(512);
   m.mbox_val = take(sizeof(double) * BB_NSLOT * BB_MAXR * 2);
   m.mbox_flag = take(sizeof(unsigned long long) * BB_NSLOT * BB_MAXR);
   m.history = take(sizeof(double) * BB_HIST_CAP);
+  m.invM_tab = take(sizeof(double) * 128);
   m.total = off;
   return m;
 }
@@ -143,10 +149,11 @@ struct Dev {
   double *r, *P[2], *q, *x;
   unsigned char *fmask, *pmask;
   double *recv[2][6];
-  double *partials;
+  double *partials, *gpartials;
   unsigned *counter;
   Scal *sc;
   double *history;
+  const double *invM_tab;         /* [128], built once by k_build_tab */
   double idx2, idy2, idz2;        /* 1/(dx*dx) ...  (per block, src/solver_kernel.cu:720-722) */
   double dx2_6, dy2_6, dz2_6;     /* dx*dx/6 ...    (src/solver_kernel.cu:683)                */
   Halo halo;

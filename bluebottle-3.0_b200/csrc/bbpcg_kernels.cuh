@@ -27,18 +27,24 @@ typedef unsigned char u8;
 /* Jacobi diagonal from the 6 flag^2 bits: PP_jacobi_init, src/solver_kernel.cu:73-80.
  * invM = -1/M, M = -idx2(fE^2+fW^2) - idy2(fN^2+fS^2) - idz2(fT^2+fB^2).  128 entries:
  * masks with FM_DEAD (ghosts behind walls) give 0 so that z = p = 0 there. */
+__global__ void k_build_tab(double *tab, double idx2, double idy2, double idz2)
+{
+  const int m = threadIdx.x;
+  if (m >= 128) return;
+  double v = 0.;
+  if (!(m & FM_DEAD)) {
+    int e = (m & FM_E) != 0, w = (m & FM_W) != 0, n = (m & FM_N) != 0, s = (m & FM_S) != 0,
+        t = (m & FM_T) != 0, b = (m & FM_B) != 0;
+    double M = -idx2 * (double)(e + w) - idy2 * (double)(n + s) - idz2 * (double)(t + b);
+    v = -1. / M;
+  }
+  tab[m] = v;
+}
+
+/* every CTA copies the 1 KB table into shared memory (L2 hit after the first CTA) */
 __device__ __forceinline__ void fill_invM_table(double *tab, const Dev &d)
 {
-  for (int m = threadIdx.x; m < 128; m += blockDim.x) {
-    double v = 0.;
-    if (!(m & FM_DEAD)) {
-      int e = (m & FM_E) != 0, w = (m & FM_W) != 0, n = (m & FM_N) != 0, s = (m & FM_S) != 0,
-          t = (m & FM_T) != 0, b = (m & FM_B) != 0;
-      double M = -d.idx2 * (double)(e + w) - d.idy2 * (double)(n + s) - d.idz2 * (double)(t + b);
-      v = -1. / M;
-    }
-    tab[m] = v;
-  }
+  for (int m = threadIdx.x; m < 128; m += blockDim.x) tab[m] = __ldg(d.invM_tab + m);
 }
 
 /* -A p at one cell, noparts operator: src/solver_kernel.cu:824-829 (same association) */
@@ -94,6 +100,9 @@ __device__ __forceinline__ double block_sum(double v, double *sh /*[32]*/)
   return s;
 }
 
+/* Two levels so that kernels made of many tiny CTAs stay cheap: the last CTA of each group of
+ * BB_GROUP CTAs sums that group's partials, the last group to finish sums the group sums.  Both
+ * orders are fixed, so the result is bit-identical run to run. */
 template <int NV>
 __device__ bool grid_reduce(const Dev &d, double (&v)[NV], int bid, int nblocks, double (&tot)[NV], bool peer_stores)
 {
@@ -104,12 +113,14 @@ __device__ bool grid_reduce(const Dev &d, double (&v)[NV], int bid, int nblocks,
   for (int n = 0; n < NV; n++) part[n] = block_sum<NV>(v[n], sh);
   if (peer_stores) __threadfence_system();       /* halo stores visible before we count in */
   __syncthreads();
+  const int grp = bid / BB_GROUP, ngrp = (nblocks + BB_GROUP - 1) / BB_GROUP;
+  const int gsize = min(BB_GROUP, nblocks - grp * BB_GROUP);
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int n = 0; n < NV; n++) d.partials[n * BB_MAXBLOCKS + bid] = part[n];
-    __threadfence_system();
-    unsigned t = atomicAdd(d.counter, 1u);
-    s_last = (t == (unsigned)(nblocks - 1));
+    if (d.comm.nranks > 1) __threadfence_system(); else __threadfence();
+    unsigned t = atomicAdd(d.counter + 4 + grp, 1u);
+    s_last = (t == (unsigned)(gsize - 1));
   }
   __syncthreads();
   if (!s_last) return false;
@@ -117,7 +128,25 @@ __device__ bool grid_reduce(const Dev &d, double (&v)[NV], int bid, int nblocks,
 #pragma unroll
   for (int n = 0; n < NV; n++) {
     double s = 0.;
-    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) s += __ldcg(&d.partials[n * BB_MAXBLOCKS + i]);
+    for (int i = threadIdx.x; i < gsize; i += blockDim.x) s += __ldcg(&d.partials[n * BB_MAXBLOCKS + grp * BB_GROUP + i]);
+    part[n] = block_sum<NV>(s, sh);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int n = 0; n < NV; n++) d.gpartials[n * BB_MAXGROUPS + grp] = part[n];
+    d.counter[4 + grp] = 0u;
+    if (d.comm.nranks > 1) __threadfence_system(); else __threadfence();
+    unsigned t = atomicAdd(d.counter, 1u);
+    s_last = (t == (unsigned)(ngrp - 1));
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+#pragma unroll
+  for (int n = 0; n < NV; n++) {
+    double s = 0.;
+    for (int i = threadIdx.x; i < ngrp; i += blockDim.x) s += __ldcg(&d.gpartials[n * BB_MAXGROUPS + i]);
     tot[n] = block_sum<NV>(s, sh);
   }
   if (threadIdx.x == 0) *d.counter = 0u;
@@ -191,6 +220,13 @@ __device__ __forceinline__ bool push_halo(const Dev &d, int which, int i, int j,
   return any;
 }
 
+/* in-plane offset (i+XOFF) + j*px of this block -> correction for a neighbour whose pitch differs */
+__device__ __forceinline__ long long j_px_fix(const Layout &L, const Layout &N, int goff)
+{
+  const int j = goff / L.px;
+  return (long long)j * (L.px - N.px);
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* k_search_spmv: see file header.  CTA tile TX x TY owned cells, marching KC planes in k.
  * Phase A (plane kk): every thread computes p_new on the halo'd tile (TX+2)x(TY+2) from
@@ -240,6 +276,8 @@ __global__ void __launch_bounds__(NT, MINB) k_search_spmv(const Dev d, const Sea
   /* per-thread item geometry, fixed across planes */
   int goff[IPT];                 /* in-plane offset of the item, -1: not a cell */
   unsigned role[IPT];            /* bit0 owned (x,y)   bit1 in-plane ghost this CTA maintains */
+  int gsrc[IPT], noff[IPT];      /* x/y ghost: face it is pulled from (-1 none) and in-plane offset there */
+  bool zint[IPT];                /* (i,j) inside the block: pulled from the T/B neighbour on ghost planes */
 #pragma unroll
   for (int n = 0; n < IPT; n++) {
     int idx = tid + n * NT;
@@ -253,6 +291,18 @@ __global__ void __launch_bounds__(NT, MINB) k_search_spmv(const Dev d, const Sea
     bool my = gy && ox && ((j == 0 && j0 == 1) || (j == L.jn + 1 && jlast == L.jn));
     goff[n] = valid ? (i + BB_XOFF) + j * L.px : -1;
     role[n] = (ox && oy ? 1u : 0u) | ((mx || my) ? 2u : 0u);
+    /* PULL model: the r value of a ghost cell is read straight from the neighbour's r array
+     * (peer memory over NVLink, or this block itself for a periodic self-wrap) -- faces only */
+    gsrc[n] = -1; noff[n] = 0;
+    if (valid && (gx != gy)) {
+      const int f = gx ? (i == 0 ? 1 : 0) : (j == 0 ? 3 : 2);
+      const NbrFace &nf = d.halo.f[f];
+      if (nf.r && (gx ? (j >= 1 && j <= L.jn) : (i >= 1 && i <= L.in))) {
+        const int ii = gx ? (i == 0 ? nf.L.in : 1) : i, jn_ = gx ? j : (j == 0 ? nf.L.jn : 1);
+        gsrc[n] = f; noff[n] = (ii + BB_XOFF) + jn_ * nf.L.px;
+      }
+    }
+    zint[n] = valid && i >= 1 && i <= L.in && j >= 1 && j <= L.jn;
   }
 
   double rr[IPT], pp[IPT], xx[IPT];
@@ -266,7 +316,15 @@ __global__ void __launch_bounds__(NT, MINB) k_search_spmv(const Dev d, const Sea
       rr[n] = 0.; pp[n] = 0.; xx[n] = 0.; mm[n] = FM_DEAD;
       if (goff[n] >= 0) {
         const long long g = pb + goff[n];
-        rr[n] = __ldg(r + g);
+        const double *rp = r + g;
+        if (kk == 0 || kk == L.kn + 1) {
+          const NbrFace &nz = d.halo.f[kk == 0 ? 5 : 4];
+          if (nz.r && zint[n]) rp = nz.r + goff[n] - j_px_fix(L, nz.L, goff[n]) + (long long)(kk == 0 ? nz.L.kn : 1) * nz.L.ps;
+        } else if (gsrc[n] >= 0) {
+          const NbrFace &nf = d.halo.f[gsrc[n]];
+          rp = nf.r + noff[n] + (long long)kk * nf.L.ps;
+        }
+        rr[n] = __ldg(rp);
         pp[n] = __ldg(pprev + g);
         mm[n] = __ldg(fmask + g);
         if (plane_owned && (role[n] & 1u)) xx[n] = x[g];
@@ -385,77 +443,71 @@ __device__ __forceinline__ void st256(double *p, const d4 &v)
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.a), "d"(v.b), "d"(v.c), "d"(v.d) : "memory");
 }
 
-/* CTA = 128 threads = XT chunk columns x YT rows; one pass = YT*UNR rows, every thread holding UNR
- * independent 4-cell chunks (UNR x (32 B r + 32 B q + 4 B mask) in flight before the first use). */
-struct ResidArgs { int cpr; int npass; };
+/* Many TINY CTAs (B200 streams best that way: measured 7.0 TB/s for this access pattern with
+ * 128-thread CTAs of one batch each, scratch/kb/triad.cu): CTA = 128 threads = XT chunk columns x
+ * YT rows, one pass = YT*UNR rows x XT chunks; every load of the pass -- r, q, mask and the
+ * scalars alpha / done -- is issued before the first use. */
+struct ResidArgs { int cpr; int ncb; int npass; int ppc; };   /* chunks per row, column blocks, passes, passes per CTA */
 
 template <int XT, int UNR>
-__global__ void __launch_bounds__(128, 4) k_resid(const Dev d, const ResidArgs a)
+__global__ void __launch_bounds__(128, 4) k_resid(const __grid_constant__ Dev d, const ResidArgs a)
 {
-  Scal *sc = d.sc;
-  if (sc->done) return;
   constexpr int NT = 128, YT = NT / XT;
   __shared__ double tab[128];
-  fill_invM_table(tab, d);
-  __syncthreads();
   const Layout L = d.L;
-  const double alpha = sc->alpha;
+  Scal *sc = d.sc;
   double *__restrict__ r = d.r;
   const double *__restrict__ qv = d.q;
   const u8 *__restrict__ fmask = d.fmask;
   const unsigned nrows = (unsigned)L.jn * (unsigned)L.kn;
   const int tx = threadIdx.x % XT, ty = threadIdx.x / XT;
-  const bool any_nbr = d.any_nbr != 0;
   double dot = 0.;
-  bool pushed = false;
-  for (int pass = blockIdx.x; pass < a.npass; pass += gridDim.x) {
-    const unsigned row0 = (unsigned)pass * (YT * UNR) + ty;
-    for (int c = tx; c < a.cpr; c += XT) {
-      d4 rv[UNR], qq[UNR];
-      unsigned mk[UNR];
-      long long g[UNR];
-      int jj[UNR], kk[UNR];
+  const int pass0 = blockIdx.x * a.ppc, pass1 = min(pass0 + a.ppc, a.npass);
+  for (int pass = pass0; pass < pass1; pass++) {
+    const int cb = pass % a.ncb, rg = pass / a.ncb;
+    const int c = cb * XT + tx;
+    const unsigned row0 = (unsigned)rg * (YT * UNR) + ty;
+    d4 rv[UNR], qq[UNR];
+    unsigned mk[UNR];
+    long long g[UNR];
+    int jj[UNR], kk[UNR];
 #pragma unroll
-      for (int u = 0; u < UNR; u++) {
-        const unsigned row = row0 + u * YT;
-        const unsigned k0 = row / (unsigned)L.jn;
-        jj[u] = (int)(row - k0 * (unsigned)L.jn) + 1; kk[u] = (int)k0 + 1;
-        g[u] = (long long)kk[u] * L.ps + (long long)jj[u] * L.px + (BB_XOFF + 1) + 4 * c;
-        if (row < nrows) {
-          rv[u] = ld256(r + g[u]);
-          qq[u] = ld256_stream(qv + g[u]);
-          mk[u] = __ldg(reinterpret_cast<const unsigned *>(fmask + g[u]));
-        } else { kk[u] = -1; }
-      }
-      const int i0 = 4 * c + 1;
-      const int nv = min(4, L.in - 4 * c);                              /* cells of this chunk inside the block */
+    for (int u = 0; u < UNR; u++) {
+      const unsigned row = row0 + u * YT;
+      const unsigned k0 = row / (unsigned)L.jn;
+      jj[u] = (int)(row - k0 * (unsigned)L.jn) + 1; kk[u] = (int)k0 + 1;
+      g[u] = (long long)kk[u] * L.ps + (long long)jj[u] * L.px + (BB_XOFF + 1) + 4 * c;
+      if (row < nrows && c < a.cpr) {
+        rv[u] = ld256(r + g[u]);
+        qq[u] = ld256_stream(qv + g[u]);
+        mk[u] = __ldg(reinterpret_cast<const unsigned *>(fmask + g[u]));
+      } else { kk[u] = -1; }
+    }
+    const double alpha = sc->alpha;
+    const int done = sc->done;
+    if (pass == pass0) { tab[threadIdx.x] = __ldg(d.invM_tab + threadIdx.x); __syncthreads(); }
+    if (done) return;                                                     /* uniform: a finished solve */
+    const int nv = min(4, L.in - 4 * c);                                  /* cells of this chunk inside the block */
 #pragma unroll
-      for (int u = 0; u < UNR; u++) {
-        if (kk[u] < 0) continue;
-        d4 v = rv[u];
-        v.a -= alpha * qq[u].a; v.b -= alpha * qq[u].b; v.c -= alpha * qq[u].c; v.d -= alpha * qq[u].d;   /* solver_kernel.cu:855 */
-        const double za = v.a * tab[mk[u] & 127u], zb = v.b * tab[(mk[u] >> 8) & 127u],
-                     zc = v.c * tab[(mk[u] >> 16) & 127u], zd = v.d * tab[(mk[u] >> 24) & 127u];          /* :858 */
-        if (nv == 4) {
-          dot += v.a * za; dot += v.b * zb; dot += v.c * zc; dot += v.d * zd;
-          st256(r + g[u], v);
-        } else {                                                          /* ragged row end: never touch the E ghost */
-          double *rp = r + g[u];
-          dot += v.a * za; rp[0] = v.a;
-          if (nv > 1) { dot += v.b * zb; rp[1] = v.b; }
-          if (nv > 2) { dot += v.c * zc; rp[2] = v.c; }
-        }
-        if (any_nbr && (c == 0 || 4 * c + 4 >= L.in || jj[u] == 1 || jj[u] == L.jn || kk[u] == 1 || kk[u] == L.kn)) {
-          pushed |= push_halo(d, 0, i0, jj[u], kk[u], v.a);
-          if (nv > 1) pushed |= push_halo(d, 0, i0 + 1, jj[u], kk[u], v.b);
-          if (nv > 2) pushed |= push_halo(d, 0, i0 + 2, jj[u], kk[u], v.c);
-          if (nv > 3) pushed |= push_halo(d, 0, i0 + 3, jj[u], kk[u], v.d);
-        }
+    for (int u = 0; u < UNR; u++) {
+      if (kk[u] < 0) continue;
+      d4 v = rv[u];
+      v.a -= alpha * qq[u].a; v.b -= alpha * qq[u].b; v.c -= alpha * qq[u].c; v.d -= alpha * qq[u].d;   /* solver_kernel.cu:855 */
+      const double za = v.a * tab[mk[u] & 127u], zb = v.b * tab[(mk[u] >> 8) & 127u],
+                   zc = v.c * tab[(mk[u] >> 16) & 127u], zd = v.d * tab[(mk[u] >> 24) & 127u];          /* :858 */
+      if (nv == 4) {
+        dot += v.a * za; dot += v.b * zb; dot += v.c * zc; dot += v.d * zd;
+        st256(r + g[u], v);
+      } else {                                                            /* ragged row end: never touch the E ghost */
+        double *rp = r + g[u];
+        dot += v.a * za; rp[0] = v.a;
+        if (nv > 1) { dot += v.b * zb; rp[1] = v.b; }
+        if (nv > 2) { dot += v.c * zc; rp[2] = v.c; }
       }
     }
   }
   double v[1] = { dot }, tot[1];
-  if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) {
+  if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, false)) {
     rank_allreduce(d, tot, 1);
     if (threadIdx.x == 0) finish_iteration(d, tot[0], false);
   }
@@ -520,7 +572,6 @@ __global__ void __launch_bounds__(NT) k_refresh_r(const Dev d, const double *__r
       double z = rv * tab[m & 127u];
       dot += rv * z;
       r[g] = rv;
-      if (j == 1 || j == L.jn || k == 1 || k == L.kn || i == 1 || i == L.in) pushed |= push_halo(d, 0, i, j, k, rv);
     }
   }
   double v[1] = { dot }, tot[1];
@@ -554,7 +605,6 @@ __global__ void __launch_bounds__(NT) k_init(const Dev d, const double *__restri
       const double z = b * tab[d.fmask[g] & 127u];
       bb += b * b;  rz += b * z;
       d.r[g] = b;
-      if (j == 1 || j == L.jn || k == 1 || k == L.kn || i == 1 || i == L.in) pushed |= push_halo(d, 0, i, j, k, b);
     }
   }
   double v[2] = { bb, rz }, tot[2];

@@ -57,7 +57,7 @@ struct bbpcg_solver {
   /* launch configuration */
   int tile;                         /* k_search_spmv variant */
   int kc;                           /* planes per CTA */
-  int resid_blocks, stream_blocks;
+  int resid_blocks, stream_blocks, resid_ppc;
   int check_every;                  /* iterations per polling batch */
   int sm_count;
   /* pinned poll words + host-mode buffers */
@@ -93,8 +93,9 @@ static void point_dev_at_arena(bbpcg_solver *s)
   d.q = (double *)(a + m.q); d.x = (double *)(a + m.x);
   d.fmask = (u8 *)(a + m.fmask); d.pmask = (u8 *)(a + m.pmask);
   for (int b = 0; b < 2; b++) for (int f = 0; f < 6; f++) d.recv[b][f] = (double *)(a + m.recv[b][f]);
-  d.partials = (double *)(a + m.partials); d.counter = (unsigned *)(a + m.counter);
+  d.partials = (double *)(a + m.partials); d.gpartials = (double *)(a + m.gpartials); d.counter = (unsigned *)(a + m.counter);
   d.sc = (Scal *)(a + m.scal); d.history = (double *)(a + m.history);
+  d.invM_tab = (const double *)(a + m.invM_tab);
 }
 
 /* neighbour tables for a set of ranks whose arenas are addressable at peer_arena[] with
@@ -165,6 +166,8 @@ extern "C" int bbpcg_create(bbpcg_solver **out, const dom_struct *dom_rank, cons
   s->fst.ws1b = dom_rank->Gfz.s1b; s->fst.ws2b = dom_rank->Gfz.s2b;
   s->fst.cs1b = g.s1b; s->fst.cs2b = g.s2b;
   { int rc = preload_kernels(); if (rc) { cudaFree(s->arena); delete s; return rc; } }
+  k_build_tab<<<1, 128>>>((double *)(s->arena + s->amap.invM_tab), d.idx2, d.idy2, d.idz2);
+  CU(cudaDeviceSynchronize());
   CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 4; i++) CU(cudaEventCreate(&s->ev[i]));
   for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&s->ev_poll[i], cudaEventDisableTiming));
@@ -338,7 +341,7 @@ static int preload_kernels()
   if (!rc) rc = preload_search<32, 8, 128, 4>();
   if (!rc) rc = preload_search<256, 4, 256, 2>();
   PL(k_resid<128, 4>); PL(k_resid<64, 4>); PL(k_resid<32, 4>); PL(k_refresh_x<256>); PL(k_refresh_r<256, false>); PL(k_refresh_r<256, true>);
-  PL(k_init<256>); PL(k_finish<256>); PL(k_rhs<256>); PL(k_masks<256>); PL(k_part_rhs_net);
+  PL(k_build_tab); PL(k_init<256>); PL(k_finish<256>); PL(k_rhs<256>); PL(k_masks<256>); PL(k_part_rhs_net);
   PL(k_coeffs_refine<256>); PL(k_zero_ghosts); PL(k_xchg_send); PL(k_xchg_recv);
   PL(k_spmv_s3b<256, false>); PL(k_spmv_s3b<256, true>);
 #undef PL
@@ -354,9 +357,14 @@ static int launch_resid_t(bbpcg_solver *s)
   constexpr int YT = 128 / XT;
   ResidArgs a;
   a.cpr = (L.in + 3) / 4;
+  a.ncb = (a.cpr + XT - 1) / XT;
   const long long nrows = (long long)L.jn * L.kn;
-  a.npass = (int)((nrows + YT * UNR - 1) / (YT * UNR));
-  k_resid<XT, UNR><<<clampi(a.npass, 1, s->resid_blocks), 128, 0, s->stream>>>(s->dev, a);
+  const long long npass = (nrows + YT * UNR - 1) / (YT * UNR) * a.ncb;
+  if (npass > 0x7fffffffll) { bbpcg_set_error("block too large"); return BBPCG_EINVAL; }
+  a.npass = (int)npass;
+  a.ppc = s->resid_ppc > 0 ? s->resid_ppc : 1;
+  if ((a.npass + a.ppc - 1) / a.ppc > BB_MAXBLOCKS) a.ppc = (a.npass + BB_MAXBLOCKS - 1) / BB_MAXBLOCKS;
+  k_resid<XT, UNR><<<(a.npass + a.ppc - 1) / a.ppc, 128, 0, s->stream>>>(s->dev, a);
   s->launches++;
   return BBPCG_OK;
 }
@@ -607,6 +615,7 @@ extern "C" int bbpcg_set_option(bbpcg_solver *s, const char *key, long long valu
   if (!strcmp(key, "tile")) { if (value < 0 || value >= k_ntiles) { bbpcg_set_error("tile must be 0..%d", k_ntiles - 1); return BBPCG_EINVAL; } s->tile = (int)value; }
   else if (!strcmp(key, "kc")) s->kc = (int)value;
   else if (!strcmp(key, "resid_blocks")) s->resid_blocks = clampi(value, 1, BB_MAXBLOCKS);
+  else if (!strcmp(key, "resid_ppc")) s->resid_ppc = clampi(value, 0, 1 << 20);
   else if (!strcmp(key, "stream_blocks")) s->stream_blocks = clampi(value, 1, BB_MAXBLOCKS);
   else if (!strcmp(key, "check_every")) s->check_every = clampi(value, 1, 1000);
   else if (!strcmp(key, "comm_timeout_ms")) s->dev.comm.timeout_cycles = value * 2000000ll;   /* ~2 GHz */
