@@ -13,6 +13,7 @@
 #include <unistd.h>
 
 #include "bbpcg_kernels.cuh"
+#include "bbpcg_search_tma.cuh"
 
 /* ---- error plumbing ---------------------------------------------------------------------- */
 static thread_local char g_err[512] = "";
@@ -70,6 +71,8 @@ struct bbpcg_solver {
   /* optional per-kernel timing (bench.py's roofline leg): events around every launch of the
    * iteration loop, on the solver's own stream */
   int last_search_grid, last_search_kc;
+  SearchMaps maps[2];               /* tensor maps of k_search_tma for TY = 8 / TY = 4 */
+  int maps_ok;
   int kernel_timing;
   cudaEvent_t *kev;                 /* [2*BB_KT_CAP+1] */
   double kt_search_ms, kt_resid_ms, kt_refresh_ms;
@@ -96,6 +99,69 @@ static void point_dev_at_arena(bbpcg_solver *s)
   d.partials = (double *)(a + m.partials); d.gpartials = (double *)(a + m.gpartials); d.counter = (unsigned *)(a + m.counter);
   d.sc = (Scal *)(a + m.scal); d.history = (double *)(a + m.history);
   d.invM_tab = (const double *)(a + m.invM_tab);
+}
+
+/* ---- TMA tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point, so the
+ * library needs no link-time dependency on libcuda) ---- */
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled encode_fn()
+{
+  static PFN_encodeTiled fn = NULL;
+  if (!fn) {
+    void *p = NULL;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+/* 3-D map over one P-layout array (px x (jn+2) x (kn+2), x fastest) with box bx x by x 1 */
+static int make_map(CUtensorMap *m, void *base, const Layout &L, bool u8, int bx, int by)
+{
+  PFN_encodeTiled fn = encode_fn();
+  if (!fn) { bbpcg_set_error("cuTensorMapEncodeTiled is not available from this driver"); return BBPCG_ECUDA; }
+  const size_t es = u8 ? 1 : 8;
+  cuuint64_t dims[3] = { (cuuint64_t)L.px, (cuuint64_t)(L.jn + 2), (cuuint64_t)(L.kn + 2) };
+  cuuint64_t strides[2] = { (cuuint64_t)L.px * es, (cuuint64_t)L.ps * es };
+  cuuint32_t box[3] = { (cuuint32_t)bx, (cuuint32_t)by, 1u }, estr[3] = { 1u, 1u, 1u };
+  CUresult r = fn(m, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { bbpcg_set_error("cuTensorMapEncodeTiled failed (%d) for box %d x %d", (int)r, bx, by); return BBPCG_ECUDA; }
+  return BBPCG_OK;
+}
+
+template <int TY>
+static int build_search_maps_t(bbpcg_solver *s, SearchMaps *M)
+{
+  typedef SearchGeom<TY, true> G;
+  const Dev &d = s->dev;
+  int rc = 0;
+  memset(M, 0, sizeof(*M));
+  if (!rc) rc = make_map(&M->r, d.r, d.L, false, G::HXP, G::HY);
+  if (!rc) rc = make_map(&M->p[0], d.P[0], d.L, false, G::HXP, G::HY);
+  if (!rc) rc = make_map(&M->p[1], d.P[1], d.L, false, G::HXP, G::HY);
+  if (!rc) rc = make_map(&M->fm, d.fmask, d.L, true, G::MXP, G::HY);
+  if (!rc) rc = make_map(&M->pm, d.pmask, d.L, true, G::TX, TY);
+  for (int f = 0; f < 6 && !rc; f++) {
+    const NbrFace &nf = d.halo.f[f];
+    if (!nf.r) { M->nb[f] = M->r; continue; }            /* never used: keeps the parameter well formed */
+    if (f < 2) rc = make_map(&M->nb[f], nf.r, nf.L, false, 2, G::HY);
+    else if (f < 4) rc = make_map(&M->nb[f], nf.r, nf.L, false, G::HXP, 1);
+    else rc = make_map(&M->nb[f], nf.r, nf.L, false, G::HXP, G::HY);
+  }
+  return rc;
+}
+
+static int build_search_maps(bbpcg_solver *s)
+{
+  s->maps_ok = 0;
+  int rc = build_search_maps_t<8>(s, &s->maps[0]);
+  if (!rc) rc = build_search_maps_t<4>(s, &s->maps[1]);
+  if (!rc) s->maps_ok = 1;
+  return rc;
 }
 
 /* neighbour tables for a set of ranks whose arenas are addressable at peer_arena[] with
@@ -180,6 +246,7 @@ extern "C" int bbpcg_create(bbpcg_solver **out, const dom_struct *dom_rank, cons
     s->peer_arena[0] = s->arena;
     int dims[1][3] = { { g.in, g.jn, g.kn } };
     build_halo(s, dims);
+    { int rc = build_search_maps(s); if (rc) { cudaFree(s->arena); delete s; return rc; } }
   } else {
     memset(&d.halo, 0, sizeof(d.halo));     /* until bbpcg_comm_import */
     d.comm.rank = dom_rank->rank; d.comm.nranks = 1;
@@ -258,12 +325,12 @@ extern "C" int bbpcg_comm_import(bbpcg_solver *s, const void *all_blobs, int nra
   }
   s->nranks = nranks;
   build_halo(s, dims);
-  return BBPCG_OK;
+  return build_search_maps(s);
 }
 
 /* ---- launch helpers ------------------------------------------------------------------------ */
 struct TileCfg { int tx, ty, nt; };
-static const TileCfg k_tiles[] = { { 128, 8, 256 }, { 128, 4, 256 }, { 64, 8, 256 }, { 128, 8, 512 }, { 32, 8, 128 }, { 256, 4, 256 } };
+static const TileCfg k_tiles[] = { { 128, 8, 256 }, { 128, 4, 256 }, { 128, 8, 256 }, { 128, 4, 256 }, { 64, 8, 256 }, { 128, 8, 512 }, { 32, 8, 128 }, { 256, 4, 256 } };
 static const int k_ntiles = sizeof(k_tiles) / sizeof(k_tiles[0]);
 
 template <int TX, int TY, int NT, int MINB>
@@ -300,15 +367,48 @@ static int launch_search_t(bbpcg_solver *s, bool parts)
   return BBPCG_OK;
 }
 
+/* the TMA-fed kernel (bbpcg_search_tma.cuh) */
+template <int TY, bool PARTS>
+static int launch_search_tma_t(bbpcg_solver *s, const SearchMaps &M)
+{
+  typedef SearchGeom<TY, PARTS> G;
+  static_assert(sizeof(Dev) + sizeof(SearchMaps) + sizeof(SearchArgs) + 192 <= 4096, "kernel parameters exceed 4 KB");
+  const Layout &L = s->dev.L;
+  if (!s->maps_ok) { bbpcg_set_error("tensor maps not built"); return BBPCG_EINVAL; }
+  SearchArgs a;
+  a.nbx = (L.in + G::TX - 1) / G::TX; a.nby = (L.jn + TY - 1) / TY;
+  int kc = s->kc;
+  if (kc <= 0) {
+    /* ~8 waves of the 2-per-SM resident CTAs, columns no shorter than 16 planes */
+    long long want = (long long)s->sm_count * 16, per = (long long)a.nbx * a.nby;
+    int nz = (int)((want + per - 1) / per);
+    if (nz < 1) nz = 1;
+    kc = (L.kn + nz - 1) / nz;
+    if (kc < 16) kc = L.kn < 16 ? L.kn : 16;
+  }
+  if (kc > L.kn) kc = L.kn;
+  a.KC = kc; a.nbz = (L.kn + kc - 1) / kc;
+  if ((long long)a.nbx * a.nby * a.nbz > BB_MAXBLOCKS) { bbpcg_set_error("grid too large for the reduction workspace"); return BBPCG_EINVAL; }
+  static bool attr_set = false;
+  if (!attr_set) { CU(cudaFuncSetAttribute(k_search_tma<TY, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM)); attr_set = true; }
+  dim3 grid(a.nbx, a.nby, a.nbz);
+  s->last_search_grid = a.nbx * a.nby * a.nbz; s->last_search_kc = kc;
+  k_search_tma<TY, PARTS><<<grid, G::NT, G::SMEM, s->stream>>>(s->dev, M, a);
+  s->launches++;
+  return BBPCG_OK;
+}
+
 static int launch_search(bbpcg_solver *s, bool parts)
 {
   switch (s->tile) {
-    case 0: return launch_search_t<128, 8, 256, 2>(s, parts);
-    case 1: return launch_search_t<128, 4, 256, 3>(s, parts);
-    case 2: return launch_search_t<64, 8, 256, 3>(s, parts);
-    case 3: return launch_search_t<128, 8, 512, 2>(s, parts);
-    case 4: return launch_search_t<32, 8, 128, 4>(s, parts);
-    case 5: return launch_search_t<256, 4, 256, 2>(s, parts);
+    case 0: return parts ? launch_search_tma_t<8, true>(s, s->maps[0]) : launch_search_tma_t<8, false>(s, s->maps[0]);
+    case 1: return parts ? launch_search_tma_t<4, true>(s, s->maps[1]) : launch_search_tma_t<4, false>(s, s->maps[1]);
+    case 2: return launch_search_t<128, 8, 256, 2>(s, parts);
+    case 3: return launch_search_t<128, 4, 256, 3>(s, parts);
+    case 4: return launch_search_t<64, 8, 256, 3>(s, parts);
+    case 5: return launch_search_t<128, 8, 512, 2>(s, parts);
+    case 6: return launch_search_t<32, 8, 128, 4>(s, parts);
+    case 7: return launch_search_t<256, 4, 256, 2>(s, parts);
   }
   bbpcg_set_error("unknown tile variant %d", s->tile);
   return BBPCG_EINVAL;
@@ -334,6 +434,7 @@ static int preload_kernels()
 {
   int rc = 0;
 #define PL(...) if (!rc) rc = preload_one(__VA_ARGS__)
+  PL(k_search_tma<8, false>); PL(k_search_tma<8, true>); PL(k_search_tma<4, false>); PL(k_search_tma<4, true>);
   if (!rc) rc = preload_search<128, 8, 256, 2>();
   if (!rc) rc = preload_search<128, 4, 256, 3>();
   if (!rc) rc = preload_search<64, 8, 256, 3>();

@@ -111,7 +111,7 @@ def test_solve_noparts_all_bc_sets(bc):
     p.close()
 
 
-@pytest.mark.parametrize("tile", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("tile", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_solve_every_tile_variant(tile):
     case = Case((40, 24, 36), bc="duct")      # ragged: not a multiple of any tile
     p = _product(case, options={"tile": tile})
