@@ -78,7 +78,7 @@ struct SearchGeom {
   static constexpr int OFF_STAGE = NPS * RT;
   static constexpr int OFF_TAB = OFF_STAGE + NRS * STAGE;
   static constexpr int OFF_BAR = OFF_TAB + 128 * 8;
-  static constexpr int SMEM = OFF_BAR + 64 + 128;      /* + slack for the manual 128-B alignment */
+  static constexpr int SMEM = OFF_BAR + 64;
 };
 
 /* item flags (per thread, fixed across planes) */
@@ -102,8 +102,7 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
   typedef SearchGeom<TY, PARTS> G;
   constexpr int TX = G::TX, HXP = G::HXP, HY = G::HY, NA = G::NA, NO = G::NO;
   static_assert(TY % 4 == 0 && TY >= 4, "TY must be a multiple of 4");
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char *smem = (unsigned char *)(((size_t)smem_raw + 127) & ~(size_t)127);
+  extern __shared__ __align__(128) unsigned char smem[];     /* plain pointer arithmetic only: keeps LDS/STS (no generic LD/ST) */
   double *tab = reinterpret_cast<double *>(smem + G::OFF_TAB);
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + G::OFF_BAR);
 
