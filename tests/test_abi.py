@@ -1,0 +1,121 @@
+"""CPU tests (no GPU): the C-ABI libraries load and export every symbol include/*.h declares;
+the binary grid contract has the reference's size; the product fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import bbpcg
+from bbpcg import lib as L
+from bbpcg.grid import BC_SETS, DomStruct, GridInfo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INC = os.path.join(ROOT, "include")
+
+
+def _declared(header):
+    """names of the functions a header declares (C prototypes ending in ';')"""
+    text = open(os.path.join(INC, header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
+    text = re.sub(r"typedef[^;{]*\{[^}]*\}[^;]*;", "", text, flags=re.S)      # struct typedefs
+    text = re.sub(r"typedef[^;]*;", "", text)                                   # other typedefs (incl. fn pointers)
+    return sorted(set(re.findall(r"\b([A-Za-z_]\w*)\s*\([^;{]*\)\s*;", text)) - {"static_assert", "_Static_assert"})
+
+
+def _exported(path):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", path], text=True)
+    return {ln.split()[-1] for ln in out.splitlines() if ln.strip()}
+
+
+def _undefined(path):
+    out = subprocess.check_output(["nm", "-D", "--undefined-only", path], text=True)
+    return {ln.split()[-1] for ln in out.splitlines() if ln.strip()}
+
+
+def test_headers_declare_what_the_binding_lists():
+    assert _declared("bbpcg.h") == sorted(L.SYMBOLS)
+    # bb_dropin_allgather is declared for the HOST to define (weak in the library)
+    assert sorted(set(_declared("bb_dropin.h")) - {"bb_dropin_allgather"}) == sorted(L.DROPIN_SYMBOLS)
+
+
+def test_libbbpcg_exports_every_declared_symbol():
+    assert os.path.exists(L.LIB_PATH), "run __graft_entry__.build() first"
+    exp = _exported(L.LIB_PATH)
+    missing = [s for s in _declared("bbpcg.h") if s not in exp]
+    assert not missing, missing
+    lib = bbpcg.load_library()
+    for s in L.SYMBOLS:
+        assert getattr(lib, s) is not None
+    assert lib.bbpcg_version().startswith(b"bbpcg")
+
+
+def test_dropin_exports_the_reference_entry_points_and_imports_its_globals():
+    assert os.path.exists(L.DROPIN_PATH)
+    exp, und = _exported(L.DROPIN_PATH), _undefined(L.DROPIN_PATH)
+    for s in L.DROPIN_SYMBOLS:
+        assert s in exp, s
+    # what the reference host program must provide (src/bluebottle.c:438-576, mpi_comm.c:26-27, particle.c:27-28)
+    for g in ("dom", "DOM", "rank", "nprocs", "bc", "rho_f", "dt", "pp_residual", "pp_max_iter", "NPARTS", "nparts",
+              "_u_star", "_v_star", "_w_star", "_flag_u", "_flag_v", "_flag_w", "_phase", "_phase_shell", "_rhs_p", "_phi",
+              "cuda_part_BC_p", "recorder_PP"):
+        assert g in und, g
+    # private scratch of the reference solver is NOT touched
+    for g in ("_invM", "_r_q", "_z_q", "_p_q", "_pb_q", "_Apb_q", "_dom"):
+        assert g not in und, g
+    # no MPI symbol anywhere
+    assert not [s for s in und if s.startswith("MPI_") or s.startswith("ompi_")]
+
+
+def test_product_does_not_link_or_import_the_oracle():
+    und = _undefined(L.LIB_PATH) | _undefined(L.DROPIN_PATH)
+    assert not [s for s in und if s.startswith("bbo_") or s.startswith("bbref_")]
+    needed = subprocess.check_output(["readelf", "-d", L.LIB_PATH], text=True)
+    assert "liboracle" not in needed and "libbbref" not in needed
+    pkg = os.path.join(ROOT, "bluebottle-3.0_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                for needle in ("import oracle", "from oracle", "liboracle", "libbbref", "pcg_ref", "oracle/"):
+                    assert needle not in txt, (os.path.join(dp, f), needle)
+
+
+def test_grid_contract_sizes():
+    assert C.sizeof(GridInfo) == 42 * 4
+    assert C.sizeof(DomStruct) == 880          # sizeof(dom_struct) in the reference build = 0x370
+    assert DomStruct.xs.offset == 4 * 42 * 4   # 4 grid_info blocks first (src/domain.h:168-173)
+    assert DomStruct.rank.offset == 4 * 42 * 4 + 3 * 40
+
+
+def test_status_codes_match_header():
+    text = open(os.path.join(INC, "bbpcg.h")).read()
+    for name, val in (("CONVERGED", 0), ("TINY_RHS", 1), ("MAXITER", 2), ("NAN", 3)):
+        assert re.search(r"#define\s+BBPCG_%s\s+%d\b" % (name, val), text)
+    assert int(re.search(r"#define\s+BBPCG_BLOB_BYTES\s+(\d+)", text).group(1)) == L.BLOB_BYTES
+
+
+def _no_gpu():
+    import torch
+    return not torch.cuda.is_available()
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="checks the behaviour WITHOUT a CUDA device")
+def test_no_cpu_fallback_create_fails_loudly():
+    """There is no CPU path: bbpcg_create reports BBPCG_ECUDA, the Python mirror raises."""
+    dec = bbpcg.Decomposition.uniform((0, 1, 0, 1, 0, 1), (8, 8, 8), (1, 1, 1), BC_SETS["periodic"])
+    lib = bbpcg.load_library()
+    h = C.c_void_p()
+    rc = lib.bbpcg_create(C.byref(h), C.byref(dec.doms[0]), C.byref(dec.DOM), C.byref(dec.bc), -1)
+    assert rc == -2 and b"no CUDA device" in lib.bbpcg_last_error()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        bbpcg.PoissonSolver(dec, 0)
+
+
+def test_missing_library_is_an_error_not_a_fallback(monkeypatch):
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", "/nonexistent/libbbpcg.so")
+    with pytest.raises(bbpcg.LibraryMissing):
+        L.load_library()
