@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--fixed-iters", type=int, default=0, help=">0: fixed iteration count per step, no stop test")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-comm-split", action="store_true", help="N > 1: skip the exposed halo/all-reduce measurement")
     ap.add_argument("--cpu-sample-grid", type=int, default=256)
     ap.add_argument("--cpu-sample-iters", type=int, default=20)
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "cuda", "port"])
@@ -73,13 +74,13 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index, period_ms=200):
+        self.index, self.proc, self.lines, self.period_ms = index, None, [], period_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -279,20 +280,49 @@ def run_bbpcg(args):
     search_s = w.max(kt["kt_search_ns"] * 1e-9 / max(kt["kt_search_n"], 1))
     resid_s = w.max(kt["kt_resid_ns"] * 1e-9 / max(kt["kt_resid_n"], 1))
     ach = BYTES_SEARCH * ncell_rank / search_s / 1e9
-    tr = traffic_from_profile()
+    tr = traffic_from_profile() or {}
+    tr_cells = tr.get("cells_per_launch", 512 ** 3)
+    tr_scale = ncell_rank / float(tr_cells)          # the capture is of the 512^3 1-GPU launch; bytes scale with the cells
+    def _traffic(key):
+        v = tr.get(key)
+        return None if v is None else v * tr_scale
     roof = {"kernel": "k_search_spmv", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": (tr or {}).get("k_search_spmv_bytes_per_launch"), "peak_source": peak_src,
+            "traffic": _traffic("k_search_spmv_bytes_per_launch"), "traffic_source": tr.get("source"), "peak_source": peak_src,
             "algorithmic_bytes_per_cell": BYTES_SEARCH, "cells_per_launch": ncell_rank,
             "avg_launch_us": search_s * 1e6, "launches_timed": kt["kt_search_n"],
             "share_of_iteration_loop": kt["kt_search_ns"] * 1e-6 / max(ms_iter, 1e-9)}
     ach2 = BYTES_RESID * ncell_rank / resid_s / 1e9
     roof2 = {"kernel": "k_resid", "bound": "hbm", "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak,
-             "traffic": (tr or {}).get("k_resid_bytes_per_launch"), "algorithmic_bytes_per_cell": BYTES_RESID,
+             "traffic": _traffic("k_resid_bytes_per_launch"), "algorithmic_bytes_per_cell": BYTES_RESID,
              "avg_launch_us": resid_s * 1e6, "launches_timed": kt["kt_resid_n"]}
     ach_it = BYTES_ITER * ncell_rank * iters / (ms_iter_max * 1e-3) / 1e9
     roof_it = {"bound": "hbm", "achieved": ach_it, "peak": peak, "unit": "GB/s", "frac": ach_it / peak,
                "model": "72 B/cell/iteration over the iteration loop only (per GPU)",
                "iter_loop_its": iters / (ms_iter_max * 1e-3), "us_per_iteration": ms_iter_max * 1e3 / max(iters, 1)}
+
+    # ---- exposed communication (N > 1): the same per-rank block solved stand-alone (no peers: no halo pull
+    # over NVLink, no cross-rank all-reduce wait), same kernels, fixed iteration count ----------------------
+    comm = None
+    if w.size > 1 and not args.no_comm_split:
+        ext1 = (dom.xs, dom.xe, dom.ys, dom.ye, dom.zs, dom.ze)
+        dec1 = bbpcg.Decomposition.uniform(ext1, (dom.xn, dom.yn, dom.zn), (1, 1, 1), BC_SETS[args.bc])
+        s1 = bbpcg.PoissonSolver(dec1, 0, device=w.local)
+        f1 = synth.flags_noparts_torch(dec1.doms[0], dec1.DOM, dec1.bc, dev)
+        s1.init_jacobi_preconditioner(*f1)
+        u1, v1, w1 = synth.velocity_star_torch(dec1.doms[0], dec1.DOM, dec1.bc, dev)
+        rhs1, phi1 = s1.empty("Gcc"), s1.empty("Gcc")
+        s1.PP_cg_noparts(u1, v1, w1, rhs1, phi1, fixed_iters=40)
+        w.barrier()
+        r1 = s1.PP_cg_noparts(u1, v1, w1, rhs1, phi1, fixed_iters=200)
+        local_us = w.max(r1.ms_iter * 1e3 / 200)
+        rN = s.PP_cg_noparts(u, v, wz, rhs, phi, rho_f=1.0, dt=1e-3, fixed_iters=200)
+        coll_us = w.max(rN.ms_iter * 1e3 / 200)
+        comm = {"us_per_iteration": coll_us, "us_per_iteration_standalone_block": local_us,
+                "exposed_halo_plus_allreduce_us": coll_us - local_us,
+                "method": "200 fixed iterations of the decomposed solve vs the same per-rank block solved as a 1x1x1 domain "
+                          "(no peer reads, no cross-rank wait); max over ranks; the difference is the exposed halo + all-reduce time"}
+        s1.close()
+        del u1, v1, w1, rhs1, phi1, f1
 
     # ---- end to end: pinned host buffers -> bbpcg_solve_host -> pinned host phi -------------------
     e2e = None
@@ -327,7 +357,7 @@ def run_bbpcg(args):
                       "l2": "inputs larger than L2 (%.1f GB of solver vectors per GPU vs 126 MB)" % (5 * 8 * ncell_rank / 1e9),
                       "fixed_iters": args.fixed_iters},
            "impl": "bbpcg", "gpu_launches": int(launches_all), "e2e": e2e, "roofline": roof, "roofline_resid": roof2,
-           "roofline_iteration": roof_it, "clocks": clk, "wall_ms_per_step": wall_ms / args.steps,
+           "roofline_iteration": roof_it, "comm": comm, "clocks": clk, "wall_ms_per_step": wall_ms / args.steps,
            "setup_ms_per_step": ms_setup / args.steps,
            "hbm_gbs_72B_model_whole_step": BYTES_ITER * ncell_glob * value / w.size / 1e9}
     if w.rank == 0 and w.size == 1 and not args.no_cpu_baseline:
@@ -405,7 +435,9 @@ def run_reference(args):
 
     for _ in range(args.warmup):
         solve_dev()
-    clocks = ClockSampler(0)
+    # 1 s period: the reference calls cudaMalloc/cudaFree inside every thrust::inner_product (2 per iteration),
+    # which serialise against NVML queries; a 200 ms sampler cost the reference arm ~35 % of its speed
+    clocks = ClockSampler(0, period_ms=1000)
     torch.cuda.synchronize()
     clocks.start()
     iters, tot_ms = 0, 0.0

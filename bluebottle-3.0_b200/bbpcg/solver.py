@@ -77,6 +77,35 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+# head of one rank's attach record (struct ExportBlob in csrc/bbpcg_solver.cu): magic, rank,
+# in, jn, kn, device, pid; the rest (arena pointer, size, CUDA IPC handle) is opaque here
+RECORD_FMT = "<Iiiiiiq"
+RECORD_MAGIC = 0xBB9C6001
+
+
+def parse_record(blob):
+    import struct
+    magic, rank, in_, jn, kn, device, pid = struct.unpack_from(RECORD_FMT, blob)
+    return {"magic": magic, "rank": rank, "in": in_, "jn": jn, "kn": kn, "device": device, "pid": pid}
+
+
+def gather_records(mine, _shuffle_for_test=False):
+    """All-gather the ranks' attach records through torch.distributed (what MPI_Allgather does
+    in the Bluebottle host) and check they arrive in rank order.  Works on any
+    backend: the records are host bytes."""
+    import torch.distributed as dist
+    n = dist.get_world_size()
+    blobs = [None] * n
+    dist.all_gather_object(blobs, bytes(mine))
+    if _shuffle_for_test:
+        blobs = blobs[1:] + blobs[:1]
+    for r, b in enumerate(blobs):
+        info = parse_record(b)
+        if len(b) != L.BLOB_BYTES or info["magic"] != RECORD_MAGIC or info["rank"] != r:
+            raise RuntimeError("attach record %d is not rank %d's export (got rank %d)" % (r, r, info["rank"]))
+    return blobs
+
+
 class PoissonSolver:
     """One rank's solver object (one per GPU)."""
 
@@ -122,9 +151,7 @@ class PoissonSolver:
         n = dist.get_world_size()
         if n == 1:
             return
-        blobs = [None] * n
-        dist.all_gather_object(blobs, self.comm_export())
-        self.comm_import(blobs)
+        self.comm_import(gather_records(self.comm_export()))
         dist.barrier()
 
     # ---- helpers ---------------------------------------------------------------------------

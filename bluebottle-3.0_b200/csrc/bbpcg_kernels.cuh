@@ -118,7 +118,11 @@ __device__ bool grid_reduce(const Dev &d, double (&v)[NV], int bid, int nblocks,
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int n = 0; n < NV; n++) d.partials[n * BB_MAXBLOCKS + bid] = part[n];
-    if (d.comm.nranks > 1) __threadfence_system(); else __threadfence();
+    /* device scope is enough here even when peers will read what this CTA wrote: the last CTA
+     * observes this release through the counter and issues ONE system-scope fence before it
+     * signals the peers (rank_allreduce); causality order is transitive across scopes.  A
+     * fence.sys in each of the ~10^4..10^5 CTAs of k_resid cost 200 us per iteration at N = 2. */
+    __threadfence();
     unsigned t = atomicAdd(d.counter + 4 + grp, 1u);
     s_last = (t == (unsigned)(gsize - 1));
   }
@@ -136,7 +140,7 @@ __device__ bool grid_reduce(const Dev &d, double (&v)[NV], int bid, int nblocks,
 #pragma unroll
     for (int n = 0; n < NV; n++) d.gpartials[n * BB_MAXGROUPS + grp] = part[n];
     d.counter[4 + grp] = 0u;
-    if (d.comm.nranks > 1) __threadfence_system(); else __threadfence();
+    __threadfence();
     unsigned t = atomicAdd(d.counter, 1u);
     s_last = (t == (unsigned)(ngrp - 1));
   }

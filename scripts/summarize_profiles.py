@@ -93,7 +93,7 @@ def full(tag, rep):
             t = val("gpu__time_duration.sum")
             f.write("\nDRAM traffic %.4f GB in %.1f us = **%.0f GB/s**.\n\n" % (b / 1e9, t * 1e6, b / t / 1e9))
             traffic.setdefault(name, []).append((b, t))
-    out = {"source": tag + "_ncu_full.csv"}
+    out = {"source": "profiles/" + tag + "_ncu_full.csv", "cells_per_launch": 512 ** 3}
     for name, v in traffic.items():
         key = "k_search_spmv" if name.startswith("k_search") else name.split("<")[0]
         out[key + "_bytes_per_launch"] = sum(b for b, _ in v) / len(v)
