@@ -22,6 +22,8 @@
 #define BB_MAXBLOCKS 65536         /* max CTAs of a reducing kernel */
 #define BB_GROUP 64                /* CTAs per first-level reduction group */
 #define BB_MAXGROUPS (BB_MAXBLOCKS / BB_GROUP)
+#define BB_FLAT_MAX 1024           /* grids up to this many CTAs reduce in ONE level (a single group) */
+#define BB_MAXZ 1024               /* max z-chunks of the search kernel */
 
 /* coefficient mask bits (fmask): squared face flags, src/solver_kernel.cu:824-829 */
 #define FM_E 1u
@@ -72,10 +74,10 @@ struct ArenaMap {
   size_t gpartials;                /* doubles[2*BB_MAXGROUPS]: group sums */
   size_t counter;                  /* unsigned[4 + BB_MAXGROUPS]: [0] groups done, [4+g] CTAs of group g done */
   size_t scal;                     /* Scal */
-  size_t mbox_val;                 /* doubles[BB_NSLOT][BB_MAXR][2] */
-  size_t mbox_flag;                /* u64[BB_NSLOT][BB_MAXR] */
+  size_t mbox;                     /* u64[BB_NSLOT][BB_MAXR][4]: {32 data bits | 32-bit tag} words */
   size_t history;                  /* doubles[hist_cap] */
   size_t invM_tab;                 /* doubles[128]: Jacobi diagonal per mask value */
+  size_t ztab;                     /* ints[BB_MAXZ + 1]: prefix offsets of the search kernel's z-chunks */
   size_t total;
 };
 
@@ -96,10 +98,10 @@ static inline ArenaMap make_arena_map(const Layout &L)
   m.gpartials = take(sizeof(double) * 2 * BB_MAXGROUPS);
   m.counter = take(sizeof(unsigned) * (4 + BB_MAXGROUPS));
   m.scal = take(512);
-  m.mbox_val = take(sizeof(double) * BB_NSLOT * BB_MAXR * 2);
-  m.mbox_flag = take(sizeof(unsigned long long) * BB_NSLOT * BB_MAXR);
+  m.mbox = take(sizeof(unsigned long long) * BB_NSLOT * BB_MAXR * 4);
   m.history = take(sizeof(double) * BB_HIST_CAP);
   m.invM_tab = take(sizeof(double) * 128);
+  m.ztab = take(sizeof(int) * (BB_MAXZ + 1));
   m.total = off;
   return m;
 }
@@ -139,8 +141,7 @@ struct Halo { NbrFace f[6]; };     /* 0:E 1:W 2:N 3:S 4:T 5:B */
 struct Comm {
   int rank, nranks;
   long long timeout_cycles;                   /* spin limit of the in-kernel all-reduce */
-  double *mbox_val[BB_MAXR];                  /* rank p's mailbox (mapped) */
-  unsigned long long *mbox_flag[BB_MAXR];
+  unsigned long long *mbox[BB_MAXR];          /* rank p's mailbox (mapped) */
 };
 
 /* everything a kernel needs about this rank, passed by value */
@@ -154,6 +155,7 @@ struct Dev {
   Scal *sc;
   double *history;
   const double *invM_tab;         /* [128], built once by k_build_tab */
+  const int *ztab;                /* [nbz + 1]: z-chunk c of the search kernel owns planes ztab[c]+1 .. ztab[c+1] */
   double idx2, idy2, idz2;        /* 1/(dx*dx) ...  (per block, src/solver_kernel.cu:720-722) */
   double dx2_6, dy2_6, dz2_6;     /* dx*dx/6 ...    (src/solver_kernel.cu:683)                */
   Halo halo;

@@ -103,6 +103,11 @@ __device__ __forceinline__ double block_sum(double v, double *sh /*[32]*/)
 /* Two levels so that kernels made of many tiny CTAs stay cheap: the last CTA of each group of
  * BB_GROUP CTAs sums that group's partials, the last group to finish sums the group sums.  Both
  * orders are fixed, so the result is bit-identical run to run. */
+/* programmatic dependent launch (PDL): the NEXT kernel of the stream may be launched while this one drains;
+ * it must not touch anything this kernel (or its predecessors) produce before pdl_wait(). */
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 template <int NV>
 __device__ bool grid_reduce(const Dev &d, double (&v)[NV], int bid, int nblocks, double (&tot)[NV], bool peer_stores)
 {
@@ -113,8 +118,10 @@ __device__ bool grid_reduce(const Dev &d, double (&v)[NV], int bid, int nblocks,
   for (int n = 0; n < NV; n++) part[n] = block_sum<NV>(v[n], sh);
   if (peer_stores) __threadfence_system();       /* halo stores visible before we count in */
   __syncthreads();
-  const int grp = bid / BB_GROUP, ngrp = (nblocks + BB_GROUP - 1) / BB_GROUP;
-  const int gsize = min(BB_GROUP, nblocks - grp * BB_GROUP);
+  /* small grids: ONE group = one level (fewer dependent atomics/fences in the tail of every kernel) */
+  const int G = nblocks <= BB_FLAT_MAX ? nblocks : BB_GROUP;
+  const int grp = bid / G, ngrp = (nblocks + G - 1) / G;
+  const int gsize = min(G, nblocks - grp * G);
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int n = 0; n < NV; n++) d.partials[n * BB_MAXBLOCKS + bid] = part[n];
@@ -132,10 +139,18 @@ __device__ bool grid_reduce(const Dev &d, double (&v)[NV], int bid, int nblocks,
 #pragma unroll
   for (int n = 0; n < NV; n++) {
     double s = 0.;
-    for (int i = threadIdx.x; i < gsize; i += blockDim.x) s += __ldcg(&d.partials[n * BB_MAXBLOCKS + grp * BB_GROUP + i]);
+    for (int i = threadIdx.x; i < gsize; i += blockDim.x) s += __ldcg(&d.partials[n * BB_MAXBLOCKS + grp * G + i]);
     part[n] = block_sum<NV>(s, sh);
   }
   __syncthreads();
+  if (ngrp == 1) {
+    if (threadIdx.x == 0) {
+      d.counter[4] = 0u;
+#pragma unroll
+      for (int n = 0; n < NV; n++) tot[n] = part[n];
+    }
+    return true;
+  }
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int n = 0; n < NV; n++) d.gpartials[n * BB_MAXGROUPS + grp] = part[n];
@@ -159,37 +174,65 @@ __device__ bool grid_reduce(const Dev &d, double (&v)[NV], int bid, int nblocks,
 
 /* Rank-ordered all-reduce of up to 2 doubles through peer-mapped mailboxes (replaces
  * MPI_Allreduce, src/cuda_solver.cu:152,170,205,232).  Called by the last CTA only.  Every
- * rank writes its partial into every rank's mailbox (one NVLink store each), then waits for
- * the N slots of its own mailbox and adds them in rank order: the sum is bit-identical on
- * all ranks and run to run.  nv == 0 makes it a barrier.  Threads 0..nranks-1 take part. */
-__device__ __forceinline__ void rank_allreduce(const Dev &d, double *v /* thread 0's values, in/out */, int nv)
+ * rank writes its partial into every rank's mailbox over NVLink, then waits for the N entries of
+ * its own mailbox and adds them in rank order: the sum is bit-identical on all ranks and run to
+ * run.  nv == 0 makes it a barrier.  Threads 0..nranks-1 take part.
+ *
+ * Wire format ("LL": data and flag travel in the SAME 8-byte store, which is atomic, so no fence
+ * is needed between payload and flag on either side): each double is sent as two u64 words
+ * { 32 data bits | 32-bit sequence tag }.  A receiver spins until all four words of a sender
+ * carry the current tag.  One NVLink one-way latency per all-reduce instead of
+ * store / fence.sys / flag / spin / fence.sys.
+ *
+ * release = true: this kernel wrote data that PEERS will read after the barrier (r in the pull
+ * model, ghost pushes): thread 0 -- which has observed every CTA's device-scope release through
+ * the counter -- issues the one system-scope fence before anything is signalled. */
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v)
+{ asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p)
+{ unsigned long long v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+
+__device__ __forceinline__ void rank_allreduce(const Dev &d, double *v /* thread 0's values, in/out */, int nv, bool release)
 {
   const Comm &c = d.comm;
   if (c.nranks <= 1) return;
-  __shared__ double s_v[2];
+  __shared__ unsigned long long s_w[4];
   __shared__ double s_in[BB_MAXR][2];
   __shared__ unsigned long long s_seq;
-  if (threadIdx.x == 0) { s_v[0] = nv > 0 ? v[0] : 0.; s_v[1] = nv > 1 ? v[1] : 0.; s_seq = ++d.sc->seq; __threadfence_system(); }
+  if (threadIdx.x == 0) {
+    const unsigned long long seq = ++d.sc->seq;
+    const unsigned long long tag = ((seq % 0xffffffffull) + 1ull) << 32;       /* never 0 */
+    const unsigned long long b0 = (unsigned long long)__double_as_longlong(nv > 0 ? v[0] : 0.);
+    const unsigned long long b1 = (unsigned long long)__double_as_longlong(nv > 1 ? v[1] : 0.);
+    s_w[0] = (b0 & 0xffffffffull) | tag; s_w[1] = (b0 >> 32) | tag;
+    s_w[2] = (b1 & 0xffffffffull) | tag; s_w[3] = (b1 >> 32) | tag;
+    s_seq = seq;
+    if (release) fence_acq_rel_sys();
+  }
   __syncthreads();
   const unsigned long long seq = s_seq;
+  const unsigned long long tag = s_w[0] >> 32;
   const int slot = (int)(seq & (BB_NSLOT - 1));
   const int t = threadIdx.x;
   if (t < c.nranks) {
-    double *dst = c.mbox_val[t] + (size_t)(slot * BB_MAXR + c.rank) * 2;
-    dst[0] = s_v[0]; dst[1] = s_v[1];
-    __threadfence_system();
-    *((volatile unsigned long long *)(c.mbox_flag[t] + slot * BB_MAXR + c.rank)) = seq;
+    unsigned long long *dst = c.mbox[t] + (size_t)(slot * BB_MAXR + c.rank) * 4;
+#pragma unroll
+    for (int w = 0; w < 4; w++) st_relaxed_sys(dst + w, s_w[w]);
     /* wait for rank t's contribution in my own mailbox */
-    volatile unsigned long long *f = (volatile unsigned long long *)(c.mbox_flag[c.rank] + slot * BB_MAXR + t);
-    long long t0 = clock64();
+    const unsigned long long *src = c.mbox[c.rank] + (size_t)(slot * BB_MAXR + t) * 4;
+    unsigned long long w0, w1, w2, w3;
+    const long long t0 = clock64();
     bool ok = true;
-    while (*f != seq) {
-      if (clock64() - t0 > c.timeout_cycles) { ok = false; break; }    /* a peer is gone */
+    for (;;) {
+      w0 = ld_relaxed_sys(src); w1 = ld_relaxed_sys(src + 1); w2 = ld_relaxed_sys(src + 2); w3 = ld_relaxed_sys(src + 3);
+      if ((w0 >> 32) == tag && (w1 >> 32) == tag && (w2 >> 32) == tag && (w3 >> 32) == tag) break;
+      if (clock64() - t0 > c.timeout_cycles) { ok = false; break; }            /* a peer is gone */
     }
-    __threadfence_system();
-    volatile double *src = (volatile double *)(c.mbox_val[c.rank] + (size_t)(slot * BB_MAXR + t) * 2);
-    s_in[t][0] = src[0]; s_in[t][1] = src[1];
+    s_in[t][0] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    s_in[t][1] = __longlong_as_double((long long)((w2 & 0xffffffffull) | (w3 << 32)));
     if (!ok) d.sc->comm_timeout = 1;
+    fence_acq_rel_sys();             /* acquire side: peers' released data is read by LATER kernels */
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -239,8 +282,7 @@ __device__ __forceinline__ long long j_px_fix(const Layout &L, const Layout &N, 
  * the block's ghost copies of p current.  Phase B (plane kk-1): 7-point operator from the
  * ring, q store, (p,q) partial.  One __syncthreads per plane. */
 struct SearchArgs {
-  int KC;          /* planes per CTA */
-  int nbx, nby, nbz;
+  int nbx, nby, nbz;   /* z-chunk c owns planes d.ztab[c]+1 .. d.ztab[c+1] */
 };
 
 template <int TX, int TY, int NT, int MINB, bool PARTS>
@@ -273,8 +315,8 @@ __global__ void __launch_bounds__(NT, MINB) k_search_spmv(const Dev d, const Sea
 
   const int tid = threadIdx.x;
   const int i0 = blockIdx.x * TX + 1, j0 = blockIdx.y * TY + 1;
-  const int k0 = blockIdx.z * a.KC + 1;
-  const int k1 = min(k0 + a.KC - 1, L.kn);
+  const int k0 = __ldg(d.ztab + blockIdx.z) + 1;
+  const int k1 = __ldg(d.ztab + blockIdx.z + 1);
   const int ilast = min(i0 + TX - 1, L.in), jlast = min(j0 + TY - 1, L.jn);
 
   /* per-thread item geometry, fixed across planes */
@@ -395,7 +437,7 @@ __global__ void __launch_bounds__(NT, MINB) k_search_spmv(const Dev d, const Sea
   const int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
   const int nblocks = gridDim.x * gridDim.y * gridDim.z;
   if (grid_reduce<1>(d, v, bid, nblocks, tot, false)) {
-    rank_allreduce(d, tot, 1);
+    rank_allreduce(d, tot, 1, false);         /* this kernel writes nothing a peer reads */
     if (threadIdx.x == 0) {
       sc->pAp = tot[0];
       sc->alpha = sc->rz / tot[0];
@@ -467,6 +509,7 @@ __global__ void __launch_bounds__(128, 4) k_resid(const __grid_constant__ Dev d,
   const int tx = threadIdx.x % XT, ty = threadIdx.x / XT;
   double dot = 0.;
   const int pass0 = blockIdx.x * a.ppc, pass1 = min(pass0 + a.ppc, a.npass);
+  pdl_wait();                                   /* q and alpha come from the search kernel before us */
   for (int pass = pass0; pass < pass1; pass++) {
     const int cb = pass % a.ncb, rg = pass / a.ncb;
     const int c = cb * XT + tx;
@@ -510,9 +553,10 @@ __global__ void __launch_bounds__(128, 4) k_resid(const __grid_constant__ Dev d,
       }
     }
   }
+  pdl_launch_dependents();
   double v[1] = { dot }, tot[1];
   if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, false)) {
-    rank_allreduce(d, tot, 1);
+    rank_allreduce(d, tot, 1, true);          /* peers pull the r written here */
     if (threadIdx.x == 0) finish_iteration(d, tot[0], false);
   }
 }
@@ -546,7 +590,7 @@ __global__ void __launch_bounds__(NT) k_refresh_x(const Dev d)
     }
   }
   double v[1] = { 0. }, tot[1];
-  if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) rank_allreduce(d, tot, 0);   /* barrier */
+  if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) rank_allreduce(d, tot, 0, true);   /* barrier */
 }
 
 template <int NT, bool PARTS>
@@ -580,7 +624,7 @@ __global__ void __launch_bounds__(NT) k_refresh_r(const Dev d, const double *__r
   }
   double v[1] = { dot }, tot[1];
   if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) {
-    rank_allreduce(d, tot, 1);
+    rank_allreduce(d, tot, 1, true);
     if (threadIdx.x == 0) finish_iteration(d, tot[0], true);
   }
 }
@@ -613,7 +657,7 @@ __global__ void __launch_bounds__(NT) k_init(const Dev d, const double *__restri
   }
   double v[2] = { bb, rz }, tot[2];
   if (grid_reduce<2>(d, v, blockIdx.x, gridDim.x, tot, pushed)) {
-    rank_allreduce(d, tot, 2);
+    rank_allreduce(d, tot, 2, true);
     if (threadIdx.x == 0) {
       Scal *sc = d.sc;
       sc->bb = tot[0]; sc->rz = tot[1]; sc->rz0 = tot[1];
@@ -717,7 +761,7 @@ __global__ void __launch_bounds__(NT) k_masks(const Dev d, FaceStrides st, const
     }
   }
   double v[1] = { 0. }, tot[1];
-  if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) rank_allreduce(d, tot, 0);
+  if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) rank_allreduce(d, tot, 0, true);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -790,7 +834,7 @@ __global__ void k_xchg_send(const Dev d, const double *__restrict__ a, int s1b, 
     pushed = true;
   }
   double v[1] = { 0. }, tot[1];
-  if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) rank_allreduce(d, tot, 0);
+  if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) rank_allreduce(d, tot, 0, true);
 }
 
 __global__ void k_xchg_recv(const Dev d, double *__restrict__ a, int s1b, int s2b, int buf)

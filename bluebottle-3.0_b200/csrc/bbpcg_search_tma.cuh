@@ -7,10 +7,10 @@
  *
  * CTA = 256 threads, tile TX = 128 x TY owned cells of one k-plane, marching KC planes in k.
  * All plane inputs except x arrive through TMA (cp.async.bulk.tensor.3d, SASS UTMALDG) into a
- * shared-memory ring, issued D = 2 planes ahead by one thread and awaited on mbarriers, so DRAM
+ * shared-memory ring, issued D (2 or 3) planes ahead by one thread and awaited on mbarriers, so DRAM
  * latency is covered without any register staging:
- *     P ring (4 slots): halo'd p_prev tile (TX+4) x (TY+2); converted IN PLACE to p_new
- *     per stage (3)   : halo'd r tile, mask tile, [pmask tile], and -- PULL model -- the r values of
+ *     P ring (D+2 slots): halo'd p_prev tile (TX+4) x (TY+2); converted IN PLACE to p_new
+ *     per stage (D+1) : halo'd r tile, mask tile, [pmask tile], and -- PULL model -- the r values of
  *                       ghost cells straight from the NEIGHBOUR's r array (peer memory over NVLink or
  *                       this block itself for a periodic self-wrap): one row per y-ghost, one
  *                       2-wide column per x-ghost, the whole tile for a z-ghost plane.
@@ -61,7 +61,7 @@ __device__ __forceinline__ double2 ldg128(const double *p)
 { double2 v; asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p)); return v; }
 
 /* geometry shared with the host (tensor-map boxes, dynamic shared memory size) */
-template <int TY, bool PARTS>
+template <int TY, bool PARTS, int DD = 2>
 struct SearchGeom {
   static constexpr int TX = 128, NT = 256, HXP = TX + 4, HY = TY + 2;
   static constexpr int MXP = 160, MX0 = 14;            /* mask tile: row pitch; byte of tile column 0 (TMA box starts must be 16-B aligned) */
@@ -72,7 +72,7 @@ struct SearchGeom {
   static constexpr int GXS = a128(HY * 16), GX = 2 * GXS;      /* two x-ghost columns (2 doubles per row) */
   static constexpr int PMT = PARTS ? a128(TX * TY) : 0;
   static constexpr int STAGE = RT + MT + GY + GX + PMT;
-  static constexpr int NPS = 4, NRS = 3, D = 2;
+  static constexpr int D = DD, NRS = DD + 1, NPS = DD + 2;   /* planes in flight, r/mask stages, p-ring slots */
   static constexpr int NO = TY / 4;                    /* owned double2 items per thread: rows rg+1+4n */
   static constexpr int NA = NO + 1;                    /* + one halo-row item for the threads rg = 0 (row 0), 1 (row HY-1) */
   static constexpr int OFF_STAGE = NPS * RT;
@@ -95,11 +95,11 @@ struct SearchGeom {
 #define SF_E1GX    0x400u
 #define SF_FAST    0x800u   /* owned row, both elements owned, nothing special                */
 
-template <int TY, bool PARTS>
+template <int TY, bool PARTS, int DD>
 __global__ void __launch_bounds__(256, 2)
 k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps tm, const SearchArgs a)
 {
-  typedef SearchGeom<TY, PARTS> G;
+  typedef SearchGeom<TY, PARTS, DD> G;
   constexpr int TX = G::TX, HXP = G::HXP, HY = G::HY, NA = G::NA, NO = G::NO;
   static_assert(TY % 4 == 0 && TY >= 4, "TY must be a multiple of 4");
   extern __shared__ __align__(128) unsigned char smem[];     /* plain pointer arithmetic only: keeps LDS/STS (no generic LD/ST) */
@@ -111,8 +111,8 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
   const int tid = threadIdx.x;
   const int bx = blockIdx.x, by = blockIdx.y;
   const int i0 = bx * TX + 1, j0 = by * TY + 1;
-  const int k0 = blockIdx.z * a.KC + 1;
-  const int k1 = min(k0 + a.KC - 1, L.kn);
+  const int k0 = __ldg(d.ztab + blockIdx.z) + 1;        /* host-written table: safe before pdl_wait() */
+  const int k1 = __ldg(d.ztab + blockIdx.z + 1);
   const int nplanes = k1 - k0 + 3;                      /* planes k0-1 .. k1+1 */
   const int x0 = BB_XOFF + 1 + bx * TX - 2;             /* array x index of tile column 0 */
   const int y0 = j0 - 1;
@@ -132,52 +132,6 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
     tma::fence_barrier_init();
   }
   __syncthreads();
-
-  const int q = sc->q;
-  /* one thread issues every TMA load of plane lp (local index; global plane pi = k0-1+lp) */
-  auto issue = [&](int lp) {
-    const int pi = k0 - 1 + lp;
-    const int rs = lp % G::NRS, ps = lp % G::NPS;
-    const unsigned bar = bar0 + 8 * rs;
-    const unsigned st = sS + rs * G::STAGE;
-    const bool inner = pi >= 1 && pi <= L.kn;
-    unsigned bytes = 2 * (HXP * HY * 8) + G::MXP * HY;
-    if (inner) {
-      if (gy0) bytes += HXP * 8;
-      if (gy1) bytes += HXP * 8;
-      if (gx0) bytes += HY * 16;
-      if (gx1) bytes += HY * 16;
-      if (PARTS) bytes += TX * TY;
-    }
-    tma::mbar_expect_tx(bar, bytes);
-    tma::load3d(sP + ps * G::RT, &tm.p[q & 1], x0, y0, pi, bar);
-    tma::load3d(st + G::RT, &tm.fm, x0 - G::MX0, y0, pi, bar);
-    if (pi == 0 && d.halo.f[5].r) tma::load3d(st, &tm.nb[5], x0, y0, d.halo.f[5].L.kn, bar);          /* B neighbour's top plane    */
-    else if (pi == L.kn + 1 && d.halo.f[4].r) tma::load3d(st, &tm.nb[4], x0, y0, 1, bar);            /* T neighbour's bottom plane */
-    else tma::load3d(st, &tm.r, x0, y0, pi, bar);
-    if (inner) {
-      if (gy0) tma::load3d(st + G::RT + G::MT, &tm.nb[3], x0, d.halo.f[3].L.jn, pi, bar);
-      if (gy1) tma::load3d(st + G::RT + G::MT + G::GYS, &tm.nb[2], x0, 1, pi, bar);
-      if (gx0) tma::load3d(st + G::RT + G::MT + G::GY, &tm.nb[1], (d.halo.f[1].L.in + BB_XOFF) & ~1, y0, pi, bar);
-      if (gx1) tma::load3d(st + G::RT + G::MT + G::GY + G::GXS, &tm.nb[0], BB_XOFF + 1, y0, pi, bar);
-      if (PARTS) tma::load3d(st + G::RT + G::MT + G::GY + G::GX, &tm.pm, BB_XOFF + 1 + bx * TX, j0, pi, bar);
-    }
-  };
-  if (tid == 0) {
-    issue(0);
-    if (nplanes > 1) issue(1);
-  }
-
-  const int done = sc->done;
-  const double beta = sc->beta, ax = sc->alpha_x;
-  double *__restrict__ pnew = d.P[(q + 1) & 1];
-  double *__restrict__ x = d.x;
-  double *__restrict__ qv = d.q;
-  if (tid < 128) tab[tid] = __ldg(d.invM_tab + tid);
-  if (done) {                       /* a finished solve: drain the loads already issued, then leave */
-    if (tid == 0) { tma::mbar_wait(bar0, 0); if (nplanes > 1) tma::mbar_wait(bar0 + 8, 0); }
-    return;
-  }
 
   /* ---- per-thread geometry: owned-row items n < NO on rows rg+1+4n, one halo-row item n = NO for
    * the thread rows rg = 0 (tile row 0) and rg = 1 (tile row HY-1), and at most one single ---- */
@@ -217,6 +171,58 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
   const bool s_gx = s_ok && ((s_i == 0 && gx0) || (s_i == L.in + 1 && gx1));      /* r from the GX buffer */
   const int gxw = (d.halo.f[1].L.in + BB_XOFF) & 1;     /* position of the wanted value in the W ghost column box */
   const bool s_store = s_ok && (s_i == 0 || s_i == L.in + 1) && s_j >= 1 && s_j <= L.jn;   /* x-ghost p kept current */
+
+  /* ---- everything above is independent of the previous kernels; from here on we read what they wrote ---- */
+  pdl_wait();
+  const int q = sc->q;
+  /* one thread issues every TMA load of plane lp (local index; global plane pi = k0-1+lp) */
+  auto issue = [&](int lp) {
+    const int pi = k0 - 1 + lp;
+    const int rs = lp % G::NRS, ps = lp % G::NPS;
+    const unsigned bar = bar0 + 8 * rs;
+    const unsigned st = sS + rs * G::STAGE;
+    const bool inner = pi >= 1 && pi <= L.kn;
+    unsigned bytes = 2 * (HXP * HY * 8) + G::MXP * HY;
+    if (inner) {
+      if (gy0) bytes += HXP * 8;
+      if (gy1) bytes += HXP * 8;
+      if (gx0) bytes += HY * 16;
+      if (gx1) bytes += HY * 16;
+      if (PARTS) bytes += TX * TY;
+    }
+    tma::mbar_expect_tx(bar, bytes);
+    tma::load3d(sP + ps * G::RT, &tm.p[q & 1], x0, y0, pi, bar);
+    tma::load3d(st + G::RT, &tm.fm, x0 - G::MX0, y0, pi, bar);
+    if (pi == 0 && d.halo.f[5].r) tma::load3d(st, &tm.nb[5], x0, y0, d.halo.f[5].L.kn, bar);          /* B neighbour's top plane    */
+    else if (pi == L.kn + 1 && d.halo.f[4].r) tma::load3d(st, &tm.nb[4], x0, y0, 1, bar);            /* T neighbour's bottom plane */
+    else tma::load3d(st, &tm.r, x0, y0, pi, bar);
+    if (inner) {
+      if (gy0) tma::load3d(st + G::RT + G::MT, &tm.nb[3], x0, d.halo.f[3].L.jn, pi, bar);
+      if (gy1) tma::load3d(st + G::RT + G::MT + G::GYS, &tm.nb[2], x0, 1, pi, bar);
+      if (gx0) tma::load3d(st + G::RT + G::MT + G::GY, &tm.nb[1], (d.halo.f[1].L.in + BB_XOFF) & ~1, y0, pi, bar);
+      if (gx1) tma::load3d(st + G::RT + G::MT + G::GY + G::GXS, &tm.nb[0], BB_XOFF + 1, y0, pi, bar);
+      if (PARTS) tma::load3d(st + G::RT + G::MT + G::GY + G::GX, &tm.pm, BB_XOFF + 1 + bx * TX, j0, pi, bar);
+    }
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int l = 0; l < G::D; l++) if (l < nplanes) issue(l);
+  }
+
+  const int done = sc->done;
+  const double beta = sc->beta, ax = sc->alpha_x;
+  double *__restrict__ pnew = d.P[(q + 1) & 1];
+  double *__restrict__ x = d.x;
+  double *__restrict__ qv = d.q;
+  if (tid < 128) tab[tid] = __ldg(d.invM_tab + tid);
+  if (done) {                       /* a finished solve: drain the loads already issued, then leave */
+    if (tid == 0) {
+#pragma unroll
+      for (int l = 0; l < G::D; l++) if (l < nplanes) tma::mbar_wait(bar0 + 8 * l, 0);
+    }
+    return;
+  }
+
 
   /* register pipeline of the owned cells: p(kc-1), p(kc), masks of kc */
   double2 pB[NO], pC[NO];
@@ -356,12 +362,13 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
     __syncthreads();
   }
 
+  pdl_launch_dependents();          /* k_resid may be scheduled behind our tail; it blocks in pdl_wait() until alpha is final */
   /* ---- (p,q): grid reduction, rank all-reduce, alpha (cuda_solver.cu:204-206) ---- */
   double v[1] = { dot }, tot[1];
   const int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
   const int nblocks = gridDim.x * gridDim.y * gridDim.z;
   if (grid_reduce<1>(d, v, bid, nblocks, tot, false)) {
-    rank_allreduce(d, tot, 1);
+    rank_allreduce(d, tot, 1, false);         /* this kernel writes nothing a peer reads */
     if (threadIdx.x == 0) {
       sc->pAp = tot[0];
       sc->alpha = sc->rz / tot[0];

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 #include <unistd.h>
 
 #include "bbpcg_kernels.cuh"
@@ -71,6 +72,12 @@ struct bbpcg_solver {
   /* optional per-kernel timing (bench.py's roofline leg): events around every launch of the
    * iteration loop, on the solver's own stream */
   int last_search_grid, last_search_kc;
+  /* z-chunk plan of the search kernel (device table Dev::ztab) */
+  int *h_ztab;                      /* pinned [BB_MAXZ + 1] */
+  int zt_cols, zt_kc, zt_g10, zt_min, zt_nbz;   /* what the uploaded table was built for */
+  int taper_g10, taper_min;         /* guided chunking: t = remaining*columns*10 / (g10*slots), >= taper_min */
+  int pdl;                          /* programmatic dependent launch of the two iteration kernels */
+  int shared_device;                /* some peer rank lives on this same GPU (single-process harness) */
   SearchMaps maps[2];               /* tensor maps of k_search_tma for TY = 8 / TY = 4 */
   int maps_ok;
   int kernel_timing;
@@ -99,6 +106,7 @@ static void point_dev_at_arena(bbpcg_solver *s)
   d.partials = (double *)(a + m.partials); d.gpartials = (double *)(a + m.gpartials); d.counter = (unsigned *)(a + m.counter);
   d.sc = (Scal *)(a + m.scal); d.history = (double *)(a + m.history);
   d.invM_tab = (const double *)(a + m.invM_tab);
+  d.ztab = (const int *)(a + m.ztab);
 }
 
 /* ---- TMA tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point, so the
@@ -187,12 +195,11 @@ static void build_halo(bbpcg_solver *s, const int (*dims)[3])
   for (int f = 0; f < 6; f++) if (d.halo.f[f].r) d.any_nbr = 1;
   d.comm.rank = s->dom.rank; d.comm.nranks = s->nranks;
   if (d.comm.timeout_cycles <= 0) d.comm.timeout_cycles = 1ll << 34;       /* ~8 s */
-  for (int p = 0; p < BB_MAXR; p++) { d.comm.mbox_val[p] = NULL; d.comm.mbox_flag[p] = NULL; }
+  for (int p = 0; p < BB_MAXR; p++) d.comm.mbox[p] = NULL;
   for (int p = 0; p < s->nranks; p++) {
     Layout L = make_layout(dims[p][0], dims[p][1], dims[p][2]);
     ArenaMap m = make_arena_map(L);
-    d.comm.mbox_val[p] = (double *)(s->peer_arena[p] + m.mbox_val);
-    d.comm.mbox_flag[p] = (unsigned long long *)(s->peer_arena[p] + m.mbox_flag);
+    d.comm.mbox[p] = (unsigned long long *)(s->peer_arena[p] + m.mbox);
   }
 }
 
@@ -239,6 +246,8 @@ extern "C" int bbpcg_create(bbpcg_solver **out, const dom_struct *dom_rank, cons
   for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&s->ev_poll[i], cudaEventDisableTiming));
   CU(cudaHostAlloc(&s->h_poll, 64, cudaHostAllocDefault));
   CU(cudaHostAlloc(&s->h_scal, sizeof(Scal), cudaHostAllocDefault));
+  CU(cudaHostAlloc(&s->h_ztab, sizeof(int) * (BB_MAXZ + 1), cudaHostAllocDefault));
+  s->zt_cols = -1; s->taper_g10 = 20; s->taper_min = 8; s->pdl = 1;
   /* single rank: neighbours are this block itself (periodic wrap) or nothing */
   s->nranks = 1;
   for (int p = 0; p < BB_MAXR; p++) { s->peer_arena[p] = NULL; s->peer_opened[p] = false; }
@@ -267,7 +276,7 @@ extern "C" void bbpcg_destroy(bbpcg_solver *s)
   for (int p = 0; p < BB_MAXR; p++) if (s->peer_opened[p]) cudaIpcCloseMemHandle(s->peer_arena[p]);
   cudaFree(s->arena);
   cudaFree(s->hb_u); cudaFree(s->hb_v); cudaFree(s->hb_w); cudaFree(s->hb_rhs); cudaFree(s->hb_phi);
-  cudaFreeHost(s->h_poll); cudaFreeHost(s->h_scal);
+  cudaFreeHost(s->h_poll); cudaFreeHost(s->h_scal); cudaFreeHost(s->h_ztab);
   if (s->kev) { for (int i = 0; i <= 2 * BB_KT_CAP; i++) cudaEventDestroy(s->kev[i]); free(s->kev); }
   for (int i = 0; i < 4; i++) cudaEventDestroy(s->ev[i]);
   for (int i = 0; i < 2; i++) cudaEventDestroy(s->ev_poll[i]);
@@ -304,6 +313,7 @@ extern "C" int bbpcg_comm_import(bbpcg_solver *s, const void *all_blobs, int nra
     if (b.magic != BB_MAGIC || b.rank != p) { bbpcg_set_error("bbpcg_comm_import: record %d is not rank %d's export", p, p); return BBPCG_ECOMM; }
     dims[p][0] = b.in; dims[p][1] = b.jn; dims[p][2] = b.kn;
     if (p == s->dom.rank) { s->peer_arena[p] = s->arena; continue; }
+    if (b.pid == mypid && b.device == s->device) s->shared_device = 1;
     if (b.pid == mypid) {
       /* same process (several ranks driven from one process): the pointer is directly usable;
        * a different device needs peer access */
@@ -330,8 +340,66 @@ extern "C" int bbpcg_comm_import(bbpcg_solver *s, const void *all_blobs, int nra
 
 /* ---- launch helpers ------------------------------------------------------------------------ */
 struct TileCfg { int tx, ty, nt; };
-static const TileCfg k_tiles[] = { { 128, 8, 256 }, { 128, 4, 256 }, { 128, 8, 256 }, { 128, 4, 256 }, { 64, 8, 256 }, { 128, 8, 512 }, { 32, 8, 128 }, { 256, 4, 256 } };
+static const TileCfg k_tiles[] = { { 128, 8, 256 }, { 128, 4, 256 }, { 128, 8, 256 }, { 128, 4, 256 }, { 64, 8, 256 }, { 128, 8, 512 },
+                                   { 32, 8, 128 }, { 256, 4, 256 }, { 128, 8, 256 }, { 128, 4, 256 } };
 static const int k_ntiles = sizeof(k_tiles) / sizeof(k_tiles[0]);
+
+/* z-chunk plan of the search kernel.  The grid is (x-tiles, y-tiles, z-chunks); CTAs are dispatched
+ * z-chunk-major, so y/x neighbours of one chunk run together (their halo rows hit L2).  kc > 0: uniform
+ * chunks of kc planes.  kc <= 0: GUIDED chunks -- each slab takes remaining*columns/(g*slots) planes
+ * (>= taper_min), i.e. long chunks first (few re-read halo planes) and short ones last, so the
+ * final partial wave of the `slots` resident CTAs is short whatever the block size.  Uploads the prefix
+ * table to Dev::ztab when the plan changed; returns nbz. */
+static int plan_zchunks(bbpcg_solver *s, int columns, int slots, int *nbz_out)
+{
+  const int kn = s->dev.L.kn;
+  if (s->zt_cols == columns && s->zt_kc == s->kc && s->zt_g10 == s->taper_g10 && s->zt_min == s->taper_min) { *nbz_out = s->zt_nbz; return BBPCG_OK; }
+  std::vector<int> sz;
+  if (s->kc > 0) {
+    for (int r = kn; r > 0; r -= s->kc) sz.push_back(r < s->kc ? r : s->kc);
+  } else {
+    const int tmin = s->taper_min < 1 ? 1 : s->taper_min;
+    int r = kn;
+    while (r > 0) {
+      long long t = ((long long)r * columns * 10 + (long long)s->taper_g10 * slots - 1) / ((long long)s->taper_g10 * slots);
+      if (t < tmin) t = tmin;
+      if (t > r || r - t < (tmin + 1) / 2) t = r;
+      sz.push_back((int)t); r -= (int)t;
+    }
+  }
+  if ((int)sz.size() > BB_MAXZ || (long long)sz.size() * columns > BB_MAXBLOCKS) {
+    /* fall back to the shortest uniform chunks that fit the workspace */
+    int nz = BB_MAXBLOCKS / columns; if (nz > BB_MAXZ) nz = BB_MAXZ;
+    if (nz < 1) { bbpcg_set_error("grid too large for the reduction workspace"); return BBPCG_EINVAL; }
+    const int kc = (kn + nz - 1) / nz;
+    sz.clear();
+    for (int r = kn; r > 0; r -= kc) sz.push_back(r < kc ? r : kc);
+  }
+  /* the copy source must stay valid until the copy ran: it is only rewritten after a stream sync */
+  CU(cudaStreamSynchronize(s->stream));
+  s->h_ztab[0] = 0;
+  for (size_t i = 0; i < sz.size(); i++) s->h_ztab[i + 1] = s->h_ztab[i] + sz[i];
+  CU(cudaMemcpyAsync((void *)s->dev.ztab, s->h_ztab, sizeof(int) * (sz.size() + 1), cudaMemcpyHostToDevice, s->stream));
+  s->zt_cols = columns; s->zt_kc = s->kc; s->zt_g10 = s->taper_g10; s->zt_min = s->taper_min; s->zt_nbz = (int)sz.size();
+  *nbz_out = s->zt_nbz;
+  return BBPCG_OK;
+}
+
+/* launch with (optionally) the programmatic-stream-serialization attribute: the kernel may be scheduled
+ * while its predecessor drains and blocks in pdl_wait() until that one is complete.  Never used when
+ * several ranks share one GPU: their waiting CTAs could starve the peer whose arrival they wait for. */
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(bbpcg_solver *s, void (*kernel)(KArgs...), dim3 grid, int nt, size_t smem, bool pdl, Args &&...args)
+{
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = dim3(nt); cfg.dynamicSmemBytes = smem; cfg.stream = s->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (pdl && s->pdl && !s->shared_device && !s->kernel_timing) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 template <int TX, int TY, int NT, int MINB>
 static int launch_search_t(bbpcg_solver *s, bool parts)
@@ -341,21 +409,10 @@ static int launch_search_t(bbpcg_solver *s, bool parts)
   const size_t smem = (size_t)(4 * NITEM + 128) * sizeof(double) + 4 * NITEM;
   SearchArgs a;
   a.nbx = (L.in + TX - 1) / TX; a.nby = (L.jn + TY - 1) / TY;
-  int kc = s->kc;
-  if (kc <= 0) {
-    /* enough CTAs for ~4 waves of resident blocks, chunks no shorter than 16 planes */
-    long long want = (long long)s->sm_count * 16;
-    long long per = (long long)a.nbx * a.nby;
-    int nz = (int)((want + per - 1) / per);
-    if (nz < 1) nz = 1;
-    kc = (L.kn + nz - 1) / nz;
-    if (kc < 16) kc = L.kn < 16 ? L.kn : 16;
-  }
-  if (kc > L.kn) kc = L.kn;
-  a.KC = kc; a.nbz = (L.kn + kc - 1) / kc;
-  if ((long long)a.nbx * a.nby * a.nbz > BB_MAXBLOCKS) { bbpcg_set_error("grid too large for the reduction workspace"); return BBPCG_EINVAL; }
+  int rc = plan_zchunks(s, a.nbx * a.nby, s->sm_count * MINB, &a.nbz);
+  if (rc) return rc;
   dim3 grid(a.nbx, a.nby, a.nbz);
-  s->last_search_grid = a.nbx * a.nby * a.nbz; s->last_search_kc = kc;
+  s->last_search_grid = a.nbx * a.nby * a.nbz; s->last_search_kc = s->h_ztab[1];
   if (parts) {
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_search_spmv<TX, TY, NT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_search_spmv<TX, TY, NT, MINB, true><<<grid, NT, smem, s->stream>>>(s->dev, a);
@@ -368,32 +425,22 @@ static int launch_search_t(bbpcg_solver *s, bool parts)
 }
 
 /* the TMA-fed kernel (bbpcg_search_tma.cuh) */
-template <int TY, bool PARTS>
+template <int TY, bool PARTS, int DD>
 static int launch_search_tma_t(bbpcg_solver *s, const SearchMaps &M)
 {
-  typedef SearchGeom<TY, PARTS> G;
+  typedef SearchGeom<TY, PARTS, DD> G;
   static_assert(sizeof(Dev) + sizeof(SearchMaps) + sizeof(SearchArgs) + 192 <= 4096, "kernel parameters exceed 4 KB");
   const Layout &L = s->dev.L;
   if (!s->maps_ok) { bbpcg_set_error("tensor maps not built"); return BBPCG_EINVAL; }
   SearchArgs a;
   a.nbx = (L.in + G::TX - 1) / G::TX; a.nby = (L.jn + TY - 1) / TY;
-  int kc = s->kc;
-  if (kc <= 0) {
-    /* ~8 waves of the 2-per-SM resident CTAs, columns no shorter than 16 planes */
-    long long want = (long long)s->sm_count * 16, per = (long long)a.nbx * a.nby;
-    int nz = (int)((want + per - 1) / per);
-    if (nz < 1) nz = 1;
-    kc = (L.kn + nz - 1) / nz;
-    if (kc < 16) kc = L.kn < 16 ? L.kn : 16;
-  }
-  if (kc > L.kn) kc = L.kn;
-  a.KC = kc; a.nbz = (L.kn + kc - 1) / kc;
-  if ((long long)a.nbx * a.nby * a.nbz > BB_MAXBLOCKS) { bbpcg_set_error("grid too large for the reduction workspace"); return BBPCG_EINVAL; }
+  int rc = plan_zchunks(s, a.nbx * a.nby, s->sm_count * 2, &a.nbz);
+  if (rc) return rc;
   static bool attr_set = false;
-  if (!attr_set) { CU(cudaFuncSetAttribute(k_search_tma<TY, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM)); attr_set = true; }
+  if (!attr_set) { CU(cudaFuncSetAttribute(k_search_tma<TY, PARTS, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM)); attr_set = true; }
   dim3 grid(a.nbx, a.nby, a.nbz);
-  s->last_search_grid = a.nbx * a.nby * a.nbz; s->last_search_kc = kc;
-  k_search_tma<TY, PARTS><<<grid, G::NT, G::SMEM, s->stream>>>(s->dev, M, a);
+  s->last_search_grid = a.nbx * a.nby * a.nbz; s->last_search_kc = s->h_ztab[1];
+  CU(launch_k(s, k_search_tma<TY, PARTS, DD>, grid, G::NT, G::SMEM, true, s->dev, M, a));
   s->launches++;
   return BBPCG_OK;
 }
@@ -401,14 +448,16 @@ static int launch_search_tma_t(bbpcg_solver *s, const SearchMaps &M)
 static int launch_search(bbpcg_solver *s, bool parts)
 {
   switch (s->tile) {
-    case 0: return parts ? launch_search_tma_t<8, true>(s, s->maps[0]) : launch_search_tma_t<8, false>(s, s->maps[0]);
-    case 1: return parts ? launch_search_tma_t<4, true>(s, s->maps[1]) : launch_search_tma_t<4, false>(s, s->maps[1]);
+    case 0: return parts ? launch_search_tma_t<8, true, 2>(s, s->maps[0]) : launch_search_tma_t<8, false, 2>(s, s->maps[0]);
+    case 1: return parts ? launch_search_tma_t<4, true, 2>(s, s->maps[1]) : launch_search_tma_t<4, false, 2>(s, s->maps[1]);
     case 2: return launch_search_t<128, 8, 256, 2>(s, parts);
     case 3: return launch_search_t<128, 4, 256, 3>(s, parts);
     case 4: return launch_search_t<64, 8, 256, 3>(s, parts);
     case 5: return launch_search_t<128, 8, 512, 2>(s, parts);
     case 6: return launch_search_t<32, 8, 128, 4>(s, parts);
     case 7: return launch_search_t<256, 4, 256, 2>(s, parts);
+    case 8: return parts ? launch_search_tma_t<8, true, 3>(s, s->maps[0]) : launch_search_tma_t<8, false, 3>(s, s->maps[0]);
+    case 9: return parts ? launch_search_tma_t<4, true, 3>(s, s->maps[1]) : launch_search_tma_t<4, false, 3>(s, s->maps[1]);
   }
   bbpcg_set_error("unknown tile variant %d", s->tile);
   return BBPCG_EINVAL;
@@ -434,7 +483,8 @@ static int preload_kernels()
 {
   int rc = 0;
 #define PL(...) if (!rc) rc = preload_one(__VA_ARGS__)
-  PL(k_search_tma<8, false>); PL(k_search_tma<8, true>); PL(k_search_tma<4, false>); PL(k_search_tma<4, true>);
+  PL(k_search_tma<8, false, 2>); PL(k_search_tma<8, true, 2>); PL(k_search_tma<4, false, 2>); PL(k_search_tma<4, true, 2>);
+  PL(k_search_tma<8, false, 3>); PL(k_search_tma<8, true, 3>); PL(k_search_tma<4, false, 3>); PL(k_search_tma<4, true, 3>);
   if (!rc) rc = preload_search<128, 8, 256, 2>();
   if (!rc) rc = preload_search<128, 4, 256, 3>();
   if (!rc) rc = preload_search<64, 8, 256, 3>();
@@ -465,7 +515,7 @@ static int launch_resid_t(bbpcg_solver *s)
   a.npass = (int)npass;
   a.ppc = s->resid_ppc > 0 ? s->resid_ppc : 1;
   if ((a.npass + a.ppc - 1) / a.ppc > BB_MAXBLOCKS) a.ppc = (a.npass + BB_MAXBLOCKS - 1) / BB_MAXBLOCKS;
-  k_resid<XT, UNR><<<(a.npass + a.ppc - 1) / a.ppc, 128, 0, s->stream>>>(s->dev, a);
+  CU(launch_k(s, k_resid<XT, UNR>, dim3((a.npass + a.ppc - 1) / a.ppc), 128, 0, true, s->dev, a));
   s->launches++;
   return BBPCG_OK;
 }
@@ -715,6 +765,9 @@ extern "C" int bbpcg_set_option(bbpcg_solver *s, const char *key, long long valu
   if (!s || !key) return BBPCG_EINVAL;
   if (!strcmp(key, "tile")) { if (value < 0 || value >= k_ntiles) { bbpcg_set_error("tile must be 0..%d", k_ntiles - 1); return BBPCG_EINVAL; } s->tile = (int)value; }
   else if (!strcmp(key, "kc")) s->kc = (int)value;
+  else if (!strcmp(key, "taper_g10")) s->taper_g10 = clampi(value, 1, 1000);
+  else if (!strcmp(key, "taper_min")) s->taper_min = clampi(value, 1, 4096);
+  else if (!strcmp(key, "pdl")) s->pdl = value != 0;
   else if (!strcmp(key, "resid_blocks")) s->resid_blocks = clampi(value, 1, BB_MAXBLOCKS);
   else if (!strcmp(key, "resid_ppc")) s->resid_ppc = clampi(value, 0, 1 << 20);
   else if (!strcmp(key, "stream_blocks")) s->stream_blocks = clampi(value, 1, BB_MAXBLOCKS);
@@ -751,5 +804,7 @@ extern "C" long long bbpcg_get_info(bbpcg_solver *s, const char *key)
   if (!strcmp(key, "kt_refresh_n")) return s->kt_refresh_n;
   if (!strcmp(key, "search_grid")) return s->last_search_grid;
   if (!strcmp(key, "search_kc")) return s->last_search_kc;
+  if (!strcmp(key, "search_nbz")) return s->zt_nbz;
+  if (!strcmp(key, "pdl")) return s->pdl && !s->shared_device;
   return -1;
 }
