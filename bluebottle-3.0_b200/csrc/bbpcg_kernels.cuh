@@ -283,6 +283,7 @@ __device__ __forceinline__ long long j_px_fix(const Layout &L, const Layout &N, 
  * ring, q store, (p,q) partial.  One __syncthreads per plane. */
 struct SearchArgs {
   int nbx, nby, nbz;   /* z-chunk c owns planes d.ztab[c]+1 .. d.ztab[c+1] */
+  int store_q;         /* 0: recompute variant, k_resid_tma re-applies the operator instead of reading q */
 };
 
 template <int TX, int TY, int NT, int MINB, bool PARTS>

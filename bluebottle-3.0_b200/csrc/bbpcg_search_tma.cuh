@@ -6,7 +6,7 @@
  *   (p,q) partial -> last CTA: rank-ordered all-reduce, alpha     src/cuda_solver.cu:204-206
  *
  * CTA = 256 threads, tile TX = 128 x TY owned cells of one k-plane, marching KC planes in k.
- * All plane inputs except x arrive through TMA (cp.async.bulk.tensor.3d, SASS UTMALDG) into a
+ * All plane inputs arrive through TMA (cp.async.bulk.tensor.3d, SASS UTMALDG) into a
  * shared-memory ring, issued D (2 or 3) planes ahead by one thread and awaited on mbarriers, so DRAM
  * latency is covered without any register staging:
  *     P ring (D+2 slots): halo'd p_prev tile (TX+4) x (TY+2); converted IN PLACE to p_new
@@ -18,7 +18,9 @@
  * cells stay in REGISTERS; only the N/S/E/W neighbours are read back from the P ring.  One
  * mbarrier wait + one __syncthreads per plane.  Stores (p_new, x, q) are 128-bit from registers.
  *
- * Algorithmic traffic: r, p_prev, x read; p_new, x, q written = 48 B per cell (+1 B mask).
+ * Algorithmic traffic: r, p_prev, x read; p_new, x, q written = 48 B per cell (+1 B mask);
+ * 40 B in the recompute variant (SearchArgs::store_q = 0: q is only used for the dot product here and
+ * re-applied by k_resid_tma, bbpcg_resid_tma.cuh).
  */
 #ifndef BBPCG_SEARCH_TMA_CUH
 #define BBPCG_SEARCH_TMA_CUH
@@ -28,6 +30,7 @@
 
 struct SearchMaps {
   CUtensorMap r, p[2], fm, pm;       /* this block: halo'd f64 tiles, halo'd u8 mask tile, owned u8 pmask tile */
+  CUtensorMap xo, ro;                /* owned (TX x TY) f64 tiles of x and r */
   CUtensorMap nb[6];                 /* neighbours' r: E,W = 2 x HY column box, N,S = row box, T,B = tile box */
 };
 
@@ -71,7 +74,8 @@ struct SearchGeom {
   static constexpr int GYS = a128(HXP * 8), GY = 2 * GYS;      /* two y-ghost rows */
   static constexpr int GXS = a128(HY * 16), GX = 2 * GXS;      /* two x-ghost columns (2 doubles per row) */
   static constexpr int PMT = PARTS ? a128(TX * TY) : 0;
-  static constexpr int STAGE = RT + MT + GY + GX + PMT;
+  static constexpr int XT = TX * TY * 8;               /* owned x tile */
+  static constexpr int STAGE = RT + MT + GY + GX + PMT + XT;
   static constexpr int D = DD, NRS = DD + 1, NPS = DD + 2;   /* planes in flight, r/mask stages, p-ring slots */
   static constexpr int NO = TY / 4;                    /* owned double2 items per thread: rows rg+1+4n */
   static constexpr int NA = NO + 1;                    /* + one halo-row item for the threads rg = 0 (row 0), 1 (row HY-1) */
@@ -190,7 +194,10 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
       if (gx1) bytes += HY * 16;
       if (PARTS) bytes += TX * TY;
     }
+    const bool owned = pi >= k0 && pi <= k1;
+    if (owned) bytes += G::XT;
     tma::mbar_expect_tx(bar, bytes);
+    if (owned) tma::load3d(st + G::RT + G::MT + G::GY + G::GX + G::PMT, &tm.xo, BB_XOFF + 1 + bx * TX, j0, pi, bar);
     tma::load3d(sP + ps * G::RT, &tm.p[q & 1], x0, y0, pi, bar);
     tma::load3d(st + G::RT, &tm.fm, x0 - G::MX0, y0, pi, bar);
     if (pi == 0 && d.halo.f[5].r) tma::load3d(st, &tm.nb[5], x0, y0, d.halo.f[5].L.kn, bar);          /* B neighbour's top plane    */
@@ -227,17 +234,9 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
   /* register pipeline of the owned cells: p(kc-1), p(kc), masks of kc */
   double2 pB[NO], pC[NO];
   unsigned mC[NO], pmC[NO];
-  double2 xn[NO];                                       /* x of the NEXT plane (prefetched) */
 #pragma unroll
-  for (int o = 0; o < NO; o++) { pB[o] = make_double2(0., 0.); pC[o] = make_double2(0., 0.); mC[o] = 0; pmC[o] = 0; xn[o] = make_double2(0., 0.); }
+  for (int o = 0; o < NO; o++) { pB[o] = make_double2(0., 0.); pC[o] = make_double2(0., 0.); mC[o] = 0; pmC[o] = 0; }
   const long long gown0 = (long long)(iA + BB_XOFF);    /* + j*px + k*ps */
-
-  auto load_x = [&](int pi) {
-#pragma unroll
-    for (int o = 0; o < NO; o++)
-      if (fl[o] & (SF_E0OWN | SF_E1OWN)) xn[o] = ldg128(x + gown0 + (long long)(y0 + rowof[o]) * L.px + (long long)pi * L.ps);
-  };
-  if (k0 <= k1) load_x(k0);                             /* first owned plane is lp = 1 */
 
   double dot = 0.;
   __syncthreads();                                      /* table ready */
@@ -248,10 +247,6 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
     if (tid == 0 && lp + G::D < nplanes) issue(lp + G::D);
     const bool plane_owned = pi >= k0 && pi <= k1;
     const bool plane_ghost = (pi == 0 || pi == L.kn + 1);
-    double2 xc[NO];
-#pragma unroll
-    for (int o = 0; o < NO; o++) xc[o] = xn[o];
-    if (pi + 1 >= k0 && pi + 1 <= k1) load_x(pi + 1);
     tma::mbar_wait(bar0 + 8 * rs, (lp / G::NRS) & 1);
 
     double *Pt = reinterpret_cast<double *>(smem + ps * G::RT);
@@ -261,6 +256,10 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
     const double *GYt = reinterpret_cast<const double *>(St + G::RT + G::MT);
     const double *GXt = reinterpret_cast<const double *>(St + G::RT + G::MT + G::GY);
     const unsigned char *PMt = St + G::RT + G::MT + G::GY + G::GX;
+    const double *Xt = reinterpret_cast<const double *>(St + G::RT + G::MT + G::GY + G::GX + G::PMT);
+    double2 xc[NO];                                     /* x of this plane: owned tile, row-major TX wide */
+#pragma unroll
+    for (int o = 0; o < NO; o++) xc[o] = plane_owned ? *reinterpret_cast<const double2 *>(Xt + (rowof[o] - 1) * TX + 2 * col2) : make_double2(0., 0.);
     const long long gplane = (long long)pi * L.ps;
 
     /* ---- phase A: p_new on the halo'd tile of plane pi ---- */
@@ -348,10 +347,10 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
         }
         const long long g = gpc + gown0 + (long long)(y0 + rowof[o]) * L.px;
         if (iA + 1 <= L.in) {
-          stg128(qv + g, q0, q1);
+          if (a.store_q) stg128(qv + g, q0, q1);
           dot += pC[o].x * q0; dot += pC[o].y * q1;
         } else {                                                          /* odd row end: element 1 is the E ghost */
-          qv[g] = q0;
+          if (a.store_q) qv[g] = q0;
           dot += pC[o].x * q0;
         }
       }

@@ -15,6 +15,7 @@
 
 #include "bbpcg_kernels.cuh"
 #include "bbpcg_search_tma.cuh"
+#include "bbpcg_resid_tma.cuh"
 
 /* ---- error plumbing ---------------------------------------------------------------------- */
 static thread_local char g_err[512] = "";
@@ -77,6 +78,8 @@ struct bbpcg_solver {
   int zt_cols, zt_kc, zt_g10, zt_min, zt_nbz;   /* what the uploaded table was built for */
   int taper_g10, taper_min;         /* guided chunking: t = remaining*columns*10 / (g10*slots), >= taper_min */
   int pdl;                          /* programmatic dependent launch of the two iteration kernels */
+  int resid_mb, resid_d;            /* k_resid_tma: CTAs per SM the register budget is compiled for (2 or 3); TMA planes in flight */
+  int recompute;                    /* 64-B iteration: k_resid_tma re-applies the operator, q is never stored */
   int shared_device;                /* some peer rank lives on this same GPU (single-process harness) */
   SearchMaps maps[2];               /* tensor maps of k_search_tma for TY = 8 / TY = 4 */
   int maps_ok;
@@ -153,6 +156,8 @@ static int build_search_maps_t(bbpcg_solver *s, SearchMaps *M)
   if (!rc) rc = make_map(&M->p[1], d.P[1], d.L, false, G::HXP, G::HY);
   if (!rc) rc = make_map(&M->fm, d.fmask, d.L, true, G::MXP, G::HY);
   if (!rc) rc = make_map(&M->pm, d.pmask, d.L, true, G::TX, TY);
+  if (!rc) rc = make_map(&M->xo, d.x, d.L, false, G::TX, TY);
+  if (!rc) rc = make_map(&M->ro, d.r, d.L, false, G::TX, TY);
   for (int f = 0; f < 6 && !rc; f++) {
     const NbrFace &nf = d.halo.f[f];
     if (!nf.r) { M->nb[f] = M->r; continue; }            /* never used: keeps the parameter well formed */
@@ -247,7 +252,7 @@ extern "C" int bbpcg_create(bbpcg_solver **out, const dom_struct *dom_rank, cons
   CU(cudaHostAlloc(&s->h_poll, 64, cudaHostAllocDefault));
   CU(cudaHostAlloc(&s->h_scal, sizeof(Scal), cudaHostAllocDefault));
   CU(cudaHostAlloc(&s->h_ztab, sizeof(int) * (BB_MAXZ + 1), cudaHostAllocDefault));
-  s->zt_cols = -1; s->taper_g10 = 20; s->taper_min = 8; s->pdl = 1;
+  s->zt_cols = -1; s->taper_g10 = 0; s->taper_min = 8; s->pdl = 1; s->recompute = 1; s->resid_mb = 2; s->resid_d = 2;
   /* single rank: neighbours are this block itself (periodic wrap) or nothing */
   s->nranks = 1;
   for (int p = 0; p < BB_MAXR; p++) { s->peer_arena[p] = NULL; s->peer_opened[p] = false; }
@@ -343,6 +348,8 @@ struct TileCfg { int tx, ty, nt; };
 static const TileCfg k_tiles[] = { { 128, 8, 256 }, { 128, 4, 256 }, { 128, 8, 256 }, { 128, 4, 256 }, { 64, 8, 256 }, { 128, 8, 512 },
                                    { 32, 8, 128 }, { 256, 4, 256 }, { 128, 8, 256 }, { 128, 4, 256 } };
 static const int k_ntiles = sizeof(k_tiles) / sizeof(k_tiles[0]);
+static bool tile_is_tma(int t) { return t == 0 || t == 1 || t == 8 || t == 9; }
+static bool recompute_active(const bbpcg_solver *s) { return s->recompute && tile_is_tma(s->tile); }
 
 /* z-chunk plan of the search kernel.  The grid is (x-tiles, y-tiles, z-chunks); CTAs are dispatched
  * z-chunk-major, so y/x neighbours of one chunk run together (their halo rows hit L2).  kc > 0: uniform
@@ -357,7 +364,7 @@ static int plan_zchunks(bbpcg_solver *s, int columns, int slots, int *nbz_out)
   std::vector<int> sz;
   if (s->kc > 0) {
     for (int r = kn; r > 0; r -= s->kc) sz.push_back(r < s->kc ? r : s->kc);
-  } else {
+  } else if (s->taper_g10 > 0) {
     const int tmin = s->taper_min < 1 ? 1 : s->taper_min;
     int r = kn;
     while (r > 0) {
@@ -366,6 +373,22 @@ static int plan_zchunks(bbpcg_solver *s, int columns, int slots, int *nbz_out)
       if (t > r || r - t < (tmin + 1) / 2) t = r;
       sz.push_back((int)t); r -= (int)t;
     }
+  } else {
+    /* default, from the measured sweeps: with many waves of resident CTAs the best chunk
+     * is ~24 planes (>= 7 waves: the ragged last wave is short, the two re-read halo planes stay cheap);
+     * with few waves what matters is the wave count itself: minimise ceil(CTAs/slots) * (kc + 6). */
+    int nz = (kn + 23) / 24;
+    if ((long long)columns * nz < 7ll * slots) {
+      long long best = -1;
+      const int nzmax = kn >= 16 ? kn / 8 : 1;
+      for (int c = 1; c <= nzmax; c++) {
+        const long long waves = ((long long)columns * c + slots - 1) / slots;
+        const long long cost = waves * ((kn + c - 1) / c + 6);    /* +6: two halo planes + pipeline fill/drain */
+        if (best < 0 || cost < best) { best = cost; nz = c; }
+      }
+    }
+    const int kc = (kn + nz - 1) / nz;
+    for (int r = kn; r > 0; r -= kc) sz.push_back(r < kc ? r : kc);
   }
   if ((int)sz.size() > BB_MAXZ || (long long)sz.size() * columns > BB_MAXBLOCKS) {
     /* fall back to the shortest uniform chunks that fit the workspace */
@@ -411,6 +434,7 @@ static int launch_search_t(bbpcg_solver *s, bool parts)
   a.nbx = (L.in + TX - 1) / TX; a.nby = (L.jn + TY - 1) / TY;
   int rc = plan_zchunks(s, a.nbx * a.nby, s->sm_count * MINB, &a.nbz);
   if (rc) return rc;
+  a.store_q = 1;
   dim3 grid(a.nbx, a.nby, a.nbz);
   s->last_search_grid = a.nbx * a.nby * a.nbz; s->last_search_kc = s->h_ztab[1];
   if (parts) {
@@ -438,11 +462,45 @@ static int launch_search_tma_t(bbpcg_solver *s, const SearchMaps &M)
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) { CU(cudaFuncSetAttribute(k_search_tma<TY, PARTS, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM)); attr_set = true; }
+  a.store_q = recompute_active(s) ? 0 : 1;
   dim3 grid(a.nbx, a.nby, a.nbz);
   s->last_search_grid = a.nbx * a.nby * a.nbz; s->last_search_kc = s->h_ztab[1];
   CU(launch_k(s, k_search_tma<TY, PARTS, DD>, grid, G::NT, G::SMEM, true, s->dev, M, a));
   s->launches++;
   return BBPCG_OK;
+}
+
+/* the residual half of the recompute variant (bbpcg_resid_tma.cuh): same tiles and z-chunks as the search kernel */
+template <int TY, bool PARTS, int MB, int DD>
+static int launch_resid_tma_t(bbpcg_solver *s, const SearchMaps &M)
+{
+  typedef ResidGeom<TY, PARTS, DD> G;
+  const Layout &L = s->dev.L;
+  SearchArgs a;
+  a.nbx = (L.in + G::TX - 1) / G::TX; a.nby = (L.jn + TY - 1) / TY;
+  int rc = plan_zchunks(s, a.nbx * a.nby, s->sm_count * 2, &a.nbz);
+  if (rc) return rc;
+  a.store_q = 0;
+  static bool attr_set = false;
+  if (!attr_set) { CU(cudaFuncSetAttribute(k_resid_tma<TY, PARTS, MB, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM)); attr_set = true; }
+  CU(launch_k(s, k_resid_tma<TY, PARTS, MB, DD>, dim3(a.nbx, a.nby, a.nbz), G::NT, G::SMEM, true, s->dev, M, a));
+  s->launches++;
+  return BBPCG_OK;
+}
+
+static int launch_resid_tma(bbpcg_solver *s, bool parts)
+{
+  const bool t8 = k_tiles[s->tile].ty == 8;
+  const SearchMaps &M = s->maps[t8 ? 0 : 1];
+  if (parts) return t8 ? launch_resid_tma_t<8, true, 2, 2>(s, M) : launch_resid_tma_t<4, true, 2, 2>(s, M);
+  if (!t8) return launch_resid_tma_t<4, false, 3, 2>(s, M);
+  switch (s->resid_mb * 10 + s->resid_d) {
+    case 22: return launch_resid_tma_t<8, false, 2, 2>(s, M);
+    case 23: return launch_resid_tma_t<8, false, 2, 3>(s, M);
+    case 32: return launch_resid_tma_t<8, false, 3, 2>(s, M);
+    case 33: return launch_resid_tma_t<8, false, 3, 3>(s, M);
+    default: return launch_resid_tma_t<8, false, 2, 2>(s, M);
+  }
 }
 
 static int launch_search(bbpcg_solver *s, bool parts)
@@ -491,6 +549,9 @@ static int preload_kernels()
   if (!rc) rc = preload_search<128, 8, 512, 2>();
   if (!rc) rc = preload_search<32, 8, 128, 4>();
   if (!rc) rc = preload_search<256, 4, 256, 2>();
+  PL(k_resid_tma<8, true, 2, 2>); PL(k_resid_tma<4, true, 2, 2>); PL(k_resid_tma<4, false, 3, 2>);
+  PL(k_resid_tma<8, false, 2, 2>); PL(k_resid_tma<8, false, 2, 3>);
+  PL(k_resid_tma<8, false, 3, 2>); PL(k_resid_tma<8, false, 3, 3>);
   PL(k_resid<128, 4>); PL(k_resid<64, 4>); PL(k_resid<32, 4>); PL(k_refresh_x<256>); PL(k_refresh_r<256, false>); PL(k_refresh_r<256, true>);
   PL(k_build_tab); PL(k_init<256>); PL(k_finish<256>); PL(k_rhs<256>); PL(k_masks<256>); PL(k_part_rhs_net);
   PL(k_coeffs_refine<256>); PL(k_zero_ghosts); PL(k_xchg_send); PL(k_xchg_recv);
@@ -624,7 +685,7 @@ static int enqueue_iteration(bbpcg_solver *s, int it, bool parts, const real *rh
     else k_refresh_r<256, false><<<nb, 256, 0, s->stream>>>(s->dev, rhs, s->fst.cs1b, s->fst.cs2b);
     s->launches += 2;
   } else {
-    rc = launch_resid(s);
+    rc = recompute_active(s) ? launch_resid_tma(s, parts) : launch_resid(s);
     if (rc) return rc;
   }
   if (kt) CU(cudaEventRecord(s->kev[2 * it], s->stream));
@@ -765,9 +826,12 @@ extern "C" int bbpcg_set_option(bbpcg_solver *s, const char *key, long long valu
   if (!s || !key) return BBPCG_EINVAL;
   if (!strcmp(key, "tile")) { if (value < 0 || value >= k_ntiles) { bbpcg_set_error("tile must be 0..%d", k_ntiles - 1); return BBPCG_EINVAL; } s->tile = (int)value; }
   else if (!strcmp(key, "kc")) s->kc = (int)value;
-  else if (!strcmp(key, "taper_g10")) s->taper_g10 = clampi(value, 1, 1000);
+  else if (!strcmp(key, "taper_g10")) s->taper_g10 = clampi(value, 0, 1000);
   else if (!strcmp(key, "taper_min")) s->taper_min = clampi(value, 1, 4096);
   else if (!strcmp(key, "pdl")) s->pdl = value != 0;
+  else if (!strcmp(key, "recompute")) s->recompute = value != 0;
+  else if (!strcmp(key, "resid_mb")) s->resid_mb = value == 2 ? 2 : 3;
+  else if (!strcmp(key, "resid_d")) s->resid_d = clampi(value, 2, 3);
   else if (!strcmp(key, "resid_blocks")) s->resid_blocks = clampi(value, 1, BB_MAXBLOCKS);
   else if (!strcmp(key, "resid_ppc")) s->resid_ppc = clampi(value, 0, 1 << 20);
   else if (!strcmp(key, "stream_blocks")) s->stream_blocks = clampi(value, 1, BB_MAXBLOCKS);
@@ -806,5 +870,6 @@ extern "C" long long bbpcg_get_info(bbpcg_solver *s, const char *key)
   if (!strcmp(key, "search_kc")) return s->last_search_kc;
   if (!strcmp(key, "search_nbz")) return s->zt_nbz;
   if (!strcmp(key, "pdl")) return s->pdl && !s->shared_device;
+  if (!strcmp(key, "recompute")) return recompute_active(s);
   return -1;
 }

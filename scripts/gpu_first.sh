@@ -11,7 +11,7 @@ timeout 600 python bench.py --impl reference > gpurun_out/bench_ref_n1.json 2> g
 cat gpurun_out/bench_ref_n1.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv \
   python bench.py --no-cpu-baseline --no-e2e > gpurun_out/bench_under_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_search_tma|k_resid' -s 20 -c 4 -f -o gpurun_out/prof_iter \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_search_tma|k_resid_tma' -s 20 -c 4 -f -o gpurun_out/prof_iter \
   python bench.py --steps 1 --warmup 0 --fixed-iters 30 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
 ls -la gpurun_out

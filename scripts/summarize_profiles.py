@@ -95,7 +95,7 @@ def full(tag, rep):
             traffic.setdefault(name, []).append((b, t))
     out = {"source": "profiles/" + tag + "_ncu_full.csv", "cells_per_launch": 512 ** 3}
     for name, v in traffic.items():
-        key = "k_search_spmv" if name.startswith("k_search") else name.split("<")[0]
+        key = "k_search_spmv" if name.startswith("k_search") else "k_resid" if name.startswith("k_resid") else name.split("<")[0]
         out[key + "_bytes_per_launch"] = sum(b for b, _ in v) / len(v)
         out[key + "_ncu_us"] = sum(t for _, t in v) / len(v) * 1e6
         out[key + "_kernel"] = name

@@ -111,10 +111,31 @@ def test_solve_noparts_all_bc_sets(bc):
     p.close()
 
 
-@pytest.mark.parametrize("tile", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("tile", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
 def test_solve_every_tile_variant(tile):
     case = Case((40, 24, 36), bc="duct")      # ragged: not a multiple of any tile
     p = _product(case, options={"tile": tile})
+    _check_solve(case, p)
+    p.close()
+
+
+@pytest.mark.parametrize("recompute,tile", [(0, 0), (1, 0), (0, 1), (1, 1), (1, 8)])
+@pytest.mark.parametrize("blocks,parts", [((1, 1, 1), False), ((2, 1, 2), False), ((1, 1, 1), True), ((1, 2, 1), True)])
+def test_recompute_variant_matches_stored_q(recompute, tile, blocks, parts):
+    """64-B iteration (k_resid_tma re-applies the operator) vs the 72-B one (q stored and re-read):
+    both against the oracle, on ragged sizes, decomposed, and with particles."""
+    kw = dict(nparts=3, radius=2.5) if parts else {}
+    case = Case((36, 28, 44), blocks=blocks, bc="sedimentation" if parts else "channel", **kw)
+    p = _product(case, options={"tile": tile, "recompute": recompute, "kc": 9})
+    assert p.solvers[0].info("recompute") == recompute
+    _check_solve(case, p, parts=parts)
+    p.close()
+
+
+@pytest.mark.parametrize("opts", [{"taper_g10": 20, "taper_min": 4}, {"taper_g10": 10, "taper_min": 8}, {"kc": 1}, {"kc": 1000}, {"pdl": 0}])
+def test_zchunk_plans(opts):
+    case = Case((24, 20, 52), bc="cavity")
+    p = _product(case, options=opts)
     _check_solve(case, p)
     p.close()
 
