@@ -267,6 +267,16 @@ __device__ __forceinline__ bool push_halo(const Dev &d, int which, int i, int j,
   return any;
 }
 
+/* Every kernel that writes r also keeps the compact x-face copies current: an x neighbour (another rank over
+ * NVLink, or this block itself for a periodic wrap) pulls its ghost COLUMN from there as one contiguous run of
+ * j values per plane -- the column inside the P-layout array is element-strided (one 16-byte piece per row),
+ * which cost 60 us per iteration of exposed NVLink time at 512^3 / 2 ranks split in x. */
+__device__ __forceinline__ void store_xface(const Dev &d, int i, int j, int k, double val)
+{
+  if (i == 1 && d.xf[0]) d.xf[0][j + (long long)k * d.pf] = val;
+  if (i == d.L.in && d.xf[1]) d.xf[1][j + (long long)k * d.pf] = val;
+}
+
 /* in-plane offset (i+XOFF) + j*px of this block -> correction for a neighbour whose pitch differs */
 __device__ __forceinline__ long long j_px_fix(const Layout &L, const Layout &N, int goff)
 {
@@ -552,6 +562,8 @@ __global__ void __launch_bounds__(128, 4) k_resid(const __grid_constant__ Dev d,
         if (nv > 1) { dot += v.b * zb; rp[1] = v.b; }
         if (nv > 2) { dot += v.c * zc; rp[2] = v.c; }
       }
+      if (c == 0) store_xface(d, 1, jj[u], kk[u], v.a);
+      if (4 * c + nv == L.in && L.in > 1) store_xface(d, L.in, jj[u], kk[u], nv == 4 ? v.d : nv == 3 ? v.c : nv == 2 ? v.b : v.a);
     }
   }
   pdl_launch_dependents();
@@ -621,6 +633,7 @@ __global__ void __launch_bounds__(NT) k_refresh_r(const Dev d, const double *__r
       double z = rv * tab[m & 127u];
       dot += rv * z;
       r[g] = rv;
+      store_xface(d, i, j, k, rv);
     }
   }
   double v[1] = { dot }, tot[1];
@@ -654,6 +667,7 @@ __global__ void __launch_bounds__(NT) k_init(const Dev d, const double *__restri
       const double z = b * tab[d.fmask[g] & 127u];
       bb += b * b;  rz += b * z;
       d.r[g] = b;
+      store_xface(d, i, j, k, b);
     }
   }
   double v[2] = { bb, rz }, tot[2];

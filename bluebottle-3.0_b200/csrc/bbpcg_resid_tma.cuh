@@ -175,10 +175,12 @@ k_resid_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps tm
           const double z1 = r1 * tab[(m >> 8) & 127u];
           stg128(r + g, r0, r1);
           dot += r0 * z0; dot += r1 * z1;
+          if (iA + 1 == L.in) store_xface(d, L.in, y0 + rowof[o], kc, r1);
         } else {                                                        /* odd row end: element 1 is the E ghost */
           r[g] = r0;
           dot += r0 * z0;
         }
+        if (iA == 1 || iA == L.in) store_xface(d, iA, y0 + rowof[o], kc, r0);
       }
     }
 #pragma unroll

@@ -12,8 +12,9 @@
  *     P ring (D+2 slots): halo'd p_prev tile (TX+4) x (TY+2); converted IN PLACE to p_new
  *     per stage (D+1) : halo'd r tile, mask tile, [pmask tile], and -- PULL model -- the r values of
  *                       ghost cells straight from the NEIGHBOUR's r array (peer memory over NVLink or
- *                       this block itself for a periodic self-wrap): one row per y-ghost, one
- *                       2-wide column per x-ghost, the whole tile for a z-ghost plane.
+ *                       this block itself for a periodic self-wrap): one row per y-ghost, one run of
+ *                       HY values from the neighbour's compact x-face buffer per x-ghost, the whole
+ *                       tile for a z-ghost plane.
  * Each thread owns the same (x,y) cells on every plane, so p(k-1), p(k), p(k+1) of its owned
  * cells stay in REGISTERS; only the N/S/E/W neighbours are read back from the P ring.  One
  * mbarrier wait + one __syncthreads per plane.  Stores (p_new, x, q) are 128-bit from registers.
@@ -31,7 +32,7 @@
 struct SearchMaps {
   CUtensorMap r, p[2], fm, pm;       /* this block: halo'd f64 tiles, halo'd u8 mask tile, owned u8 pmask tile */
   CUtensorMap xo, ro;                /* owned (TX x TY) f64 tiles of x and r */
-  CUtensorMap nb[6];                 /* neighbours' r: E,W = 2 x HY column box, N,S = row box, T,B = tile box */
+  CUtensorMap nb[6];                 /* neighbours' r: E,W = HY-run box on the 2-D compact face buffer, N,S = row box, T,B = tile box */
 };
 
 namespace tma {
@@ -55,6 +56,11 @@ __device__ __forceinline__ void load3d(unsigned dst, const CUtensorMap *map, int
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void load2d(unsigned dst, const CUtensorMap *map, int c0, int c1, unsigned bar)
+{
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void prefetch_map(const CUtensorMap *map) { asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory"); }
 }
 
@@ -72,7 +78,7 @@ struct SearchGeom {
   static constexpr int RT = a128(HXP * HY * 8);        /* halo'd f64 tile */
   static constexpr int MT = a128(MXP * HY);            /* halo'd mask tile */
   static constexpr int GYS = a128(HXP * 8), GY = 2 * GYS;      /* two y-ghost rows */
-  static constexpr int GXS = a128(HY * 16), GX = 2 * GXS;      /* two x-ghost columns (2 doubles per row) */
+  static constexpr int GXS = a128(HY * 8), GX = 2 * GXS;       /* two x-ghost columns: HY contiguous values from the neighbour's face buffer */
   static constexpr int PMT = PARTS ? a128(TX * TY) : 0;
   static constexpr int XT = TX * TY * 8;               /* owned x tile */
   static constexpr int STAGE = RT + MT + GY + GX + PMT + XT;
@@ -173,7 +179,6 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
   const int s_i = i0 + s_col - 2, s_j = y0 + s_row;
   const bool s_ok = has_single && s_j <= L.jn + 1 && s_i <= L.in + 1;
   const bool s_gx = s_ok && ((s_i == 0 && gx0) || (s_i == L.in + 1 && gx1));      /* r from the GX buffer */
-  const int gxw = (d.halo.f[1].L.in + BB_XOFF) & 1;     /* position of the wanted value in the W ghost column box */
   const bool s_store = s_ok && (s_i == 0 || s_i == L.in + 1) && s_j >= 1 && s_j <= L.jn;   /* x-ghost p kept current */
 
   /* ---- everything above is independent of the previous kernels; from here on we read what they wrote ---- */
@@ -190,8 +195,8 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
     if (inner) {
       if (gy0) bytes += HXP * 8;
       if (gy1) bytes += HXP * 8;
-      if (gx0) bytes += HY * 16;
-      if (gx1) bytes += HY * 16;
+      if (gx0) bytes += HY * 8;
+      if (gx1) bytes += HY * 8;
       if (PARTS) bytes += TX * TY;
     }
     const bool owned = pi >= k0 && pi <= k1;
@@ -206,8 +211,8 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
     if (inner) {
       if (gy0) tma::load3d(st + G::RT + G::MT, &tm.nb[3], x0, d.halo.f[3].L.jn, pi, bar);
       if (gy1) tma::load3d(st + G::RT + G::MT + G::GYS, &tm.nb[2], x0, 1, pi, bar);
-      if (gx0) tma::load3d(st + G::RT + G::MT + G::GY, &tm.nb[1], (d.halo.f[1].L.in + BB_XOFF) & ~1, y0, pi, bar);
-      if (gx1) tma::load3d(st + G::RT + G::MT + G::GY + G::GXS, &tm.nb[0], BB_XOFF + 1, y0, pi, bar);
+      if (gx0) tma::load2d(st + G::RT + G::MT + G::GY, &tm.nb[1], y0, pi, bar);               /* W neighbour's E face, j = y0 .. */
+      if (gx1) tma::load2d(st + G::RT + G::MT + G::GY + G::GXS, &tm.nb[0], y0, pi, bar);      /* E neighbour's W face          */
       if (PARTS) tma::load3d(st + G::RT + G::MT + G::GY + G::GX, &tm.pm, BB_XOFF + 1 + bx * TX, j0, pi, bar);
     }
   };
@@ -278,8 +283,8 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
       if (!(f & SF_FAST)) {
         if (!plane_ghost) {
           if (f & SF_GY) r2 = *reinterpret_cast<const double2 *>(GYt + ((f & SF_GYSIDE) ? G::GYS / 8 : 0) + cA);
-          if ((f & SF_E0GX) && gx1) r2.x = GXt[G::GXS / 8 + row * 2];
-          if ((f & SF_E1GX) && gx1) r2.y = GXt[G::GXS / 8 + row * 2];
+          if ((f & SF_E0GX) && gx1) r2.x = GXt[G::GXS / 8 + row];
+          if ((f & SF_E1GX) && gx1) r2.y = GXt[G::GXS / 8 + row];
         }
         if (!(f & SF_E0OK)) m2 = (m2 & 0xff00u) | FM_DEAD;
         if (!(f & SF_E1OK)) m2 = (m2 & 0x00ffu) | (FM_DEAD << 8);
@@ -317,7 +322,7 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
     if (s_ok) {
       const int so = s_row * HXP + s_col;
       double rv = Rt[so];
-      if (s_gx && !plane_ghost) rv = GXt[(s_i == 0 ? gxw : G::GXS / 8) + s_row * 2];
+      if (s_gx && !plane_ghost) rv = GXt[(s_i == 0 ? 0 : G::GXS / 8) + s_row];
       const double pn = rv * tab[Mt[s_row * G::MXP + G::MX0 + s_col] & 127u] + beta * Pt[so];
       Pt[so] = pn;
       if (s_store && plane_owned) pnew[gplane + (s_i + BB_XOFF) + (long long)s_j * L.px] = pn;
