@@ -459,6 +459,7 @@ def run_reference(args):
     for _ in range(args.steps):
         n, m = solve_dev()
         iters += n; tot_ms += m
+        sys.stderr.write("reference arm: device-resident solve %d iterations %.1f ms\n" % (n, m))
     torch.cuda.synchronize()
     clk = clocks.stop()
     k_e2e = max(1, min(args.steps, 3))
@@ -467,6 +468,7 @@ def run_reference(args):
     for _ in range(k_e2e):
         n, m = solve_host()
         it_e += n; ms_e += m
+        sys.stderr.write("reference arm: host-buffer solve %d iterations %.1f ms\n" % (n, m))
     value = iters / (tot_ms * 1e-3)
     ncell = cells[0] * cells[1] * cells[2]
     peak, peak_src = measured_peak()

@@ -1,0 +1,121 @@
+/* dropin_host.cu -- a miniature stand-in for Bluebottle's host program (src/bluebottle.c) that exercises
+ * libbbpcg_dropin.so exactly the way the reference does: it DEFINES the globals the reference defines
+ * (src/bluebottle.c:438-576, src/mpi_comm.c:26-27, src/particle.c:27-28), allocates the device arrays in the
+ * reference's layouts (src/cuda_bluebottle.cu:144-432), and calls the reference's entry-point names
+ *
+ *     cuda_PP_init_jacobi_preconditioner();   // src/bluebottle.c:139
+ *     cuda_PP_cg_noparts();  or  cuda_PP_cg(); // src/bluebottle.c:228-232
+ *     mpi_cuda_exchange_Gcc(_phi);             // src/bluebottle.c:233
+ *
+ * with `void f(void)` signatures.  recorder_PP() and cuda_part_BC_p() -- callees the library calls back -- are
+ * this file's own small stand-ins (same signature; recorder_PP writes the solver_expd.rec line in the column
+ * format of src/recorder.c:190-221).  TEST CODE: built and run by tests/test_gpu_dropin.py; single rank.
+ *
+ *   dropin_host <flow.config> <decomp.config> <inputs.bin> <phi_out.bin> <record_dir> <noparts|parts> [pp_max_iter]
+ *
+ * inputs.bin: flag_u, flag_v, flag_w (int32, Gfx/Gfy/Gfz s3b), phase, phase_shell (int32, Gcc s3b),
+ *             u_star, v_star, w_star (float64, Gfx/Gfy/Gfz s3b), in that order, raw.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "../include/bbpcg.h"
+#include "../include/bb_dropin.h"
+
+extern "C" {
+/* ---- the globals the drop-in layer imports ---- */
+dom_struct *dom = NULL;
+dom_struct DOM;
+int rank = 0, nprocs = 1;
+bb_pressure_bc bc;                      /* the reference's BC struct opens with these six ints */
+real rho_f = 1., dt = 1e-3, pp_residual = 1e-6, ttime = 0.;
+int pp_max_iter = 2000, stepnum = 0;
+int NPARTS = 0, nparts = 0;
+real *_u_star = NULL, *_v_star = NULL, *_w_star = NULL, *_rhs_p = NULL, *_phi = NULL;
+int *_flag_u = NULL, *_flag_v = NULL, *_flag_w = NULL, *_phase = NULL, *_phase_shell = NULL;
+static char g_record_dir[1024] = ".";
+
+/* stand-in for src/recorder.c:190-221 (same columns, single rank: no MPI average) */
+void recorder_PP(char *name, int niter, real resid, real etime)
+{
+  char path[2048];
+  snprintf(path, sizeof(path), "%s/%s", g_record_dir, name);
+  FILE *rec = fopen(path, "a");
+  if (!rec) { fprintf(stderr, "cannot open %s\n", path); exit(EXIT_FAILURE); }
+  fprintf(rec, "\n");
+  fprintf(rec, "%-12d", stepnum);
+  fprintf(rec, "%-15e", ttime);
+  fprintf(rec, "%-15e", dt);
+  fprintf(rec, "%-8d", niter);
+  fprintf(rec, "%-15e", resid);
+  fprintf(rec, "%-15e", etime);
+  fclose(rec);
+}
+}
+
+/* stand-in for cuda_part_BC_p (src/cuda_particle.cu:1680): the net effect of part_BC_p on rhs
+ * (src/particle_kernel.cu:1753): zero in every cell that is solid or outside the particle shell mask */
+__global__ void k_host_part_bc(real *rhs, const int *phase, const int *phase_shell, long long n)
+{
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) rhs[i] = (real)(phase[i] < 0 && phase_shell[i]) * rhs[i];
+}
+extern "C" void cuda_part_BC_p(void)
+{
+  const long long n = dom[rank].Gcc.s3b;
+  k_host_part_bc<<<(unsigned)((n + 255) / 256), 256>>>(_rhs_p, _phase, _phase_shell, n);   /* default stream, like the reference */
+}
+
+template <typename T> static T *upload(FILE *f, size_t n, bool have_gpu)
+{
+  std::vector<T> h(n);
+  if (fread(h.data(), sizeof(T), n, f) != n) { fprintf(stderr, "inputs.bin too short\n"); exit(2); }
+  if (!have_gpu) return NULL;
+  T *d = NULL;
+  if (cudaMalloc(&d, n * sizeof(T)) != cudaSuccess || cudaMemcpy(d, h.data(), n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+    fprintf(stderr, "device allocation failed\n"); exit(2);
+  }
+  return d;
+}
+
+int main(int argc, char **argv)
+{
+  if (argc < 7) { fprintf(stderr, "usage: %s flow.config decomp.config inputs.bin phi_out.bin record_dir noparts|parts [pp_max_iter]\n", argv[0]); return 2; }
+  bb_flow_params fp;
+  if (bb_domain_read(argv[1], argv[2], &DOM, &dom, &bc, &fp)) { fprintf(stderr, "%s\n", bbpcg_last_error()); return 2; }
+  if (DOM.In * DOM.Jn * DOM.Kn != 1) { fprintf(stderr, "this miniature host is single rank\n"); return 2; }
+  rho_f = fp.rho_f; pp_residual = fp.pp_residual; pp_max_iter = argc > 7 ? atoi(argv[7]) : fp.pp_max_iter;
+  snprintf(g_record_dir, sizeof(g_record_dir), "%s", argv[5]);
+  const bool parts = strcmp(argv[6], "parts") == 0;
+  NPARTS = nparts = parts ? 1 : 0;
+  int ndev = 0;
+  const bool have_gpu = cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0;
+  const dom_struct *d = &dom[rank];
+  FILE *f = fopen(argv[3], "rb");
+  if (!f) { fprintf(stderr, "cannot open %s\n", argv[3]); return 2; }
+  _flag_u = upload<int>(f, d->Gfx.s3b, have_gpu); _flag_v = upload<int>(f, d->Gfy.s3b, have_gpu); _flag_w = upload<int>(f, d->Gfz.s3b, have_gpu);
+  _phase = upload<int>(f, d->Gcc.s3b, have_gpu); _phase_shell = upload<int>(f, d->Gcc.s3b, have_gpu);
+  _u_star = upload<real>(f, d->Gfx.s3b, have_gpu); _v_star = upload<real>(f, d->Gfy.s3b, have_gpu); _w_star = upload<real>(f, d->Gfz.s3b, have_gpu);
+  fclose(f);
+  if (have_gpu) {
+    cudaMalloc(&_rhs_p, sizeof(real) * d->Gcc.s3b); cudaMalloc(&_phi, sizeof(real) * d->Gcc.s3b);
+    cudaMemset(_phi, 0, sizeof(real) * d->Gcc.s3b);
+  }
+  /* ---- what src/bluebottle.c does ---- */
+  cuda_PP_init_jacobi_preconditioner();                 /* :139 -- without a GPU this prints and exits(EXIT_FAILURE) */
+  stepnum = 1; ttime = dt;
+  if (parts) cuda_PP_cg(); else cuda_PP_cg_noparts();   /* :228-232 */
+  mpi_cuda_exchange_Gcc(_phi);                          /* :233 */
+  std::vector<real> phi(d->Gcc.s3b);
+  cudaMemcpy(phi.data(), _phi, sizeof(real) * phi.size(), cudaMemcpyDeviceToHost);
+  FILE *o = fopen(argv[4], "wb");
+  fwrite(phi.data(), sizeof(real), phi.size(), o);
+  fclose(o);
+  bbpcg_dropin_finalize();
+  bb_domain_free(dom);
+  printf("dropin_host: done\n");
+  return 0;
+}

@@ -1,0 +1,98 @@
+"""The drop-in layer driven the way Bluebottle drives it: tests/dropin_host.cu defines the reference's globals and
+calls the reference's entry-point NAMES (void f(void)) in libbbpcg_dropin.so.  CPU: it links (every imported
+global / callee resolves) and fails loudly without a GPU.  GPU: phi equals the oracle's, the solver_expd.rec line
+is written through recorder_PP, non-convergence prints the reference's messages and exits with EXIT_FAILURE."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from cases import Case, rel_l2
+from oracle import binding as ob
+from test_domain import _write_flow
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "bluebottle-3.0_b200", "lib")
+BUILD = os.path.join(ROOT, "tests", "_build")
+EXE = os.path.join(BUILD, "dropin_host")
+
+
+def _build():
+    os.makedirs(BUILD, exist_ok=True)
+    src = os.path.join(ROOT, "tests", "dropin_host.cu")
+    deps = [src, os.path.join(LIB, "libbbpcg.so"), os.path.join(LIB, "libbbpcg_dropin.so")]
+    if os.path.exists(EXE) and all(os.path.getmtime(EXE) >= os.path.getmtime(d) for d in deps):
+        return EXE
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-o", EXE, src,
+                           "-L" + LIB, "-lbbpcg_dropin", "-lbbpcg", "-Xlinker", "-rpath", "-Xlinker", LIB, "-lcudart"])
+    return EXE
+
+
+def _write_case(tmp, case, blocks=(1, 1, 1)):
+    from bbpcg.grid import BC_SETS
+    flow, dec, inp = str(tmp / "flow.config"), str(tmp / "decomp.config"), str(tmp / "inputs.bin")
+    _write_flow(flow, case.extent, case.cells, blocks, BC_SETS[case.bcname])
+    txt = open(flow).read().replace("rho_f 2.5", "rho_f 1.0").replace("pp_max_iter 1234", "pp_max_iter 2000").replace("pp_residual 1e-7", "pp_residual 1e-6")
+    open(flow, "w").write(txt)
+    import bbpcg
+    bbpcg.Decomposition.uniform(case.extent, case.cells, blocks, BC_SETS[case.bcname]).write_decomp(dec, prec=6)
+    a = case.inputs(0)
+    with open(inp, "wb") as f:
+        for k in ("flag_u", "flag_v", "flag_w", "phase", "phase_shell", "u_star", "v_star", "w_star"):
+            f.write(np.ascontiguousarray(a[k]).tobytes())
+    (tmp / "record").mkdir(exist_ok=True)
+    return flow, dec, inp
+
+
+def _no_gpu():
+    import torch
+    return not torch.cuda.is_available()
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="checks the behaviour WITHOUT a CUDA device")
+def test_host_links_and_fails_loudly_without_a_gpu(tmp_path):
+    exe = _build()
+    case = Case((12, 10, 8), bc="duct")
+    flow, dec, inp = _write_case(tmp_path, case)
+    p = subprocess.run([exe, flow, dec, inp, str(tmp_path / "phi.bin"), str(tmp_path / "record"), "noparts"], capture_output=True, text=True)
+    assert p.returncode == 1                                   # EXIT_FAILURE, the reference's error convention
+    assert "bbpcg_create" in p.stderr and "no CUDA device" in p.stderr
+    assert not os.path.exists(tmp_path / "phi.bin")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bc,parts", [("duct", False), ("cavity", False), ("sedimentation", True)])
+def test_dropin_solve_matches_oracle(tmp_path, bc, parts):
+    exe = _build()
+    case = Case((32, 28, 36), bc=bc, nparts=3 if parts else 0, radius=2.5)
+    flow, dec, inp = _write_case(tmp_path, case)
+    out = str(tmp_path / "phi.bin")
+    p = subprocess.run([exe, flow, dec, inp, out, str(tmp_path / "record"), "parts" if parts else "noparts"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    ores, _ = case.solve_oracle()
+    g = case.o.dom(0).Gcc
+    phi = np.fromfile(out, dtype=np.float64).reshape(g.get("knb"), g.get("jnb"), g.get("inb"))
+    assert rel_l2(phi[1:-1, 1:-1, 1:-1], case.o.gather_interior(ob.PHI)) < 1e-10
+    # mpi_cuda_exchange_Gcc(_phi) ran after the solve: ghosts equal the oracle's exchange of its own phi
+    case.o.exchange_Gcc(ob.PHI)
+    ophi = case.o.array(0, ob.PHI)
+    for sl in ((slice(1, -1), slice(1, -1), 0), (slice(1, -1), slice(1, -1), -1), (slice(1, -1), 0, slice(1, -1)),
+               (slice(1, -1), -1, slice(1, -1)), (0, slice(1, -1), slice(1, -1)), (-1, slice(1, -1), slice(1, -1))):
+        assert np.allclose(phi[sl], ophi[sl], rtol=0, atol=1e-10 * np.abs(ophi).max())
+    # recorder_PP received (niter, resid): one line in the reference's column format (src/recorder.c:190-221)
+    rec = open(tmp_path / "record" / "solver_expd.rec").read().split()
+    assert int(rec[0]) == 1 and int(rec[3]) == ores.niter and abs(float(rec[4]) - ores.resid) <= 1e-5 * ores.resid
+
+
+@pytest.mark.gpu
+def test_dropin_nonconvergence_prints_and_exits(tmp_path):
+    """src/cuda_solver.cu:734-742: three printf lines and exit(EXIT_FAILURE) after pp_max_iter + 1 iterations"""
+    exe = _build()
+    case = Case((24, 24, 24), bc="periodic")
+    flow, dec, inp = _write_case(tmp_path, case)
+    p = subprocess.run([exe, flow, dec, inp, str(tmp_path / "phi.bin"), str(tmp_path / "record"), "noparts", "4"], capture_output=True, text=True)
+    assert p.returncode == 1
+    assert "The pressure-Poisson equation did not converge." in p.stdout
+    assert "Residual at iteration 5 is" in p.stdout and "(rhs, rhs) is" in p.stdout
+    assert not os.path.exists(tmp_path / "phi.bin")
