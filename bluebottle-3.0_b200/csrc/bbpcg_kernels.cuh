@@ -294,6 +294,8 @@ __device__ __forceinline__ long long j_px_fix(const Layout &L, const Layout &N, 
 struct SearchArgs {
   int nbx, nby, nbz;   /* z-chunk c owns planes d.ztab[c]+1 .. d.ztab[c+1] */
   int store_q;         /* 0: recompute variant, k_resid_tma re-applies the operator instead of reading q */
+  const double *rhs;   /* refresh form of k_resid_tma only: the caller's right-hand side (Gcc s3b) and its strides */
+  int s1b, s2b;
 };
 
 template <int TX, int TY, int NT, int MINB, bool PARTS>
@@ -606,6 +608,60 @@ __global__ void __launch_bounds__(NT) k_refresh_x(const Dev d)
   if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) rank_allreduce(d, tot, 0, true);   /* barrier */
 }
 
+/* k_refresh_x in the streaming form of k_resid: 256-bit accesses, tiny CTAs; only boundary cells take the
+ * (possibly remote) halo-push path */
+template <int XT, int UNR>
+__global__ void __launch_bounds__(128, 4) k_refresh_x4(const __grid_constant__ Dev d, const ResidArgs a)
+{
+  constexpr int NT = 128, YT = NT / XT;
+  const Layout L = d.L;
+  Scal *sc = d.sc;
+  if (sc->done) return;
+  const double alpha = sc->alpha;
+  const double *__restrict__ pcur = d.P[(sc->q + 1) & 1];     /* p of the iteration in flight */
+  double *__restrict__ x = d.x;
+  const unsigned nrows = (unsigned)L.jn * (unsigned)L.kn;
+  const int tx = threadIdx.x % XT, ty = threadIdx.x / XT;
+  bool pushed = false;
+  const int pass0 = blockIdx.x * a.ppc, pass1 = min(pass0 + a.ppc, a.npass);
+  for (int pass = pass0; pass < pass1; pass++) {
+    const int cb = pass % a.ncb, rg = pass / a.ncb;
+    const int c = cb * XT + tx;
+    const unsigned row0 = (unsigned)rg * (YT * UNR) + ty;
+    d4 xv[UNR], pv[UNR];
+    long long g[UNR];
+    int jj[UNR], kk[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      const unsigned row = row0 + u * YT;
+      const unsigned k0 = row / (unsigned)L.jn;
+      jj[u] = (int)(row - k0 * (unsigned)L.jn) + 1; kk[u] = (int)k0 + 1;
+      g[u] = (long long)kk[u] * L.ps + (long long)jj[u] * L.px + (BB_XOFF + 1) + 4 * c;
+      if (row < nrows && c < a.cpr) { xv[u] = ld256(x + g[u]); pv[u] = ld256(pcur + g[u]); }
+      else kk[u] = -1;
+    }
+    const int nv = min(4, L.in - 4 * c);
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      if (kk[u] < 0) continue;
+      d4 v = xv[u];
+      v.a += alpha * pv[u].a; v.b += alpha * pv[u].b; v.c += alpha * pv[u].c; v.d += alpha * pv[u].d;   /* solver_kernel.cu:876 */
+      if (nv == 4) st256(x + g[u], v);
+      else { double *xp = x + g[u]; xp[0] = v.a; if (nv > 1) xp[1] = v.b; if (nv > 2) xp[2] = v.c; }
+      const int j = jj[u], k = kk[u], i0 = 4 * c + 1;
+      if (d.any_nbr && (j == 1 || j == L.jn || k == 1 || k == L.kn || i0 == 1 || i0 + nv - 1 == L.in)) {
+        const double e[4] = { v.a, v.b, v.c, v.d };
+        for (int n = 0; n < nv; n++) {
+          const int i = i0 + n;
+          if (j == 1 || j == L.jn || k == 1 || k == L.kn || i == 1 || i == L.in) pushed |= push_halo(d, 1, i, j, k, e[n]);
+        }
+      }
+    }
+  }
+  double v[1] = { 0. }, tot[1];
+  if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) rank_allreduce(d, tot, 0, true);   /* barrier */
+}
+
 template <int NT, bool PARTS>
 __global__ void __launch_bounds__(NT) k_refresh_r(const Dev d, const double *__restrict__ rhs_s3b, int s1b, int s2b)
 {
@@ -734,6 +790,56 @@ __global__ void __launch_bounds__(NT) k_rhs(int in, int jn, int kn, FaceStrides 
       t *= rho_idt;
       rhs[i + (long long)j * st.cs1b + (long long)k * st.cs2b] = -t;
     }
+  }
+}
+
+/* Tiled PP_rhs: u-star is stored j-fastest (Gfx) and v-star k-fastest (Gfy) while rhs is i-fastest, so a kernel that
+ * walks rows in i reads u-star and v-star with a stride of a whole plane (6.1 ms at 512^3, DRAM sector efficiency 1/4).
+ * Here a CTA owns a 32 x 8 x 8 (i,j,k) tile: u-star is fetched as runs of 8 consecutive j, v-star as runs of 8
+ * consecutive k (64-byte pieces), transposed through shared memory, and rhs is written in 256-byte rows.
+ * Same expression and association as k_rhs / src/solver_kernel.cu:152-157,173. */
+#define RHS_TI 32
+#define RHS_TJ 8
+#define RHS_TK 8
+__global__ void __launch_bounds__(256) k_rhs_tiled(int in, int jn, int kn, FaceStrides st, const double *__restrict__ u,
+                                                   const double *__restrict__ v, const double *__restrict__ w,
+                                                   double *__restrict__ rhs, double idx, double idy, double idz, double rho_idt)
+{
+  __shared__ double su[RHS_TI + 1][RHS_TK * RHS_TJ + 1];      /* [i'][k*8 + j], padded: lanes vary i' at compute time */
+  __shared__ double sv[RHS_TJ + 1][RHS_TK][RHS_TI + 1];       /* [j'][k][i],    padded: lanes vary k at load, i at compute */
+  const int nbi = (in + RHS_TI - 1) / RHS_TI, nbj = (jn + RHS_TJ - 1) / RHS_TJ;
+  const int bi = blockIdx.x % nbi, bj = (blockIdx.x / nbi) % nbj, bk = blockIdx.x / (nbi * nbj);
+  const int i0 = bi * RHS_TI + 1, j0 = bj * RHS_TJ + 1, k0 = bk * RHS_TK + 1;
+  const int t = threadIdx.x;
+  /* u*(i', j, k), i' = i0 .. i0+32: runs of 8 j for each (i', k) */
+  for (int pr = t / 8; pr < (RHS_TI + 1) * RHS_TK; pr += 32) {
+    const int ii = pr / RHS_TK, kk = pr % RHS_TK, jj = t % 8;
+    const int i = i0 + ii, j = j0 + jj, k = k0 + kk;
+    double val = 0.;
+    if (i <= in + 1 && j <= jn && k <= kn) val = u[j + (long long)k * st.us1b + (long long)i * st.us2b];
+    su[ii][kk * RHS_TJ + jj] = val;
+  }
+  /* v*(i, j', k), j' = j0 .. j0+8: runs of 8 k for each (i, j') */
+  for (int pr = t / 8; pr < RHS_TI * (RHS_TJ + 1); pr += 32) {
+    const int jj = pr / RHS_TI, ii = pr % RHS_TI, kk = t % 8;
+    const int i = i0 + ii, j = j0 + jj, k = k0 + kk;
+    double val = 0.;
+    if (i <= in && j <= jn + 1 && k <= kn) val = v[k + (long long)i * st.vs1b + (long long)j * st.vs2b];
+    sv[jj][kk][ii] = val;
+  }
+  __syncthreads();
+  const int ii = t % RHS_TI, i = i0 + ii;
+  for (int pr = t / RHS_TI; pr < RHS_TJ * RHS_TK; pr += 8) {
+    const int jj = pr % RHS_TJ, kk = pr / RHS_TJ;
+    const int j = j0 + jj, k = k0 + kk;
+    if (i > in || j > jn || k > kn) continue;
+    const double wB = w[i + (long long)j * st.ws1b + (long long)k * st.ws2b];
+    const double wT = w[i + (long long)j * st.ws1b + (long long)(k + 1) * st.ws2b];
+    double tt = (su[ii + 1][kk * RHS_TJ + jj] - su[ii][kk * RHS_TJ + jj]) * idx;
+    tt += (sv[jj + 1][kk][ii] - sv[jj][kk][ii]) * idy;
+    tt += (wT - wB) * idz;
+    tt *= rho_idt;
+    rhs[i + (long long)j * st.cs1b + (long long)k * st.cs2b] = -tt;
   }
 }
 

@@ -43,7 +43,10 @@ struct ResidGeom {
   static constexpr int SMEM = OFF_BAR + 64;
 };
 
-template <int TY, bool PARTS, int MB, int DD>
+/* REFRESH = true is the every-50th-iteration true-residual form (src/cuda_solver.cu:209-223, PP_update_residual
+ * src/solver_kernel.cu:883-904): the operator is applied to x (whose ghosts k_refresh_x4 just made current)
+ * instead of p, and r = b - (-A x) with b read from the caller's right-hand side array. */
+template <int TY, bool PARTS, int MB, int DD, bool REFRESH>
 __global__ void __launch_bounds__(256, MB)
 k_resid_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps tm, const SearchArgs a)
 {
@@ -100,11 +103,11 @@ k_resid_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps tm
     const bool inner = pi >= 1 && pi <= L.kn;
     unsigned bytes = HXP * HY * 8 + G::MXP * HY;
     if (PARTS && inner) bytes += TX * TY;
-    const bool owned = pi >= k0 && pi <= k1;
+    const bool owned = !REFRESH && pi >= k0 && pi <= k1;
     if (owned) bytes += G::ROT;
     tma::mbar_expect_tx(bar, bytes);
     if (owned) tma::load3d(st + G::MT + G::PMT, &tm.ro, BB_XOFF + 1 + bx * TX, j0, pi, bar);
-    tma::load3d(sP + ps * G::RT, &tm.p[(q + 1) & 1], x0, y0, pi, bar);      /* p of the iteration in flight, ghosts current */
+    tma::load3d(sP + ps * G::RT, REFRESH ? &tm.xh : &tm.p[(q + 1) & 1], x0, y0, pi, bar);   /* p of the iteration in flight (ghosts current) / x */
     tma::load3d(st, &tm.fm, x0 - G::MX0, y0, pi, bar);
     if (PARTS && inner) tma::load3d(st + G::MT, &tm.pm, BB_XOFF + 1 + bx * TX, j0, pi, bar);
   };
@@ -123,9 +126,9 @@ k_resid_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps tm
     return;
   }
 
-  double2 pB[NO], pC[NO];
+  double2 pB[NO], pC[NO], bn[NO];                       /* bn: refresh form, b of the NEXT plane to be computed */
 #pragma unroll
-  for (int o = 0; o < NO; o++) { pB[o] = make_double2(0., 0.); pC[o] = make_double2(0., 0.); }
+  for (int o = 0; o < NO; o++) { pB[o] = make_double2(0., 0.); pC[o] = make_double2(0., 0.); bn[o] = make_double2(0., 0.); }
 
   double dot = 0.;
   for (int lp = 0; lp < nplanes; lp++) {
@@ -133,6 +136,18 @@ k_resid_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps tm
     const int ms = lp % G::NMS, ps = lp % G::NPS;
     if (tid == 0 && lp + G::D < nplanes) issue(lp + G::D);
     const bool plane_owned = pi >= k0 && pi <= k1;
+    double2 bc[NO];
+    if (REFRESH) {                                      /* b(kc) was requested one iteration ago; request b(kc+1) = b(pi) now */
+#pragma unroll
+      for (int o = 0; o < NO; o++) {
+        bc[o] = bn[o];
+        if (plane_owned && e0[o]) {
+          const long long gb = (long long)iA + (long long)(y0 + rowof[o]) * a.s1b + (long long)pi * a.s2b;    /* caller's Gcc s3b index */
+          bn[o].x = a.rhs[gb];
+          if (e1[o]) bn[o].y = a.rhs[gb + 1];
+        }
+      }
+    }
     tma::mbar_wait(bar0 + 8 * ms, (lp / G::NMS) & 1);
 
     const double *Pt = reinterpret_cast<const double *>(smem + ps * G::RT);
@@ -156,7 +171,9 @@ k_resid_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps tm
         const double2 pS = *reinterpret_cast<const double2 *>(Pc + so - HXP);
         const double pW = Pc[so - 1], pE = Pc[so + 2];
         const unsigned m = *reinterpret_cast<const unsigned short *>(Mc + rowof[o] * G::MXP + G::MX0 + cA);
-        const double2 rc = *reinterpret_cast<const double2 *>(Rc + (rowof[o] - 1) * TX + 2 * col2);
+        double2 rc;
+        if (REFRESH) rc = bc[o];
+        else rc = *reinterpret_cast<const double2 *>(Rc + (rowof[o] - 1) * TX + 2 * col2);
         double q0, q1;
         if (PARTS) {
           const unsigned pm = *reinterpret_cast<const unsigned short *>(PMc + (rowof[o] - 1) * TX + 2 * col2);
@@ -168,10 +185,10 @@ k_resid_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps tm
         }
         const long long g = gpc + gown0 + (long long)(y0 + rowof[o]) * L.px;
         double r0 = rc.x, r1 = rc.y;
-        r0 -= alpha * q0;                                               /* solver_kernel.cu:855 */
+        if (REFRESH) r0 -= q0; else r0 -= alpha * q0;                   /* solver_kernel.cu:897 / :855 */
         const double z0 = r0 * tab[m & 127u];                           /* :858 */
         if (e1[o]) {
-          r1 -= alpha * q1;
+          if (REFRESH) r1 -= q1; else r1 -= alpha * q1;
           const double z1 = r1 * tab[(m >> 8) & 127u];
           stg128(r + g, r0, r1);
           dot += r0 * z0; dot += r1 * z1;
@@ -195,7 +212,7 @@ k_resid_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps tm
   const int nblocks = gridDim.x * gridDim.y * gridDim.z;
   if (grid_reduce<1>(d, v, bid, nblocks, tot, false)) {
     rank_allreduce(d, tot, 1, true);          /* peers pull the r written here */
-    if (threadIdx.x == 0) finish_iteration(d, tot[0], false);
+    if (threadIdx.x == 0) finish_iteration(d, tot[0], REFRESH);
   }
 }
 

@@ -32,6 +32,7 @@
 struct SearchMaps {
   CUtensorMap r, p[2], fm, pm;       /* this block: halo'd f64 tiles, halo'd u8 mask tile, owned u8 pmask tile */
   CUtensorMap xo, ro;                /* owned (TX x TY) f64 tiles of x and r */
+  CUtensorMap xh;                    /* halo'd tile of x (refresh form of k_resid_tma) */
   CUtensorMap nb[6];                 /* neighbours' r: E,W = HY-run box on the 2-D compact face buffer, N,S = row box, T,B = tile box */
 };
 

@@ -79,6 +79,8 @@ struct bbpcg_solver {
   int taper_g10, taper_min;         /* guided chunking: t = remaining*columns*10 / (g10*slots), >= taper_min */
   int pdl;                          /* programmatic dependent launch of the two iteration kernels */
   int resid_mb, resid_d;            /* k_resid_tma: CTAs per SM the register budget is compiled for (2 or 3); TMA planes in flight */
+  int fast_refresh;                 /* q%50 refresh through k_refresh_x4 + the refresh form of k_resid_tma */
+  int rhs_tiled;                    /* PP_rhs through shared-memory transposes (default) or the row-walking kernel */
   int recompute;                    /* 64-B iteration: k_resid_tma re-applies the operator, q is never stored */
   int shared_device;                /* some peer rank lives on this same GPU (single-process harness) */
   SearchMaps maps[2];               /* tensor maps of k_search_tma for TY = 8 / TY = 4 */
@@ -173,6 +175,7 @@ static int build_search_maps_t(bbpcg_solver *s, SearchMaps *M)
   if (!rc) rc = make_map(&M->pm, d.pmask, d.L, true, G::TX, TY);
   if (!rc) rc = make_map(&M->xo, d.x, d.L, false, G::TX, TY);
   if (!rc) rc = make_map(&M->ro, d.r, d.L, false, G::TX, TY);
+  if (!rc) rc = make_map(&M->xh, d.x, d.L, false, G::HXP, G::HY);
   for (int f = 0; f < 6 && !rc; f++) {
     const NbrFace &nf = d.halo.f[f];
     if (!nf.r) { M->nb[f] = M->r; continue; }            /* never used: keeps the parameter well formed */
@@ -271,7 +274,7 @@ extern "C" int bbpcg_create(bbpcg_solver **out, const dom_struct *dom_rank, cons
   CU(cudaHostAlloc(&s->h_poll, 64, cudaHostAllocDefault));
   CU(cudaHostAlloc(&s->h_scal, sizeof(Scal), cudaHostAllocDefault));
   CU(cudaHostAlloc(&s->h_ztab, sizeof(int) * (BB_MAXZ + 1), cudaHostAllocDefault));
-  s->zt_cols = -1; s->taper_g10 = 0; s->taper_min = 8; s->pdl = 1; s->recompute = 1; s->resid_mb = 2; s->resid_d = 2;
+  s->zt_cols = -1; s->taper_g10 = 0; s->taper_min = 8; s->pdl = 1; s->recompute = 1; s->rhs_tiled = 1; s->fast_refresh = 1; s->resid_mb = 2; s->resid_d = 2;
   /* single rank: neighbours are this block itself (periodic wrap) or nothing */
   s->nranks = 1;
   for (int p = 0; p < BB_MAXR; p++) { s->peer_arena[p] = NULL; s->peer_opened[p] = false; }
@@ -490,8 +493,8 @@ static int launch_search_tma_t(bbpcg_solver *s, const SearchMaps &M)
 }
 
 /* the residual half of the recompute variant (bbpcg_resid_tma.cuh): same tiles and z-chunks as the search kernel */
-template <int TY, bool PARTS, int MB, int DD>
-static int launch_resid_tma_t(bbpcg_solver *s, const SearchMaps &M)
+template <int TY, bool PARTS, int MB, int DD, bool REFRESH>
+static int launch_resid_tma_t(bbpcg_solver *s, const SearchMaps &M, const real *rhs)
 {
   typedef ResidGeom<TY, PARTS, DD> G;
   const Layout &L = s->dev.L;
@@ -499,10 +502,10 @@ static int launch_resid_tma_t(bbpcg_solver *s, const SearchMaps &M)
   a.nbx = (L.in + G::TX - 1) / G::TX; a.nby = (L.jn + TY - 1) / TY;
   int rc = plan_zchunks(s, a.nbx * a.nby, s->sm_count * 2, &a.nbz);
   if (rc) return rc;
-  a.store_q = 0;
+  a.store_q = 0; a.rhs = rhs; a.s1b = s->fst.cs1b; a.s2b = s->fst.cs2b;
   static bool attr_set = false;
-  if (!attr_set) { CU(cudaFuncSetAttribute(k_resid_tma<TY, PARTS, MB, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM)); attr_set = true; }
-  CU(launch_k(s, k_resid_tma<TY, PARTS, MB, DD>, dim3(a.nbx, a.nby, a.nbz), G::NT, G::SMEM, true, s->dev, M, a));
+  if (!attr_set) { CU(cudaFuncSetAttribute(k_resid_tma<TY, PARTS, MB, DD, REFRESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM)); attr_set = true; }
+  CU(launch_k(s, k_resid_tma<TY, PARTS, MB, DD, REFRESH>, dim3(a.nbx, a.nby, a.nbz), G::NT, G::SMEM, !REFRESH, s->dev, M, a));
   s->launches++;
   return BBPCG_OK;
 }
@@ -511,15 +514,50 @@ static int launch_resid_tma(bbpcg_solver *s, bool parts)
 {
   const bool t8 = k_tiles[s->tile].ty == 8;
   const SearchMaps &M = s->maps[t8 ? 0 : 1];
-  if (parts) return t8 ? launch_resid_tma_t<8, true, 2, 2>(s, M) : launch_resid_tma_t<4, true, 2, 2>(s, M);
-  if (!t8) return launch_resid_tma_t<4, false, 3, 2>(s, M);
+  if (parts) return t8 ? launch_resid_tma_t<8, true, 2, 2, false>(s, M, NULL) : launch_resid_tma_t<4, true, 2, 2, false>(s, M, NULL);
+  if (!t8) return launch_resid_tma_t<4, false, 3, 2, false>(s, M, NULL);
   switch (s->resid_mb * 10 + s->resid_d) {
-    case 22: return launch_resid_tma_t<8, false, 2, 2>(s, M);
-    case 23: return launch_resid_tma_t<8, false, 2, 3>(s, M);
-    case 32: return launch_resid_tma_t<8, false, 3, 2>(s, M);
-    case 33: return launch_resid_tma_t<8, false, 3, 3>(s, M);
-    default: return launch_resid_tma_t<8, false, 2, 2>(s, M);
+    case 23: return launch_resid_tma_t<8, false, 2, 3, false>(s, M, NULL);
+    case 32: return launch_resid_tma_t<8, false, 3, 2, false>(s, M, NULL);
+    case 33: return launch_resid_tma_t<8, false, 3, 3, false>(s, M, NULL);
+    default: return launch_resid_tma_t<8, false, 2, 2, false>(s, M, NULL);
   }
+}
+
+/* true-residual refresh with the same tiles: r = b - (-A x) */
+static int launch_refresh_r_tma(bbpcg_solver *s, bool parts, const real *rhs)
+{
+  const bool t8 = k_tiles[s->tile].ty == 8;
+  const SearchMaps &M = s->maps[t8 ? 0 : 1];
+  if (parts) return t8 ? launch_resid_tma_t<8, true, 2, 2, true>(s, M, rhs) : launch_resid_tma_t<4, true, 2, 2, true>(s, M, rhs);
+  return t8 ? launch_resid_tma_t<8, false, 2, 2, true>(s, M, rhs) : launch_resid_tma_t<4, false, 2, 2, true>(s, M, rhs);
+}
+
+template <int XT, int UNR>
+static int launch_refresh_x4_t(bbpcg_solver *s)
+{
+  const Layout &L = s->dev.L;
+  constexpr int YT = 128 / XT;
+  ResidArgs a;
+  a.cpr = (L.in + 3) / 4;
+  a.ncb = (a.cpr + XT - 1) / XT;
+  const long long nrows = (long long)L.jn * L.kn;
+  const long long npass = (nrows + YT * UNR - 1) / (YT * UNR) * a.ncb;
+  if (npass > 0x7fffffffll) { bbpcg_set_error("block too large"); return BBPCG_EINVAL; }
+  a.npass = (int)npass;
+  a.ppc = 1;
+  if (a.npass > BB_MAXBLOCKS) a.ppc = (a.npass + BB_MAXBLOCKS - 1) / BB_MAXBLOCKS;
+  k_refresh_x4<XT, UNR><<<(a.npass + a.ppc - 1) / a.ppc, 128, 0, s->stream>>>(s->dev, a);
+  s->launches++;
+  return BBPCG_OK;
+}
+
+static int launch_refresh_x4(bbpcg_solver *s)
+{
+  const int cpr = (s->dev.L.in + 3) / 4;
+  if (cpr > 64) return launch_refresh_x4_t<128, 4>(s);
+  if (cpr > 32) return launch_refresh_x4_t<64, 4>(s);
+  return launch_refresh_x4_t<32, 4>(s);
 }
 
 static int launch_search(bbpcg_solver *s, bool parts)
@@ -568,11 +606,13 @@ static int preload_kernels()
   if (!rc) rc = preload_search<128, 8, 512, 2>();
   if (!rc) rc = preload_search<32, 8, 128, 4>();
   if (!rc) rc = preload_search<256, 4, 256, 2>();
-  PL(k_resid_tma<8, true, 2, 2>); PL(k_resid_tma<4, true, 2, 2>); PL(k_resid_tma<4, false, 3, 2>);
-  PL(k_resid_tma<8, false, 2, 2>); PL(k_resid_tma<8, false, 2, 3>);
-  PL(k_resid_tma<8, false, 3, 2>); PL(k_resid_tma<8, false, 3, 3>);
+  PL(k_resid_tma<8, true, 2, 2, false>); PL(k_resid_tma<4, true, 2, 2, false>); PL(k_resid_tma<4, false, 3, 2, false>);
+  PL(k_resid_tma<8, false, 2, 2, false>); PL(k_resid_tma<8, false, 2, 3, false>);
+  PL(k_resid_tma<8, false, 3, 2, false>); PL(k_resid_tma<8, false, 3, 3, false>);
+  PL(k_resid_tma<8, true, 2, 2, true>); PL(k_resid_tma<4, true, 2, 2, true>); PL(k_resid_tma<8, false, 2, 2, true>); PL(k_resid_tma<4, false, 2, 2, true>);
+  PL(k_refresh_x4<128, 4>); PL(k_refresh_x4<64, 4>); PL(k_refresh_x4<32, 4>);
   PL(k_resid<128, 4>); PL(k_resid<64, 4>); PL(k_resid<32, 4>); PL(k_refresh_x<256>); PL(k_refresh_r<256, false>); PL(k_refresh_r<256, true>);
-  PL(k_build_tab); PL(k_init<256>); PL(k_finish<256>); PL(k_rhs<256>); PL(k_masks<256>); PL(k_part_rhs_net);
+  PL(k_build_tab); PL(k_init<256>); PL(k_finish<256>); PL(k_rhs<256>); PL(k_rhs_tiled); PL(k_masks<256>); PL(k_part_rhs_net);
   PL(k_coeffs_refine<256>); PL(k_zero_ghosts); PL(k_xchg_send); PL(k_xchg_recv);
   PL(k_spmv_s3b<256, false>); PL(k_spmv_s3b<256, true>);
 #undef PL
@@ -630,8 +670,13 @@ static int enqueue_rhs(bbpcg_solver *s, const real *u, const real *v, const real
   const dom_struct &d = s->dom;
   CU(cudaMemsetAsync(rhs, 0, sizeof(real) * (size_t)d.Gcc.s3b, s->stream));            /* cuda_solver.cu:122 */
   const long long nrows = (long long)d.Gcc.jn * d.Gcc.kn;
-  k_rhs<256><<<clampi(nrows, 1, s->stream_blocks), 256, 0, s->stream>>>(d.Gcc.in, d.Gcc.jn, d.Gcc.kn, s->fst, u, v, w, rhs,
-                                                                        1. / d.dx, 1. / d.dy, 1. / d.dz, rho_f / dt);
+  if (s->rhs_tiled) {
+    const long long nb = (long long)((d.Gcc.in + RHS_TI - 1) / RHS_TI) * ((d.Gcc.jn + RHS_TJ - 1) / RHS_TJ) * ((d.Gcc.kn + RHS_TK - 1) / RHS_TK);
+    if (nb > 0x7fffffffll) { bbpcg_set_error("block too large"); return BBPCG_EINVAL; }
+    k_rhs_tiled<<<(unsigned)nb, 256, 0, s->stream>>>(d.Gcc.in, d.Gcc.jn, d.Gcc.kn, s->fst, u, v, w, rhs, 1. / d.dx, 1. / d.dy, 1. / d.dz, rho_f / dt);
+  } else
+    k_rhs<256><<<clampi(nrows, 1, s->stream_blocks), 256, 0, s->stream>>>(d.Gcc.in, d.Gcc.jn, d.Gcc.kn, s->fst, u, v, w, rhs,
+                                                                          1. / d.dx, 1. / d.dy, 1. / d.dz, rho_f / dt);
   s->launches++;
   return BBPCG_OK;
 }
@@ -698,11 +743,17 @@ static int enqueue_iteration(bbpcg_solver *s, int it, bool parts, const real *rh
   if (rc) return rc;
   if (kt) CU(cudaEventRecord(s->kev[2 * it - 1], s->stream));
   if (it % 50 == 0) {                                     /* cuda_solver.cu:209-223 */
-    const int nb = clampi(nrows, 1, s->stream_blocks);
-    k_refresh_x<256><<<nb, 256, 0, s->stream>>>(s->dev);
-    if (parts) k_refresh_r<256, true><<<nb, 256, 0, s->stream>>>(s->dev, rhs, s->fst.cs1b, s->fst.cs2b);
-    else k_refresh_r<256, false><<<nb, 256, 0, s->stream>>>(s->dev, rhs, s->fst.cs1b, s->fst.cs2b);
-    s->launches += 2;
+    if (recompute_active(s) && s->fast_refresh) {
+      rc = launch_refresh_x4(s);
+      if (!rc) rc = launch_refresh_r_tma(s, parts, rhs);
+      if (rc) return rc;
+    } else {
+      const int nb = clampi(nrows, 1, s->stream_blocks);
+      k_refresh_x<256><<<nb, 256, 0, s->stream>>>(s->dev);
+      if (parts) k_refresh_r<256, true><<<nb, 256, 0, s->stream>>>(s->dev, rhs, s->fst.cs1b, s->fst.cs2b);
+      else k_refresh_r<256, false><<<nb, 256, 0, s->stream>>>(s->dev, rhs, s->fst.cs1b, s->fst.cs2b);
+      s->launches += 2;
+    }
   } else {
     rc = recompute_active(s) ? launch_resid_tma(s, parts) : launch_resid(s);
     if (rc) return rc;
@@ -849,6 +900,8 @@ extern "C" int bbpcg_set_option(bbpcg_solver *s, const char *key, long long valu
   else if (!strcmp(key, "taper_min")) s->taper_min = clampi(value, 1, 4096);
   else if (!strcmp(key, "pdl")) s->pdl = value != 0;
   else if (!strcmp(key, "recompute")) s->recompute = value != 0;
+  else if (!strcmp(key, "rhs_tiled")) s->rhs_tiled = value != 0;
+  else if (!strcmp(key, "fast_refresh")) s->fast_refresh = value != 0;
   else if (!strcmp(key, "resid_mb")) s->resid_mb = value == 2 ? 2 : 3;
   else if (!strcmp(key, "resid_d")) s->resid_d = clampi(value, 2, 3);
   else if (!strcmp(key, "resid_blocks")) s->resid_blocks = clampi(value, 1, BB_MAXBLOCKS);

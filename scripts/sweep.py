@@ -57,6 +57,7 @@ def main():
                    "frac72": 72 * ncell / (us * 1e-6) / 1e9 / 6543.1,
                    "search_us": s.info("kt_search_ns") / max(s.info("kt_search_n"), 1) / 1e3,
                    "resid_us": s.info("kt_resid_ns") / max(s.info("kt_resid_n"), 1) / 1e3,
+                   "refresh_us": s.info("kt_refresh_ns") / max(s.info("kt_refresh_n"), 1) / 1e3,
                    "search_grid": s.info("search_grid"), "search_kc": s.info("search_kc")}
             print(json.dumps(rec), flush=True)
             f.write(json.dumps(rec) + "\n")

@@ -132,9 +132,10 @@ def test_recompute_variant_matches_stored_q(recompute, tile, blocks, parts):
     p.close()
 
 
-@pytest.mark.parametrize("opts", [{"taper_g10": 20, "taper_min": 4}, {"taper_g10": 10, "taper_min": 8}, {"kc": 1}, {"kc": 1000}, {"pdl": 0}])
+@pytest.mark.parametrize("opts", [{"taper_g10": 20, "taper_min": 4}, {"taper_g10": 10, "taper_min": 8}, {"kc": 1}, {"kc": 1000}, {"pdl": 0},
+                                  {"fast_refresh": 0}, {"rhs_tiled": 0}, {"fast_refresh": 0, "recompute": 0}])
 def test_zchunk_plans(opts):
-    case = Case((24, 20, 52), bc="cavity")
+    case = Case((24, 20, 52), bc="cavity")      # > 100 iterations: two true-residual refreshes
     p = _product(case, options=opts)
     _check_solve(case, p)
     p.close()
