@@ -44,6 +44,9 @@ for p in (ROOT, os.path.join(ROOT, "bluebottle-3.0_b200"), os.path.join(ROOT, "t
 BYTES_SEARCH = {0: 48, 1: 40}
 BYTES_RESID = 24
 BYTES_ITER = 72
+# solve epilogue: project 8 (phi) + 24 (u*,v*,w*) + 12 (int flags) + 24 (u,v,w) = 68; update_p 8 (p0) + 4 (phase) + 8 (p) = 20;
+# mean subtraction 16 (p read + write): 104 B per cell
+BYTES_EPILOGUE = 104
 BLOCKS_FOR = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}
 
 
@@ -63,6 +66,7 @@ def parse():
     ap.add_argument("--fixed-iters", type=int, default=0, help=">0: fixed iteration count per step, no stop test")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-epilogue", action="store_true", help="skip the solve-epilogue measurement (project + update_p)")
     ap.add_argument("--no-comm-split", action="store_true", help="N > 1: skip the exposed halo/all-reduce measurement")
     ap.add_argument("--cpu-sample-grid", type=int, default=256)
     ap.add_argument("--cpu-sample-iters", type=int, default=20)
@@ -361,6 +365,29 @@ def run_bbpcg(args):
                "api": "bbpcg_solve_host (C ABI): u*,v*,w* pinned host -> device, solve, phi -> pinned host"}
         del hu, hv, hw, hphi
 
+    # ---- the solve epilogue: exchange(phi) + dom_BC_p + cuda_project + cuda_update_p, one fused
+    # call per step; reported beside the headline, not part of `value` -------------------------------------
+    epi = None
+    if not args.no_epilogue:
+        from bbpcg.grid import grid_shape
+        fu, fv, fw = synth.flags_noparts_torch(dom, dec.DOM, dec.bc, dev)
+        un, vn, wn, pn = s.empty("Gfx"), s.empty("Gfy"), s.empty("Gfz"), s.empty("Gcc")
+        p0 = torch.rand(grid_shape(dom, "Gcc"), dtype=torch.float64, device=dev)
+        phase = torch.full(grid_shape(dom, "Gcc"), -1, dtype=torch.int32, device=dev)
+        ea = (phi, u, v, wz, fu, fv, fw, un, vn, wn, p0, phase, pn)
+        s.epilogue(*ea)
+        w.barrier()
+        n_epi = 5
+        ms_epi = sum(s.epilogue(*ea) for _ in range(n_epi)) / n_epi
+        ms_epi = w.max(ms_epi)
+        gbs = BYTES_EPILOGUE * ncell_rank / (ms_epi * 1e-3) / 1e9
+        epi = {"ms_per_call": ms_epi, "calls_timed": n_epi, "launches_per_call": 5, "bound": "hbm",
+               "algorithmic_bytes_per_cell": BYTES_EPILOGUE, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+               "what": "bbpcg_epilogue (C ABI): mpi_cuda_exchange_Gcc(phi) + cuda_dom_BC_p(phi) + cuda_project + cuda_update_p "
+                       "(src/bluebottle.c:233-250) as k_xchg_send/recv + k_bc_p + k_epilogue + k_sub_mean; CUDA events on the solver stream",
+               "mean_p_after": float(pn[1:-1, 1:-1, 1:-1].mean())}
+        del fu, fv, fw, un, vn, wn, pn, p0, phase
+
     out = {"metric": "Poisson PCG iterations/s (FP64, %d^3)" % args.grid if args.scaling == "strong" else
            "Poisson PCG iterations/s (FP64, %d^3 per GPU)" % args.grid,
            "value": value, "unit": "PCG iterations/s", "n_gpus": w.size, "steps": args.steps, "warmup": args.warmup,
@@ -373,7 +400,7 @@ def run_bbpcg(args):
                       "fixed_iters": args.fixed_iters},
            "impl": "bbpcg", "gpu_launches": int(launches_all), "e2e": e2e, "roofline": roof, "roofline_resid": roof2,
            "roofline_iteration": roof_it, "comm": comm, "clocks": clk, "wall_ms_per_step": wall_ms / args.steps,
-           "setup_ms_per_step": ms_setup / args.steps,
+           "setup_ms_per_step": ms_setup / args.steps, "epilogue": epi,
            "hbm_gbs_72B_model_whole_step": BYTES_ITER * ncell_glob * value / w.size / 1e9}
     if w.rank == 0 and w.size == 1 and not args.no_cpu_baseline:
         try:
@@ -472,6 +499,21 @@ def run_reference(args):
     value = iters / (tot_ms * 1e-3)
     ncell = cells[0] * cells[1] * cells[2]
     peak, peak_src = measured_peak()
+    epi = None
+    if not args.no_epilogue and hasattr(lib, "bbref_epilogue"):
+        # the reference's own epilogue kernels on the phi its solve left on the device (src/bluebottle.c:233-250)
+        hp0 = torch.rand(grid_shape(dom, "Gcc"), dtype=torch.float64).pin_memory()
+        pbc = (C.c_int * 6)(*BC_SETS[args.bc])
+        ems = C.c_float()
+        tot_e, n_epi = 0.0, 3
+        for i in range(n_epi + 1):
+            assert lib.bbref_epilogue(None, P(hp0), C.cast(pbc, C.c_void_p), 1.0, 1e-3, 0.01, None, None, None, None, None, C.byref(ems)) == 0
+            if i:
+                tot_e += ems.value
+        epi = {"ms_per_call": tot_e / n_epi, "calls_timed": n_epi, "algorithmic_bytes_per_cell": BYTES_EPILOGUE,
+               "achieved": BYTES_EPILOGUE * ncell / (tot_e / n_epi * 1e-3) / 1e9, "unit": "GB/s",
+               "what": "the reference's pack/unpack + BC_p_*_N + project_u/v/w + update_p_laplacian + update_p + copy_p_p_noghost + "
+                       "thrust::reduce + forcing_add_c_const, host sequence of cuda_bluebottle.cu:2495-2589 (CUDA events, default stream)"}
     out = dict(base, value=value, ms_per_step=tot_ms / args.steps,
                config={"workload": "synthetic FP64 pressure-Poisson, %dx%dx%d cells, %s boundary set, the reference's own "
                                    "cuda_PP_init_jacobi_preconditioner + cuda_PP_cg_noparts, unmodified kernels recompiled for "
@@ -485,7 +527,7 @@ def run_reference(args):
                     "steps": k_e2e, "ms_per_step": ms_e / k_e2e},
                roofline_iteration={"bound": "hbm", "achieved": BYTES_ITER * ncell * value / 1e9, "peak": peak, "unit": "GB/s",
                                    "frac": BYTES_ITER * ncell * value / 1e9 / peak, "model": "72 B/cell/iteration, whole step"},
-               clocks=clk, gpus_used=1)
+               clocks=clk, gpus_used=1, epilogue=epi)
     print(json.dumps(out))
 
 

@@ -39,15 +39,24 @@ class SolveArgs(C.Structure):
                 ("part_bc", PART_BC_FN)]
 
 
+class EpilogueArgs(C.Structure):
+    _fields_ = [("u_star", C.c_void_p), ("v_star", C.c_void_p), ("w_star", C.c_void_p),
+                ("flag_u", C.c_void_p), ("flag_v", C.c_void_p), ("flag_w", C.c_void_p),
+                ("phi", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("w", C.c_void_p),
+                ("p0", C.c_void_p), ("phase", C.c_void_p), ("p", C.c_void_p),
+                ("rho_f", C.c_double), ("dt", C.c_double), ("phi_ghosts_valid", C.c_int)]
+
+
 # every symbol include/bbpcg.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "bb_domain_read", "bb_domain_fill", "bb_domain_split", "bb_domain_write_decomp", "bb_domain_free",
     "bbpcg_create", "bbpcg_destroy", "bbpcg_comm_export", "bbpcg_comm_import", "bbpcg_set_coefficients",
     "bbpcg_solve", "bbpcg_solve_host", "bbpcg_history", "bbpcg_exchange_Gcc", "bbpcg_rhs", "bbpcg_spmv",
     "bbpcg_set_option", "bbpcg_get_info", "bbpcg_last_error", "bbpcg_version",
+    "bbpcg_dom_BC_p", "bbpcg_epilogue",
 ]
 DROPIN_SYMBOLS = ["cuda_PP_init_jacobi_preconditioner", "cuda_PP_cg", "cuda_PP_cg_noparts", "cuda_PP_cg_timed",
-                  "mpi_cuda_exchange_Gcc", "bbpcg_dropin_finalize"]
+                  "mpi_cuda_exchange_Gcc", "cuda_dom_BC_p", "cuda_project", "cuda_update_p", "bbpcg_dropin_finalize"]
 
 _lib = None
 
@@ -81,6 +90,8 @@ def load_library():
     lib.bbpcg_exchange_Gcc.argtypes = [vp, vp]
     lib.bbpcg_rhs.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp]
     lib.bbpcg_spmv.argtypes = [vp, vp, vp, C.c_int]
+    lib.bbpcg_dom_BC_p.argtypes = [vp, vp]
+    lib.bbpcg_epilogue.argtypes = [vp, C.POINTER(EpilogueArgs), dp]
     lib.bbpcg_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
     lib.bbpcg_get_info.argtypes = [vp, C.c_char_p]
     lib.bbpcg_get_info.restype = C.c_longlong

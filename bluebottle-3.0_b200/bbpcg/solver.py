@@ -4,6 +4,9 @@
 `PoissonSolver.init_jacobi_preconditioner` = cuda_PP_init_jacobi_preconditioner (src/cuda_solver.cu:31-36)
 `PoissonSolver.PP_cg / PP_cg_noparts`      = cuda_PP_cg / cuda_PP_cg_noparts (src/cuda_solver.cu:38-300,573-761)
 `PoissonSolver.exchange_Gcc`               = mpi_cuda_exchange_Gcc (src/mpi_comm.c:257-315)
+`PoissonSolver.dom_BC_p`                   = cuda_dom_BC_p (src/cuda_bluebottle.cu:2536-2589)
+`PoissonSolver.project / update_p`         = cuda_project / cuda_update_p (src/cuda_bluebottle.cu:2495-2534)
+`PoissonSolver.epilogue`                   = the sequence src/bluebottle.c:233-256 runs on phi, fused
 
 Array arguments are torch CUDA tensors in the reference's ghosted layouts (grid.grid_shape).
 """
@@ -221,6 +224,33 @@ class PoissonSolver:
     def exchange_Gcc(self, array):
         self._sync_caller_stream()
         L.check(self.lib.bbpcg_exchange_Gcc(self.h, _ptr(array)), "bbpcg_exchange_Gcc")
+
+    def dom_BC_p(self, array):
+        self._sync_caller_stream()
+        L.check(self.lib.bbpcg_dom_BC_p(self.h, _ptr(array)), "bbpcg_dom_BC_p")
+
+    def epilogue(self, phi, u_star=None, v_star=None, w_star=None, flag_u=None, flag_v=None, flag_w=None,
+                 u=None, v=None, w=None, p0=None, phase=None, p=None, rho_f=1.0, dt=1e-3, phi_ghosts_valid=False):
+        """[exchange_Gcc(phi); dom_BC_p(phi);] cuda_project; cuda_update_p.  u=None skips the projection,
+        p=None the pressure update.  Returns the device milliseconds of the call."""
+        a = L.EpilogueArgs()
+        for k, t in (("u_star", u_star), ("v_star", v_star), ("w_star", w_star), ("flag_u", flag_u), ("flag_v", flag_v),
+                     ("flag_w", flag_w), ("phi", phi), ("u", u), ("v", v), ("w", w), ("p0", p0), ("phase", phase), ("p", p)):
+            setattr(a, k, None if t is None else t.data_ptr())
+        a.rho_f, a.dt, a.phi_ghosts_valid = rho_f, dt, int(phi_ghosts_valid)
+        ms = C.c_double()
+        self._sync_caller_stream()
+        L.check(self.lib.bbpcg_epilogue(self.h, C.byref(a), C.byref(ms)), "bbpcg_epilogue")
+        return ms.value
+
+    def project(self, u_star, v_star, w_star, phi, flag_u, flag_v, flag_w, u, v, w, rho_f=1.0, dt=1e-3):
+        """cuda_project(): phi's ghost faces must be current (exchange_Gcc + dom_BC_p), as in bluebottle.c:233-237."""
+        return self.epilogue(phi, u_star, v_star, w_star, flag_u, flag_v, flag_w, u, v, w, rho_f=rho_f, dt=dt,
+                             phi_ghosts_valid=True)
+
+    def update_p(self, p0, phi, phase, p):
+        """cuda_update_p(): p = (phase < 0)(p0 + phi) - global mean."""
+        return self.epilogue(phi, p0=p0, phase=phase, p=p, phi_ghosts_valid=True)
 
     def rhs(self, u_star, v_star, w_star, rhs_p, rho_f=1.0, dt=1e-3):
         self._sync_caller_stream()

@@ -22,6 +22,7 @@ extern real rho_f, dt, pp_residual, ttime;    /* src/bluebottle.h:524,560,572,24
 extern int pp_max_iter, stepnum;              /* src/bluebottle.h:2389,2487 */
 extern int NPARTS, nparts;                    /* src/particle.h:319,331 */
 extern real *_u_star, *_v_star, *_w_star, *_rhs_p, *_phi;
+extern real *_u, *_v, *_w, *_p, *_p0;         /* src/bluebottle.h:961,1037,1137-1161 (epilogue) */
 extern int *_flag_u, *_flag_v, *_flag_w, *_phase, *_phase_shell;
 void cuda_part_BC_p(void);                    /* src/cuda_particle.cu:1680 */
 void recorder_PP(char *name, int niter, real resid, real etime);   /* src/recorder.c:190 */
@@ -109,5 +110,26 @@ extern "C" void mpi_cuda_exchange_Gcc(real *array)
   cudaDeviceSynchronize();
   if (bbpcg_exchange_Gcc(solver(), array)) die("bbpcg_exchange_Gcc");
 }
+
+/* ---- solve epilogue, src/bluebottle.c:233-256 ---- */
+extern "C" void cuda_dom_BC_p(real *array)                  /* src/cuda_bluebottle.cu:2536-2589 */
+{
+  cudaDeviceSynchronize();
+  if (bbpcg_dom_BC_p(solver(), array)) die("bbpcg_dom_BC_p");
+}
+
+static void epilogue(int project, int update)
+{
+  bbpcg_epilogue_args a;
+  memset(&a, 0, sizeof(a));
+  a.phi = _phi; a.rho_f = rho_f; a.dt = dt;
+  a.phi_ghosts_valid = 1;                                   /* the caller ran mpi_cuda_exchange_Gcc(_phi); cuda_dom_BC_p(_phi) (bluebottle.c:233-234) */
+  if (project) { a.u_star = _u_star; a.v_star = _v_star; a.w_star = _w_star; a.flag_u = _flag_u; a.flag_v = _flag_v; a.flag_w = _flag_w; a.u = _u; a.v = _v; a.w = _w; }
+  if (update) { a.p0 = _p0; a.phase = _phase; a.p = _p; }
+  cudaDeviceSynchronize();
+  if (bbpcg_epilogue(solver(), &a, NULL)) die("bbpcg_epilogue");
+}
+extern "C" void cuda_project(void) { epilogue(1, 0); }      /* src/cuda_bluebottle.cu:2495-2503 */
+extern "C" void cuda_update_p(void) { epilogue(0, 1); }     /* src/cuda_bluebottle.cu:2505-2534 */
 
 extern "C" void bbpcg_dropin_finalize(void) { bbpcg_destroy(g_solver); g_solver = NULL; }

@@ -1,0 +1,193 @@
+/* bbpcg_epilogue.cuh -- the solve EPILOGUE: what src/bluebottle.c:233-256 runs on phi right
+ * after cuda_PP_cg, fused into one pass over the block.
+ *
+ *   cuda_dom_BC_p(phi)   src/cuda_bluebottle.cu:2536-2589, BC_p_{W,E,S,N,B,T}_N src/bluebottle_kernel.cu:26-102
+ *                        -> k_bc_p: Neumann ghost copy on the faces that have no neighbour
+ *   cuda_project()       src/cuda_bluebottle.cu:2495-2503, project_{u,v,w} src/bluebottle_kernel.cu:2303-2355
+ *   cuda_update_p()      src/cuda_bluebottle.cu:2505-2534, update_p src/bluebottle_kernel.cu:2385-2402 (the Laplacian of
+ *                        :2357-2383 is computed by the reference but NOT used, :2396 vs :2399), copy_p_p_noghost +
+ *                        thrust::reduce + MPI_Allreduce (mean), forcing_add_c_const(-pmean) :1507-1518
+ *                        -> k_epilogue<PROJECT, UPDATE_P> + k_sub_mean
+ *
+ * The reference walks each face grid with its SLOW index in the inner loop (project_u: threads over (j,k), loop over i),
+ * so phi is read with a stride of a row per lane, three times, and update_p adds a cudaMalloc'ed Laplacian pass, a
+ * ghost-free copy, a Thrust reduction and a host MPI_Allreduce.  Here a CTA owns a 16^3 tile of cells: phi is staged
+ * once in shared memory (18^3 with the halo), and u*, v*, w*, the flags and the outputs are each touched in THEIR
+ * fastest index (Gfx: j, Gfy: k, Gfz/Gcc: i) as 128-byte runs.  The mean of p is a deterministic grid + rank reduction
+ * whose result stays on the device.
+ *
+ * Algorithmic traffic per cell: project 8 (phi) + 24 (u*,v*,w*) + 12 (int flags) + 24 (u,v,w) = 68 B;
+ * update_p 8 (p0) + 4 (phase) + 8 (p) = 20 B fused (phi is already on chip) + 16 B for the mean subtraction.
+ */
+#ifndef BBPCG_EPILOGUE_CUH
+#define BBPCG_EPILOGUE_CUH
+
+#include "bbpcg_kernels.cuh"
+
+#define EPI_T 16                       /* tile edge (cells) */
+#define EPI_H (EPI_T + 2)              /* with the halo */
+#define EPI_SJ 19                      /* smem row pitch: odd, so 16 lanes varying j hit 16 different bank pairs */
+#define EPI_SK (EPI_H * EPI_SJ + 1)    /* smem plane pitch: odd as well (lanes varying k) */
+#define EPI_SMEM (EPI_H * EPI_SK * 8)
+
+struct EpiArgs {
+  const double *u_star, *v_star, *w_star;     /* Gfx / Gfy / Gfz s3b */
+  const int *flag_u, *flag_v, *flag_w;
+  double *u, *v, *w;
+  const double *phi;                          /* Gcc s3b, ghost FACES valid */
+  const double *p0;  const int *phase;  double *p;
+  double ddx, ddy, ddz;                       /* 1/dx ... (cuda_bluebottle.cu:2498-2502) */
+  double dt_rho;                              /* dt / rho_f, evaluated first as in project_u (bluebottle_kernel.cu:2316) */
+  int nti, ntj, ntk;                          /* tiles per direction */
+};
+
+/* cuda_dom_BC_p: ghost = adjacent interior cell on every face in `faces` (bit f: 0 E, 1 W, 2 N, 3 S, 4 T, 5 B), j/k/i
+ * ranges 1..n as in BC_p_*_N (faces only, no edges) */
+__global__ void k_bc_p(int in, int jn, int kn, int s1b, int s2b, double *__restrict__ a, unsigned faces)
+{
+  const long long fi = (long long)jn * kn, fj = (long long)in * kn, fk = (long long)in * jn;
+  const long long total = 2 * (fi + fj + fk);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    long long u = t;
+    int f; long long pp;
+    if (u < 2 * fi) { f = (int)(u / fi); pp = u % fi; }
+    else if ((u -= 2 * fi) < 2 * fj) { f = 2 + (int)(u / fj); pp = u % fj; }
+    else { u -= 2 * fj; f = 4 + (int)(u / fk); pp = u % fk; }
+    if (!((faces >> f) & 1u)) continue;
+    int i, j, k, gi, gj, gk;
+    if (f < 2) { j = gj = (int)(pp % jn) + 1; k = gk = (int)(pp / jn) + 1; i = (f == 0) ? in : 1; gi = (f == 0) ? in + 1 : 0; }
+    else if (f < 4) { i = gi = (int)(pp % in) + 1; k = gk = (int)(pp / in) + 1; j = (f == 2) ? jn : 1; gj = (f == 2) ? jn + 1 : 0; }
+    else { i = gi = (int)(pp % in) + 1; j = gj = (int)(pp / in) + 1; k = (f == 4) ? kn : 1; gk = (f == 4) ? kn + 1 : 0; }
+    a[gi + (long long)gj * s1b + (long long)gk * s2b] = a[i + (long long)j * s1b + (long long)k * s2b];
+  }
+}
+
+
+/* (element indices are ints, as everywhere in the reference: every s3b of grid_info is an int)
+ * one thread's line of faces: all loads of a batch are issued before the first store (the outputs never alias the
+ * inputs: _u and _u_star are distinct arrays in the reference, src/bluebottle.h:1088,1137) */
+#define EPI_NB 9
+__device__ __forceinline__ void project_line(const double *__restrict__ star, const int *__restrict__ flag, double *__restrict__ out,
+                                             int c0, int cstride, int nf, const double *ph, int pstride,
+                                             double dd, double dt_rho)
+{
+  for (int f0 = 0; f0 < nf; f0 += EPI_NB) {
+    asm volatile("" ::: "memory");            /* keep the batches apart: one batch of loads in flight per thread, not all phases' */
+    double sv[EPI_NB]; int fv[EPI_NB];
+#pragma unroll
+    for (int b = 0; b < EPI_NB; b++) {
+      if (f0 + b < nf) { const int c = c0 + (f0 + b) * cstride; sv[b] = __ldg(star + c); fv[b] = __ldg(flag + c); }
+    }
+#pragma unroll
+    for (int b = 0; b < EPI_NB; b++) {
+      if (f0 + b < nf) {
+        const int f = f0 + b;
+        const double gradPhi = abs(fv[b]) * dd * (ph[(f + 1) * pstride] - ph[f * pstride]);   /* bluebottle_kernel.cu:2315,2333,2351 */
+        out[c0 + f * cstride] = (sv[b] - dt_rho * gradPhi);                          /* :2316,2334,2352 */
+      }
+    }
+  }
+}
+
+/* project_u / project_v / project_w / update_p on one 16^3 tile per loop trip.
+ * Face ownership: a tile writes the W, S and B faces of its cells; the last tile of a direction also writes the closing
+ * face (i = in+1 etc.), so every face of Gf?._is.._ie is written exactly once (project_u loops i = _is.._ie = 1..in+1). */
+template <bool PROJECT, bool UPDATE_P>
+__global__ void __launch_bounds__(256, 3) k_epilogue(const __grid_constant__ Dev d, const FaceStrides st, const EpiArgs a)
+{
+  extern __shared__ __align__(16) double sphi[];           /* [kk][jj][ii] at kk*EPI_SK + jj*EPI_SJ + ii: cell (i0-1+ii, ...) */
+  const int in = d.L.in, jn = d.L.jn, kn = d.L.kn;
+  const int t = threadIdx.x;
+  const int lo = t & 15, hi = t >> 4;                      /* fast / slow lane coordinate of every phase */
+  const long long ntiles = (long long)a.nti * a.ntj * a.ntk;
+  double psum = 0.;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int bi = (int)(tile % a.nti), bj = (int)((tile / a.nti) % a.ntj), bk = (int)(tile / ((long long)a.nti * a.ntj));
+    const int i0 = bi * EPI_T + 1, j0 = bj * EPI_T + 1, k0 = bk * EPI_T + 1;
+    const int ni = min(EPI_T, in - i0 + 1), nj = min(EPI_T, jn - j0 + 1), nk = min(EPI_T, kn - k0 + 1);
+    __syncthreads();                                       /* previous tile's readers are done */
+    /* ---- phi tile with its halo: rows of ni+2 contiguous values ---- */
+    {
+      const int wi = ni + 2, wj = nj + 2, wk = nk + 2;
+      const int total = wi * wj * wk;
+      for (int e = t; e < total; e += 256) {
+        const int ii = e % wi, jj = (e / wi) % wj, kk = e / (wi * wj);
+        sphi[kk * EPI_SK + jj * EPI_SJ + ii] =
+            a.phi[(i0 - 1 + ii) + (long long)(j0 - 1 + jj) * st.cs1b + (long long)(k0 - 1 + kk) * st.cs2b];
+      }
+    }
+    __syncthreads();
+    if (PROJECT) {
+      /* u (Gfx, j fastest): lanes (j, k), walk the faces i';  v (Gfy, k fastest): lanes (k, i), walk j';
+       * w (Gfz, i fastest): lanes (i, j), walk k'.  One copy of the line code (the phase loop is NOT unrolled: three
+       * inlined copies made ptxas keep all three batches live, 158 registers). */
+#pragma unroll 1
+      for (int phase = 0; phase < 3; phase++) {
+        const double *star; const int *flag; double *out; const double *ph;
+        int c0, cstride, nf, pstride, nlo, nhi; double dd;
+        if (phase == 0) {
+          star = a.u_star; flag = a.flag_u; out = a.u; dd = a.ddx; nlo = nj; nhi = nk;
+          c0 = (j0 + lo) + (k0 + hi) * st.us1b + i0 * st.us2b; cstride = st.us2b; nf = ni + (i0 + ni - 1 == in ? 1 : 0);
+          ph = sphi + (hi + 1) * EPI_SK + (lo + 1) * EPI_SJ; pstride = 1;
+        } else if (phase == 1) {
+          star = a.v_star; flag = a.flag_v; out = a.v; dd = a.ddy; nlo = nk; nhi = ni;
+          c0 = (k0 + lo) + (i0 + hi) * st.vs1b + j0 * st.vs2b; cstride = st.vs2b; nf = nj + (j0 + nj - 1 == jn ? 1 : 0);
+          ph = sphi + (lo + 1) * EPI_SK + (hi + 1); pstride = EPI_SJ;
+        } else {
+          star = a.w_star; flag = a.flag_w; out = a.w; dd = a.ddz; nlo = ni; nhi = nj;
+          c0 = (i0 + lo) + (j0 + hi) * st.ws1b + k0 * st.ws2b; cstride = st.ws2b; nf = nk + (k0 + nk - 1 == kn ? 1 : 0);
+          ph = sphi + (hi + 1) * EPI_SJ + (lo + 1); pstride = EPI_SK;
+        }
+        if (lo < nlo && hi < nhi) project_line(star, flag, out, c0, cstride, nf, ph, pstride, dd, a.dt_rho);
+      }
+    }
+    if (UPDATE_P) {
+      /* ---- p = (phase < 0)(p0 + phi) on the cells of the tile (Gcc, i fastest); partial sum for the mean ---- */
+      const int i = i0 + lo, j = j0 + hi;
+      if (lo < ni && hi < nj) {
+        const int base = i + j * st.cs1b + k0 * st.cs2b;
+        const double *ph = sphi + EPI_SK + (hi + 1) * EPI_SJ + (lo + 1);
+        const double *__restrict__ p0 = a.p0;
+        const int *__restrict__ phase = a.phase;
+        double *__restrict__ p = a.p;
+        for (int f0 = 0; f0 < nk; f0 += 8) {
+          double pv[8]; int fv[8];
+#pragma unroll
+          for (int b = 0; b < 8; b++) if (f0 + b < nk) { const int c = base + (f0 + b) * st.cs2b; pv[b] = __ldg(p0 + c); fv[b] = __ldg(phase + c); }
+#pragma unroll
+          for (int b = 0; b < 8; b++) {
+            if (f0 + b < nk) {
+              const double val = (fv[b] < 0) * (pv[b] + ph[(f0 + b) * EPI_SK]);        /* bluebottle_kernel.cu:2396 */
+              p[base + (f0 + b) * st.cs2b] = val;
+              psum += val;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (UPDATE_P) {
+    /* mean pressure: thrust::reduce + MPI_Allreduce of cuda_bluebottle.cu:2524-2527, kept on the device */
+    double v[1] = { psum }, tot[1];
+    if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, false)) {
+      rank_allreduce(d, tot, 1, false);
+      if (threadIdx.x == 0) d.sc->p_sum = tot[0];
+    }
+  }
+}
+
+/* forcing_add_c_const(-pmean, p), src/bluebottle_kernel.cu:1507-1518: interior cells only.
+ * pmean = sum / DOM.Gcc.s3 (cuda_bluebottle.cu:2528). */
+__global__ void __launch_bounds__(256) k_sub_mean(const __grid_constant__ Dev d, double *__restrict__ p, int s1b, int s2b, double global_cells)
+{
+  const int in = d.L.in, jn = d.L.jn;
+  const long long nrows = (long long)jn * d.L.kn;
+  const double val = -(d.sc->p_sum / global_cells);
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int j = (int)(row % jn) + 1, k = (int)(row / jn) + 1;
+    double *pr = p + (long long)j * s1b + (long long)k * s2b;
+    for (int i = threadIdx.x + 1; i <= in; i += 256) pr[i] += val;
+  }
+}
+
+#endif

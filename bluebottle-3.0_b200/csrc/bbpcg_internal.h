@@ -131,6 +131,7 @@ struct Scal {
   int comm_timeout;     /* set if a peer never showed up                  */
   int pad0, pad1;
   unsigned long long seq;   /* publish counter, never reset               */
+  double p_sum;         /* epilogue: sum of p over all ranks' interior cells (cuda_bluebottle.cu:2524-2527) */
 };
 
 /* where this block's boundary values go: the neighbour's (or, for a periodic wrap onto the

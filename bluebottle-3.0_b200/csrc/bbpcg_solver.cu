@@ -16,6 +16,7 @@
 #include "bbpcg_kernels.cuh"
 #include "bbpcg_search_tma.cuh"
 #include "bbpcg_resid_tma.cuh"
+#include "bbpcg_epilogue.cuh"
 
 /* ---- error plumbing ---------------------------------------------------------------------- */
 static thread_local char g_err[512] = "";
@@ -615,6 +616,7 @@ static int preload_kernels()
   PL(k_build_tab); PL(k_init<256>); PL(k_finish<256>); PL(k_rhs<256>); PL(k_rhs_tiled); PL(k_masks<256>); PL(k_part_rhs_net);
   PL(k_coeffs_refine<256>); PL(k_zero_ghosts); PL(k_xchg_send); PL(k_xchg_recv);
   PL(k_spmv_s3b<256, false>); PL(k_spmv_s3b<256, true>);
+  PL(k_bc_p); PL(k_epilogue<true, true>); PL(k_epilogue<true, false>); PL(k_epilogue<false, true>); PL(k_sub_mean);
 #undef PL
   return rc;
 }
@@ -730,6 +732,90 @@ extern "C" int bbpcg_spmv(bbpcg_solver *s, const real *src_s3b, real *Ap_s3, int
   s->launches++;
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(s->stream));
+  return BBPCG_OK;
+}
+
+/* ---- solve epilogue: cuda_dom_BC_p / cuda_project / cuda_update_p (bbpcg_epilogue.cuh) ------- */
+static unsigned neumann_wall_faces(const bbpcg_solver *s)
+{
+  /* cuda_dom_BC_p: `dom[rank].w == MPI_PROC_NULL` and `bc.pW == NEUMANN` (cuda_bluebottle.cu:2541-2587) */
+  const int bct[6] = { s->bc.pE, s->bc.pW, s->bc.pN, s->bc.pS, s->bc.pT, s->bc.pB };
+  unsigned m = 0;
+  for (int f = 0; f < 6; f++) if (nbr_rank(s->dom, f) < 0 && bct[f] == BB_NEUMANN) m |= 1u << f;
+  return m;
+}
+
+static int enqueue_bc_p(bbpcg_solver *s, real *array)
+{
+  const unsigned faces = neumann_wall_faces(s);
+  if (!faces) return BBPCG_OK;
+  const Layout &L = s->dev.L;
+  const long long total = 2ll * ((long long)L.jn * L.kn + (long long)L.in * L.kn + (long long)L.in * L.jn);
+  k_bc_p<<<clampi((total + 255) / 256, 1, s->sm_count * 8), 256, 0, s->stream>>>(L.in, L.jn, L.kn, s->fst.cs1b, s->fst.cs2b, array, faces);
+  s->launches++;
+  return BBPCG_OK;
+}
+
+extern "C" int bbpcg_dom_BC_p(bbpcg_solver *s, real *array)
+{
+  if (!s || !array) { bbpcg_set_error("bbpcg_dom_BC_p: NULL argument"); return BBPCG_EINVAL; }
+  CU(cudaSetDevice(s->device));
+  int rc = enqueue_bc_p(s, array);
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  return BBPCG_OK;
+}
+
+extern "C" int bbpcg_epilogue(bbpcg_solver *s, const bbpcg_epilogue_args *a, double *ms_out)
+{
+  if (!s || !a || !a->phi) { bbpcg_set_error("bbpcg_epilogue: NULL argument"); return BBPCG_EINVAL; }
+  const bool project = a->u != NULL, update = a->p != NULL;
+  if (project && (!a->v || !a->w || !a->u_star || !a->v_star || !a->w_star || !a->flag_u || !a->flag_v || !a->flag_w)) {
+    bbpcg_set_error("bbpcg_epilogue: cuda_project needs u,v,w, u*,v*,w* and the three flag arrays"); return BBPCG_EINVAL;
+  }
+  if (update && (!a->p0 || !a->phase)) { bbpcg_set_error("bbpcg_epilogue: cuda_update_p needs p0 and phase"); return BBPCG_EINVAL; }
+  if (!project && !update) { bbpcg_set_error("bbpcg_epilogue: nothing to do (u == NULL and p == NULL)"); return BBPCG_EINVAL; }
+  if (s->nranks == 1 && s->DOM.In * s->DOM.Jn * s->DOM.Kn != 1) { bbpcg_set_error("decomposition has %d blocks: call bbpcg_comm_import first", s->DOM.In * s->DOM.Jn * s->DOM.Kn); return BBPCG_ECOMM; }
+  CU(cudaSetDevice(s->device));
+  const dom_struct &d = s->dom;
+  const Layout &L = s->dev.L;
+  CU(cudaEventRecord(s->ev[0], s->stream));
+  if (!a->phi_ghosts_valid) {                               /* bluebottle.c:233-234 */
+    int rc = enqueue_exchange(s, a->phi);
+    if (!rc) rc = enqueue_bc_p(s, a->phi);
+    if (rc) return rc;
+  }
+  EpiArgs e;
+  memset(&e, 0, sizeof(e));
+  e.u_star = a->u_star; e.v_star = a->v_star; e.w_star = a->w_star;
+  e.flag_u = a->flag_u; e.flag_v = a->flag_v; e.flag_w = a->flag_w;
+  e.u = a->u; e.v = a->v; e.w = a->w; e.phi = a->phi; e.p0 = a->p0; e.phase = a->phase; e.p = a->p;
+  e.ddx = 1. / d.dx; e.ddy = 1. / d.dy; e.ddz = 1. / d.dz;
+  e.dt_rho = a->dt / a->rho_f;
+  e.nti = (L.in + EPI_T - 1) / EPI_T; e.ntj = (L.jn + EPI_T - 1) / EPI_T; e.ntk = (L.kn + EPI_T - 1) / EPI_T;
+  const long long ntiles = (long long)e.nti * e.ntj * e.ntk;
+  const int grid = clampi(ntiles, 1, BB_MAXBLOCKS);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(k_epilogue<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EPI_SMEM));
+    CU(cudaFuncSetAttribute(k_epilogue<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EPI_SMEM));
+    CU(cudaFuncSetAttribute(k_epilogue<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EPI_SMEM));
+    attr_set = true;
+  }
+  if (project && update) k_epilogue<true, true><<<grid, 256, EPI_SMEM, s->stream>>>(s->dev, s->fst, e);
+  else if (project) k_epilogue<true, false><<<grid, 256, EPI_SMEM, s->stream>>>(s->dev, s->fst, e);
+  else k_epilogue<false, true><<<grid, 256, EPI_SMEM, s->stream>>>(s->dev, s->fst, e);
+  s->launches++;
+  if (update) {
+    const long long nrows = (long long)L.jn * L.kn;
+    k_sub_mean<<<clampi(nrows, 1, s->sm_count * 16), 256, 0, s->stream>>>(s->dev, a->p, s->fst.cs1b, s->fst.cs2b, (double)s->DOM.xn * (double)s->DOM.yn * (double)s->DOM.zn);
+    s->launches++;
+  }
+  CU(cudaEventRecord(s->ev[1], s->stream));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  if (ms_out) { float ms = 0.f; cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]); *ms_out = ms; }
   return BBPCG_OK;
 }
 

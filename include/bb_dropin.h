@@ -10,12 +10,16 @@
  *   cuda_PP_cg_noparts                   src/bluebottle.h:3112, called src/bluebottle.c:231
  *   cuda_PP_cg_timed                     src/bluebottle.h:3098, no caller in the reference
  *   mpi_cuda_exchange_Gcc(real *array)   src/mpi_comm.h:318, 19 call sites outside the solver
+ * and, for the solve epilogue (link instead of the same-named functions of cuda_bluebottle.o):
+ *   cuda_dom_BC_p(real *array)           src/cuda_bluebottle.cu:2536, called src/bluebottle.c:234,255
+ *   cuda_project                         src/cuda_bluebottle.cu:2495, called src/bluebottle.c:237
+ *   cuda_update_p                        src/cuda_bluebottle.cu:2505, called src/bluebottle.c:250
  *
  * They read these globals of the host program (defined in src/bluebottle.c:438-576,
  * src/mpi_comm.c:26-27, src/particle.c:27-28):
  *   dom, DOM, rank, nprocs, bc, rho_f, dt, pp_residual, pp_max_iter, stepnum, ttime,
  *   NPARTS, nparts, _u_star, _v_star, _w_star, _flag_u, _flag_v, _flag_w, _phase,
- *   _phase_shell, _rhs_p, _phi
+ *   _phase_shell, _rhs_p, _phi, and for the epilogue _u, _v, _w, _p, _p0
  * and call back into reference code at: cuda_part_BC_p() (src/cuda_particle.cu:1680) and
  * recorder_PP() (src/recorder.c:190).  `_invM,_r_q,_z_q,_p_q,_pb_q,_Apb_q` are NOT used: the
  * library keeps its own padded workspace.
@@ -36,6 +40,9 @@ void cuda_PP_cg(void);
 void cuda_PP_cg_noparts(void);
 void cuda_PP_cg_timed(void);
 void mpi_cuda_exchange_Gcc(real *array);
+void cuda_dom_BC_p(real *array);
+void cuda_project(void);
+void cuda_update_p(void);
 /* extra: release the workspace before mpi_end(); optional */
 void bbpcg_dropin_finalize(void);
 /* host-provided (weak) all-gather used once at start-up when nprocs > 1 */

@@ -140,6 +140,34 @@ int  bbpcg_history(bbpcg_solver *s, double *out, int cap);
  * from the neighbouring blocks (periodic wrap included; faces only, no edges/corners). */
 int  bbpcg_exchange_Gcc(bbpcg_solver *s, real *array);
 
+/* ---- solve epilogue (what src/bluebottle.c:233-256 runs on phi right after the solve) -------
+ * = cuda_dom_BC_p(array) (src/cuda_bluebottle.cu:2536-2589): on every face of this block that has
+ * no neighbour and whose pressure BC is NEUMANN, ghost = adjacent interior cell (faces only). */
+int  bbpcg_dom_BC_p(bbpcg_solver *s, real *array);
+
+typedef struct bbpcg_epilogue_args {
+  const real *u_star, *v_star, *w_star;   /* Gfx / Gfy / Gfz s3b, device                           */
+  const int  *flag_u, *flag_v, *flag_w;   /* Gfx / Gfy / Gfz s3b, device                           */
+  real       *phi;                        /* Gcc s3b, device: interior from the solve               */
+  real       *u, *v, *w;                  /* OUT (Gf?._is.._ie faces); NULL u: skip cuda_project    */
+  const real *p0;                         /* Gcc s3b, device                                        */
+  const int  *phase;                      /* Gcc s3b, device (all -1 without particles)             */
+  real       *p;                          /* OUT interior; NULL: skip cuda_update_p                 */
+  real        rho_f, dt;
+  int         phi_ghosts_valid;           /* 0: run mpi_cuda_exchange_Gcc(phi) + cuda_dom_BC_p(phi)
+                                             first (bluebottle.c:233-234); 1: the caller did        */
+} bbpcg_epilogue_args;
+
+/* = [mpi_cuda_exchange_Gcc(phi); cuda_dom_BC_p(phi);] cuda_project(); cuda_update_p()
+ * (src/cuda_bluebottle.cu:2495-2534) in ONE pass over the block plus the mean subtraction:
+ *   u = u* - dt/rho_f |flag_u| (phi_C - phi_W)/dx  (same for v, w; src/bluebottle_kernel.cu:2303-2355)
+ *   p = (phase < 0)(p0 + phi) - mean over all ranks  (src/bluebottle_kernel.cu:2396, cuda_bluebottle.cu:2519-2533)
+ * Either half may be skipped (u == NULL / p == NULL).  COLLECTIVE when p != NULL or the exchange runs.
+ * The velocity BCs the reference applies between the two halves (bluebottle.c:243-248) touch neither
+ * phi, p0, phase nor p, so running both halves together gives the same state.
+ * ms_out (may be NULL): device time of the call (CUDA events). */
+int  bbpcg_epilogue(bbpcg_solver *s, const bbpcg_epilogue_args *args, double *ms_out);
+
 /* Unit entry points used by the parity tests (same kernels the solve uses). */
 int  bbpcg_rhs(bbpcg_solver *s, const real *u_star, const real *v_star, const real *w_star,
                real rho_f, real dt, real *rhs_p);

@@ -15,10 +15,11 @@ sys.path.insert(0, os.path.join(os.path.dirname(_HERE), "bluebottle-3.0_b200"))
 from bbpcg.grid import DomStruct, PressureBC, grid_shape  # noqa: E402  (types only: the grid contract)
 
 (FLAG_U, FLAG_V, FLAG_W, PHASE, PHASE_SHELL, U_STAR, V_STAR, W_STAR, RHS_P, PHI, PB_Q,
- INVM, R_Q, Z_Q, P_Q, APB_Q) = range(16)
+ INVM, R_Q, Z_Q, P_Q, APB_Q, U, V, W, P0, P) = range(21)
 
 _GRID_OF = {FLAG_U: "Gfx", FLAG_V: "Gfy", FLAG_W: "Gfz", PHASE: "Gcc", PHASE_SHELL: "Gcc",
-            U_STAR: "Gfx", V_STAR: "Gfy", W_STAR: "Gfz", RHS_P: "Gcc", PHI: "Gcc", PB_Q: "Gcc"}
+            U_STAR: "Gfx", V_STAR: "Gfy", W_STAR: "Gfz", RHS_P: "Gcc", PHI: "Gcc", PB_Q: "Gcc",
+            U: "Gfx", V: "Gfy", W: "Gfz", P0: "Gcc", P: "Gcc"}
 _INT_IDS = (FLAG_U, FLAG_V, FLAG_W, PHASE, PHASE_SHELL)
 
 
@@ -68,6 +69,12 @@ def load(omp=False):
     lib.bbo_solve.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                               dp, C.c_int, C.POINTER(Result)]
     lib.bbo_iterate_fixed.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int]
+    lib.bbo_dom_BC_p.argtypes = [C.c_void_p, C.c_int]
+    lib.bbo_project.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    lib.bbo_update_p.argtypes = [C.c_void_p]
+    lib.bbo_update_p.restype = C.c_double
+    lib.bbo_epilogue.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    lib.bbo_epilogue.restype = C.c_double
     lib.bbo_omp_threads.restype = C.c_int
     _libs[omp] = lib
     return lib
@@ -137,6 +144,19 @@ class Oracle:
 
     def spmv(self, aid, parts=False):
         (self.lib.bbo_spmv_parts if parts else self.lib.bbo_spmv_noparts)(self.h, aid)
+
+    def dom_BC_p(self, aid):
+        self.lib.bbo_dom_BC_p(self.h, aid)
+
+    def project(self, rho_f=1.0, dt=1e-3):
+        self.lib.bbo_project(self.h, rho_f, dt)
+
+    def update_p(self):
+        return self.lib.bbo_update_p(self.h)
+
+    def epilogue(self, rho_f=1.0, dt=1e-3):
+        """exchange_Gcc(phi); dom_BC_p(phi); project; update_p -- returns the subtracted mean"""
+        return self.lib.bbo_epilogue(self.h, rho_f, dt)
 
     def solve(self, rho_f=1.0, dt=1e-3, pp_residual=1e-6, pp_max_iter=2000, parts=False):
         cap = pp_max_iter + 3

@@ -42,6 +42,8 @@ typedef struct bbo_block {
   real *rhs_p, *phi, *pb_q;            /* Gcc s3b                (bluebottle.h:974-1013)   */
   real *invM, *r_q, *z_q, *p_q, *Apb_q;/* Gcc s3                                          */
   real *send[6], *recv[6];             /* e,w,n,s,t,b packing buffers (cuda_bluebottle.cu:255-319) */
+  real *u, *v, *w;                     /* Gfx/Gfy/Gfz s3b: projected velocity (bluebottle.h:1137-1161) */
+  real *p0, *p;                        /* Gcc s3b: previous / updated pressure (bluebottle.h:961,1037)  */
 } bbo_block;
 
 typedef struct bbo_state {
@@ -60,7 +62,8 @@ enum { BBO_E = 0, BBO_W, BBO_N, BBO_S, BBO_T, BBO_B };
 enum {
   BBO_FLAG_U = 0, BBO_FLAG_V, BBO_FLAG_W, BBO_PHASE, BBO_PHASE_SHELL,
   BBO_U_STAR, BBO_V_STAR, BBO_W_STAR, BBO_RHS_P, BBO_PHI, BBO_PB_Q,
-  BBO_INVM, BBO_R_Q, BBO_Z_Q, BBO_P_Q, BBO_APB_Q
+  BBO_INVM, BBO_R_Q, BBO_Z_Q, BBO_P_Q, BBO_APB_Q,
+  BBO_VEL_U, BBO_VEL_V, BBO_VEL_W, BBO_P0, BBO_P
 };
 
 /* ------------------------------------------------------------------------------------ */
@@ -192,6 +195,8 @@ static void alloc_block(bbo_block *b, const dom_struct *d)
   b->w_star = xcalloc(d->Gfz.s3b, sizeof(real));
   b->rhs_p = xcalloc(d->Gcc.s3b, sizeof(real)); b->phi = xcalloc(d->Gcc.s3b, sizeof(real));
   b->pb_q = xcalloc(d->Gcc.s3b, sizeof(real));   /* cudaMemset 0, cuda_bluebottle.cu:373 */
+  b->u = xcalloc(d->Gfx.s3b, sizeof(real)); b->v = xcalloc(d->Gfy.s3b, sizeof(real)); b->w = xcalloc(d->Gfz.s3b, sizeof(real));
+  b->p0 = xcalloc(d->Gcc.s3b, sizeof(real)); b->p = xcalloc(d->Gcc.s3b, sizeof(real));
   b->invM = xcalloc(d->Gcc.s3, sizeof(real)); b->r_q = xcalloc(d->Gcc.s3, sizeof(real));
   b->z_q = xcalloc(d->Gcc.s3, sizeof(real)); b->p_q = xcalloc(d->Gcc.s3, sizeof(real));
   b->Apb_q = xcalloc(d->Gcc.s3, sizeof(real));
@@ -263,6 +268,7 @@ void bbo_destroy(bbo_state *s)
     free(b->flag_u); free(b->flag_v); free(b->flag_w); free(b->phase); free(b->phase_shell);
     free(b->u_star); free(b->v_star); free(b->w_star); free(b->rhs_p); free(b->phi); free(b->pb_q);
     free(b->invM); free(b->r_q); free(b->z_q); free(b->p_q); free(b->Apb_q);
+    free(b->u); free(b->v); free(b->w); free(b->p0); free(b->p);
     for (f = 0; f < 6; f++) { free(b->send[f]); free(b->recv[f]); }
   }
   free(s->blk); free(s->dom); free(s->plane_partial); free(s);
@@ -282,6 +288,8 @@ void *bbo_array(bbo_state *s, int rank, int id)
     case BBO_RHS_P: return b->rhs_p;    case BBO_PHI: return b->phi;        case BBO_PB_Q: return b->pb_q;
     case BBO_INVM: return b->invM;      case BBO_R_Q: return b->r_q;        case BBO_Z_Q: return b->z_q;
     case BBO_P_Q: return b->p_q;        case BBO_APB_Q: return b->Apb_q;
+    case BBO_VEL_U: return b->u;        case BBO_VEL_V: return b->v;        case BBO_VEL_W: return b->w;
+    case BBO_P0: return b->p0;          case BBO_P: return b->p;
   }
   return NULL;
 }
@@ -551,7 +559,8 @@ void bbo_rhs(bbo_state *s, real rho_f, real dt)
  * Buffer layouts: E/W pp=(j-1)+jn(k-1); N/S pp=(k-1)+kn(i-1); T/B pp=(i-1)+in(j-1). */
 static real *blk_gcc_array(bbo_block *b, int id)
 {
-  switch (id) { case BBO_RHS_P: return b->rhs_p; case BBO_PHI: return b->phi; case BBO_PB_Q: return b->pb_q; }
+  switch (id) { case BBO_RHS_P: return b->rhs_p; case BBO_PHI: return b->phi; case BBO_PB_Q: return b->pb_q;
+                case BBO_P0: return b->p0; case BBO_P: return b->p; }
   return NULL;
 }
 
@@ -592,6 +601,122 @@ void bbo_exchange_Gcc(bbo_state *s, int array_id)
     if (d->t >= 0) for (j = 1; j <= g->_je; j++) for (i = 1; i <= g->_ie; i++) a[GCC_LOC(i, j, g->_keb, g->s1b, g->s2b)] = b->recv[BBO_T][(i - 1) + g->in * (j - 1)];
     if (d->b >= 0) for (j = 1; j <= g->_je; j++) for (i = 1; i <= g->_ie; i++) a[GCC_LOC(i, j, g->_ksb, g->s1b, g->s2b)] = b->recv[BBO_B][(i - 1) + g->in * (j - 1)];
   }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* The solve epilogue, src/bluebottle.c:233-256.
+ *
+ * cuda_dom_BC_p, src/cuda_bluebottle.cu:2536-2589 with BC_p_{W,E,S,N,B,T}_N, src/bluebottle_kernel.cu:26-102:
+ * on a side with no neighbour (MPI_PROC_NULL) whose pressure BC is NEUMANN, ghost = adjacent interior
+ * cell, for the interior ranges of the other two indices only (faces, no edges). */
+void bbo_dom_BC_p(bbo_state *s, int array_id)
+{
+  int c, i, j, k;
+  for (c = 0; c < s->nblocks; c++) {
+    const dom_struct *d = &s->dom[c];
+    const grid_info *g = &d->Gcc;
+    real *a = blk_gcc_array(&s->blk[c], array_id);
+    if (d->w < 0 && s->bc.pW == BB_NEUMANN) for (k = 1; k <= g->kn; k++) for (j = 1; j <= g->jn; j++) a[GCC_LOC(g->_isb, j, k, g->s1b, g->s2b)] = a[GCC_LOC(g->_is, j, k, g->s1b, g->s2b)];
+    if (d->e < 0 && s->bc.pE == BB_NEUMANN) for (k = 1; k <= g->kn; k++) for (j = 1; j <= g->jn; j++) a[GCC_LOC(g->_ieb, j, k, g->s1b, g->s2b)] = a[GCC_LOC(g->_ie, j, k, g->s1b, g->s2b)];
+    if (d->s < 0 && s->bc.pS == BB_NEUMANN) for (k = 1; k <= g->kn; k++) for (i = 1; i <= g->in; i++) a[GCC_LOC(i, g->_jsb, k, g->s1b, g->s2b)] = a[GCC_LOC(i, g->_js, k, g->s1b, g->s2b)];
+    if (d->n < 0 && s->bc.pN == BB_NEUMANN) for (k = 1; k <= g->kn; k++) for (i = 1; i <= g->in; i++) a[GCC_LOC(i, g->_jeb, k, g->s1b, g->s2b)] = a[GCC_LOC(i, g->_je, k, g->s1b, g->s2b)];
+    if (d->b < 0 && s->bc.pB == BB_NEUMANN) for (j = 1; j <= g->jn; j++) for (i = 1; i <= g->in; i++) a[GCC_LOC(i, j, g->_ksb, g->s1b, g->s2b)] = a[GCC_LOC(i, j, g->_ks, g->s1b, g->s2b)];
+    if (d->t < 0 && s->bc.pT == BB_NEUMANN) for (j = 1; j <= g->jn; j++) for (i = 1; i <= g->in; i++) a[GCC_LOC(i, j, g->_keb, g->s1b, g->s2b)] = a[GCC_LOC(i, j, g->_ke, g->s1b, g->s2b)];
+  }
+}
+
+/* cuda_project, src/cuda_bluebottle.cu:2495-2503; project_u/v/w, src/bluebottle_kernel.cu:2303-2355:
+ *   gradPhi = abs(flag) * ddx * (phi[C] - phi[W]);  u = u_star - dt / rho_f * gradPhi
+ * over Gfx._is.._ie (in = xn+1 faces) x interior j,k; same for v, w.  phi ghosts as given. */
+void bbo_project(bbo_state *s, real rho_f, real dt)
+{
+  int c;
+  for (c = 0; c < s->nblocks; c++) {
+    const dom_struct *d = &s->dom[c];
+    bbo_block *b = &s->blk[c];
+    const real ddx = 1. / d->dx, ddy = 1. / d->dy, ddz = 1. / d->dz;
+    const int cs1 = d->Gcc.s1b, cs2 = d->Gcc.s2b;
+    int k;
+#pragma omp parallel for schedule(static)
+    for (k = d->Gfx._ks; k <= d->Gfx._ke; k++) {
+      int i, j;
+      for (j = d->Gfx._js; j <= d->Gfx._je; j++) for (i = d->Gfx._is; i <= d->Gfx._ie; i++) {
+        int cf = GFX_LOC(i, j, k, d->Gfx.s1b, d->Gfx.s2b);
+        real gradPhi = abs(b->flag_u[cf]) * ddx * (b->phi[GCC_LOC(i, j, k, cs1, cs2)] - b->phi[GCC_LOC(i - 1, j, k, cs1, cs2)]);
+        b->u[cf] = (b->u_star[cf] - dt / rho_f * gradPhi);
+      }
+    }
+#pragma omp parallel for schedule(static)
+    for (k = d->Gfy._ks; k <= d->Gfy._ke; k++) {
+      int i, j;
+      for (j = d->Gfy._js; j <= d->Gfy._je; j++) for (i = d->Gfy._is; i <= d->Gfy._ie; i++) {
+        int cf = GFY_LOC(i, j, k, d->Gfy.s1b, d->Gfy.s2b);
+        real gradPhi = abs(b->flag_v[cf]) * ddy * (b->phi[GCC_LOC(i, j, k, cs1, cs2)] - b->phi[GCC_LOC(i, j - 1, k, cs1, cs2)]);
+        b->v[cf] = (b->v_star[cf] - dt / rho_f * gradPhi);
+      }
+    }
+#pragma omp parallel for schedule(static)
+    for (k = d->Gfz._ks; k <= d->Gfz._ke; k++) {
+      int i, j;
+      for (j = d->Gfz._js; j <= d->Gfz._je; j++) for (i = d->Gfz._is; i <= d->Gfz._ie; i++) {
+        int cf = GFZ_LOC(i, j, k, d->Gfz.s1b, d->Gfz.s2b);
+        real gradPhi = abs(b->flag_w[cf]) * ddz * (b->phi[GCC_LOC(i, j, k, cs1, cs2)] - b->phi[GCC_LOC(i, j, k - 1, cs1, cs2)]);
+        b->w[cf] = (b->w_star[cf] - dt / rho_f * gradPhi);
+      }
+    }
+  }
+}
+
+/* cuda_update_p, src/cuda_bluebottle.cu:2505-2534: update_p (src/bluebottle_kernel.cu:2385-2402; the Laplacian of
+ * :2357-2383 is computed but unused, :2396 vs the commented :2399) then the mean over ALL ranks' interior cells
+ * (copy_p_p_noghost + thrust::reduce + MPI_Allreduce, pmean /= DOM.Gcc.s3) is subtracted from the interior
+ * (forcing_add_c_const(-pmean), :1507-1518).  Summation order is ours (rows -> planes -> ranks), see dot_s3. */
+real bbo_update_p(bbo_state *s)
+{
+  int c, k;
+  real total = 0., pmean;
+  for (c = 0; c < s->nblocks; c++) {
+    const grid_info *g = &s->dom[c].Gcc;
+    bbo_block *b = &s->blk[c];
+    real *pp = s->plane_partial, tot = 0.;
+#pragma omp parallel for schedule(static)
+    for (k = g->_ks; k <= g->_ke; k++) {
+      real pk = 0.;
+      int i, j;
+      for (j = g->_js; j <= g->_je; j++) {
+        real pj = 0.;
+        for (i = g->_is; i <= g->_ie; i++) {
+          int C = GCC_LOC(i, j, k, g->s1b, g->s2b);
+          b->p[C] = (b->phase[C] < 0) * (b->p0[C] + b->phi[C]);
+          pj += b->p[C];
+        }
+        pk += pj;
+      }
+      pp[k] = pk;
+    }
+    for (k = g->_ks; k <= g->_ke; k++) tot += pp[k];
+    total += tot;
+  }
+  pmean = total / (real)s->DOM.Gcc.s3;
+  for (c = 0; c < s->nblocks; c++) {
+    const grid_info *g = &s->dom[c].Gcc;
+    bbo_block *b = &s->blk[c];
+#pragma omp parallel for schedule(static)
+    for (k = g->_ks; k <= g->_ke; k++) {
+      int i, j;
+      for (j = g->_js; j <= g->_je; j++) for (i = g->_is; i <= g->_ie; i++) b->p[GCC_LOC(i, j, k, g->s1b, g->s2b)] += -pmean;
+    }
+  }
+  return pmean;
+}
+
+/* bluebottle.c:233-256 restricted to what touches phi / p: exchange(phi), dom_BC_p(phi), project, update_p */
+real bbo_epilogue(bbo_state *s, real rho_f, real dt)
+{
+  bbo_exchange_Gcc(s, BBO_PHI);
+  bbo_dom_BC_p(s, BBO_PHI);
+  bbo_project(s, rho_f, dt);
+  return bbo_update_p(s);
 }
 
 /* ------------------------------------------------------------------------------------ */

@@ -16,6 +16,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <cuda_runtime.h>
+#include <thrust/device_ptr.h>
+#include <thrust/reduce.h>
 
 #include "cuda_solver.h"      /* reference header (from -I $(REF)/src): types + kernel prototypes */
 #include "cuda_bluebottle.h"  /* pack/unpack kernel prototypes */
@@ -33,6 +35,10 @@ real *_phi, *_rhs_p, *_r_q, *_z_q, *_p_q, *_pb_q, *_Apb_q, *_invM;
 real *_u_star, *_v_star, *_w_star;
 int *_flag_u, *_flag_v, *_flag_w, *_phase, *_phase_shell;
 static real *_send_Gcc[6], *_recv_Gcc[6];   /* e w n s t b */
+/* epilogue (bluebottle.c:233-256): projected velocity, pressures, the BC table (only bc.p* is read) */
+real *_u, *_v, *_w, *_p, *_p0;
+real nu;
+BC bc;
 
 static int  g_niter = -1;
 static real g_resid = -1., g_etime = 0.;
@@ -104,6 +110,14 @@ static void shim_blocks_init(const dom_struct *d)
   bx = nblk(d->Gcc.in, tx - 2); by = nblk(d->Gcc.jn, ty - 2); bz = nblk(d->Gcc.kn, tz - 2);
   blocks.Gcc.dim_in_s = dim3(ty, tz); blocks.Gcc.dim_jn_s = dim3(tz, tx); blocks.Gcc.dim_kn_s = dim3(tx, ty);
   blocks.Gcc.num_in_s = dim3(by, bz); blocks.Gcc.num_jn_s = dim3(bz, bx); blocks.Gcc.num_kn_s = dim3(bx, by);
+  /* face grids, cuda_bluebottle.cu:583-760: same rule per grid; only the shapes the epilogue launches are needed
+   * (project_u: Gfx.num_in/dim_in, project_v: Gfy.num_jn/dim_jn, project_w: Gfz.num_kn/dim_kn) */
+  tx = thr(d->Gfx.in); ty = thr(d->Gfx.jn); tz = thr(d->Gfx.kn);
+  blocks.Gfx.dim_in = dim3(ty, tz); blocks.Gfx.num_in = dim3(nblk(d->Gfx.jn, ty), nblk(d->Gfx.kn, tz));
+  tx = thr(d->Gfy.in); ty = thr(d->Gfy.jn); tz = thr(d->Gfy.kn);
+  blocks.Gfy.dim_jn = dim3(tz, tx); blocks.Gfy.num_jn = dim3(nblk(d->Gfy.kn, tz), nblk(d->Gfy.in, tx));
+  tx = thr(d->Gfz.in); ty = thr(d->Gfz.jn); tz = thr(d->Gfz.kn);
+  blocks.Gfz.dim_kn = dim3(tx, ty); blocks.Gfz.num_kn = dim3(nblk(d->Gfz.in, tx), nblk(d->Gfz.jn, ty));
   /* ghost-inclusive shapes used by zero_rhs_ghost_{i,j,k} (cuda_bluebottle.cu:545-560) */
   tx = thr(d->Gcc.inb); ty = thr(d->Gcc.jnb); tz = thr(d->Gcc.knb);
   bx = nblk(d->Gcc.inb, tx); by = nblk(d->Gcc.jnb, ty); bz = nblk(d->Gcc.knb, tz);
@@ -142,6 +156,11 @@ int bbref_init(const dom_struct *d, const dom_struct *D)
     size_t n = (f < 2) ? d->Gcc.s2_i : (f < 4) ? d->Gcc.s2_j : d->Gcc.s2_k;
     CK(cudaMalloc(&_send_Gcc[f], n * sizeof(real)));  CK(cudaMalloc(&_recv_Gcc[f], n * sizeof(real)));
   }
+  CK(cudaMalloc(&_u, (size_t)d->Gfx.s3b * sizeof(real)));  CK(cudaMemset(_u, 0, (size_t)d->Gfx.s3b * sizeof(real)));
+  CK(cudaMalloc(&_v, (size_t)d->Gfy.s3b * sizeof(real)));  CK(cudaMemset(_v, 0, (size_t)d->Gfy.s3b * sizeof(real)));
+  CK(cudaMalloc(&_w, (size_t)d->Gfz.s3b * sizeof(real)));  CK(cudaMemset(_w, 0, (size_t)d->Gfz.s3b * sizeof(real)));
+  CK(cudaMalloc(&_p, s3b * sizeof(real)));   CK(cudaMemset(_p, 0, s3b * sizeof(real)));
+  CK(cudaMalloc(&_p0, s3b * sizeof(real)));  CK(cudaMemset(_p0, 0, s3b * sizeof(real)));
   return 0;
 }
 
@@ -255,5 +274,81 @@ int bbref_exchange(real *arr_host)
   CK(cudaMemcpy(arr_host, _pb_q, (size_t)d->Gcc.s3b * sizeof(real), cudaMemcpyDeviceToHost));
   return 0;
 }
+
+/* ---- the solve epilogue with the reference's own kernels -----------------------------------------
+ * Host sequences restated from cuda_dom_BC_p (cuda_bluebottle.cu:2536-2589), cuda_project (:2495-2503) and
+ * cuda_update_p (:2505-2534) -- cuda_bluebottle.cu itself is not linked (it drags in the whole program's
+ * globals); every kernel launched here is the reference's, from bluebottle_kernel.cu. */
+static void shim_dom_BC_p(real *array)
+{
+  const dom_struct *d = &dom[rank];
+  if (d->w == MPI_PROC_NULL && bc.pW == NEUMANN) BC_p_W_N<<<blocks.Gcc.num_in, blocks.Gcc.dim_in>>>(array);
+  if (d->e == MPI_PROC_NULL && bc.pE == NEUMANN) BC_p_E_N<<<blocks.Gcc.num_in, blocks.Gcc.dim_in>>>(array);
+  if (d->s == MPI_PROC_NULL && bc.pS == NEUMANN) BC_p_S_N<<<blocks.Gcc.num_jn, blocks.Gcc.dim_jn>>>(array);
+  if (d->n == MPI_PROC_NULL && bc.pN == NEUMANN) BC_p_N_N<<<blocks.Gcc.num_jn, blocks.Gcc.dim_jn>>>(array);
+  if (d->b == MPI_PROC_NULL && bc.pB == NEUMANN) BC_p_B_N<<<blocks.Gcc.num_kn, blocks.Gcc.dim_kn>>>(array);
+  if (d->t == MPI_PROC_NULL && bc.pT == NEUMANN) BC_p_T_N<<<blocks.Gcc.num_kn, blocks.Gcc.dim_kn>>>(array);
+}
+
+static void shim_project(void)
+{
+  project_u<<<blocks.Gfx.num_in, blocks.Gfx.dim_in>>>(_u_star, _phi, rho_f, dt, _u, 1. / dom[rank].dx, _flag_u);
+  project_v<<<blocks.Gfy.num_jn, blocks.Gfy.dim_jn>>>(_v_star, _phi, rho_f, dt, _v, 1. / dom[rank].dy, _flag_v);
+  project_w<<<blocks.Gfz.num_kn, blocks.Gfz.dim_kn>>>(_w_star, _phi, rho_f, dt, _w, 1. / dom[rank].dz, _flag_w);
+}
+
+static int shim_update_p(void)
+{
+  real *_Lp, *_p_mean;
+  CK(cudaMalloc((void **)&_Lp, sizeof(real) * dom[rank].Gcc.s3b));
+  update_p_laplacian<<<blocks.Gcc.num_kn, blocks.Gcc.dim_kn>>>(_Lp, _phi);
+  update_p<<<blocks.Gcc.num_kn, blocks.Gcc.dim_kn>>>(_Lp, _p0, _p, _phi, nu, dt, _phase);
+  CK(cudaFree(_Lp));
+  CK(cudaMalloc((void **)&_p_mean, sizeof(real) * dom[rank].Gcc.s3));
+  copy_p_p_noghost<<<blocks.Gcc.num_kn, blocks.Gcc.dim_kn>>>(_p_mean, _p);
+  thrust::device_ptr<real> t_p_mean(_p_mean);
+  real pmean = thrust::reduce(t_p_mean, t_p_mean + dom[rank].Gcc.s3, 0., thrust::plus<real>());
+  pmean /= (real)DOM.Gcc.s3;                          /* 1 rank: the MPI_Allreduce is the identity */
+  CK(cudaFree(_p_mean));
+  forcing_add_c_const<<<blocks.Gcc.num_kn, blocks.Gcc.dim_kn>>>(-pmean, _p);
+  return 0;
+}
+
+/* bluebottle.c:233-256 restricted to what touches phi / p.  phi_h != NULL replaces the solver's _phi interior+ghosts
+ * first (a seeded test vector); p0_h is the previous pressure.  pbc[6] = bc.pW,pE,pS,pN,pB,pT.  Outputs to the host:
+ * u, v, w (Gf? s3b), p and the ghost-filled phi (Gcc s3b).  *ms = CUDA-event time of the sequence. */
+int bbref_epilogue(const real *phi_h, const real *p0_h, const int *pbc, real rho_f_, real dt_, real nu_,
+                   real *u_h, real *v_h, real *w_h, real *p_h, real *phi_out_h, float *ms)
+{
+  const dom_struct *d = &dom[rank];
+  const size_t s3b = d->Gcc.s3b;
+  rho_f = rho_f_; dt = dt_; nu = nu_;
+  memset(&bc, 0, sizeof(bc));
+  bc.pW = pbc[0]; bc.pE = pbc[1]; bc.pS = pbc[2]; bc.pN = pbc[3]; bc.pB = pbc[4]; bc.pT = pbc[5];
+  if (phi_h) CK(cudaMemcpy(_phi, phi_h, s3b * sizeof(real), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(_p0, p0_h, s3b * sizeof(real), cudaMemcpyHostToDevice));
+  CK(cudaMemset(_p, 0, s3b * sizeof(real)));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, 0));
+  mpi_cuda_exchange_Gcc(_phi);                        /* bluebottle.c:233 */
+  shim_dom_BC_p(_phi);                                /* :234 */
+  shim_project();                                     /* :237 */
+  if (shim_update_p()) return -1;                     /* :250 */
+  CK(cudaEventRecord(e1, 0));
+  CK(cudaEventSynchronize(e1));
+  CK(cudaGetLastError());
+  if (ms) CK(cudaEventElapsedTime(ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (u_h) CK(cudaMemcpy(u_h, _u, (size_t)d->Gfx.s3b * sizeof(real), cudaMemcpyDeviceToHost));
+  if (v_h) CK(cudaMemcpy(v_h, _v, (size_t)d->Gfy.s3b * sizeof(real), cudaMemcpyDeviceToHost));
+  if (w_h) CK(cudaMemcpy(w_h, _w, (size_t)d->Gfz.s3b * sizeof(real), cudaMemcpyDeviceToHost));
+  if (p_h) CK(cudaMemcpy(p_h, _p, s3b * sizeof(real), cudaMemcpyDeviceToHost));
+  if (phi_out_h) CK(cudaMemcpy(phi_out_h, _phi, s3b * sizeof(real), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+/* device pointers of the reference's arrays, for the benchmark's device-resident leg: 0 phi, 1 p0, 2 p */
+void *bbref_dev_ptr(int which) { return which == 0 ? (void *)_phi : which == 1 ? (void *)_p0 : (void *)_p; }
 
 } /* extern "C" */

@@ -46,6 +46,20 @@ class Case:
         kw.setdefault("parts", self.nparts > 0)
         return self.o.solve(**kw)
 
+    def seed_epilogue(self, seed=23, phi=True):
+        """Seeded inputs of the solve epilogue in the oracle's arrays: p0 everywhere and -- unless the phi of a
+        solve is to be kept -- phi INCLUDING its ghosts (so the exchange and the Neumann copy have work to undo)."""
+        for r in range(self.o.nblocks):
+            rng = np.random.default_rng(seed + 1000 * r)
+            shape = self.o.array(r, ob.PHI).shape
+            vals = rng.standard_normal(shape)
+            if phi:
+                self.o.array(r, ob.PHI)[...] = vals
+            self.o.array(r, ob.P0)[...] = rng.standard_normal(shape)
+
+    def epilogue_inputs(self, rank=0):
+        return dict(phi=self.o.array(rank, ob.PHI).copy(), p0=self.o.array(rank, ob.P0).copy())
+
 
 def rel_l2(a, b):
     return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
@@ -66,4 +80,29 @@ def load_ref():
     lib.bbref_get.argtypes = [C.c_int, vp]
     lib.bbref_spmv.argtypes = [vp, C.c_int, vp]
     lib.bbref_exchange.argtypes = [vp]
+    lib.bbref_epilogue.argtypes = [vp, vp, vp, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
+    lib.bbref_dev_ptr.argtypes = [C.c_int]
+    lib.bbref_dev_ptr.restype = C.c_void_p
     return lib
+
+
+def ref_epilogue(lib, case, phi, p0, rho_f=1.0, dt=1e-3):
+    """The reference's own epilogue kernels (O1) on one block: returns u, v, w, p, ghost-filled phi and the ms."""
+    from bbpcg.grid import BC_SETS, grid_shape
+    d = case.o.dom(0)
+    out = {k: np.zeros(grid_shape(d, g)) for k, g in (("u", "Gfx"), ("v", "Gfy"), ("w", "Gfz"), ("p", "Gcc"), ("phi", "Gcc"))}
+    pbc = (C.c_int * 6)(*BC_SETS[case.bcname])
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    ms = C.c_float()
+    phi_c = None if phi is None else np.ascontiguousarray(phi)
+    p0_c = np.ascontiguousarray(p0)
+    rc = lib.bbref_epilogue(None if phi_c is None else P(phi_c), P(p0_c), C.cast(pbc, C.c_void_p), rho_f, dt, 0.01,
+                            P(out["u"]), P(out["v"]), P(out["w"]), P(out["p"]), P(out["phi"]), C.byref(ms))
+    assert rc == 0
+    out["ms"] = ms.value
+    return out
+
+
+def face_interior(d, grid, a):
+    """the entries cuda_project writes: Gf?._is.._ie x interior of the other two (all of a Gf? minus its ghosts)"""
+    return a[1:-1, 1:-1, 1:-1]

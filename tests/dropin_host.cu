@@ -6,12 +6,16 @@
  *     cuda_PP_init_jacobi_preconditioner();   // src/bluebottle.c:139
  *     cuda_PP_cg_noparts();  or  cuda_PP_cg(); // src/bluebottle.c:228-232
  *     mpi_cuda_exchange_Gcc(_phi);             // src/bluebottle.c:233
+ *     cuda_dom_BC_p(_phi); cuda_project(); cuda_update_p();   // src/bluebottle.c:234,237,250 (when an epilogue file is asked for)
  *
  * with `void f(void)` signatures.  recorder_PP() and cuda_part_BC_p() -- callees the library calls back -- are
  * this file's own small stand-ins (same signature; recorder_PP writes the solver_expd.rec line in the column
  * format of src/recorder.c:190-221).  TEST CODE: built and run by tests/test_gpu_dropin.py; single rank.
  *
- *   dropin_host <flow.config> <decomp.config> <inputs.bin> <phi_out.bin> <record_dir> <noparts|parts> [pp_max_iter]
+ *   dropin_host <flow.config> <decomp.config> <inputs.bin> <phi_out.bin> <record_dir> <noparts|parts> [pp_max_iter [epilogue_out.bin]]
+ *
+ * epilogue_out.bin: u, v, w (float64, Gfx/Gfy/Gfz s3b) and p (Gcc s3b) after the epilogue with the previous pressure
+ *             p0[C] = ((C * 2654435761 mod 2^32) >> 8) / 2^24 - 0.5 (exactly reproducible in numpy).
  *
  * inputs.bin: flag_u, flag_v, flag_w (int32, Gfx/Gfy/Gfz s3b), phase, phase_shell (int32, Gcc s3b),
  *             u_star, v_star, w_star (float64, Gfx/Gfy/Gfz s3b), in that order, raw.
@@ -35,6 +39,7 @@ real rho_f = 1., dt = 1e-3, pp_residual = 1e-6, ttime = 0.;
 int pp_max_iter = 2000, stepnum = 0;
 int NPARTS = 0, nparts = 0;
 real *_u_star = NULL, *_v_star = NULL, *_w_star = NULL, *_rhs_p = NULL, *_phi = NULL;
+real *_u = NULL, *_v = NULL, *_w = NULL, *_p = NULL, *_p0 = NULL;
 int *_flag_u = NULL, *_flag_v = NULL, *_flag_w = NULL, *_phase = NULL, *_phase_shell = NULL;
 static char g_record_dir[1024] = ".";
 
@@ -109,6 +114,27 @@ int main(int argc, char **argv)
   stepnum = 1; ttime = dt;
   if (parts) cuda_PP_cg(); else cuda_PP_cg_noparts();   /* :228-232 */
   mpi_cuda_exchange_Gcc(_phi);                          /* :233 */
+  if (argc > 8) {                                       /* the solve epilogue, src/bluebottle.c:234-250 */
+    std::vector<real> p0(d->Gcc.s3b);
+    for (size_t C = 0; C < p0.size(); C++) p0[C] = (real)(((unsigned)(C * 2654435761ull)) >> 8) / 16777216. - 0.5;
+    cudaMalloc(&_u, sizeof(real) * d->Gfx.s3b); cudaMalloc(&_v, sizeof(real) * d->Gfy.s3b); cudaMalloc(&_w, sizeof(real) * d->Gfz.s3b);
+    cudaMalloc(&_p, sizeof(real) * d->Gcc.s3b); cudaMalloc(&_p0, sizeof(real) * d->Gcc.s3b);
+    cudaMemset(_u, 0, sizeof(real) * d->Gfx.s3b); cudaMemset(_v, 0, sizeof(real) * d->Gfy.s3b); cudaMemset(_w, 0, sizeof(real) * d->Gfz.s3b);
+    cudaMemset(_p, 0, sizeof(real) * d->Gcc.s3b);
+    cudaMemcpy(_p0, p0.data(), sizeof(real) * p0.size(), cudaMemcpyHostToDevice);
+    cuda_dom_BC_p(_phi);                                /* :234 */
+    cuda_project();                                     /* :237 */
+    cuda_update_p();                                    /* :250 */
+    FILE *e = fopen(argv[8], "wb");
+    const size_t ns[4] = { (size_t)d->Gfx.s3b, (size_t)d->Gfy.s3b, (size_t)d->Gfz.s3b, (size_t)d->Gcc.s3b };
+    real *src[4] = { _u, _v, _w, _p };
+    for (int a = 0; a < 4; a++) {
+      std::vector<real> h(ns[a]);
+      cudaMemcpy(h.data(), src[a], sizeof(real) * ns[a], cudaMemcpyDeviceToHost);
+      fwrite(h.data(), sizeof(real), ns[a], e);
+    }
+    fclose(e);
+  }
   std::vector<real> phi(d->Gcc.s3b);
   cudaMemcpy(phi.data(), _phi, sizeof(real) * phi.size(), cudaMemcpyDeviceToHost);
   FILE *o = fopen(argv[4], "wb");

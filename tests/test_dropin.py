@@ -96,3 +96,31 @@ def test_dropin_nonconvergence_prints_and_exits(tmp_path):
     assert "The pressure-Poisson equation did not converge." in p.stdout
     assert "Residual at iteration 5 is" in p.stdout and "(rhs, rhs) is" in p.stdout
     assert not os.path.exists(tmp_path / "phi.bin")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bc", ["duct", "box"])
+def test_dropin_epilogue_matches_oracle(tmp_path, bc):
+    """cuda_dom_BC_p(_phi); cuda_project(); cuda_update_p() by their reference names (src/bluebottle.c:234-250)"""
+    exe = _build()
+    case = Case((20, 18, 22), bc=bc)
+    flow, dec, inp = _write_case(tmp_path, case)
+    out, epi = str(tmp_path / "phi.bin"), str(tmp_path / "epi.bin")
+    p = subprocess.run([exe, flow, dec, inp, out, str(tmp_path / "record"), "noparts", "2000", epi], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    case.solve_oracle()
+    d = case.o.dom(0)
+    n = case.o.array(0, ob.P0).size
+    C = np.arange(n, dtype=np.uint64)
+    p0 = (((C * np.uint64(2654435761)) & np.uint64(0xFFFFFFFF)) >> np.uint64(8)).astype(np.float64) / 16777216.0 - 0.5
+    case.o.array(0, ob.P0)[...] = p0.reshape(case.o.array(0, ob.P0).shape)
+    case.o.epilogue(1.0, 1e-3)
+    raw = np.fromfile(epi, dtype=np.float64)
+    off = 0
+    for aid in (ob.U, ob.V, ob.W, ob.P):
+        ref = case.o.array(0, aid)
+        got = raw[off:off + ref.size].reshape(ref.shape)
+        off += ref.size
+        # phi comes from two different solvers (1e-10 relative L2): compare at the solve's accuracy
+        assert np.abs(got - ref)[1:-1, 1:-1, 1:-1].max() <= 1e-8 * np.abs(ref).max(), aid
+    assert off == raw.size

@@ -1,0 +1,162 @@
+"""GPU parity of the solve epilogue (bbpcg_dom_BC_p / bbpcg_epilogue through the C ABI):
+exchange(phi) + cuda_dom_BC_p(phi) + cuda_project + cuda_update_p, src/bluebottle.c:233-250.
+
+Three-way where the reference library is present: the reference's own kernels (O1, oracle/_ref/libbbref.so) vs the
+CPU oracle (O2, oracle/pcg_ref.c) vs the product.  Tolerances: ghost fills are copies -> bit-exact; u, v, w differ
+from O1 by nothing but possible FMA-contraction choices (1e-14 of the field's max; O2 is compiled without
+contraction); p by the summation order of the mean (1e-12)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from cases import Case, load_ref, ref_epilogue
+from oracle import binding as ob
+
+pytestmark = pytest.mark.gpu
+
+VEL_TOL = 1e-14
+P_TOL = 1e-12
+INNER = (slice(1, -1),) * 3
+
+
+def _product(case, options=None):
+    from gpu_util import Product
+    p = Product(case, options)
+    for r, s in enumerate(p.solvers):
+        d = p.dev[r]
+        ein = case.epilogue_inputs(r)
+        d["phi"] = s.to_device(ein["phi"])
+        d["p0"] = s.to_device(ein["p0"])
+        d["u"], d["v"], d["w"], d["p"] = s.empty("Gfx"), s.empty("Gfy"), s.empty("Gfz"), s.empty("Gcc")
+    return p
+
+
+def _fused(p, **kw):
+    return p.each(lambda r, s, d: s.epilogue(d["phi"], d["u_star"], d["v_star"], d["w_star"], d["flag_u"], d["flag_v"], d["flag_w"],
+                                             d["u"], d["v"], d["w"], d["p0"], d["phase"], d["p"], **kw))
+
+
+def _close(a, b, tol):
+    return np.abs(a - b).max() <= tol * np.abs(b).max()
+
+
+def _check_against_oracle(case, p):
+    for r in range(p.n):
+        dev = p.dev[r]
+        assert np.array_equal(dev["phi"].cpu().numpy(), case.o.array(r, ob.PHI))       # ghost faces filled, nothing else touched
+        for key, aid in (("u", ob.U), ("v", ob.V), ("w", ob.W)):
+            assert _close(dev[key].cpu().numpy()[INNER], case.o.array(r, aid)[INNER], VEL_TOL), (r, key)
+        assert _close(dev["p"].cpu().numpy()[INNER], case.o.array(r, ob.P)[INNER], P_TOL), r
+
+
+@pytest.mark.parametrize("cells,bc,nparts", [((32, 28, 36), "cavity", 0), ((32, 28, 36), "duct", 0), ((32, 28, 36), "periodic", 0),
+                                             ((33, 17, 9), "box", 0), ((16, 16, 16), "channel", 0), ((40, 40, 40), "sedimentation", 3)])
+def test_epilogue_three_way(cells, bc, nparts):
+    case = Case(cells, bc=bc, nparts=nparts, radius=2.5)
+    case.seed_epilogue(23)
+    ein = case.epilogue_inputs(0)
+    p = _product(case)
+    _fused(p)
+    case.o.epilogue(1.0, 1e-3)
+    _check_against_oracle(case, p)
+    lib = load_ref()
+    if lib is not None:                                   # the reference's own kernels
+        dom, DOM = case.o.dom(0), case.o.DOM
+        assert lib.bbref_init(C.byref(dom), C.byref(DOM)) == 0
+        P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        k = {n: np.ascontiguousarray(v) for n, v in case.inputs(0).items()}
+        assert lib.bbref_set_inputs(P(k["flag_u"]), P(k["flag_v"]), P(k["flag_w"]), P(k["phase"]), P(k["phase_shell"]),
+                                    P(k["u_star"]), P(k["v_star"]), P(k["w_star"]), nparts) == 0
+        ref = ref_epilogue(lib, case, ein["phi"], ein["p0"])
+        dev = p.dev[0]
+        assert np.array_equal(dev["phi"].cpu().numpy(), ref["phi"])
+        for key in ("u", "v", "w"):
+            assert _close(dev[key].cpu().numpy()[INNER], ref[key][INNER], VEL_TOL), key
+            assert _close(case.o.array(0, getattr(ob, key.upper()))[INNER], ref[key][INNER], VEL_TOL), key
+        assert _close(dev["p"].cpu().numpy()[INNER], ref["p"][INNER], P_TOL)
+        assert _close(case.o.array(0, ob.P)[INNER], ref["p"][INNER], P_TOL)
+    p.close()
+
+
+@pytest.mark.parametrize("blocks,bc", [((2, 1, 1), "duct"), ((1, 2, 2), "cavity"), ((2, 2, 2), "periodic"), ((1, 1, 3), "sedimentation"),
+                                       ((2, 2, 1), "channel")])
+def test_epilogue_decomposed(blocks, bc):
+    """several ranks (one process, one GPU; same kernels, peer stores and in-kernel all-reduce as a multi-GPU run)"""
+    case = Case((36, 34, 30), blocks=blocks, bc=bc)
+    case.seed_epilogue(31)
+    p = _product(case)
+    _fused(p)
+    case.o.epilogue(1.0, 1e-3)
+    _check_against_oracle(case, p)
+    # every rank subtracted the same global mean: the assembled field has zero mean
+    full = p.gather("p")
+    assert abs(full.mean()) <= 1e-13 * np.abs(full).max()
+    p.close()
+
+
+def test_epilogue_halves_equal_the_fused_call():
+    """mpi_cuda_exchange_Gcc + cuda_dom_BC_p + cuda_project + cuda_update_p called one by one (the drop-in order,
+    src/bluebottle.c:233-250) give bit-identical arrays to the single fused call"""
+    case = Case((40, 24, 20), blocks=(2, 1, 1), bc="cavity")
+    case.seed_epilogue(41)
+    a, b = _product(case), _product(case)
+    _fused(a)
+    b.each(lambda r, s, d: s.exchange_Gcc(d["phi"]))
+    b.each(lambda r, s, d: s.dom_BC_p(d["phi"]))
+    b.each(lambda r, s, d: s.project(d["u_star"], d["v_star"], d["w_star"], d["phi"], d["flag_u"], d["flag_v"], d["flag_w"],
+                                     d["u"], d["v"], d["w"]))
+    b.each(lambda r, s, d: s.update_p(d["p0"], d["phi"], d["phase"], d["p"]))
+    for r in range(a.n):
+        for key in ("phi", "u", "v", "w", "p"):
+            assert np.array_equal(a.dev[r][key].cpu().numpy(), b.dev[r][key].cpu().numpy()), (r, key)
+    # run to run
+    _fused(b, phi_ghosts_valid=True)
+    for r in range(a.n):
+        assert np.array_equal(a.dev[r]["p"].cpu().numpy(), b.dev[r]["p"].cpu().numpy())
+    a.close(); b.close()
+
+
+def test_epilogue_argument_errors():
+    import bbpcg
+    case = Case((8, 8, 8), bc="duct")
+    case.seed_epilogue(1)
+    p = _product(case)
+    s, d = p.solvers[0], p.dev[0]
+    with pytest.raises(RuntimeError, match="nothing to do"):
+        s.epilogue(d["phi"])
+    with pytest.raises(RuntimeError, match="cuda_project needs"):
+        s.epilogue(d["phi"], u=d["u"])
+    with pytest.raises(RuntimeError, match="cuda_update_p needs"):
+        s.epilogue(d["phi"], p=d["p"])
+    p.close()
+
+
+def test_solve_then_epilogue_128_properties():
+    """BASELINE-sized behaviour through size-independent properties: after the solve the projected velocity is
+    discretely divergence free to the solve tolerance, and the updated pressure has zero mean"""
+    import torch
+    case = Case((128, 128, 128), bc="duct", omp=True)
+    case.seed_epilogue(3, phi=False)
+    p = _product(case)
+    p.set_coefficients()
+    res = p.solve(pp_residual=1e-9)[0]
+    assert res.status == "converged"
+    ms = _fused(p)[0]
+    assert ms > 0
+    d = case.o.dom(0)
+    dev = p.dev[0]
+
+    def div(u, v, w):
+        u, v, w = u[INNER], v[INNER], w[INNER]
+        return ((u[1:] - u[:-1]).permute(1, 2, 0) / d.dx + (v[1:] - v[:-1]).permute(2, 0, 1) / d.dy + (w[1:] - w[:-1]) / d.dz)
+    before = div(dev["u_star"], dev["v_star"], dev["w_star"])
+    after = div(dev["u"], dev["v"], dev["w"])
+    assert float(torch.linalg.norm(after)) < 1e-5 * float(torch.linalg.norm(before))
+    pin = dev["p"][INNER]
+    assert abs(float(pin.mean())) <= 1e-12 * float(pin.abs().max())
+    # p = p0 + phi - mean in every (fluid) cell
+    expect = (dev["p0"] + dev["phi"])[INNER]
+    expect = expect - expect.mean()
+    assert float((pin - expect).abs().max()) <= 1e-11 * float(expect.abs().max())
+    p.close()

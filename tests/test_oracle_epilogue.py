@@ -1,0 +1,146 @@
+"""CPU tests (no GPU) of the solve-epilogue restatement in the oracle (oracle/pcg_ref.c: bbo_dom_BC_p, bbo_project,
+bbo_update_p = cuda_dom_BC_p / cuda_project / cuda_update_p, src/cuda_bluebottle.cu:2495-2589).
+
+tests/golden/epi_*.npz are OUTPUTS OF THE REFERENCE'S OWN KERNELS (oracle/make_golden_epilogue.py, run on a B200).
+Tolerances: ghost fills are copies -> bit-exact; u, v, w agree to the FMA contraction nvcc applies to
+`u_star - dt/rho_f*gradPhi` (1e-14 of the field's max); p agrees to the summation order of the mean (1e-12).
+Also: properties that need no golden vector (decomposition independence, zero mean, untouched edges)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from cases import Case
+from oracle import binding as ob
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MAN = os.path.join(GOLD, "EPILOGUE_MANIFEST.json")
+MANIFEST = json.load(open(MAN)) if os.path.exists(MAN) else {"cases": {}, "seed": 23}
+CASES = MANIFEST["cases"]
+
+VEL_TOL = 1e-14
+P_TOL = 1e-12
+
+
+def _gather_faces(case, aid, axis):
+    """global face field from the blocks' Gf? arrays; the face shared by two blocks must agree"""
+    o = case.o
+    D = o.DOM
+    shape = {0: (D.xn + 1, D.zn, D.yn), 1: (D.yn + 1, D.xn, D.zn), 2: (D.zn + 1, D.yn, D.xn)}[axis]
+    out = np.full(shape, np.nan)
+    for r in range(o.nblocks):
+        d = o.dom(r)
+        a = o.array(r, aid)[1:-1, 1:-1, 1:-1]
+        i0, j0, k0 = d.Gcc.get("is") - 1, d.Gcc.get("js") - 1, d.Gcc.get("ks") - 1
+        if axis == 0:
+            sl = (slice(i0, i0 + d.xn + 1), slice(k0, k0 + d.zn), slice(j0, j0 + d.yn))
+        elif axis == 1:
+            sl = (slice(j0, j0 + d.yn + 1), slice(i0, i0 + d.xn), slice(k0, k0 + d.zn))
+        else:
+            sl = (slice(k0, k0 + d.zn + 1), slice(j0, j0 + d.yn), slice(i0, i0 + d.xn))
+        old = out[sl]
+        both = ~np.isnan(old)
+        assert np.array_equal(old[both], a[both])       # duplicated block-boundary faces carry the same value
+        out[sl] = a
+    assert not np.isnan(out).any()
+    return out
+
+
+def test_manifest_lists_every_epilogue_fixture():
+    assert CASES and sorted(CASES) == sorted(f[:-4] for f in os.listdir(GOLD) if f.startswith("epi_") and f.endswith(".npz"))
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_epilogue_matches_reference_kernels(name):
+    spec = CASES[name]
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    case = Case(tuple(spec["cells"]), bc=spec["bc"], nparts=spec.get("nparts", 0), radius=spec.get("radius", 1.0))
+    case.seed_epilogue(MANIFEST["seed"])
+    ein = case.epilogue_inputs(0)
+    assert float(np.abs(ein["phi"]).sum() + np.abs(ein["p0"]).sum()) == float(gold["input_checksum"])
+    case.o.epilogue(MANIFEST["rho_f"], MANIFEST["dt"])
+    assert np.array_equal(case.o.array(0, ob.PHI), gold["phi"])               # exchange + Neumann copy: pure copies
+    for key, aid in (("u", ob.U), ("v", ob.V), ("w", ob.W)):
+        mine, ref = case.o.array(0, aid)[1:-1, 1:-1, 1:-1], gold[key][1:-1, 1:-1, 1:-1]
+        assert np.abs(mine - ref).max() <= VEL_TOL * np.abs(ref).max(), key
+    mine, ref = case.o.array(0, ob.P)[1:-1, 1:-1, 1:-1], gold["p"][1:-1, 1:-1, 1:-1]
+    assert np.abs(mine - ref).max() <= P_TOL * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("bc", ["cavity", "duct", "box", "periodic"])
+def test_dom_BC_p_touches_only_wall_faces(bc):
+    from bbpcg.grid import BC_SETS, NEUMANN
+    case = Case((9, 7, 8), bc=bc)
+    case.seed_epilogue(5)
+    before = case.o.array(0, ob.PHI).copy()
+    case.o.dom_BC_p(ob.PHI)
+    after = case.o.array(0, ob.PHI)
+    pW, pE, pS, pN, pB, pT = BC_SETS[bc]
+    I = slice(1, -1)
+    faces = {"W": ((I, I, 0), (I, I, 1), pW), "E": ((I, I, -1), (I, I, -2), pE), "S": ((I, 0, I), (I, 1, I), pS),
+             "N": ((I, -1, I), (I, -2, I), pN), "B": ((0, I, I), (1, I, I), pB), "T": ((-1, I, I), (-2, I, I), pT)}
+    expect = before.copy()
+    for ghost, inner, t in faces.values():
+        if t == NEUMANN:                       # single block: a NEUMANN side has no neighbour
+            expect[ghost] = before[inner]
+    assert np.array_equal(after, expect)       # edges, corners and periodic sides untouched
+
+
+@pytest.mark.parametrize("blocks,bc", [((2, 1, 1), "duct"), ((1, 2, 2), "cavity"), ((2, 2, 2), "periodic"), ((1, 1, 3), "sedimentation")])
+def test_epilogue_is_decomposition_independent(blocks, bc):
+    """same global phi/p0 on 1 block and on a decomposition: identical u, v, w (bit for bit) and p (to the mean's summation order)"""
+    cells = (12, 10, 12)
+    one, many = Case(cells, bc=bc), Case(cells, blocks=blocks, bc=bc)
+    rng = np.random.default_rng(3)
+    gphi, gp0 = rng.standard_normal(cells[::-1]), rng.standard_normal(cells[::-1])
+    for case in (one, many):
+        for r in range(case.o.nblocks):
+            d = case.o.dom(r)
+            i0, j0, k0 = d.Gcc.get("is") - 1, d.Gcc.get("js") - 1, d.Gcc.get("ks") - 1
+            sl = (slice(k0, k0 + d.zn), slice(j0, j0 + d.yn), slice(i0, i0 + d.xn))
+            case.o.array(r, ob.PHI)[...] = 7.0                              # ghosts start wrong everywhere
+            case.o.array(r, ob.PHI)[1:-1, 1:-1, 1:-1] = gphi[sl]
+            case.o.array(r, ob.P0)[1:-1, 1:-1, 1:-1] = gp0[sl]
+        case.o.epilogue(1.0, 1e-3)
+    for aid, axis in ((ob.U, 0), (ob.V, 1), (ob.W, 2)):
+        assert np.array_equal(_gather_faces(one, aid, axis), _gather_faces(many, aid, axis))
+    p1, pm = one.o.gather_interior(ob.P), many.o.gather_interior(ob.P)
+    assert np.abs(p1 - pm).max() <= 1e-13 * np.abs(p1).max()
+    assert abs(pm.mean()) <= 1e-13 * np.abs(pm).max()                          # mean pressure removed
+
+
+def test_update_p_zeroes_solid_cells_before_the_mean():
+    """p = (phase < 0)(p0 + phi) - mean: solid cells end at exactly -mean (src/bluebottle_kernel.cu:2396, :1507-1518)"""
+    case = Case((16, 16, 16), bc="sedimentation", nparts=1, radius=3.0)
+    case.seed_epilogue(9)
+    mean = case.o.update_p()
+    phase = case.o.array(0, ob.PHASE)[1:-1, 1:-1, 1:-1]
+    p = case.o.array(0, ob.P)[1:-1, 1:-1, 1:-1]
+    assert (phase > -1).sum() > 0
+    assert np.array_equal(p[phase > -1], np.full((phase > -1).sum(), -mean))
+    fluid = phase < 0
+    expect = (case.o.array(0, ob.P0) + case.o.array(0, ob.PHI))[1:-1, 1:-1, 1:-1]
+    assert np.array_equal(p[fluid], expect[fluid] + (-mean))
+
+
+def test_projection_removes_the_divergence():
+    """after a converged solve, div(u) = div(u*) - dt/rho L(phi) is the solver's residual: the projected field is
+    discretely divergence free to the solve tolerance (what the pressure-Poisson step is for)"""
+    case = Case((24, 20, 16), bc="duct")
+    res, _ = case.solve_oracle(pp_residual=1e-10)
+    assert res.status == 0
+    case.seed_epilogue(1, phi=False)
+    case.o.epilogue(1.0, 1e-3)
+    d = case.o.dom(0)
+
+    def div(u, v, w):
+        u, v, w = u[1:-1, 1:-1, 1:-1], v[1:-1, 1:-1, 1:-1], w[1:-1, 1:-1, 1:-1]
+        du = (u[1:] - u[:-1]).transpose(1, 2, 0)          # Gfx a[i,k,j] -> [k,j,i]
+        dv = (v[1:] - v[:-1]).transpose(2, 0, 1)          # Gfy a[j,i,k] -> [k,j,i]
+        dw = w[1:] - w[:-1]
+        return du / d.dx + dv / d.dy + dw / d.dz
+    a = case.o.array
+    before = div(a(0, ob.U_STAR), a(0, ob.V_STAR), a(0, ob.W_STAR))
+    after = div(a(0, ob.U), a(0, ob.V), a(0, ob.W))
+    assert np.linalg.norm(after) < 1e-6 * np.linalg.norm(before)
