@@ -4,6 +4,7 @@
 `PoissonSolver.init_jacobi_preconditioner` = cuda_PP_init_jacobi_preconditioner (src/cuda_solver.cu:31-36)
 `PoissonSolver.PP_cg / PP_cg_noparts`      = cuda_PP_cg / cuda_PP_cg_noparts (src/cuda_solver.cu:38-300,573-761)
 `PoissonSolver.exchange_Gcc`               = mpi_cuda_exchange_Gcc (src/mpi_comm.c:257-315)
+`PoissonSolver.exchange_Gfx/Gfy/Gfz`       = mpi_cuda_exchange_Gfx/_Gfy/_Gfz (src/mpi_comm.c:317-405)
 `PoissonSolver.dom_BC_p`                   = cuda_dom_BC_p (src/cuda_bluebottle.cu:2536-2589)
 `PoissonSolver.project / update_p`         = cuda_project / cuda_update_p (src/cuda_bluebottle.cu:2495-2534)
 `PoissonSolver.epilogue`                   = the sequence src/bluebottle.c:233-256 runs on phi, fused
@@ -224,6 +225,20 @@ class PoissonSolver:
     def exchange_Gcc(self, array):
         self._sync_caller_stream()
         L.check(self.lib.bbpcg_exchange_Gcc(self.h, _ptr(array)), "bbpcg_exchange_Gcc")
+
+    def exchange(self, array, grid):
+        """mpi_cuda_exchange_G{cc,fx,fy,fz}(array): grid in {"Gcc", "Gfx", "Gfy", "Gfz"}"""
+        self._sync_caller_stream()
+        L.check(self.lib.bbpcg_exchange(self.h, _ptr(array), L.GRID_CODE[grid]), "bbpcg_exchange")
+
+    def exchange_Gfx(self, array):
+        self.exchange(array, "Gfx")
+
+    def exchange_Gfy(self, array):
+        self.exchange(array, "Gfy")
+
+    def exchange_Gfz(self, array):
+        self.exchange(array, "Gfz")
 
     def dom_BC_p(self, array):
         self._sync_caller_stream()

@@ -111,6 +111,16 @@ extern "C" void mpi_cuda_exchange_Gcc(real *array)
   if (bbpcg_exchange_Gcc(solver(), array)) die("bbpcg_exchange_Gcc");
 }
 
+/* the face-grid exchanges on the same transport, src/mpi_comm.c:317-405 */
+static void exchange_face(real *array, int grid)
+{
+  cudaDeviceSynchronize();
+  if (bbpcg_exchange(solver(), array, grid)) die("bbpcg_exchange");
+}
+extern "C" void mpi_cuda_exchange_Gfx(real *array) { exchange_face(array, BBPCG_GFX); }
+extern "C" void mpi_cuda_exchange_Gfy(real *array) { exchange_face(array, BBPCG_GFY); }
+extern "C" void mpi_cuda_exchange_Gfz(real *array) { exchange_face(array, BBPCG_GFZ); }
+
 /* ---- solve epilogue, src/bluebottle.c:233-256 ---- */
 extern "C" void cuda_dom_BC_p(real *array)                  /* src/cuda_bluebottle.cu:2536-2589 */
 {

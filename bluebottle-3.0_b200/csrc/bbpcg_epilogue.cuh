@@ -89,6 +89,21 @@ __device__ __forceinline__ void project_line(const double *__restrict__ star, co
   }
 }
 
+/* stage the halo'd phi tile: element e of the (wi x wj x wk) box -> sphi[kk][jj][ii].
+ * (An explicit 8-deep register batch of these loads, and a constant-divisor specialisation for full tiles, both pushed the
+ * kernel over its 80-register budget: the spills showed up as +22 % DRAM writes and +0.5 ms in ncu,
+ * profiles/r01f_epilogue_launches.md.  The plain loop it is.) */
+__device__ __forceinline__ void load_phi_tile(double *sphi, const double *__restrict__ phi, int i0, int j0, int k0,
+                                              int wi, int wj, int wk, int s1b, int s2b, int t)
+{
+  const int total = wi * wj * wk;
+  const double *src = phi + (i0 - 1) + (long long)(j0 - 1) * s1b + (long long)(k0 - 1) * s2b;
+  for (int e = t; e < total; e += 256) {
+    const int ii = e % wi, r = e / wi, jj = r % wj, kk = r / wj;
+    sphi[kk * EPI_SK + jj * EPI_SJ + ii] = src[ii + jj * s1b + (long long)kk * s2b];
+  }
+}
+
 /* project_u / project_v / project_w / update_p on one 16^3 tile per loop trip.
  * Face ownership: a tile writes the W, S and B faces of its cells; the last tile of a direction also writes the closing
  * face (i = in+1 etc.), so every face of Gf?._is.._ie is written exactly once (project_u loops i = _is.._ie = 1..in+1). */
@@ -107,15 +122,7 @@ __global__ void __launch_bounds__(256, 3) k_epilogue(const __grid_constant__ Dev
     const int ni = min(EPI_T, in - i0 + 1), nj = min(EPI_T, jn - j0 + 1), nk = min(EPI_T, kn - k0 + 1);
     __syncthreads();                                       /* previous tile's readers are done */
     /* ---- phi tile with its halo: rows of ni+2 contiguous values ---- */
-    {
-      const int wi = ni + 2, wj = nj + 2, wk = nk + 2;
-      const int total = wi * wj * wk;
-      for (int e = t; e < total; e += 256) {
-        const int ii = e % wi, jj = (e / wi) % wj, kk = e / (wi * wj);
-        sphi[kk * EPI_SK + jj * EPI_SJ + ii] =
-            a.phi[(i0 - 1 + ii) + (long long)(j0 - 1 + jj) * st.cs1b + (long long)(k0 - 1 + kk) * st.cs2b];
-      }
-    }
+    load_phi_tile(sphi, a.phi, i0, j0, k0, ni + 2, nj + 2, nk + 2, st.cs1b, st.cs2b, t);
     __syncthreads();
     if (PROJECT) {
       /* u (Gfx, j fastest): lanes (j, k), walk the faces i';  v (Gfy, k fastest): lanes (k, i), walk j';
@@ -180,13 +187,24 @@ __global__ void __launch_bounds__(256, 3) k_epilogue(const __grid_constant__ Dev
  * pmean = sum / DOM.Gcc.s3 (cuda_bluebottle.cu:2528). */
 __global__ void __launch_bounds__(256) k_sub_mean(const __grid_constant__ Dev d, double *__restrict__ p, int s1b, int s2b, double global_cells)
 {
+  constexpr int R = 4;                     /* rows in flight per thread: all loads of a batch before its stores */
   const int in = d.L.in, jn = d.L.jn;
   const long long nrows = (long long)jn * d.L.kn;
   const double val = -(d.sc->p_sum / global_cells);
-  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
-    const int j = (int)(row % jn) + 1, k = (int)(row / jn) + 1;
-    double *pr = p + (long long)j * s1b + (long long)k * s2b;
-    for (int i = threadIdx.x + 1; i <= in; i += 256) pr[i] += val;
+  for (long long row0 = (long long)blockIdx.x * R; row0 < nrows; row0 += (long long)gridDim.x * R) {
+    long long base[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const long long row = row0 + r;
+      base[r] = row < nrows ? (long long)((int)(row % jn) + 1) * s1b + (long long)((int)(row / jn) + 1) * s2b : -1;
+    }
+    for (int i = threadIdx.x + 1; i <= in; i += 256) {
+      double v[R];
+#pragma unroll
+      for (int r = 0; r < R; r++) if (base[r] >= 0) v[r] = p[base[r] + i];
+#pragma unroll
+      for (int r = 0; r < R; r++) if (base[r] >= 0) p[base[r] + i] = v[r] + val;
+    }
   }
 }
 

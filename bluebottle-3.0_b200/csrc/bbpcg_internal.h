@@ -95,7 +95,8 @@ static inline ArenaMap make_arena_map(const Layout &L)
   size_t vec = (size_t)L.n * sizeof(double);
   m.r = take(vec); m.p0 = take(vec); m.p1 = take(vec); m.q = take(vec); m.x = take(vec);
   m.fmask = take((size_t)L.n); m.pmask = take((size_t)L.n);
-  size_t fi = (size_t)L.jn * L.kn, fj = (size_t)L.in * L.kn, fk = (size_t)L.in * L.jn;
+  /* staging faces sized for the largest of the four grids (a face grid is one entry longer along its normal) */
+  size_t fi = (size_t)(L.jn + 1) * (L.kn + 1), fj = (size_t)(L.in + 1) * (L.kn + 1), fk = (size_t)(L.in + 1) * (L.jn + 1);
   for (int b = 0; b < 2; b++) for (int f = 0; f < 6; f++)
     m.recv[b][f] = take(sizeof(double) * (f < 2 ? fi : f < 4 ? fj : fk));
   m.partials = take(sizeof(double) * 2 * BB_MAXBLOCKS);

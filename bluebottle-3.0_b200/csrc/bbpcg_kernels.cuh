@@ -927,54 +927,61 @@ __global__ void k_zero_ghosts(double *a, int inb, int jnb, int knb)
 }
 
 /* ------------------------------------------------------------------------------------ */
-/* generic Gcc halo exchange on a caller-owned s3b array: mpi_cuda_exchange_Gcc,
- * src/mpi_comm.c:257-315.  k_xchg_send reads my interior faces (what pack_planes_Gcc_* read,
- * src/bluebottle_kernel.cu:684-780) and stores them directly into the neighbour's staging
- * buffer for the opposite face (that is the MPI_Put, mpi_comm.c:293-306), same buffer layouts
- * E/W pp=(j-1)+jn(k-1), N/S pp=(k-1)+kn(i-1), T/B pp=(i-1)+in(j-1); the last CTA runs the rank
- * barrier (the MPI_Win_fence); k_xchg_recv is unpack_planes_Gcc_* (:1083-1177). */
-__global__ void k_xchg_send(const Dev d, const double *__restrict__ a, int s1b, int s2b, int buf)
+/* generic halo exchange on a caller-owned s3b array of ANY of the four grids: mpi_cuda_exchange_Gcc / _Gfx / _Gfy /
+ * _Gfz, src/mpi_comm.c:257-405.  k_xchg_send reads my interior faces (what pack_planes_G??_* read,
+ * src/bluebottle_kernel.cu:684-1081) and stores them directly into the neighbour's staging buffer for the
+ * opposite face (that is the MPI_Put, mpi_comm.c:293-306), same buffer layouts E/W pp=(j-1)+jn(k-1),
+ * N/S pp=(k-1)+kn(i-1), T/B pp=(i-1)+in(j-1) with the GRID's extents; the last CTA runs the rank barrier (the
+ * MPI_Win_fence); k_xchg_recv is unpack_planes_G??_* (:1083-1466).
+ * A face grid is one entry longer along its own normal and shares the block-boundary face with the neighbour
+ * (src/domain.c:1292-1301), so along that axis the planes sent are _ie-1 / _is+1 instead of _ie / _is
+ * (pack_planes_Gfx_east/west :782-815, Gfy_north/south :916-948, Gfz_top/bottom :1048-1081). */
+struct XchgGrid {
+  int n[3];            /* interior extents in, jn, kn of the grid                      */
+  long long st[3];     /* array strides of i, j, k (elements): the grid's index macro  */
+  int send_hi[3];      /* plane sent to the E / N / T neighbour (its ghost 0)          */
+  int send_lo[3];      /* plane sent to the W / S / B neighbour (its ghost n+1)        */
+};
+
+__device__ __forceinline__ void xchg_decode(const XchgGrid &g, long long t, int &f, long long &pp, int &i, int &j, int &k)
 {
-  const Layout L = d.L;
-  const long long fi = (long long)L.jn * L.kn, fj = (long long)L.in * L.kn, fk = (long long)L.in * L.jn;
-  const long long total = 2 * (fi + fj + fk);
+  const long long fi = (long long)g.n[1] * g.n[2], fj = (long long)g.n[0] * g.n[2];
+  long long u = t;
+  if (u < 2 * fi) { f = (int)(u / fi); pp = u % fi; j = (int)(pp % g.n[1]) + 1; k = (int)(pp / g.n[1]) + 1; i = 0; }
+  else if ((u -= 2 * fi) < 2 * fj) { f = 2 + (int)(u / fj); pp = u % fj; k = (int)(pp % g.n[2]) + 1; i = (int)(pp / g.n[2]) + 1; j = 0; }
+  else { u -= 2 * fj; const long long fk = (long long)g.n[0] * g.n[1]; f = 4 + (int)(u / fk); pp = u % fk; i = (int)(pp % g.n[0]) + 1; j = (int)(pp / g.n[0]) + 1; k = 0; }
+}
+
+__global__ void k_xchg_send(const Dev d, const XchgGrid g, const double *__restrict__ a, int buf)
+{
+  const long long total = 2 * ((long long)g.n[1] * g.n[2] + (long long)g.n[0] * g.n[2] + (long long)g.n[0] * g.n[1]);
   bool pushed = false;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    long long u = t;
-    int f; long long pp;
-    if (u < 2 * fi) { f = (int)(u / fi); pp = u % fi; }
-    else if ((u -= 2 * fi) < 2 * fj) { f = 2 + (int)(u / fj); pp = u % fj; }
-    else { u -= 2 * fj; f = 4 + (int)(u / fk); pp = u % fk; }
+    int f, i, j, k; long long pp;
+    xchg_decode(g, t, f, pp, i, j, k);
     const NbrFace &nf = d.halo.f[f];
     if (!nf.recv[buf]) continue;
-    int i, j, k;
-    if (f < 2) { j = (int)(pp % L.jn) + 1; k = (int)(pp / L.jn) + 1; i = (f == 0) ? L.in : 1; }
-    else if (f < 4) { k = (int)(pp % L.kn) + 1; i = (int)(pp / L.kn) + 1; j = (f == 2) ? L.jn : 1; }
-    else { i = (int)(pp % L.in) + 1; j = (int)(pp / L.in) + 1; k = (f == 4) ? L.kn : 1; }
-    nf.recv[buf][pp] = a[i + (long long)j * s1b + (long long)k * s2b];
+    if (f < 2) i = (f == 0) ? g.send_hi[0] : g.send_lo[0];
+    else if (f < 4) j = (f == 2) ? g.send_hi[1] : g.send_lo[1];
+    else k = (f == 4) ? g.send_hi[2] : g.send_lo[2];
+    nf.recv[buf][pp] = a[i * g.st[0] + j * g.st[1] + k * g.st[2]];
     pushed = true;
   }
   double v[1] = { 0. }, tot[1];
   if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) rank_allreduce(d, tot, 0, true);
 }
 
-__global__ void k_xchg_recv(const Dev d, double *__restrict__ a, int s1b, int s2b, int buf)
+__global__ void k_xchg_recv(const Dev d, const XchgGrid g, double *__restrict__ a, int buf)
 {
-  const Layout L = d.L;
-  const long long fi = (long long)L.jn * L.kn, fj = (long long)L.in * L.kn, fk = (long long)L.in * L.jn;
-  const long long total = 2 * (fi + fj + fk);
+  const long long total = 2 * ((long long)g.n[1] * g.n[2] + (long long)g.n[0] * g.n[2] + (long long)g.n[0] * g.n[1]);
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    long long u = t;
-    int f; long long pp;
-    if (u < 2 * fi) { f = (int)(u / fi); pp = u % fi; }
-    else if ((u -= 2 * fi) < 2 * fj) { f = 2 + (int)(u / fj); pp = u % fj; }
-    else { u -= 2 * fj; f = 4 + (int)(u / fk); pp = u % fk; }
+    int f, i, j, k; long long pp;
+    xchg_decode(g, t, f, pp, i, j, k);
     if (!d.halo.f[f].recv[buf]) continue;           /* no neighbour on this side: ghost untouched */
-    int i, j, k;
-    if (f < 2) { j = (int)(pp % L.jn) + 1; k = (int)(pp / L.jn) + 1; i = (f == 0) ? L.in + 1 : 0; }
-    else if (f < 4) { k = (int)(pp % L.kn) + 1; i = (int)(pp / L.kn) + 1; j = (f == 2) ? L.jn + 1 : 0; }
-    else { i = (int)(pp % L.in) + 1; j = (int)(pp / L.in) + 1; k = (f == 4) ? L.kn + 1 : 0; }
-    a[i + (long long)j * s1b + (long long)k * s2b] = d.recv[buf][f][pp];
+    if (f < 2) i = (f == 0) ? g.n[0] + 1 : 0;       /* _ieb / _isb */
+    else if (f < 4) j = (f == 2) ? g.n[1] + 1 : 0;
+    else k = (f == 4) ? g.n[2] + 1 : 0;
+    a[i * g.st[0] + j * g.st[1] + k * g.st[2]] = d.recv[buf][f][pp];
   }
 }
 

@@ -78,7 +78,7 @@ struct bbpcg_solver {
   int *h_ztab;                      /* pinned [BB_MAXZ + 1] */
   int zt_cols, zt_kc, zt_g10, zt_min, zt_nbz;   /* what the uploaded table was built for */
   int taper_g10, taper_min;         /* guided chunking: t = remaining*columns*10 / (g10*slots), >= taper_min */
-  int pdl;                          /* programmatic dependent launch of the two iteration kernels */
+  int pdl;                          /* programmatic dependent launch of the two iteration kernels: 0 off, 1 on, 2 auto */
   int resid_mb, resid_d;            /* k_resid_tma: CTAs per SM the register budget is compiled for (2 or 3); TMA planes in flight */
   int fast_refresh;                 /* q%50 refresh through k_refresh_x4 + the refresh form of k_resid_tma */
   int rhs_tiled;                    /* PP_rhs through shared-memory transposes (default) or the row-walking kernel */
@@ -275,7 +275,7 @@ extern "C" int bbpcg_create(bbpcg_solver **out, const dom_struct *dom_rank, cons
   CU(cudaHostAlloc(&s->h_poll, 64, cudaHostAllocDefault));
   CU(cudaHostAlloc(&s->h_scal, sizeof(Scal), cudaHostAllocDefault));
   CU(cudaHostAlloc(&s->h_ztab, sizeof(int) * (BB_MAXZ + 1), cudaHostAllocDefault));
-  s->zt_cols = -1; s->taper_g10 = 0; s->taper_min = 8; s->pdl = 1; s->recompute = 1; s->rhs_tiled = 1; s->fast_refresh = 1; s->resid_mb = 2; s->resid_d = 2;
+  s->zt_cols = -1; s->taper_g10 = 0; s->taper_min = 8; s->pdl = 2; s->recompute = 1; s->rhs_tiled = 1; s->fast_refresh = 1; s->resid_mb = 2; s->resid_d = 2;
   /* single rank: neighbours are this block itself (periodic wrap) or nothing */
   s->nranks = 1;
   for (int p = 0; p < BB_MAXR; p++) { s->peer_arena[p] = NULL; s->peer_opened[p] = false; }
@@ -431,6 +431,18 @@ static int plan_zchunks(bbpcg_solver *s, int columns, int slots, int *nbz_out)
   return BBPCG_OK;
 }
 
+/* PDL policy.  Measured on 2 B200s (scripts/comm_probe.py, profiles/r01e_comm_probe.jsonl): with 67 M cells per rank PDL
+ * saves 22 us of 786 per iteration; with 16.7 M cells per rank (the 8-GPU share of 512^3) it COSTS 13 us of 237 in a
+ * decomposed run (the early-launched CTAs of the next kernel hold SM slots while the last CTA of this one waits for its
+ * peers) and gains nothing stand-alone.  auto = on, except for decomposed runs with small blocks. */
+static bool pdl_active(const bbpcg_solver *s)
+{
+  if (s->shared_device || !s->pdl) return false;
+  if (s->pdl == 1) return true;
+  const long long cells = (long long)s->dev.L.in * s->dev.L.jn * s->dev.L.kn;
+  return !(s->nranks > 1 && cells < 24ll * 1000 * 1000);
+}
+
 /* launch with (optionally) the programmatic-stream-serialization attribute: the kernel may be scheduled
  * while its predecessor drains and blocks in pdl_wait() until that one is complete.  Never used when
  * several ranks share one GPU: their waiting CTAs could starve the peer whose arrival they wait for. */
@@ -443,7 +455,7 @@ static cudaError_t launch_k(bbpcg_solver *s, void (*kernel)(KArgs...), dim3 grid
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = (pdl && s->pdl && !s->shared_device && !s->kernel_timing) ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = (pdl && pdl_active(s) && !s->kernel_timing) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
@@ -695,28 +707,48 @@ extern "C" int bbpcg_rhs(bbpcg_solver *s, const real *u, const real *v, const re
 }
 
 /* ---- halo exchange on caller arrays -------------------------------------------------------- */
-static int enqueue_exchange(bbpcg_solver *s, real *array)
+static XchgGrid xchg_grid(const bbpcg_solver *s, int grid)
 {
-  const Layout &L = s->dev.L;
-  const long long total = 2ll * ((long long)L.jn * L.kn + (long long)L.in * L.kn + (long long)L.in * L.jn);
+  const dom_struct &d = s->dom;
+  XchgGrid g;
+  const grid_info &gi = grid == BBPCG_GFX ? d.Gfx : grid == BBPCG_GFY ? d.Gfy : grid == BBPCG_GFZ ? d.Gfz : d.Gcc;
+  g.n[0] = gi.in; g.n[1] = gi.jn; g.n[2] = gi.kn;
+  /* index macros, src/bluebottle.h:70-73 */
+  if (grid == BBPCG_GFX) { g.st[0] = gi.s2b; g.st[1] = 1; g.st[2] = gi.s1b; }
+  else if (grid == BBPCG_GFY) { g.st[0] = gi.s1b; g.st[1] = gi.s2b; g.st[2] = 1; }
+  else { g.st[0] = 1; g.st[1] = gi.s1b; g.st[2] = gi.s2b; }
+  for (int ax = 0; ax < 3; ax++) { g.send_hi[ax] = g.n[ax]; g.send_lo[ax] = 1; }         /* _ie -> nbr _isb, _is -> nbr _ieb */
+  const int normal = grid == BBPCG_GFX ? 0 : grid == BBPCG_GFY ? 1 : grid == BBPCG_GFZ ? 2 : -1;
+  if (normal >= 0) { g.send_hi[normal] = g.n[normal] - 1; g.send_lo[normal] = 2; }       /* _ie-1 / _is+1: the shared face is skipped */
+  return g;
+}
+
+static int enqueue_exchange(bbpcg_solver *s, real *array, int grid = BBPCG_GCC)
+{
+  const XchgGrid g = xchg_grid(s, grid);
+  const long long total = 2ll * ((long long)g.n[1] * g.n[2] + (long long)g.n[0] * g.n[2] + (long long)g.n[0] * g.n[1]);
   const int nb = clampi((total + 255) / 256, 1, s->sm_count * 4);
   const int buf = (int)(s->exchange_count++ & 1u);
-  k_xchg_send<<<nb, 256, 0, s->stream>>>(s->dev, array, s->fst.cs1b, s->fst.cs2b, buf);
-  k_xchg_recv<<<nb, 256, 0, s->stream>>>(s->dev, array, s->fst.cs1b, s->fst.cs2b, buf);
+  k_xchg_send<<<nb, 256, 0, s->stream>>>(s->dev, g, array, buf);
+  k_xchg_recv<<<nb, 256, 0, s->stream>>>(s->dev, g, array, buf);
   s->launches += 2;
   return BBPCG_OK;
 }
 
-extern "C" int bbpcg_exchange_Gcc(bbpcg_solver *s, real *array)
+extern "C" int bbpcg_exchange(bbpcg_solver *s, real *array, int grid)
 {
-  if (!s || !array) { bbpcg_set_error("bbpcg_exchange_Gcc: NULL argument"); return BBPCG_EINVAL; }
+  if (!s || !array) { bbpcg_set_error("bbpcg_exchange: NULL argument"); return BBPCG_EINVAL; }
+  if (grid < BBPCG_GCC || grid > BBPCG_GFZ) { bbpcg_set_error("bbpcg_exchange: grid must be BBPCG_GCC/GFX/GFY/GFZ"); return BBPCG_EINVAL; }
+  if (s->nranks == 1 && s->DOM.In * s->DOM.Jn * s->DOM.Kn != 1) { bbpcg_set_error("decomposition has %d blocks: call bbpcg_comm_import first", s->DOM.In * s->DOM.Jn * s->DOM.Kn); return BBPCG_ECOMM; }
   CU(cudaSetDevice(s->device));
-  int rc = enqueue_exchange(s, array);
+  int rc = enqueue_exchange(s, array, grid);
   if (rc) return rc;
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(s->stream));
   return BBPCG_OK;
 }
+
+extern "C" int bbpcg_exchange_Gcc(bbpcg_solver *s, real *array) { return bbpcg_exchange(s, array, BBPCG_GCC); }
 
 extern "C" int bbpcg_spmv(bbpcg_solver *s, const real *src_s3b, real *Ap_s3, int use_phase)
 {
@@ -984,7 +1016,7 @@ extern "C" int bbpcg_set_option(bbpcg_solver *s, const char *key, long long valu
   else if (!strcmp(key, "kc")) s->kc = (int)value;
   else if (!strcmp(key, "taper_g10")) s->taper_g10 = clampi(value, 0, 1000);
   else if (!strcmp(key, "taper_min")) s->taper_min = clampi(value, 1, 4096);
-  else if (!strcmp(key, "pdl")) s->pdl = value != 0;
+  else if (!strcmp(key, "pdl")) s->pdl = clampi(value, 0, 2);
   else if (!strcmp(key, "recompute")) s->recompute = value != 0;
   else if (!strcmp(key, "rhs_tiled")) s->rhs_tiled = value != 0;
   else if (!strcmp(key, "fast_refresh")) s->fast_refresh = value != 0;
@@ -1027,7 +1059,7 @@ extern "C" long long bbpcg_get_info(bbpcg_solver *s, const char *key)
   if (!strcmp(key, "search_grid")) return s->last_search_grid;
   if (!strcmp(key, "search_kc")) return s->last_search_kc;
   if (!strcmp(key, "search_nbz")) return s->zt_nbz;
-  if (!strcmp(key, "pdl")) return s->pdl && !s->shared_device;
+  if (!strcmp(key, "pdl")) return pdl_active(s);
   if (!strcmp(key, "recompute")) return recompute_active(s);
   return -1;
 }

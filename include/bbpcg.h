@@ -140,6 +140,16 @@ int  bbpcg_history(bbpcg_solver *s, double *out, int cap);
  * from the neighbouring blocks (periodic wrap included; faces only, no edges/corners). */
 int  bbpcg_exchange_Gcc(bbpcg_solver *s, real *array);
 
+/* The same transport for the three face grids: = mpi_cuda_exchange_Gfx / _Gfy / _Gfz (src/mpi_comm.c:317-405)
+ * on a caller-owned Gfx / Gfy / Gfz s3b device array.  A face grid shares its block-boundary face with the
+ * neighbour (src/domain.c:1292-1301), so along its own normal the planes _ie-1 / _is+1 travel
+ * (src/bluebottle_kernel.cu:782-815,916-948,1048-1081); faces only, no edges/corners.  COLLECTIVE. */
+#define BBPCG_GCC 0
+#define BBPCG_GFX 1
+#define BBPCG_GFY 2
+#define BBPCG_GFZ 3
+int  bbpcg_exchange(bbpcg_solver *s, real *array, int grid);
+
 /* ---- solve epilogue (what src/bluebottle.c:233-256 runs on phi right after the solve) -------
  * = cuda_dom_BC_p(array) (src/cuda_bluebottle.cu:2536-2589): on every face of this block that has
  * no neighbour and whose pressure BC is NEUMANN, ghost = adjacent interior cell (faces only). */

@@ -69,6 +69,7 @@ def load(omp=False):
     lib.bbo_solve.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                               dp, C.c_int, C.POINTER(Result)]
     lib.bbo_iterate_fixed.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int]
+    lib.bbo_exchange.argtypes = [C.c_void_p, C.c_int]
     lib.bbo_dom_BC_p.argtypes = [C.c_void_p, C.c_int]
     lib.bbo_project.argtypes = [C.c_void_p, C.c_double, C.c_double]
     lib.bbo_update_p.argtypes = [C.c_void_p]
@@ -141,6 +142,10 @@ class Oracle:
 
     def exchange_Gcc(self, aid):
         self.lib.bbo_exchange_Gcc(self.h, aid)
+
+    def exchange(self, aid):
+        """mpi_cuda_exchange_G{cc,fx,fy,fz} on the array `aid` (the grid follows from the array)"""
+        self.lib.bbo_exchange(self.h, aid)
 
     def spmv(self, aid, parts=False):
         (self.lib.bbo_spmv_parts if parts else self.lib.bbo_spmv_noparts)(self.h, aid)

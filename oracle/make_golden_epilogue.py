@@ -47,7 +47,14 @@ def run_case(name, outdir):
                                 P(keep["phase_shell"]), P(keep["u_star"]), P(keep["v_star"]), P(keep["w_star"]), nparts) == 0
     ein = case.epilogue_inputs(0)
     out = ref_epilogue(lib, case, ein["phi"], ein["p0"])
-    np.savez_compressed(os.path.join(outdir, name + ".npz"), u=out["u"], v=out["v"], w=out["w"], p=out["p"], phi=out["phi"],
+    # the face-grid halo exchanges (pack / self-put / unpack kernels of Gfx, Gfy, Gfz) on seeded arrays
+    from cases import face_exchange_inputs
+    ex = {}
+    for key, (arr, code) in face_exchange_inputs(case, 0, SEED + 6).items():
+        a = np.ascontiguousarray(arr).copy()
+        assert lib.bbref_exchange_face(P(a), code) == 0
+        ex["ex_" + key] = a
+    np.savez_compressed(os.path.join(outdir, name + ".npz"), u=out["u"], v=out["v"], w=out["w"], p=out["p"], phi=out["phi"], **ex,
                         input_checksum=np.float64(float(np.abs(ein["phi"]).sum() + np.abs(ein["p0"]).sum())))
     print(name, "ms %.3f" % out["ms"], "mean(p) %.3e" % out["p"][1:-1, 1:-1, 1:-1].mean())
 

@@ -200,8 +200,8 @@ static void alloc_block(bbo_block *b, const dom_struct *d)
   b->invM = xcalloc(d->Gcc.s3, sizeof(real)); b->r_q = xcalloc(d->Gcc.s3, sizeof(real));
   b->z_q = xcalloc(d->Gcc.s3, sizeof(real)); b->p_q = xcalloc(d->Gcc.s3, sizeof(real));
   b->Apb_q = xcalloc(d->Gcc.s3, sizeof(real));
-  for (f = 0; f < 6; f++) {
-    int n = (f < 2) ? d->Gcc.s2_i : (f < 4) ? d->Gcc.s2_j : d->Gcc.s2_k;
+  for (f = 0; f < 6; f++) {     /* sized for the largest of the four grids (cuda_bluebottle.cu:255-319 has one set per grid) */
+    int n = (f < 2) ? (d->yn + 1) * (d->zn + 1) : (f < 4) ? (d->xn + 1) * (d->zn + 1) : (d->xn + 1) * (d->yn + 1);
     b->send[f] = xcalloc(n, sizeof(real)); b->recv[f] = xcalloc(n, sizeof(real));
   }
   /* host initialisation when NPARTS == 0: phase = phase_shell = -1 (particle.c:556-568) */
@@ -600,6 +600,71 @@ void bbo_exchange_Gcc(bbo_state *s, int array_id)
     if (d->s >= 0) for (i = 1; i <= g->_ie; i++) for (k = 1; k <= g->_ke; k++) a[GCC_LOC(i, g->_jsb, k, g->s1b, g->s2b)] = b->recv[BBO_S][(k - 1) + g->kn * (i - 1)];
     if (d->t >= 0) for (j = 1; j <= g->_je; j++) for (i = 1; i <= g->_ie; i++) a[GCC_LOC(i, j, g->_keb, g->s1b, g->s2b)] = b->recv[BBO_T][(i - 1) + g->in * (j - 1)];
     if (d->b >= 0) for (j = 1; j <= g->_je; j++) for (i = 1; i <= g->_ie; i++) a[GCC_LOC(i, j, g->_ksb, g->s1b, g->s2b)] = b->recv[BBO_B][(i - 1) + g->in * (j - 1)];
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* mpi_cuda_exchange_Gfx / _Gfy / _Gfz, src/mpi_comm.c:317-405, pack/unpack kernels src/bluebottle_kernel.cu:782-1081,
+ * 1179-1466.  Same scheme as the Gcc exchange with the grid's own extents and index macro; along the grid's own normal
+ * the block-boundary face is shared with the neighbour, so the planes _ie-1 / _is+1 are sent (:795,:812 for Gfx,
+ * :926,:943 for Gfy, :1059,:1076 for Gfz) into the ghosts _isb / _ieb. */
+static real *blk_face_array(bbo_block *b, int id, int *grid)
+{
+  switch (id) {
+    case BBO_U_STAR: *grid = 1; return b->u_star;  case BBO_VEL_U: *grid = 1; return b->u;
+    case BBO_V_STAR: *grid = 2; return b->v_star;  case BBO_VEL_V: *grid = 2; return b->v;
+    case BBO_W_STAR: *grid = 3; return b->w_star;  case BBO_VEL_W: *grid = 3; return b->w;
+  }
+  *grid = 0;
+  return blk_gcc_array(b, id);
+}
+
+static size_t grid_loc(int grid, const grid_info *g, int i, int j, int k)
+{
+  switch (grid) {
+    case 1: return (size_t)GFX_LOC(i, j, k, g->s1b, g->s2b);
+    case 2: return (size_t)GFY_LOC(i, j, k, g->s1b, g->s2b);
+    case 3: return (size_t)GFZ_LOC(i, j, k, g->s1b, g->s2b);
+  }
+  return (size_t)GCC_LOC(i, j, k, g->s1b, g->s2b);
+}
+
+void bbo_exchange(bbo_state *s, int array_id)
+{
+  int c, i, j, k, grid = 0, pass;
+  for (pass = 0; pass < 3; pass++) {                       /* 0 pack, 1 put, 2 unpack */
+    for (c = 0; c < s->nblocks; c++) {
+      const dom_struct *d = &s->dom[c];
+      bbo_block *b = &s->blk[c];
+      real *a = blk_face_array(b, array_id, &grid);
+      const grid_info *g = grid == 1 ? &d->Gfx : grid == 2 ? &d->Gfy : grid == 3 ? &d->Gfz : &d->Gcc;
+      /* planes sent east/west, north/south, top/bottom */
+      const int ie = g->_ie - (grid == 1), is = g->_is + (grid == 1);
+      const int je = g->_je - (grid == 2), js = g->_js + (grid == 2);
+      const int ke = g->_ke - (grid == 3), ks = g->_ks + (grid == 3);
+      if (pass == 0) {
+        if (d->e >= 0) for (k = 1; k <= g->_ke; k++) for (j = 1; j <= g->_je; j++) b->send[BBO_E][(j - 1) + g->jn * (k - 1)] = a[grid_loc(grid, g, ie, j, k)];
+        if (d->w >= 0) for (k = 1; k <= g->_ke; k++) for (j = 1; j <= g->_je; j++) b->send[BBO_W][(j - 1) + g->jn * (k - 1)] = a[grid_loc(grid, g, is, j, k)];
+        if (d->n >= 0) for (i = 1; i <= g->_ie; i++) for (k = 1; k <= g->_ke; k++) b->send[BBO_N][(k - 1) + g->kn * (i - 1)] = a[grid_loc(grid, g, i, je, k)];
+        if (d->s >= 0) for (i = 1; i <= g->_ie; i++) for (k = 1; k <= g->_ke; k++) b->send[BBO_S][(k - 1) + g->kn * (i - 1)] = a[grid_loc(grid, g, i, js, k)];
+        if (d->t >= 0) for (j = 1; j <= g->_je; j++) for (i = 1; i <= g->_ie; i++) b->send[BBO_T][(i - 1) + g->in * (j - 1)] = a[grid_loc(grid, g, i, j, ke)];
+        if (d->b >= 0) for (j = 1; j <= g->_je; j++) for (i = 1; i <= g->_ie; i++) b->send[BBO_B][(i - 1) + g->in * (j - 1)] = a[grid_loc(grid, g, i, j, ks)];
+      } else if (pass == 1) {                              /* mpi_comm.c:326-343 */
+        if (d->w >= 0) memcpy(s->blk[d->w].recv[BBO_E], b->send[BBO_W], sizeof(real) * g->s2_i);
+        if (d->e >= 0) memcpy(s->blk[d->e].recv[BBO_W], b->send[BBO_E], sizeof(real) * g->s2_i);
+        if (d->s >= 0) memcpy(s->blk[d->s].recv[BBO_N], b->send[BBO_S], sizeof(real) * g->s2_j);
+        if (d->n >= 0) memcpy(s->blk[d->n].recv[BBO_S], b->send[BBO_N], sizeof(real) * g->s2_j);
+        if (d->b >= 0) memcpy(s->blk[d->b].recv[BBO_T], b->send[BBO_B], sizeof(real) * g->s2_k);
+        if (d->t >= 0) memcpy(s->blk[d->t].recv[BBO_B], b->send[BBO_T], sizeof(real) * g->s2_k);
+      } else {
+        if (d->e >= 0) for (k = 1; k <= g->_ke; k++) for (j = 1; j <= g->_je; j++) a[grid_loc(grid, g, g->_ieb, j, k)] = b->recv[BBO_E][(j - 1) + g->jn * (k - 1)];
+        if (d->w >= 0) for (k = 1; k <= g->_ke; k++) for (j = 1; j <= g->_je; j++) a[grid_loc(grid, g, g->_isb, j, k)] = b->recv[BBO_W][(j - 1) + g->jn * (k - 1)];
+        if (d->n >= 0) for (i = 1; i <= g->_ie; i++) for (k = 1; k <= g->_ke; k++) a[grid_loc(grid, g, i, g->_jeb, k)] = b->recv[BBO_N][(k - 1) + g->kn * (i - 1)];
+        if (d->s >= 0) for (i = 1; i <= g->_ie; i++) for (k = 1; k <= g->_ke; k++) a[grid_loc(grid, g, i, g->_jsb, k)] = b->recv[BBO_S][(k - 1) + g->kn * (i - 1)];
+        if (d->t >= 0) for (j = 1; j <= g->_je; j++) for (i = 1; i <= g->_ie; i++) a[grid_loc(grid, g, i, j, g->_keb)] = b->recv[BBO_T][(i - 1) + g->in * (j - 1)];
+        if (d->b >= 0) for (j = 1; j <= g->_je; j++) for (i = 1; i <= g->_ie; i++) a[grid_loc(grid, g, i, j, g->_ksb)] = b->recv[BBO_B][(i - 1) + g->in * (j - 1)];
+      }
+    }
   }
 }
 

@@ -110,14 +110,14 @@ static void shim_blocks_init(const dom_struct *d)
   bx = nblk(d->Gcc.in, tx - 2); by = nblk(d->Gcc.jn, ty - 2); bz = nblk(d->Gcc.kn, tz - 2);
   blocks.Gcc.dim_in_s = dim3(ty, tz); blocks.Gcc.dim_jn_s = dim3(tz, tx); blocks.Gcc.dim_kn_s = dim3(tx, ty);
   blocks.Gcc.num_in_s = dim3(by, bz); blocks.Gcc.num_jn_s = dim3(bz, bx); blocks.Gcc.num_kn_s = dim3(bx, by);
-  /* face grids, cuda_bluebottle.cu:583-760: same rule per grid; only the shapes the epilogue launches are needed
-   * (project_u: Gfx.num_in/dim_in, project_v: Gfy.num_jn/dim_jn, project_w: Gfz.num_kn/dim_kn) */
-  tx = thr(d->Gfx.in); ty = thr(d->Gfx.jn); tz = thr(d->Gfx.kn);
-  blocks.Gfx.dim_in = dim3(ty, tz); blocks.Gfx.num_in = dim3(nblk(d->Gfx.jn, ty), nblk(d->Gfx.kn, tz));
-  tx = thr(d->Gfy.in); ty = thr(d->Gfy.jn); tz = thr(d->Gfy.kn);
-  blocks.Gfy.dim_jn = dim3(tz, tx); blocks.Gfy.num_jn = dim3(nblk(d->Gfy.kn, tz), nblk(d->Gfy.in, tx));
-  tx = thr(d->Gfz.in); ty = thr(d->Gfz.jn); tz = thr(d->Gfz.kn);
-  blocks.Gfz.dim_kn = dim3(tx, ty); blocks.Gfz.num_kn = dim3(nblk(d->Gfz.in, tx), nblk(d->Gfz.jn, ty));
+  /* face grids, cuda_bluebottle.cu:583-760: the same rule per grid (project_u/v/w and the Gf? pack/unpack kernels) */
+#define SHIM_FACE_BLOCKS(G)                                                                              \
+  tx = thr(d->G.in); ty = thr(d->G.jn); tz = thr(d->G.kn);                                               \
+  bx = nblk(d->G.in, tx); by = nblk(d->G.jn, ty); bz = nblk(d->G.kn, tz);                                \
+  blocks.G.dim_in = dim3(ty, tz); blocks.G.dim_jn = dim3(tz, tx); blocks.G.dim_kn = dim3(tx, ty);        \
+  blocks.G.num_in = dim3(by, bz); blocks.G.num_jn = dim3(bz, bx); blocks.G.num_kn = dim3(bx, by);
+  SHIM_FACE_BLOCKS(Gfx) SHIM_FACE_BLOCKS(Gfy) SHIM_FACE_BLOCKS(Gfz)
+#undef SHIM_FACE_BLOCKS
   /* ghost-inclusive shapes used by zero_rhs_ghost_{i,j,k} (cuda_bluebottle.cu:545-560) */
   tx = thr(d->Gcc.inb); ty = thr(d->Gcc.jnb); tz = thr(d->Gcc.knb);
   bx = nblk(d->Gcc.inb, tx); by = nblk(d->Gcc.jnb, ty); bz = nblk(d->Gcc.knb, tz);
@@ -345,6 +345,45 @@ int bbref_epilogue(const real *phi_h, const real *p0_h, const int *pbc, real rho
   if (w_h) CK(cudaMemcpy(w_h, _w, (size_t)d->Gfz.s3b * sizeof(real), cudaMemcpyDeviceToHost));
   if (p_h) CK(cudaMemcpy(p_h, _p, s3b * sizeof(real), cudaMemcpyDeviceToHost));
   if (phi_out_h) CK(cudaMemcpy(phi_out_h, _phi, s3b * sizeof(real), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+/* mpi_cuda_exchange_Gfx / _Gfy / _Gfz (mpi_comm.c:317-405) for one rank, with the reference's own pack / unpack kernels
+ * (cuda_pack_planes_Gf?, cuda_bluebottle.cu:1576-1651; cuda_unpack_planes_Gf?, :1677-1752) and a device-to-device
+ * copy for the self MPI_Put.  grid: 1 Gfx, 2 Gfy, 3 Gfz.  The array travels host -> device -> host. */
+typedef void (*shim_plane_kernel)(real *, real *);
+int bbref_exchange_face(real *arr_host, int grid)
+{
+  const dom_struct *d = &dom[rank];
+  const grid_info *g = grid == 1 ? &d->Gfx : grid == 2 ? &d->Gfy : &d->Gfz;
+  static const shim_plane_kernel pack[3][6] = {
+    { pack_planes_Gfx_east, pack_planes_Gfx_west, pack_planes_Gfx_north, pack_planes_Gfx_south, pack_planes_Gfx_top, pack_planes_Gfx_bottom },
+    { pack_planes_Gfy_east, pack_planes_Gfy_west, pack_planes_Gfy_north, pack_planes_Gfy_south, pack_planes_Gfy_top, pack_planes_Gfy_bottom },
+    { pack_planes_Gfz_east, pack_planes_Gfz_west, pack_planes_Gfz_north, pack_planes_Gfz_south, pack_planes_Gfz_top, pack_planes_Gfz_bottom } };
+  static const shim_plane_kernel unpack[3][6] = {
+    { unpack_planes_Gfx_east, unpack_planes_Gfx_west, unpack_planes_Gfx_north, unpack_planes_Gfx_south, unpack_planes_Gfx_top, unpack_planes_Gfx_bottom },
+    { unpack_planes_Gfy_east, unpack_planes_Gfy_west, unpack_planes_Gfy_north, unpack_planes_Gfy_south, unpack_planes_Gfy_top, unpack_planes_Gfy_bottom },
+    { unpack_planes_Gfz_east, unpack_planes_Gfz_west, unpack_planes_Gfz_north, unpack_planes_Gfz_south, unpack_planes_Gfz_top, unpack_planes_Gfz_bottom } };
+  const cuda_blocks_info *bi = grid == 1 ? &blocks.Gfx : grid == 2 ? &blocks.Gfy : &blocks.Gfz;
+  const dim3 num[6] = { bi->num_in, bi->num_in, bi->num_jn, bi->num_jn, bi->num_kn, bi->num_kn };
+  const dim3 dim[6] = { bi->dim_in, bi->dim_in, bi->dim_jn, bi->dim_jn, bi->dim_kn, bi->dim_kn };
+  const int nbr[6] = { d->e, d->w, d->n, d->s, d->t, d->b };
+  const int opp[6] = { 1, 0, 3, 2, 5, 4 };
+  const size_t fsz[6] = { (size_t)g->s2_i, (size_t)g->s2_i, (size_t)g->s2_j, (size_t)g->s2_j, (size_t)g->s2_k, (size_t)g->s2_k };
+  real *arr, *snd[6], *rcv[6];
+  CK(cudaMalloc(&arr, (size_t)g->s3b * sizeof(real)));
+  CK(cudaMemcpy(arr, arr_host, (size_t)g->s3b * sizeof(real), cudaMemcpyHostToDevice));
+  for (int f = 0; f < 6; f++) { CK(cudaMalloc(&snd[f], fsz[f] * sizeof(real))); CK(cudaMalloc(&rcv[f], fsz[f] * sizeof(real))); }
+  for (int f = 0; f < 6; f++) if (nbr[f] != MPI_PROC_NULL) pack[grid - 1][f]<<<num[f], dim[f]>>>(arr, snd[f]);
+  CK(cudaDeviceSynchronize());
+  /* w -> the west neighbour's recv_e, e -> recv_w, ... (mpi_comm.c:326-343); the only possible neighbour is this rank */
+  for (int f = 0; f < 6; f++) if (nbr[f] == rank) CK(cudaMemcpy(rcv[opp[f]], snd[f], fsz[f] * sizeof(real), cudaMemcpyDeviceToDevice));
+  for (int f = 0; f < 6; f++) if (nbr[f] != MPI_PROC_NULL) unpack[grid - 1][f]<<<num[f], dim[f]>>>(arr, rcv[f]);
+  CK(cudaDeviceSynchronize());
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(arr_host, arr, (size_t)g->s3b * sizeof(real), cudaMemcpyDeviceToHost));
+  for (int f = 0; f < 6; f++) { cudaFree(snd[f]); cudaFree(rcv[f]); }
+  cudaFree(arr);
   return 0;
 }
 

@@ -81,6 +81,7 @@ def load_ref():
     lib.bbref_spmv.argtypes = [vp, C.c_int, vp]
     lib.bbref_exchange.argtypes = [vp]
     lib.bbref_epilogue.argtypes = [vp, vp, vp, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
+    lib.bbref_exchange_face.argtypes = [vp, C.c_int]
     lib.bbref_dev_ptr.argtypes = [C.c_int]
     lib.bbref_dev_ptr.restype = C.c_void_p
     return lib
@@ -106,3 +107,11 @@ def ref_epilogue(lib, case, phi, p0, rho_f=1.0, dt=1e-3):
 def face_interior(d, grid, a):
     """the entries cuda_project writes: Gf?._is.._ie x interior of the other two (all of a Gf? minus its ghosts)"""
     return a[1:-1, 1:-1, 1:-1]
+
+
+def face_exchange_inputs(case, rank, seed):
+    """seeded Gfx / Gfy / Gfz arrays (ghosts included) for the face-grid halo exchanges: {name: (array, BBPCG grid code)}"""
+    from bbpcg.grid import grid_shape
+    d = case.o.dom(rank)
+    rng = np.random.default_rng(seed + 1000 * rank)
+    return {k: (rng.standard_normal(grid_shape(d, g)), code) for k, g, code in (("u", "Gfx", 1), ("v", "Gfy", 2), ("w", "Gfz", 3))}

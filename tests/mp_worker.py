@@ -162,6 +162,23 @@ def main():
             if res.niter == ores.niter:
                 assert err < 1e-10, err
             out.update(niter=res.niter, oracle_niter=ores.niter, rel_l2=err, ms_iter=res.ms_iter, launches=res.launches)
+        # the solve epilogue across real GPUs (exchange of phi over NVLink, rank-ordered mean): seeded phi/p0 per block,
+        # against the multi-block oracle
+        case.seed_epilogue(77)
+        ein = case.epilogue_inputs(rank)
+        ephi, ep0 = s.to_device(ein["phi"]), s.to_device(ein["p0"])
+        un, vn, wn, pn = s.empty("Gfx"), s.empty("Gfy"), s.empty("Gfz"), s.empty("Gcc")
+        s.epilogue(ephi, inp["u_star"], inp["v_star"], inp["w_star"], inp["flag_u"], inp["flag_v"], inp["flag_w"], un, vn, wn,
+                   ep0, inp["phase"], pn)
+        case.o.epilogue(1.0, 1e-3)
+        I = (slice(1, -1),) * 3
+        assert np.array_equal(ephi.cpu().numpy(), case.o.array(rank, ob.PHI)), "epilogue: phi ghosts differ on rank %d" % rank
+        for t, aid in ((un, ob.U), (vn, ob.V), (wn, ob.W)):
+            ref = case.o.array(rank, aid)[I]
+            assert np.abs(t.cpu().numpy()[I] - ref).max() <= 1e-14 * np.abs(ref).max(), "epilogue: velocity differs on rank %d" % rank
+        ref = case.o.array(rank, ob.P)[I]
+        assert np.abs(pn.cpu().numpy()[I] - ref).max() <= 1e-12 * np.abs(ref).max(), "epilogue: p differs on rank %d" % rank
+        out["epilogue"] = "ok"
         s.close()
         dist.barrier()
     if rank == 0:

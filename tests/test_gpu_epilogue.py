@@ -160,3 +160,62 @@ def test_solve_then_epilogue_128_properties():
     expect = expect - expect.mean()
     assert float((pin - expect).abs().max()) <= 1e-11 * float(expect.abs().max())
     p.close()
+
+
+# ---- face-grid halo exchanges: bbpcg_exchange = mpi_cuda_exchange_Gfx / _Gfy / _Gfz (src/mpi_comm.c:317-405) -----
+FACE = {"u": ("Gfx", ob.U), "v": ("Gfy", ob.V), "w": ("Gfz", ob.W)}
+
+
+@pytest.mark.parametrize("blocks,bc", [((1, 1, 1), "periodic"), ((1, 1, 1), "duct"), ((2, 1, 1), "periodic"), ((1, 2, 2), "channel"),
+                                       ((2, 2, 2), "periodic"), ((3, 1, 2), "sedimentation")])
+def test_face_exchange_matches_oracle(blocks, bc):
+    """pure copies: bit-exact against the oracle's multi-block exchange, ghost edges/corners and wall ghosts untouched"""
+    from cases import face_exchange_inputs
+    from gpu_util import Product
+    case = Case((24, 14, 18), blocks=blocks, bc=bc)
+    p = Product(case)
+    for key, (grid, aid) in FACE.items():
+        for r in range(p.n):
+            arr = face_exchange_inputs(case, r, 61)[key][0]
+            case.o.array(r, aid)[...] = arr
+            p.dev[r]["x" + key] = p.solvers[r].to_device(arr)
+        case.o.exchange(aid)
+        p.each(lambda r, s, d: s.exchange(d["x" + key], grid))
+        for r in range(p.n):
+            assert np.array_equal(p.dev[r]["x" + key].cpu().numpy(), case.o.array(r, aid)), (key, r)
+    # the Gcc entry point is the grid code 0 of the same kernels
+    for r in range(p.n):
+        arr = np.random.default_rng(5 + r).standard_normal(case.o.array(r, ob.PHI).shape)
+        case.o.array(r, ob.PHI)[...] = arr
+        p.dev[r]["xc"] = p.solvers[r].to_device(arr)
+    case.o.exchange_Gcc(ob.PHI)
+    p.each(lambda r, s, d: s.exchange(d["xc"], "Gcc"))
+    for r in range(p.n):
+        assert np.array_equal(p.dev[r]["xc"].cpu().numpy(), case.o.array(r, ob.PHI))
+    p.close()
+
+
+@pytest.mark.parametrize("bc", ["periodic", "channel"])
+def test_face_exchange_three_way(bc):
+    """the reference's own pack / unpack kernels (O1) vs the oracle vs the product, single block (periodic self-wrap)"""
+    from cases import face_exchange_inputs
+    from gpu_util import Product
+    lib = load_ref()
+    if lib is None:
+        pytest.skip("oracle/_ref/libbbref.so not built")
+    case = Case((20, 12, 16), bc=bc)
+    dom, DOM = case.o.dom(0), case.o.DOM
+    assert lib.bbref_init(C.byref(dom), C.byref(DOM)) == 0
+    p = Product(case)
+    s = p.solvers[0]
+    for key, (arr, code) in face_exchange_inputs(case, 0, 67).items():
+        grid, aid = FACE[key]
+        ref = np.ascontiguousarray(arr).copy()
+        assert lib.bbref_exchange_face(ref.ctypes.data_as(C.c_void_p), code) == 0
+        case.o.array(0, aid)[...] = arr
+        case.o.exchange(aid)
+        mine = s.to_device(arr)
+        s.exchange(mine, grid)
+        assert np.array_equal(case.o.array(0, aid), ref), key
+        assert np.array_equal(mine.cpu().numpy(), ref), key
+    p.close()

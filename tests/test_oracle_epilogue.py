@@ -144,3 +144,62 @@ def test_projection_removes_the_divergence():
     before = div(a(0, ob.U_STAR), a(0, ob.V_STAR), a(0, ob.W_STAR))
     after = div(a(0, ob.U), a(0, ob.V), a(0, ob.W))
     assert np.linalg.norm(after) < 1e-6 * np.linalg.norm(before)
+
+
+# ---- face-grid halo exchanges: mpi_cuda_exchange_Gfx / _Gfy / _Gfz (src/mpi_comm.c:317-405) ---------------------
+FACE_IDS = {"u": ob.U, "v": ob.V, "w": ob.W}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_face_exchange_matches_reference_kernels(name):
+    """bit-exact against the reference's pack / unpack kernels (golden vectors, single block: periodic self-wrap)"""
+    from cases import face_exchange_inputs
+    spec = CASES[name]
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    if "ex_u" not in gold.files:
+        pytest.skip("fixture predates the face-exchange vectors")
+    case = Case(tuple(spec["cells"]), bc=spec["bc"], nparts=spec.get("nparts", 0), radius=spec.get("radius", 1.0))
+    for key, (arr, _) in face_exchange_inputs(case, 0, MANIFEST["seed"] + 6).items():
+        case.o.array(0, FACE_IDS[key])[...] = arr
+        case.o.exchange(FACE_IDS[key])
+        assert np.array_equal(case.o.array(0, FACE_IDS[key]), gold["ex_" + key]), key
+
+
+@pytest.mark.parametrize("blocks", [(1, 1, 1), (2, 1, 1), (1, 2, 1), (1, 1, 2), (2, 2, 2), (3, 1, 2)])
+def test_face_exchange_reproduces_a_periodic_field_in_the_ghosts(blocks):
+    """the reference's own halo test idea (cuda_BC_test_periodic, src/cuda_testing.cu:749-933) on all four grids: a smooth
+    periodic function of the GLOBAL position, written to the interior only, must appear in every ghost FACE after the
+    exchange -- across block boundaries and across the periodic wrap, with the shared face of a face grid skipped"""
+    cells = (12, 8, 12)
+    case = Case(cells, blocks=blocks, bc="periodic")
+    o = case.o
+    D = o.DOM
+    L = (D.xe - D.xs, D.ye - D.ys, D.ze - D.zs)
+
+    def field(x, y, z):
+        return np.cos(2 * np.pi * x / L[0]) + 2 * np.cos(2 * np.pi * y / L[1]) + 3 * np.cos(2 * np.pi * z / L[2])
+    for aid, grid in ((ob.PB_Q, "Gcc"), (ob.U, "Gfx"), (ob.V, "Gfy"), (ob.W, "Gfz")):
+        exact = []
+        for r in range(o.nblocks):
+            d = o.dom(r)
+            n = [d.xn + (grid == "Gfx"), d.yn + (grid == "Gfy"), d.zn + (grid == "Gfz")]
+            # position of local index l (ghosts 0 and n+1): cell centres (l - 0.5) h, faces (l - 1) h, from the block's start
+            ax = []
+            for a_, (s0, h, nn, face) in enumerate(((d.xs, d.dx, n[0], grid == "Gfx"), (d.ys, d.dy, n[1], grid == "Gfy"), (d.zs, d.dz, n[2], grid == "Gfz"))):
+                l = np.arange(nn + 2)
+                ax.append(s0 + ((l - 1.0) if face else (l - 0.5)) * h)
+            X, Y, Z = np.meshgrid(ax[0], ax[1], ax[2], indexing="ij")            # [i, j, k]
+            F = field(X, Y, Z)
+            full = {"Gcc": F.transpose(2, 1, 0), "Gfz": F.transpose(2, 1, 0), "Gfx": F.transpose(0, 2, 1), "Gfy": F.transpose(1, 0, 2)}[grid]
+            exact.append(np.ascontiguousarray(full))
+            a = o.array(r, aid)
+            a[...] = -99.0
+            a[1:-1, 1:-1, 1:-1] = full[1:-1, 1:-1, 1:-1]
+        o.exchange(aid)
+        for r in range(o.nblocks):
+            a, ex = o.array(r, aid), exact[r]
+            I = slice(1, -1)
+            for sl in ((0, I, I), (-1, I, I), (I, 0, I), (I, -1, I), (I, I, 0), (I, I, -1)):
+                assert np.abs(a[sl] - ex[sl]).max() < 1e-12, (grid, r, sl)
+            # edges and corners are NOT exchanged (faces only)
+            assert a[0, 0, 0] == -99.0 and a[-1, -1, 0] == -99.0 and a[0, -1, 5] == -99.0
