@@ -7,4 +7,4 @@ call needs the CUDA library and a GPU and fails loudly otherwise.
 """
 from . import grid, synth  # noqa: F401
 from .lib import load_library, LibraryMissing  # noqa: F401
-from .solver import PoissonSolver, SolveResult, Decomposition  # noqa: F401
+from .solver import PoissonSolver, SolveResult, Decomposition, read_restart, restart_path  # noqa: F401

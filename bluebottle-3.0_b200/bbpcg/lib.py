@@ -48,9 +48,21 @@ class EpilogueArgs(C.Structure):
                 ("rho_f", C.c_double), ("dt", C.c_double), ("phi_ghosts_valid", C.c_int)]
 
 
+class Restart(C.Structure):
+    _fields_ = [("ttime", C.c_double), ("dt0", C.c_double), ("dt", C.c_double), ("stepnum", C.c_int),
+                ("rec_vtk_stepnum_out", C.c_int), ("rec_cgns_flow_ttime_out", C.c_double),
+                ("rec_cgns_part_ttime_out", C.c_double), ("rec_vtk_ttime_out", C.c_double),
+                ("u", C.c_void_p), ("v", C.c_void_p), ("w", C.c_void_p),
+                ("u_star", C.c_void_p), ("v_star", C.c_void_p), ("w_star", C.c_void_p),
+                ("p", C.c_void_p), ("phi", C.c_void_p), ("p0", C.c_void_p),
+                ("phase", C.c_void_p), ("phase_shell", C.c_void_p),
+                ("flag_u", C.c_void_p), ("flag_v", C.c_void_p), ("flag_w", C.c_void_p), ("nparts_subdom", C.c_int)]
+
+
 # every symbol include/bbpcg.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "bb_domain_read", "bb_domain_fill", "bb_domain_split", "bb_domain_write_decomp", "bb_domain_free",
+    "bb_restart_path", "bb_restart_read", "bb_restart_free",
     "bbpcg_create", "bbpcg_destroy", "bbpcg_comm_export", "bbpcg_comm_import", "bbpcg_set_coefficients",
     "bbpcg_solve", "bbpcg_solve_host", "bbpcg_history", "bbpcg_exchange_Gcc", "bbpcg_rhs", "bbpcg_spmv",
     "bbpcg_set_option", "bbpcg_get_info", "bbpcg_last_error", "bbpcg_version",
@@ -79,6 +91,10 @@ def load_library():
     lib.bb_domain_write_decomp.argtypes = [C.c_char_p, D, D, C.c_int]
     lib.bb_domain_free.argtypes = [D]
     lib.bb_domain_free.restype = None
+    lib.bb_restart_path.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int, C.c_int]
+    lib.bb_restart_read.argtypes = [C.c_char_p, D, C.POINTER(Restart)]
+    lib.bb_restart_free.argtypes = [C.POINTER(Restart)]
+    lib.bb_restart_free.restype = None
     lib.bbpcg_create.argtypes = [C.POINTER(vp), D, D, C.POINTER(PressureBC), C.c_int]
     lib.bbpcg_destroy.argtypes = [vp]
     lib.bbpcg_destroy.restype = None

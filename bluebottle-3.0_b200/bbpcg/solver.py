@@ -77,6 +77,37 @@ class Decomposition:
                 "bb_domain_write_decomp")
 
 
+RESTART_FIELDS = {"u": ("Gfx", np.float64), "v": ("Gfy", np.float64), "w": ("Gfz", np.float64),
+                  "u_star": ("Gfx", np.float64), "v_star": ("Gfy", np.float64), "w_star": ("Gfz", np.float64),
+                  "p": ("Gcc", np.float64), "phi": ("Gcc", np.float64), "p0": ("Gcc", np.float64),
+                  "phase": ("Gcc", np.int32), "phase_shell": ("Gcc", np.int32),
+                  "flag_u": ("Gfx", np.int32), "flag_v": ("Gfy", np.int32), "flag_w": ("Gfz", np.int32)}
+
+
+def restart_path(directory, rank, nranks):
+    """<dir>/restart.config-<rank>, zero-padded like out_restart (src/domain.c:3008-3017)"""
+    buf = C.create_string_buffer(4096)
+    L.check(L.load_library().bb_restart_path(buf, 4096, directory.encode(), rank, nranks), "bb_restart_path")
+    return buf.value.decode()
+
+
+def read_restart(path, dom):
+    """One rank's Bluebottle restart file (out_restart, src/domain.c:3005-3085) -> dict of numpy arrays in the
+    reference's ghosted layouts + the header scalars.  Host only."""
+    lib = L.load_library()
+    r = L.Restart()
+    L.check(lib.bb_restart_read(path.encode(), C.byref(dom), C.byref(r)), "bb_restart_read")
+    out = {k: getattr(r, k) for k in ("ttime", "dt0", "dt", "stepnum", "rec_vtk_stepnum_out", "rec_cgns_flow_ttime_out",
+                                      "rec_cgns_part_ttime_out", "rec_vtk_ttime_out", "nparts_subdom")}
+    for k, (grid, dt) in RESTART_FIELDS.items():
+        shape = grid_shape(dom, grid)
+        n = int(np.prod(shape))
+        ct = C.c_double if dt == np.float64 else C.c_int
+        out[k] = np.frombuffer((ct * n).from_address(getattr(r, k)), dtype=dt).reshape(shape).copy()
+    lib.bb_restart_free(C.byref(r))
+    return out
+
+
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 

@@ -251,3 +251,75 @@ int bb_domain_read(const char *flow_config, const char *decomp_config, dom_struc
 }
 
 void bb_domain_free(dom_struct *dom) { free(dom); }
+
+/* ---- restart files as fixtures: out_restart / in_restart, src/domain.c:3005-3180 ------------------------------- */
+int bb_restart_path(char *out, size_t cap, const char *dir, int rank, int S3)
+{
+  int sigfigs = 1, v;
+  if (!out || !dir || rank < 0 || S3 < 1 || rank >= S3) { bbpcg_set_error("bb_restart_path: bad arguments"); return BBPCG_EINVAL; }
+  for (v = S3 - 1; v >= 10; v /= 10) sigfigs++;            /* floor(log10(S3 - 1)) + 1, 1 for S3 == 1 (domain.c:3009-3014) */
+  if (snprintf(out, cap, "%s/restart.config-%0*d", dir, sigfigs, rank) >= (int)cap) { bbpcg_set_error("bb_restart_path: path too long"); return BBPCG_EINVAL; }
+  return BBPCG_OK;
+}
+
+void bb_restart_free(bb_restart *r)
+{
+  if (!r) return;
+  free(r->u); free(r->v); free(r->w); free(r->u_star); free(r->v_star); free(r->w_star);
+  free(r->p); free(r->phi); free(r->p0); free(r->phase); free(r->phase_shell);
+  free(r->flag_u); free(r->flag_v); free(r->flag_w);
+  memset(r, 0, sizeof(*r));
+}
+
+static int rd(FILE *f, void *dst, size_t size, size_t n) { return fread(dst, size, n, f) == n ? 0 : -1; }
+static int skip(FILE *f, size_t size, size_t n) { return fseek(f, (long)(size * n), SEEK_CUR); }
+static void *grab(FILE *f, size_t size, size_t n, int *err)
+{
+  void *p = malloc(size * (n ? n : 1));
+  if (!p || rd(f, p, size, n)) { free(p); *err = 1; return NULL; }
+  return p;
+}
+
+int bb_restart_read(const char *path, const dom_struct *d, bb_restart *r)
+{
+  FILE *f;
+  int err = 0, g;
+  if (!path || !d || !r) { bbpcg_set_error("bb_restart_read: NULL argument"); return BBPCG_EINVAL; }
+  memset(r, 0, sizeof(*r));
+  f = fopen(path, "rb");
+  if (!f) { bbpcg_set_error("File %s could not be opened.", path); return BBPCG_EIO; }          /* the reference's message, domain.c:3098 */
+  /* header, domain.c:3026-3033 */
+  err |= rd(f, &r->ttime, sizeof(real), 1) | rd(f, &r->dt0, sizeof(real), 1) | rd(f, &r->dt, sizeof(real), 1);
+  err |= rd(f, &r->stepnum, sizeof(int), 1) | rd(f, &r->rec_vtk_stepnum_out, sizeof(int), 1);
+  err |= rd(f, &r->rec_cgns_flow_ttime_out, sizeof(real), 1) | rd(f, &r->rec_cgns_part_ttime_out, sizeof(real), 1) |
+         rd(f, &r->rec_vtk_ttime_out, sizeof(real), 1);
+  /* seven arrays per velocity component, domain.c:3036-3058: X, X0, diff0, conv0, diff, conv, X_star */
+  for (g = 0; g < 3 && !err; g++) {
+    const size_t n = (size_t)(g == 0 ? d->Gfx.s3b : g == 1 ? d->Gfy.s3b : d->Gfz.s3b);
+    real **vel = g == 0 ? &r->u : g == 1 ? &r->v : &r->w;
+    real **star = g == 0 ? &r->u_star : g == 1 ? &r->v_star : &r->w_star;
+    *vel = (real *)grab(f, sizeof(real), n, &err);
+    if (!err && skip(f, sizeof(real), 5 * n)) err = 1;
+    if (!err) *star = (real *)grab(f, sizeof(real), n, &err);
+  }
+  if (!err) {                                                                                   /* domain.c:3060-3068 */
+    const size_t n = (size_t)d->Gcc.s3b;
+    r->p = (real *)grab(f, sizeof(real), n, &err);
+    if (!err) r->phi = (real *)grab(f, sizeof(real), n, &err);
+    if (!err) r->p0 = (real *)grab(f, sizeof(real), n, &err);
+    if (!err) r->phase = (int *)grab(f, sizeof(int), n, &err);
+    if (!err) r->phase_shell = (int *)grab(f, sizeof(int), n, &err);
+    if (!err) r->flag_u = (int *)grab(f, sizeof(int), (size_t)d->Gfx.s3b, &err);
+    if (!err) r->flag_v = (int *)grab(f, sizeof(int), (size_t)d->Gfy.s3b, &err);
+    if (!err) r->flag_w = (int *)grab(f, sizeof(int), (size_t)d->Gfz.s3b, &err);
+    if (!err) err |= rd(f, &r->nparts_subdom, sizeof(int), 1);                                  /* :3070 */
+  }
+  fclose(f);
+  if (err) {
+    bb_restart_free(r);
+    bbpcg_set_error("%s: shorter than a restart file of a %d x %d x %d block (or out of memory)", path, d->xn, d->yn, d->zn);
+    return BBPCG_EIO;
+  }
+  if (r->nparts_subdom < 0) { bb_restart_free(r); bbpcg_set_error("%s: negative particle count -- not a restart file of this block", path); return BBPCG_EIO; }
+  return BBPCG_OK;
+}

@@ -81,6 +81,31 @@ int  bb_domain_split(dom_struct *DOM, dom_struct *dom);
 int  bb_domain_write_decomp(const char *path, const dom_struct *DOM, const dom_struct *dom, int prec);
 void bb_domain_free(dom_struct *dom);
 
+/* ---- restart files as fixtures (no GPU needed) ---------------------------------------------
+ * Reader for the per-rank binary `restart.config-<rank>` files Bluebottle writes (out_restart, src/domain.c:3005-3085;
+ * read back by in_restart, :3087-3180), so that the state of a production run -- u*, v*, w*, flags, phase, phi, p, p0 --
+ * can be replayed through this library without MPI.  Layout (sequential fwrite's, no padding): ttime, dt0, dt (real),
+ * stepnum, rec_vtk_stepnum_out (int), three output times (real); then u, u0, diff0_u, conv0_u, diff_u, conv_u, u_star on
+ * Gfx s3b, the same seven for v (Gfy) and w (Gfz); p, phi, p0 (real) and phase, phase_shell (int) on Gcc s3b; flag_u,
+ * flag_v, flag_w (int); nparts_subdom (int); the particle structs and scalar-field arrays that follow are not read.
+ * Every array is malloc'ed in the reference's ghosted layout (include/bb_grid.h); free with bb_restart_free. */
+typedef struct bb_restart {
+  real ttime, dt0, dt;
+  int  stepnum, rec_vtk_stepnum_out;
+  real rec_cgns_flow_ttime_out, rec_cgns_part_ttime_out, rec_vtk_ttime_out;
+  real *u, *v, *w;                 /* Gfx / Gfy / Gfz s3b */
+  real *u_star, *v_star, *w_star;
+  real *p, *phi, *p0;              /* Gcc s3b */
+  int  *phase, *phase_shell;       /* Gcc s3b */
+  int  *flag_u, *flag_v, *flag_w;  /* Gfx / Gfy / Gfz s3b */
+  int  nparts_subdom;
+} bb_restart;
+
+/* "<dir>/restart.config-<rank>" with the rank zero-padded to floor(log10(S3-1))+1 digits (src/domain.c:3008-3017) */
+int  bb_restart_path(char *out, size_t cap, const char *dir, int rank, int S3);
+int  bb_restart_read(const char *path, const dom_struct *dom_rank, bb_restart *out);
+void bb_restart_free(bb_restart *r);
+
 /* ---- solver object ------------------------------------------------------------------------ */
 /* dom_rank: this rank's filled block; DOM: the global domain; bc: pressure BC types.
  * device: CUDA ordinal, or -1 for the current device.  Allocates the private workspace

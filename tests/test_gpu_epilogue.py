@@ -219,3 +219,39 @@ def test_face_exchange_three_way(bc):
         assert np.array_equal(case.o.array(0, aid), ref), key
         assert np.array_equal(mine.cpu().numpy(), ref), key
     p.close()
+
+
+def test_replay_from_a_restart_file(tmp_path):
+    """a Bluebottle restart file (out_restart, src/domain.c:3005-3085) replayed through the library:
+    flags, phase and u* come from the file; the solve and the epilogue equal the run fed from the arrays directly"""
+    import bbpcg
+    from gpu_util import Product
+    from test_restart import write_restart
+    case = Case((24, 20, 28), bc="duct")
+    case.seed_epilogue(13, phi=False)
+    d0 = case.o.dom(0)
+    inp = case.inputs(0)
+    fields = dict(u=np.zeros_like(inp["u_star"]), v=np.zeros_like(inp["v_star"]), w=np.zeros_like(inp["w_star"]),
+                  u_star=inp["u_star"], v_star=inp["v_star"], w_star=inp["w_star"], p=case.o.array(0, ob.P),
+                  phi=case.o.array(0, ob.PHI), p0=case.o.array(0, ob.P0), phase=inp["phase"], phase_shell=inp["phase_shell"],
+                  flag_u=inp["flag_u"], flag_v=inp["flag_v"], flag_w=inp["flag_w"])
+    path = bbpcg.restart_path(str(tmp_path), 0, 1)
+    write_restart(path, d0, fields, dt=1e-3)
+    rst = bbpcg.read_restart(path, d0)
+    p = Product(case)
+    s = p.solvers[0]
+    dev = {k: s.to_device(rst[k]) for k in ("u_star", "v_star", "w_star", "flag_u", "flag_v", "flag_w", "phase", "p0")}
+    rhs, phi = s.empty("Gcc"), s.empty("Gcc")
+    un, vn, wn, pn = s.empty("Gfx"), s.empty("Gfy"), s.empty("Gfz"), s.empty("Gcc")
+    s.init_jacobi_preconditioner(dev["flag_u"], dev["flag_v"], dev["flag_w"])
+    res = s.PP_cg_noparts(dev["u_star"], dev["v_star"], dev["w_star"], rhs, phi, dt=rst["dt"])
+    s.epilogue(phi, dev["u_star"], dev["v_star"], dev["w_star"], dev["flag_u"], dev["flag_v"], dev["flag_w"], un, vn, wn,
+               dev["p0"], dev["phase"], pn, dt=rst["dt"])
+    ores, _ = case.solve_oracle()
+    case.o.epilogue(1.0, 1e-3)
+    assert res.status == "converged" and res.niter == ores.niter
+    from cases import rel_l2
+    assert rel_l2(phi.cpu().numpy()[INNER], case.o.array(0, ob.PHI)[INNER]) < 1e-10
+    assert np.abs(un.cpu().numpy()[INNER] - case.o.array(0, ob.U)[INNER]).max() < 1e-9
+    assert np.abs(pn.cpu().numpy()[INNER] - case.o.array(0, ob.P)[INNER]).max() < 1e-9 * np.abs(case.o.array(0, ob.P)).max()
+    p.close()
