@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libbbpcg.so")
 DROPIN_PATH = os.path.join(LIB_DIR, "libbbpcg_dropin.so")
 
 BLOB_BYTES = 256
+OUT_PLANE = {"WEST": 0, "EAST": 1, "SOUTH": 2, "NORTH": 3, "BOTTOM": 4, "TOP": 5, "HOMOGENEOUS": 10}   # src/bluebottle.h:353-425
 GRID_CODE = {"Gcc": 0, "Gfx": 1, "Gfy": 2, "Gfz": 3}      # BBPCG_GCC .. BBPCG_GFZ
 OK = 0
 STATUS = {0: "converged", 1: "tiny_rhs", 2: "max_iter", 3: "nan", 4: "comm_timeout"}
@@ -66,10 +67,10 @@ SYMBOLS = [
     "bbpcg_create", "bbpcg_destroy", "bbpcg_comm_export", "bbpcg_comm_import", "bbpcg_set_coefficients",
     "bbpcg_solve", "bbpcg_solve_host", "bbpcg_history", "bbpcg_exchange_Gcc", "bbpcg_rhs", "bbpcg_spmv",
     "bbpcg_set_option", "bbpcg_get_info", "bbpcg_last_error", "bbpcg_version",
-    "bbpcg_dom_BC_p", "bbpcg_epilogue", "bbpcg_exchange",
+    "bbpcg_dom_BC_p", "bbpcg_epilogue", "bbpcg_exchange", "bbpcg_solvability",
 ]
 DROPIN_SYMBOLS = ["cuda_PP_init_jacobi_preconditioner", "cuda_PP_cg", "cuda_PP_cg_noparts", "cuda_PP_cg_timed",
-                  "mpi_cuda_exchange_Gcc", "mpi_cuda_exchange_Gfx", "mpi_cuda_exchange_Gfy", "mpi_cuda_exchange_Gfz", "cuda_dom_BC_p", "cuda_project", "cuda_update_p", "bbpcg_dropin_finalize"]
+                  "mpi_cuda_exchange_Gcc", "mpi_cuda_exchange_Gfx", "mpi_cuda_exchange_Gfy", "mpi_cuda_exchange_Gfz", "cuda_solvability", "cuda_dom_BC_p", "cuda_project", "cuda_update_p", "bbpcg_dropin_finalize"]
 
 _lib = None
 
@@ -108,6 +109,7 @@ def load_library():
     lib.bbpcg_rhs.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp]
     lib.bbpcg_spmv.argtypes = [vp, vp, vp, C.c_int]
     lib.bbpcg_exchange.argtypes = [vp, vp, C.c_int]
+    lib.bbpcg_solvability.argtypes = [vp, vp, vp, vp, C.c_int, dp]
     lib.bbpcg_dom_BC_p.argtypes = [vp, vp]
     lib.bbpcg_epilogue.argtypes = [vp, C.POINTER(EpilogueArgs), dp]
     lib.bbpcg_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]

@@ -5,6 +5,7 @@
 `PoissonSolver.PP_cg / PP_cg_noparts`      = cuda_PP_cg / cuda_PP_cg_noparts (src/cuda_solver.cu:38-300,573-761)
 `PoissonSolver.exchange_Gcc`               = mpi_cuda_exchange_Gcc (src/mpi_comm.c:257-315)
 `PoissonSolver.exchange_Gfx/Gfy/Gfz`       = mpi_cuda_exchange_Gfx/_Gfy/_Gfz (src/mpi_comm.c:317-405)
+`PoissonSolver.solvability`                = cuda_solvability (src/cuda_bluebottle.cu:2313-2492)
 `PoissonSolver.dom_BC_p`                   = cuda_dom_BC_p (src/cuda_bluebottle.cu:2536-2589)
 `PoissonSolver.project / update_p`         = cuda_project / cuda_update_p (src/cuda_bluebottle.cu:2495-2534)
 `PoissonSolver.epilogue`                   = the sequence src/bluebottle.c:233-256 runs on phi, fused
@@ -270,6 +271,14 @@ class PoissonSolver:
 
     def exchange_Gfz(self, array):
         self.exchange(array, "Gfz")
+
+    def solvability(self, u_star, v_star, w_star, out_plane="HOMOGENEOUS"):
+        """cuda_solvability(): remove the net boundary flux of u* from the outflow plane(s); returns eps[3]"""
+        eps = (C.c_double * 3)()
+        self._sync_caller_stream()
+        L.check(self.lib.bbpcg_solvability(self.h, _ptr(u_star), _ptr(v_star), _ptr(w_star), L.OUT_PLANE[out_plane], eps),
+                "bbpcg_solvability")
+        return [eps[0], eps[1], eps[2]]
 
     def dom_BC_p(self, array):
         self._sync_caller_stream()

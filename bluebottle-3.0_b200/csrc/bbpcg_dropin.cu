@@ -24,6 +24,7 @@ extern int NPARTS, nparts;                    /* src/particle.h:319,331 */
 extern real *_u_star, *_v_star, *_w_star, *_rhs_p, *_phi;
 extern real *_u, *_v, *_w, *_p, *_p0;         /* src/bluebottle.h:961,1037,1137-1161 (epilogue) */
 extern int *_flag_u, *_flag_v, *_flag_w, *_phase, *_phase_shell;
+extern int out_plane;                         /* src/bluebottle.h:650 (solvability) */
 void cuda_part_BC_p(void);                    /* src/cuda_particle.cu:1680 */
 void recorder_PP(char *name, int niter, real resid, real etime);   /* src/recorder.c:190 */
 int bb_dropin_allgather(const void *send, void *recv, int bytes_per_rank) __attribute__((weak));
@@ -120,6 +121,13 @@ static void exchange_face(real *array, int grid)
 extern "C" void mpi_cuda_exchange_Gfx(real *array) { exchange_face(array, BBPCG_GFX); }
 extern "C" void mpi_cuda_exchange_Gfy(real *array) { exchange_face(array, BBPCG_GFY); }
 extern "C" void mpi_cuda_exchange_Gfz(real *array) { exchange_face(array, BBPCG_GFZ); }
+
+/* ---- solve prologue: src/bluebottle.c:221, src/cuda_bluebottle.cu:2313-2492 ---- */
+extern "C" void cuda_solvability(void)
+{
+  cudaDeviceSynchronize();
+  if (bbpcg_solvability(solver(), _u_star, _v_star, _w_star, out_plane, NULL)) die("bbpcg_solvability");
+}
 
 /* ---- solve epilogue, src/bluebottle.c:233-256 ---- */
 extern "C" void cuda_dom_BC_p(real *array)                  /* src/cuda_bluebottle.cu:2536-2589 */

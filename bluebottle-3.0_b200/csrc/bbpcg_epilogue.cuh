@@ -208,4 +208,78 @@ __global__ void __launch_bounds__(256) k_sub_mean(const __grid_constant__ Dev d,
   }
 }
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * cuda_solvability (src/cuda_bluebottle.cu:2313-2492), the solve PROLOGUE's compatibility fix: the net flux of u* through
+ * the six faces of the GLOBAL domain (surf_int_{x,y,z}{s,e}, src/bluebottle_kernel.cu:2135-2229, + thrust::reduce, scaled by
+ * the face area), summed over ranks (MPI_Allreduce of 3 values), is removed from the outflow plane(s)
+ * (plane_eps_*, :2231-2301).  The reference cudaMalloc's a plane, copies, reduces with Thrust six times and all-reduces on
+ * the host; here one kernel sums the (contiguous: the normal index is the slowest of a face grid) boundary planes with the
+ * deterministic grid + rank reduction and a second one applies the correction from device-resident scalars. */
+struct SolvArgs {
+  double *u, *v, *w;                   /* u*, v*, w*: Gfx / Gfy / Gfz s3b */
+  unsigned planes;                     /* bit 0 xs, 1 xe, 2 ys, 3 ye, 4 zs, 5 ze: this block touches that global face */
+  double ayz, azx, axy;                /* dy*dz, dz*dx, dx*dy of this block (cuda_bluebottle.cu:2345 ...) */
+  double Ayz, Azx, Axy;                /* DOM.yl*DOM.zl, DOM.zl*DOM.xl, DOM.xl*DOM.yl (:2428 ...) */
+  int out_plane;                       /* WEST 0 .. TOP 5, HOMOGENEOUS 10 (src/bluebottle.h:353-425) */
+};
+
+/* value (a, b) of a face plane: a = fast, b = middle index of the grid, both 1-based interior */
+__device__ __forceinline__ long long plane_index(const FaceStrides &st, int axis, int n_normal, bool end, int a, int b)
+{
+  const int c = end ? n_normal : 1;    /* _ie = in (= xn+1 faces) / _is = 1 */
+  if (axis == 0) return a + (long long)b * st.us1b + (long long)c * st.us2b;     /* Gfx: (j, k), i = c */
+  if (axis == 1) return a + (long long)b * st.vs1b + (long long)c * st.vs2b;     /* Gfy: (k, i), j = c */
+  return a + (long long)b * st.ws1b + (long long)c * st.ws2b;                    /* Gfz: (i, j), k = c */
+}
+
+__global__ void __launch_bounds__(256) k_solv_sum(const __grid_constant__ Dev d, const FaceStrides st, const SolvArgs a)
+{
+  const int in = d.L.in, jn = d.L.jn, kn = d.L.kn;
+  /* plane p: axis p/2, end p&1; extents (fast, middle): x planes (jn, kn), y planes (kn, in), z planes (in, jn) */
+  const int na[3] = { jn, kn, in }, nb[3] = { kn, in, jn }, nn[3] = { in + 1, jn + 1, kn + 1 };
+  const double *arr[3] = { a.u, a.v, a.w };
+  double acc[6] = { 0., 0., 0., 0., 0., 0. };
+  const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x, gstride = (long long)gridDim.x * blockDim.x;
+#pragma unroll
+  for (int p = 0; p < 6; p++) {
+    if (!((a.planes >> p) & 1u)) continue;
+    const int ax = p >> 1;
+    const long long total = (long long)na[ax] * nb[ax];
+    for (long long t = gtid; t < total; t += gstride)
+      acc[p] += arr[ax][plane_index(st, ax, nn[ax], p & 1, (int)(t % na[ax]) + 1, (int)(t / na[ax]) + 1)];
+  }
+  /* eps_?e - eps_?s, each scaled by the face area first (cuda_bluebottle.cu:2345,2358,...,2414-2416) */
+  double v[3] = { acc[1] * a.ayz - acc[0] * a.ayz, acc[3] * a.azx - acc[2] * a.azx, acc[5] * a.axy - acc[4] * a.axy }, tot[3];
+  if (grid_reduce<3>(d, v, blockIdx.x, gridDim.x, tot, false)) {
+    rank_allreduce(d, tot, 2, false);                /* the MPI_Allreduce of 3 values (:2420) in two mailbox rounds */
+    rank_allreduce(d, tot + 2, 1, false);
+    if (threadIdx.x == 0) { d.sc->eps[0] = tot[0]; d.sc->eps[1] = tot[1]; d.sc->eps[2] = tot[2]; }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_solv_apply(const __grid_constant__ Dev d, const FaceStrides st, const SolvArgs a)
+{
+  const int in = d.L.in, jn = d.L.jn, kn = d.L.kn;
+  const int na[3] = { jn, kn, in }, nb[3] = { kn, in, jn }, nn[3] = { in + 1, jn + 1, kn + 1 };
+  double *arr[3] = { a.u, a.v, a.w };
+  const double e0 = d.sc->eps[0], e1 = d.sc->eps[1], e2 = d.sc->eps[2];
+  const double area[3] = { a.Ayz, a.Azx, a.Axy };
+  const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x, gstride = (long long)gridDim.x * blockDim.x;
+#pragma unroll
+  for (int p = 0; p < 6; p++) {
+    if (!((a.planes >> p) & 1u)) continue;
+    const int ax = p >> 1;
+    double val;
+    if (a.out_plane == 10) val = 0.5 * (ax == 0 ? e0 : ax == 1 ? e1 : e2) / area[ax];      /* HOMOGENEOUS, :2470-2472 */
+    else if (a.out_plane == p) val = (e0 + e1 + e2) / area[ax];                            /* :2428 ... */
+    else continue;
+    if (p & 1) val = -val;                                                                 /* start planes + eps, end planes - eps (:2239,:2251) */
+    const long long total = (long long)na[ax] * nb[ax];
+    for (long long t = gtid; t < total; t += gstride) {
+      const long long c = plane_index(st, ax, nn[ax], p & 1, (int)(t % na[ax]) + 1, (int)(t / na[ax]) + 1);
+      arr[ax][c] = arr[ax][c] + val;
+    }
+  }
+}
+
 #endif

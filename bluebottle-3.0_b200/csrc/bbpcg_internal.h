@@ -73,8 +73,8 @@ struct ArenaMap {
   size_t r, p0, p1, q, x;          /* doubles[L.n] */
   size_t fmask, pmask;             /* bytes[L.n]   */
   size_t recv[2][6];               /* doubles, generic exchange staging (double-buffered) */
-  size_t partials;                 /* doubles[2*BB_MAXBLOCKS] */
-  size_t gpartials;                /* doubles[2*BB_MAXGROUPS]: group sums */
+  size_t partials;                 /* doubles[4*BB_MAXBLOCKS]: up to 4 values per CTA */
+  size_t gpartials;                /* doubles[4*BB_MAXGROUPS]: group sums */
   size_t counter;                  /* unsigned[4 + BB_MAXGROUPS]: [0] groups done, [4+g] CTAs of group g done */
   size_t scal;                     /* Scal */
   size_t mbox;                     /* u64[BB_NSLOT][BB_MAXR][4]: {32 data bits | 32-bit tag} words */
@@ -99,8 +99,8 @@ static inline ArenaMap make_arena_map(const Layout &L)
   size_t fi = (size_t)(L.jn + 1) * (L.kn + 1), fj = (size_t)(L.in + 1) * (L.kn + 1), fk = (size_t)(L.in + 1) * (L.jn + 1);
   for (int b = 0; b < 2; b++) for (int f = 0; f < 6; f++)
     m.recv[b][f] = take(sizeof(double) * (f < 2 ? fi : f < 4 ? fj : fk));
-  m.partials = take(sizeof(double) * 2 * BB_MAXBLOCKS);
-  m.gpartials = take(sizeof(double) * 2 * BB_MAXGROUPS);
+  m.partials = take(sizeof(double) * 4 * BB_MAXBLOCKS);
+  m.gpartials = take(sizeof(double) * 4 * BB_MAXGROUPS);
   m.counter = take(sizeof(unsigned) * (4 + BB_MAXGROUPS));
   m.scal = take(512);
   m.mbox = take(sizeof(unsigned long long) * BB_NSLOT * BB_MAXR * 4);
@@ -133,6 +133,7 @@ struct Scal {
   int pad0, pad1;
   unsigned long long seq;   /* publish counter, never reset               */
   double p_sum;         /* epilogue: sum of p over all ranks' interior cells (cuda_bluebottle.cu:2524-2527) */
+  double eps[3];        /* solvability: net outflow per axis over all ranks (cuda_bluebottle.cu:2414-2420) */
 };
 
 /* where this block's boundary values go: the neighbour's (or, for a periodic wrap onto the

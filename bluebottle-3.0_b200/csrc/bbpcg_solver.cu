@@ -628,6 +628,7 @@ static int preload_kernels()
   PL(k_build_tab); PL(k_init<256>); PL(k_finish<256>); PL(k_rhs<256>); PL(k_rhs_tiled); PL(k_masks<256>); PL(k_part_rhs_net);
   PL(k_coeffs_refine<256>); PL(k_zero_ghosts); PL(k_xchg_send); PL(k_xchg_recv);
   PL(k_spmv_s3b<256, false>); PL(k_spmv_s3b<256, true>);
+  PL(k_solv_sum); PL(k_solv_apply);
   PL(k_bc_p); PL(k_epilogue<true, true>); PL(k_epilogue<true, false>); PL(k_epilogue<false, true>); PL(k_sub_mean);
 #undef PL
   return rc;
@@ -848,6 +849,35 @@ extern "C" int bbpcg_epilogue(bbpcg_solver *s, const bbpcg_epilogue_args *a, dou
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(s->stream));
   if (ms_out) { float ms = 0.f; cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]); *ms_out = ms; }
+  return BBPCG_OK;
+}
+
+/* ---- solve prologue: cuda_solvability (bbpcg_epilogue.cuh) -------------------------------------------------- */
+extern "C" int bbpcg_solvability(bbpcg_solver *s, real *u_star, real *v_star, real *w_star, int out_plane, real *eps_out)
+{
+  if (!s || !u_star || !v_star || !w_star) { bbpcg_set_error("bbpcg_solvability: NULL argument"); return BBPCG_EINVAL; }
+  if (!((out_plane >= 0 && out_plane <= 5) || out_plane == 10)) { bbpcg_set_error("bbpcg_solvability: out_plane must be WEST 0 .. TOP 5 or HOMOGENEOUS 10"); return BBPCG_EINVAL; }
+  if (s->nranks == 1 && s->DOM.In * s->DOM.Jn * s->DOM.Kn != 1) { bbpcg_set_error("decomposition has %d blocks: call bbpcg_comm_import first", s->DOM.In * s->DOM.Jn * s->DOM.Kn); return BBPCG_ECOMM; }
+  CU(cudaSetDevice(s->device));
+  const dom_struct &d = s->dom;
+  SolvArgs a;
+  a.u = u_star; a.v = v_star; a.w = w_star; a.out_plane = out_plane;
+  a.planes = (d.I == 0 ? 1u : 0u) | (d.I == s->DOM.In - 1 ? 2u : 0u) | (d.J == 0 ? 4u : 0u) | (d.J == s->DOM.Jn - 1 ? 8u : 0u) |
+             (d.K == 0 ? 16u : 0u) | (d.K == s->DOM.Kn - 1 ? 32u : 0u);              /* dom[rank].I == DOM.Is ... (cuda_bluebottle.cu:2332-2411) */
+  a.ayz = d.dy * d.dz; a.azx = d.dz * d.dx; a.axy = d.dx * d.dy;
+  a.Ayz = s->DOM.yl * s->DOM.zl; a.Azx = s->DOM.zl * s->DOM.xl; a.Axy = s->DOM.xl * s->DOM.yl;
+  const Layout &L = s->dev.L;
+  long long big = (long long)L.jn * L.kn;
+  if ((long long)L.in * L.kn > big) big = (long long)L.in * L.kn;
+  if ((long long)L.in * L.jn > big) big = (long long)L.in * L.jn;
+  const int nb = clampi((big + 255) / 256, 1, s->sm_count * 2);
+  k_solv_sum<<<nb, 256, 0, s->stream>>>(s->dev, s->fst, a);
+  k_solv_apply<<<nb, 256, 0, s->stream>>>(s->dev, s->fst, a);
+  s->launches += 2;
+  if (eps_out) CU(cudaMemcpyAsync(s->h_scal, s->dev.sc, sizeof(Scal), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  if (eps_out) { eps_out[0] = s->h_scal->eps[0]; eps_out[1] = s->h_scal->eps[1]; eps_out[2] = s->h_scal->eps[2]; }
   return BBPCG_OK;
 }
 

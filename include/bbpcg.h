@@ -203,6 +203,15 @@ typedef struct bbpcg_epilogue_args {
  * ms_out (may be NULL): device time of the call (CUDA events). */
 int  bbpcg_epilogue(bbpcg_solver *s, const bbpcg_epilogue_args *args, double *ms_out);
 
+/* ---- solve prologue --------------------------------------------------------------------------
+ * = cuda_solvability() (src/cuda_bluebottle.cu:2313-2492): the net flux of u* through the six faces of the GLOBAL domain
+ * (face sums x face area, summed over all ranks) is removed from the outflow plane `out_plane` (WEST 0, EAST 1, SOUTH 2,
+ * NORTH 3, BOTTOM 4, TOP 5; src/bluebottle.h:365-425) or, for HOMOGENEOUS (10, :353), half of each axis' imbalance from
+ * both planes of that axis, so that the Poisson right-hand side sums to zero.  u*, v*, w* are modified in place on the
+ * boundary planes only.  eps_out (may be NULL) receives the three per-axis imbalances (host).  COLLECTIVE. */
+#define BBPCG_HOMOGENEOUS 10
+int  bbpcg_solvability(bbpcg_solver *s, real *u_star, real *v_star, real *w_star, int out_plane, real *eps_out);
+
 /* Unit entry points used by the parity tests (same kernels the solve uses). */
 int  bbpcg_rhs(bbpcg_solver *s, const real *u_star, const real *v_star, const real *w_star,
                real rho_f, real dt, real *rhs_p);

@@ -70,6 +70,7 @@ def load(omp=False):
                               dp, C.c_int, C.POINTER(Result)]
     lib.bbo_iterate_fixed.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int]
     lib.bbo_exchange.argtypes = [C.c_void_p, C.c_int]
+    lib.bbo_solvability.argtypes = [C.c_void_p, C.c_int, dp]
     lib.bbo_dom_BC_p.argtypes = [C.c_void_p, C.c_int]
     lib.bbo_project.argtypes = [C.c_void_p, C.c_double, C.c_double]
     lib.bbo_update_p.argtypes = [C.c_void_p]
@@ -149,6 +150,12 @@ class Oracle:
 
     def spmv(self, aid, parts=False):
         (self.lib.bbo_spmv_parts if parts else self.lib.bbo_spmv_noparts)(self.h, aid)
+
+    def solvability(self, out_plane=10):
+        """cuda_solvability on the oracle's u_star / v_star / w_star (in place); returns eps[3]"""
+        eps = (C.c_double * 3)()
+        self.lib.bbo_solvability(self.h, out_plane, eps)
+        return [eps[0], eps[1], eps[2]]
 
     def dom_BC_p(self, aid):
         self.lib.bbo_dom_BC_p(self.h, aid)

@@ -54,6 +54,18 @@ def run_case(name, outdir):
         a = np.ascontiguousarray(arr).copy()
         assert lib.bbref_exchange_face(P(a), code) == 0
         ex["ex_" + key] = a
+    # cuda_solvability with the reference's surf_int_* / plane_eps_* kernels on the same seeded arrays
+    for out_plane in (10, 1, 4):
+        arrs = {k: np.ascontiguousarray(v[0]).copy() for k, v in face_exchange_inputs(case, 0, SEED + 6).items()}
+        eps = (C.c_double * 3)()
+        assert lib.bbref_solvability(P(arrs["u"]), P(arrs["v"]), P(arrs["w"]), out_plane, eps) == 0
+        ex["sol_eps_%d" % out_plane] = np.array([eps[0], eps[1], eps[2]])
+        fresh = {k: v[0] for k, v in face_exchange_inputs(case, 0, SEED + 6).items()}
+        for k in "uvw":                                       # only the arrays the reference changed are stored
+            if out_plane == 10 or not np.array_equal(arrs[k], fresh[k]):
+                ex["sol_%s_%d" % (k, out_plane)] = arrs[k]
+            else:
+                ex["sol_same_%s_%d" % (k, out_plane)] = np.int8(1)
     np.savez_compressed(os.path.join(outdir, name + ".npz"), u=out["u"], v=out["v"], w=out["w"], p=out["p"], phi=out["phi"], **ex,
                         input_checksum=np.float64(float(np.abs(ein["phi"]).sum() + np.abs(ein["p0"]).sum())))
     print(name, "ms %.3f" % out["ms"], "mean(p) %.3e" % out["p"][1:-1, 1:-1, 1:-1].mean())

@@ -669,6 +669,67 @@ void bbo_exchange(bbo_state *s, int array_id)
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* cuda_solvability, src/cuda_bluebottle.cu:2313-2492: per-rank face integrals of u_star on the six faces of the GLOBAL
+ * domain (surf_int_*, src/bluebottle_kernel.cu:2135-2229, thrust::reduce, times the face area), eps[axis] = end - start
+ * summed over ranks (:2414-2420), then the correction of the outflow plane(s) (:2423-2491, plane_eps_* :2231-2301).
+ * Summation order is ours (rows, then ranks in rank order). */
+static real plane_sum(const real *a, int grid, const grid_info *g, int c)
+{
+  real tot = 0.;
+  int p, q;
+  if (grid == 1) { for (q = g->_ks; q <= g->_ke; q++) { real r = 0.; for (p = g->_js; p <= g->_je; p++) r += a[GFX_LOC(c, p, q, g->s1b, g->s2b)]; tot += r; } }
+  else if (grid == 2) { for (q = g->_is; q <= g->_ie; q++) { real r = 0.; for (p = g->_ks; p <= g->_ke; p++) r += a[GFY_LOC(q, c, p, g->s1b, g->s2b)]; tot += r; } }
+  else { for (q = g->_js; q <= g->_je; q++) { real r = 0.; for (p = g->_is; p <= g->_ie; p++) r += a[GFZ_LOC(p, q, c, g->s1b, g->s2b)]; tot += r; } }
+  return tot;
+}
+
+static void plane_add(real *a, int grid, const grid_info *g, int c, real val)
+{
+  int p, q;
+  if (grid == 1) { for (q = g->_ks; q <= g->_ke; q++) for (p = g->_js; p <= g->_je; p++) { size_t C = GFX_LOC(c, p, q, g->s1b, g->s2b); a[C] = a[C] + val; } }
+  else if (grid == 2) { for (q = g->_is; q <= g->_ie; q++) for (p = g->_ks; p <= g->_ke; p++) { size_t C = GFY_LOC(q, c, p, g->s1b, g->s2b); a[C] = a[C] + val; } }
+  else { for (q = g->_js; q <= g->_je; q++) for (p = g->_is; p <= g->_ie; p++) { size_t C = GFZ_LOC(p, q, c, g->s1b, g->s2b); a[C] = a[C] + val; } }
+}
+
+void bbo_solvability(bbo_state *s, int out_plane, real eps[3])
+{
+  const dom_struct *D = &s->DOM;
+  int c;
+  eps[0] = eps[1] = eps[2] = 0.;
+  for (c = 0; c < s->nblocks; c++) {
+    const dom_struct *d = &s->dom[c];
+    bbo_block *b = &s->blk[c];
+    real xs = 0., xe = 0., ys = 0., ye = 0., zs = 0., ze = 0.;
+    if (d->I == 0)         { xs = plane_sum(b->u_star, 1, &d->Gfx, d->Gfx._is); xs *= d->dy * d->dz; }
+    if (d->I == D->In - 1) { xe = plane_sum(b->u_star, 1, &d->Gfx, d->Gfx._ie); xe *= d->dy * d->dz; }
+    if (d->J == 0)         { ys = plane_sum(b->v_star, 2, &d->Gfy, d->Gfy._js); ys *= d->dz * d->dx; }
+    if (d->J == D->Jn - 1) { ye = plane_sum(b->v_star, 2, &d->Gfy, d->Gfy._je); ye *= d->dz * d->dx; }
+    if (d->K == 0)         { zs = plane_sum(b->w_star, 3, &d->Gfz, d->Gfz._ks); zs *= d->dx * d->dy; }
+    if (d->K == D->Kn - 1) { ze = plane_sum(b->w_star, 3, &d->Gfz, d->Gfz._ke); ze *= d->dx * d->dy; }
+    eps[0] += xe - xs; eps[1] += ye - ys; eps[2] += ze - zs;
+  }
+  for (c = 0; c < s->nblocks; c++) {
+    const dom_struct *d = &s->dom[c];
+    bbo_block *b = &s->blk[c];
+    const real all = eps[0] + eps[1] + eps[2];
+    if (out_plane == 10) {                                   /* HOMOGENEOUS, :2469-2488 */
+      const real sx = 0.5 * eps[0] / (D->yl * D->zl), sy = 0.5 * eps[1] / (D->zl * D->xl), sz = 0.5 * eps[2] / (D->xl * D->yl);
+      if (d->I == 0) plane_add(b->u_star, 1, &d->Gfx, d->Gfx._is, sx);
+      if (d->I == D->In - 1) plane_add(b->u_star, 1, &d->Gfx, d->Gfx._ie, -sx);
+      if (d->J == 0) plane_add(b->v_star, 2, &d->Gfy, d->Gfy._js, sy);
+      if (d->J == D->Jn - 1) plane_add(b->v_star, 2, &d->Gfy, d->Gfy._je, -sy);
+      if (d->K == 0) plane_add(b->w_star, 3, &d->Gfz, d->Gfz._ks, sz);
+      if (d->K == D->Kn - 1) plane_add(b->w_star, 3, &d->Gfz, d->Gfz._ke, -sz);
+    } else if (out_plane == 0 && d->I == 0) plane_add(b->u_star, 1, &d->Gfx, d->Gfx._is, all / (D->yl * D->zl));
+    else if (out_plane == 1 && d->I == D->In - 1) plane_add(b->u_star, 1, &d->Gfx, d->Gfx._ie, -(all / (D->yl * D->zl)));
+    else if (out_plane == 2 && d->J == 0) plane_add(b->v_star, 2, &d->Gfy, d->Gfy._js, all / (D->zl * D->xl));
+    else if (out_plane == 3 && d->J == D->Jn - 1) plane_add(b->v_star, 2, &d->Gfy, d->Gfy._je, -(all / (D->zl * D->xl)));
+    else if (out_plane == 4 && d->K == 0) plane_add(b->w_star, 3, &d->Gfz, d->Gfz._ks, all / (D->xl * D->yl));
+    else if (out_plane == 5 && d->K == D->Kn - 1) plane_add(b->w_star, 3, &d->Gfz, d->Gfz._ke, -(all / (D->xl * D->yl)));
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* The solve epilogue, src/bluebottle.c:233-256.
  *
  * cuda_dom_BC_p, src/cuda_bluebottle.cu:2536-2589 with BC_p_{W,E,S,N,B,T}_N, src/bluebottle_kernel.cu:26-102:

@@ -387,6 +387,68 @@ int bbref_exchange_face(real *arr_host, int grid)
   return 0;
 }
 
+/* cuda_solvability (cuda_bluebottle.cu:2313-2492) for one rank, with the reference's surf_int_* / plane_eps_* kernels and
+ * thrust::reduce; the host sequence is restated (its TU is not linked).  One rank: it owns all six global faces and the
+ * MPI_Allreduce is the identity.  u*, v*, w* travel host -> device -> host; eps_out[3] as after :2416. */
+static int shim_face_sum(void (*kern)(real *, real *), dim3 num, dim3 dim, real *arr, int n, real *out)
+{
+  real *tmp;
+  CK(cudaMalloc((void **)&tmp, (size_t)n * sizeof(real)));
+  kern<<<num, dim>>>(arr, tmp);
+  thrust::device_ptr<real> t(tmp);
+  *out = thrust::reduce(t, t + n, 0., thrust::plus<real>());
+  CK(cudaFree(tmp));
+  return 0;
+}
+
+int bbref_solvability(real *u_h, real *v_h, real *w_h, int out_plane_, real *eps_out)
+{
+  const dom_struct *d = &dom[rank];
+  CK(cudaMemcpy(_u_star, u_h, (size_t)d->Gfx.s3b * sizeof(real), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(_v_star, v_h, (size_t)d->Gfy.s3b * sizeof(real), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(_w_star, w_h, (size_t)d->Gfz.s3b * sizeof(real), cudaMemcpyHostToDevice));
+  real exs, exe, eys, eye, ezs, eze, eps[3];
+  if (shim_face_sum(surf_int_xs, blocks.Gfx.num_in, blocks.Gfx.dim_in, _u_star, d->Gfx.s2_i, &exs)) return -1;
+  exs *= d->dy * d->dz;
+  if (shim_face_sum(surf_int_xe, blocks.Gfx.num_in, blocks.Gfx.dim_in, _u_star, d->Gfx.s2_i, &exe)) return -1;
+  exe *= d->dy * d->dz;
+  if (shim_face_sum(surf_int_ys, blocks.Gfy.num_jn, blocks.Gfy.dim_jn, _v_star, d->Gfy.s2_j, &eys)) return -1;
+  eys *= d->dz * d->dx;
+  if (shim_face_sum(surf_int_ye, blocks.Gfy.num_jn, blocks.Gfy.dim_jn, _v_star, d->Gfy.s2_j, &eye)) return -1;
+  eye *= d->dz * d->dx;
+  if (shim_face_sum(surf_int_zs, blocks.Gfz.num_kn, blocks.Gfz.dim_kn, _w_star, d->Gfz.s2_k, &ezs)) return -1;
+  ezs *= d->dx * d->dy;
+  if (shim_face_sum(surf_int_ze, blocks.Gfz.num_kn, blocks.Gfz.dim_kn, _w_star, d->Gfz.s2_k, &eze)) return -1;
+  eze *= d->dx * d->dy;
+  eps[0] = exe - exs; eps[1] = eye - eys; eps[2] = eze - ezs;
+  real sum;
+  switch (out_plane_) {
+    case WEST:   sum = (eps[0] + eps[1] + eps[2]) / (DOM.yl * DOM.zl); plane_eps_x_W<<<blocks.Gfx.num_in, blocks.Gfx.dim_in>>>(_u_star, sum); break;
+    case EAST:   sum = (eps[0] + eps[1] + eps[2]) / (DOM.yl * DOM.zl); plane_eps_x_E<<<blocks.Gfx.num_in, blocks.Gfx.dim_in>>>(_u_star, sum); break;
+    case SOUTH:  sum = (eps[0] + eps[1] + eps[2]) / (DOM.zl * DOM.xl); plane_eps_y_S<<<blocks.Gfy.num_jn, blocks.Gfy.dim_jn>>>(_v_star, sum); break;
+    case NORTH:  sum = (eps[0] + eps[1] + eps[2]) / (DOM.zl * DOM.xl); plane_eps_y_N<<<blocks.Gfy.num_jn, blocks.Gfy.dim_jn>>>(_v_star, sum); break;
+    case BOTTOM: sum = (eps[0] + eps[1] + eps[2]) / (DOM.xl * DOM.yl); plane_eps_z_B<<<blocks.Gfz.num_kn, blocks.Gfz.dim_kn>>>(_w_star, sum); break;
+    case TOP:    sum = (eps[0] + eps[1] + eps[2]) / (DOM.xl * DOM.yl); plane_eps_z_T<<<blocks.Gfz.num_kn, blocks.Gfz.dim_kn>>>(_w_star, sum); break;
+    case HOMOGENEOUS: {
+      real sum_x = 0.5 * eps[0] / (DOM.yl * DOM.zl), sum_y = 0.5 * eps[1] / (DOM.zl * DOM.xl), sum_z = 0.5 * eps[2] / (DOM.xl * DOM.yl);
+      plane_eps_x_W<<<blocks.Gfx.num_in, blocks.Gfx.dim_in>>>(_u_star, sum_x);
+      plane_eps_x_E<<<blocks.Gfx.num_in, blocks.Gfx.dim_in>>>(_u_star, sum_x);
+      plane_eps_y_S<<<blocks.Gfy.num_jn, blocks.Gfy.dim_jn>>>(_v_star, sum_y);
+      plane_eps_y_N<<<blocks.Gfy.num_jn, blocks.Gfy.dim_jn>>>(_v_star, sum_y);
+      plane_eps_z_B<<<blocks.Gfz.num_kn, blocks.Gfz.dim_kn>>>(_w_star, sum_z);
+      plane_eps_z_T<<<blocks.Gfz.num_kn, blocks.Gfz.dim_kn>>>(_w_star, sum_z);
+      break; }
+    default: return -1;
+  }
+  CK(cudaDeviceSynchronize());
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(u_h, _u_star, (size_t)d->Gfx.s3b * sizeof(real), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(v_h, _v_star, (size_t)d->Gfy.s3b * sizeof(real), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(w_h, _w_star, (size_t)d->Gfz.s3b * sizeof(real), cudaMemcpyDeviceToHost));
+  if (eps_out) { eps_out[0] = eps[0]; eps_out[1] = eps[1]; eps_out[2] = eps[2]; }
+  return 0;
+}
+
 /* device pointers of the reference's arrays, for the benchmark's device-resident leg: 0 phi, 1 p0, 2 p */
 void *bbref_dev_ptr(int which) { return which == 0 ? (void *)_phi : which == 1 ? (void *)_p0 : (void *)_p; }
 

@@ -82,6 +82,7 @@ def load_ref():
     lib.bbref_exchange.argtypes = [vp]
     lib.bbref_epilogue.argtypes = [vp, vp, vp, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
     lib.bbref_exchange_face.argtypes = [vp, C.c_int]
+    lib.bbref_solvability.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_double)]
     lib.bbref_dev_ptr.argtypes = [C.c_int]
     lib.bbref_dev_ptr.restype = C.c_void_p
     return lib

@@ -255,3 +255,47 @@ def test_replay_from_a_restart_file(tmp_path):
     assert np.abs(un.cpu().numpy()[INNER] - case.o.array(0, ob.U)[INNER]).max() < 1e-9
     assert np.abs(pn.cpu().numpy()[INNER] - case.o.array(0, ob.P)[INNER]).max() < 1e-9 * np.abs(case.o.array(0, ob.P)).max()
     p.close()
+
+
+# ---- cuda_solvability (src/cuda_bluebottle.cu:2313-2492): bbpcg_solvability -----------------------------------------
+@pytest.mark.parametrize("blocks,out_plane", [((1, 1, 1), "HOMOGENEOUS"), ((1, 1, 1), "EAST"), ((1, 1, 1), "BOTTOM"), ((2, 1, 2), "HOMOGENEOUS"),
+                                              ((2, 2, 1), "NORTH"), ((1, 3, 1), "WEST"), ((2, 2, 2), "TOP")])
+def test_solvability_matches_oracle_and_reference(blocks, out_plane):
+    """sums differ from the oracle's / Thrust's only in summation order (1e-12 of the summed magnitude); the planes that
+    must not change are bit-identical; afterwards the net boundary flux is zero"""
+    from bbpcg.lib import OUT_PLANE
+    from cases import face_exchange_inputs
+    from gpu_util import Product
+    case = Case((24, 18, 16), blocks=blocks, bc="box")
+    p = Product(case)
+    scale = 0.0
+    for r in range(p.n):
+        fx = face_exchange_inputs(case, r, 71)
+        for key, aid, name in (("u", ob.U_STAR, "u_star"), ("v", ob.V_STAR, "v_star"), ("w", ob.W_STAR, "w_star")):
+            case.o.array(r, aid)[...] = fx[key][0]
+            p.dev[r][name] = p.solvers[r].to_device(fx[key][0])
+            scale += np.abs(fx[key][0]).sum() * 0.01
+    oeps = case.o.solvability(OUT_PLANE[out_plane])
+    eps = p.each(lambda r, s, d: s.solvability(d["u_star"], d["v_star"], d["w_star"], out_plane))
+    for r in range(p.n):
+        assert eps[r] == eps[0]                                      # every rank holds the same bits
+        assert np.abs(np.array(eps[r]) - np.array(oeps)).max() <= 1e-12 * scale
+        for aid, name in ((ob.U_STAR, "u_star"), (ob.V_STAR, "v_star"), (ob.W_STAR, "w_star")):
+            mine, ref = p.dev[r][name].cpu().numpy(), case.o.array(r, aid)
+            assert np.abs(mine - ref).max() <= 1e-12 * np.abs(ref).max(), (r, name)
+            same = ref == face_exchange_inputs(case, r, 71)[name[0]][0]
+            assert np.array_equal(mine[same], ref[same])            # untouched entries are untouched
+    if blocks == (1, 1, 1):
+        lib = load_ref()
+        if lib is not None:
+            dom, DOM = case.o.dom(0), case.o.DOM
+            assert lib.bbref_init(C.byref(dom), C.byref(DOM)) == 0
+            fx = face_exchange_inputs(case, 0, 71)
+            arrs = {k: np.ascontiguousarray(v[0]).copy() for k, v in fx.items()}
+            reps = (C.c_double * 3)()
+            P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+            assert lib.bbref_solvability(P(arrs["u"]), P(arrs["v"]), P(arrs["w"]), OUT_PLANE[out_plane], reps) == 0
+            assert np.abs(np.array(list(reps)) - np.array(eps[0])).max() <= 1e-12 * scale
+            for k, name in (("u", "u_star"), ("v", "v_star"), ("w", "w_star")):
+                assert np.abs(p.dev[0][name].cpu().numpy() - arrs[k]).max() <= 1e-12 * np.abs(arrs[k]).max(), k
+    p.close()

@@ -203,3 +203,92 @@ def test_face_exchange_reproduces_a_periodic_field_in_the_ghosts(blocks):
                 assert np.abs(a[sl] - ex[sl]).max() < 1e-12, (grid, r, sl)
             # edges and corners are NOT exchanged (faces only)
             assert a[0, 0, 0] == -99.0 and a[-1, -1, 0] == -99.0 and a[0, -1, 5] == -99.0
+
+
+# ---- cuda_solvability (src/cuda_bluebottle.cu:2313-2492) ----------------------------------------------------------
+def _seed_star(case, seed):
+    from cases import face_exchange_inputs
+    for r in range(case.o.nblocks):
+        fx = face_exchange_inputs(case, r, seed)
+        for key, aid in (("u", ob.U_STAR), ("v", ob.V_STAR), ("w", ob.W_STAR)):
+            case.o.array(r, aid)[...] = fx[key][0]
+
+
+def _net_flux(case):
+    """sum over the global boundary faces of u* . n dA, from the blocks that touch them"""
+    o, D = case.o, case.o.DOM
+    tot = 0.0
+    for r in range(o.nblocks):
+        d = o.dom(r)
+        u, v, w = (o.array(r, a)[1:-1, 1:-1, 1:-1] for a in (ob.U_STAR, ob.V_STAR, ob.W_STAR))
+        if d.I == D.In - 1:
+            tot += u[-1].sum() * d.dy * d.dz
+        if d.I == 0:
+            tot -= u[0].sum() * d.dy * d.dz
+        if d.J == D.Jn - 1:
+            tot += v[-1].sum() * d.dz * d.dx
+        if d.J == 0:
+            tot -= v[0].sum() * d.dz * d.dx
+        if d.K == D.Kn - 1:
+            tot += w[-1].sum() * d.dx * d.dy
+        if d.K == 0:
+            tot -= w[0].sum() * d.dx * d.dy
+    return tot
+
+
+@pytest.mark.parametrize("blocks", [(1, 1, 1), (2, 1, 2), (1, 3, 1)])
+@pytest.mark.parametrize("out_plane", [10, 0, 1, 2, 3, 4, 5])
+def test_solvability_removes_the_net_boundary_flux(blocks, out_plane):
+    """the property the function exists for: afterwards the net outflow through the global boundary is zero (to round-off),
+    only the designated plane(s) changed, and by a constant"""
+    case = Case((12, 9, 8), blocks=blocks, bc="box")
+    _seed_star(case, 17)
+    before = [[case.o.array(r, a).copy() for a in (ob.U_STAR, ob.V_STAR, ob.W_STAR)] for r in range(case.o.nblocks)]
+    flux0 = _net_flux(case)
+    eps = case.o.solvability(out_plane)
+    assert abs(sum(eps) - flux0) <= 1e-12 * abs(flux0)
+    scale = sum(np.abs(b).sum() for blk in before for b in blk) * 0.01
+    assert abs(_net_flux(case)) <= 1e-13 * scale
+    D = case.o.DOM
+    for r in range(case.o.nblocks):
+        d = case.o.dom(r)
+        for g, aid in enumerate((ob.U_STAR, ob.V_STAR, ob.W_STAR)):
+            diff = case.o.array(r, aid) - before[r][g]
+            lo_rank = (d.I, d.J, d.K)[g] == 0
+            hi_rank = (d.I, d.J, d.K)[g] == (D.In, D.Jn, D.Kn)[g] - 1
+            touched_lo = (out_plane == 10 or out_plane == 2 * g) and lo_rank
+            touched_hi = (out_plane == 10 or out_plane == 2 * g + 1) and hi_rank
+            inner = diff[2:-2]                                         # planes strictly between the two boundary faces
+            assert not inner.any()
+            assert not diff[0].any() and not diff[-1].any()            # ghosts along the normal untouched
+            for plane, touched in ((diff[1], touched_lo), (diff[-2], touched_hi)):
+                core = plane[1:-1, 1:-1]
+                if touched:
+                    assert np.ptp(core) <= 1e-15 * max(1.0, np.abs(core).max()) and core.flat[0] != 0.0
+                    edge = plane.copy(); edge[1:-1, 1:-1] = 0
+                    assert not edge.any()                              # ghosts of the other two directions untouched
+                else:
+                    assert not plane.any()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_solvability_matches_reference_kernels(name):
+    spec = CASES[name]
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    if "sol_eps_10" not in gold.files:
+        pytest.skip("fixture predates the solvability vectors")
+    for out_plane in (10, 1, 4):
+        case = Case(tuple(spec["cells"]), bc=spec["bc"], nparts=spec.get("nparts", 0), radius=spec.get("radius", 1.0))
+        _seed_star(case, MANIFEST["seed"] + 6)
+        eps = case.o.solvability(out_plane)
+        from cases import face_exchange_inputs
+        fresh = {k: v[0] for k, v in face_exchange_inputs(case, 0, MANIFEST["seed"] + 6).items()}
+        ref_eps = gold["sol_eps_%d" % out_plane]
+        scale = sum(np.abs(v).sum() for v in fresh.values()) * 0.01
+        assert np.abs(np.array(eps) - ref_eps).max() <= 1e-12 * scale
+        for k, aid in (("u", ob.U_STAR), ("v", ob.V_STAR), ("w", ob.W_STAR)):
+            if "sol_same_%s_%d" % (k, out_plane) in gold.files:          # the reference left this array alone
+                assert np.array_equal(case.o.array(0, aid), fresh[k]), (k, out_plane)
+                continue
+            ref = gold["sol_%s_%d" % (k, out_plane)]
+            assert np.abs(case.o.array(0, aid) - ref).max() <= 1e-12 * np.abs(ref).max(), (k, out_plane)
