@@ -495,8 +495,6 @@ static int launch_search_tma_t(bbpcg_solver *s, const SearchMaps &M)
   a.nbx = (L.in + G::TX - 1) / G::TX; a.nby = (L.jn + TY - 1) / TY;
   int rc = plan_zchunks(s, a.nbx * a.nby, s->sm_count * 2, &a.nbz);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) { CU(cudaFuncSetAttribute(k_search_tma<TY, PARTS, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM)); attr_set = true; }
   a.store_q = recompute_active(s) ? 0 : 1;
   dim3 grid(a.nbx, a.nby, a.nbz);
   s->last_search_grid = a.nbx * a.nby * a.nbz; s->last_search_kc = s->h_ztab[1];
@@ -516,8 +514,6 @@ static int launch_resid_tma_t(bbpcg_solver *s, const SearchMaps &M, const real *
   int rc = plan_zchunks(s, a.nbx * a.nby, s->sm_count * 2, &a.nbz);
   if (rc) return rc;
   a.store_q = 0; a.rhs = rhs; a.s1b = s->fst.cs1b; a.s2b = s->fst.cs2b;
-  static bool attr_set = false;
-  if (!attr_set) { CU(cudaFuncSetAttribute(k_resid_tma<TY, PARTS, MB, DD, REFRESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM)); attr_set = true; }
   CU(launch_k(s, k_resid_tma<TY, PARTS, MB, DD, REFRESH>, dim3(a.nbx, a.nby, a.nbz), G::NT, G::SMEM, !REFRESH, s->dev, M, a));
   s->launches++;
   return BBPCG_OK;
@@ -595,12 +591,17 @@ static int launch_search(bbpcg_solver *s, bool parts)
  * launch, and that load takes a context-wide lock; when several ranks share one context (the
  * single-process test harness) a first launch on one rank's host thread would block the other
  * ranks' launches while a collective kernel already on the device waits for them. */
-template <typename K> static int preload_one(K kernel)
+template <typename K> static int preload_one(K kernel, int dyn_smem = 0)
 {
   cudaFuncAttributes at;
   CU(cudaFuncGetAttributes(&at, kernel));
+  /* the > 48 KB opt-in is a per-device function attribute: set it here, once per solver (= per device), not behind a
+   * process-wide flag at the first launch */
+  if (dyn_smem > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
   return BBPCG_OK;
 }
+template <int TY, bool PARTS, int DD> static int preload_search_tma() { return preload_one(k_search_tma<TY, PARTS, DD>, SearchGeom<TY, PARTS, DD>::SMEM); }
+template <int TY, bool PARTS, int MB, int DD, bool REFRESH> static int preload_resid_tma() { return preload_one(k_resid_tma<TY, PARTS, MB, DD, REFRESH>, ResidGeom<TY, PARTS, DD>::SMEM); }
 template <int TX, int TY, int NT, int MINB> static int preload_search()
 {
   int rc = preload_one(k_search_spmv<TX, TY, NT, MINB, false>);
@@ -611,25 +612,30 @@ static int preload_kernels()
 {
   int rc = 0;
 #define PL(...) if (!rc) rc = preload_one(__VA_ARGS__)
-  PL(k_search_tma<8, false, 2>); PL(k_search_tma<8, true, 2>); PL(k_search_tma<4, false, 2>); PL(k_search_tma<4, true, 2>);
-  PL(k_search_tma<8, false, 3>); PL(k_search_tma<8, true, 3>); PL(k_search_tma<4, false, 3>); PL(k_search_tma<4, true, 3>);
+#define PS(...) if (!rc) rc = preload_search_tma<__VA_ARGS__>()
+#define PR(...) if (!rc) rc = preload_resid_tma<__VA_ARGS__>()
+  PS(8, false, 2); PS(8, true, 2); PS(4, false, 2); PS(4, true, 2); PS(8, false, 3); PS(8, true, 3); PS(4, false, 3); PS(4, true, 3);
   if (!rc) rc = preload_search<128, 8, 256, 2>();
   if (!rc) rc = preload_search<128, 4, 256, 3>();
   if (!rc) rc = preload_search<64, 8, 256, 3>();
   if (!rc) rc = preload_search<128, 8, 512, 2>();
   if (!rc) rc = preload_search<32, 8, 128, 4>();
   if (!rc) rc = preload_search<256, 4, 256, 2>();
-  PL(k_resid_tma<8, true, 2, 2, false>); PL(k_resid_tma<4, true, 2, 2, false>); PL(k_resid_tma<4, false, 3, 2, false>);
-  PL(k_resid_tma<8, false, 2, 2, false>); PL(k_resid_tma<8, false, 2, 3, false>);
-  PL(k_resid_tma<8, false, 3, 2, false>); PL(k_resid_tma<8, false, 3, 3, false>);
-  PL(k_resid_tma<8, true, 2, 2, true>); PL(k_resid_tma<4, true, 2, 2, true>); PL(k_resid_tma<8, false, 2, 2, true>); PL(k_resid_tma<4, false, 2, 2, true>);
+  PR(8, true, 2, 2, false); PR(4, true, 2, 2, false); PR(4, false, 3, 2, false);
+  PR(8, false, 2, 2, false); PR(8, false, 2, 3, false); PR(8, false, 3, 2, false); PR(8, false, 3, 3, false);
+  PR(8, true, 2, 2, true); PR(4, true, 2, 2, true); PR(8, false, 2, 2, true); PR(4, false, 2, 2, true);
+#undef PS
+#undef PR
   PL(k_refresh_x4<128, 4>); PL(k_refresh_x4<64, 4>); PL(k_refresh_x4<32, 4>);
   PL(k_resid<128, 4>); PL(k_resid<64, 4>); PL(k_resid<32, 4>); PL(k_refresh_x<256>); PL(k_refresh_r<256, false>); PL(k_refresh_r<256, true>);
   PL(k_build_tab); PL(k_init<256>); PL(k_finish<256>); PL(k_rhs<256>); PL(k_rhs_tiled); PL(k_masks<256>); PL(k_part_rhs_net);
   PL(k_coeffs_refine<256>); PL(k_zero_ghosts); PL(k_xchg_send); PL(k_xchg_recv);
   PL(k_spmv_s3b<256, false>); PL(k_spmv_s3b<256, true>);
   PL(k_solv_sum); PL(k_solv_apply);
-  PL(k_bc_p); PL(k_epilogue<true, true>); PL(k_epilogue<true, false>); PL(k_epilogue<false, true>); PL(k_sub_mean);
+  PL(k_bc_p); PL(k_sub_mean);
+  if (!rc) rc = preload_one(k_epilogue<true, true>, EPI_SMEM);
+  if (!rc) rc = preload_one(k_epilogue<true, false>, EPI_SMEM);
+  if (!rc) rc = preload_one(k_epilogue<false, true>, EPI_SMEM);
 #undef PL
   return rc;
 }
@@ -829,13 +835,6 @@ extern "C" int bbpcg_epilogue(bbpcg_solver *s, const bbpcg_epilogue_args *a, dou
   e.nti = (L.in + EPI_T - 1) / EPI_T; e.ntj = (L.jn + EPI_T - 1) / EPI_T; e.ntk = (L.kn + EPI_T - 1) / EPI_T;
   const long long ntiles = (long long)e.nti * e.ntj * e.ntk;
   const int grid = clampi(ntiles, 1, BB_MAXBLOCKS);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU(cudaFuncSetAttribute(k_epilogue<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EPI_SMEM));
-    CU(cudaFuncSetAttribute(k_epilogue<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EPI_SMEM));
-    CU(cudaFuncSetAttribute(k_epilogue<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EPI_SMEM));
-    attr_set = true;
-  }
   if (project && update) k_epilogue<true, true><<<grid, 256, EPI_SMEM, s->stream>>>(s->dev, s->fst, e);
   else if (project) k_epilogue<true, false><<<grid, 256, EPI_SMEM, s->stream>>>(s->dev, s->fst, e);
   else k_epilogue<false, true><<<grid, 256, EPI_SMEM, s->stream>>>(s->dev, s->fst, e);
