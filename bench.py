@@ -385,7 +385,7 @@ def run_bbpcg(args):
                "algorithmic_bytes_per_cell": BYTES_EPILOGUE, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                "what": "bbpcg_epilogue (C ABI): mpi_cuda_exchange_Gcc(phi) + cuda_dom_BC_p(phi) + cuda_project + cuda_update_p "
                        "(src/bluebottle.c:233-250) as k_xchg_send/recv + k_bc_p + k_epilogue + k_sub_mean; CUDA events on the solver stream",
-               "mean_p_after": float(pn[1:-1, 1:-1, 1:-1].mean())}
+               "mean_p_after": w.sum(float(pn[1:-1, 1:-1, 1:-1].sum())) / ncell_glob}      # over ALL ranks' cells
         # solve prologue: cuda_solvability on u*, v*, w* (6 boundary planes, one 3-value all-reduce); wall clock around the
         # host-synchronous C-ABI call (2 launches); the correction it applies is undone by calling it on copies
         uc, vc, wc = u.clone(), v.clone(), wz.clone()
