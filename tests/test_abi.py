@@ -60,7 +60,8 @@ def test_dropin_exports_the_reference_entry_points_and_imports_its_globals():
     # what the reference host program must provide (src/bluebottle.c:438-576, mpi_comm.c:26-27, particle.c:27-28)
     for g in ("dom", "DOM", "rank", "nprocs", "bc", "rho_f", "dt", "pp_residual", "pp_max_iter", "NPARTS", "nparts",
               "_u_star", "_v_star", "_w_star", "_flag_u", "_flag_v", "_flag_w", "_phase", "_phase_shell", "_rhs_p", "_phi",
-              "cuda_part_BC_p", "recorder_PP"):
+              "cuda_part_BC_p", "recorder_PP",
+              "_u", "_v", "_w", "_p", "_p0", "out_plane"):            # epilogue / solvability entry points
         assert g in und, g
     # private scratch of the reference solver is NOT touched
     for g in ("_invM", "_r_q", "_z_q", "_p_q", "_pb_q", "_Apb_q", "_dom"):
@@ -119,3 +120,35 @@ def test_missing_library_is_an_error_not_a_fallback(monkeypatch):
     monkeypatch.setattr(L, "LIB_PATH", "/nonexistent/libbbpcg.so")
     with pytest.raises(bbpcg.LibraryMissing):
         L.load_library()
+
+
+def test_ctypes_mirrors_match_the_c_structs(tmp_path):
+    """the Python mirror binds by struct layout: sizes and field offsets of every struct of bbpcg.h, from the C compiler"""
+    src = tmp_path / "layout.c"
+    fields = {
+        "bbpcg_result": (L.Result, ["status", "niter", "resid", "sp_rhs", "sp_rq0", "ms_setup", "ms_iter", "ms_total", "launches"]),
+        "bb_flow_params": (L.FlowParams, ["rho_f", "pp_residual", "pp_max_iter"]),
+        "bbpcg_solve_args": (L.SolveArgs, ["u_star", "v_star", "w_star", "rhs_p", "phi", "phase", "phase_shell", "rho_f", "dt",
+                                           "pp_residual", "pp_max_iter", "use_phase", "fixed_iters", "part_bc"]),
+        "bbpcg_epilogue_args": (L.EpilogueArgs, ["u_star", "v_star", "w_star", "flag_u", "flag_v", "flag_w", "phi", "u", "v", "w",
+                                                 "p0", "phase", "p", "rho_f", "dt", "phi_ghosts_valid"]),
+        "bb_restart": (L.Restart, ["ttime", "dt0", "dt", "stepnum", "rec_vtk_stepnum_out", "rec_cgns_flow_ttime_out",
+                                   "rec_cgns_part_ttime_out", "rec_vtk_ttime_out", "u", "v", "w", "u_star", "v_star", "w_star",
+                                   "p", "phi", "p0", "phase", "phase_shell", "flag_u", "flag_v", "flag_w", "nparts_subdom"]),
+        "bb_pressure_bc": (bbpcg.grid.PressureBC, ["pW", "pE", "pS", "pN", "pB", "pT"]),
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "bbpcg.h"', "int main(void) {"]
+    for name, (_, fl) in fields.items():
+        lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for f in fl:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, f, name, f))
+    lines += ["  return 0;", "}"]
+    src.write_text("\n".join(lines))
+    exe = str(tmp_path / "layout")
+    subprocess.check_call(["gcc", "-std=c99", "-I", INC, "-o", exe, str(src)])
+    got = dict(ln.split() for ln in subprocess.check_output([exe], text=True).splitlines())
+    for name, (ct, fl) in fields.items():
+        assert C.sizeof(ct) == int(got[name]), name
+        assert [f for f, _ in ct._fields_] == fl, name              # same fields, same order
+        for f in fl:
+            assert getattr(ct, f).offset == int(got["%s.%s" % (name, f)]), (name, f)
