@@ -93,7 +93,7 @@ def restart_path(directory, rank, nranks):
 
 
 def read_restart(path, dom):
-    """One rank's Bluebottle restart file (out_restart, src/domain.c:3005-3085) -> dict of numpy arrays in the
+    """One rank's Bluebottle restart file (out_restart, src/domain.c:3005-3092) -> dict of numpy arrays in the
     reference's ghosted layouts + the header scalars.  Host only."""
     lib = L.load_library()
     r = L.Restart()

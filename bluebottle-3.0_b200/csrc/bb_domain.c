@@ -252,7 +252,7 @@ int bb_domain_read(const char *flow_config, const char *decomp_config, dom_struc
 
 void bb_domain_free(dom_struct *dom) { free(dom); }
 
-/* ---- restart files as fixtures: out_restart / in_restart, src/domain.c:3005-3180 ------------------------------- */
+/* ---- restart files as fixtures: out_restart / in_restart, src/domain.c:3005-3260 ------------------------------- */
 int bb_restart_path(char *out, size_t cap, const char *dir, int rank, int S3)
 {
   int sigfigs = 1, v;

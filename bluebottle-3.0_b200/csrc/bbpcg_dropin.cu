@@ -22,7 +22,7 @@ extern real rho_f, dt, pp_residual, ttime;    /* src/bluebottle.h:524,560,572,24
 extern int pp_max_iter, stepnum;              /* src/bluebottle.h:2389,2487 */
 extern int NPARTS, nparts;                    /* src/particle.h:319,331 */
 extern real *_u_star, *_v_star, *_w_star, *_rhs_p, *_phi;
-extern real *_u, *_v, *_w, *_p, *_p0;         /* src/bluebottle.h:961,1037,1137-1161 (epilogue) */
+extern real *_u, *_v, *_w, *_p, *_p0;         /* src/bluebottle.h:961,1037,1137,1186,1235 (epilogue) */
 extern int *_flag_u, *_flag_v, *_flag_w, *_phase, *_phase_shell;
 extern int out_plane;                         /* src/bluebottle.h:650 (solvability) */
 void cuda_part_BC_p(void);                    /* src/cuda_particle.cu:1680 */
@@ -122,7 +122,7 @@ extern "C" void mpi_cuda_exchange_Gfx(real *array) { exchange_face(array, BBPCG_
 extern "C" void mpi_cuda_exchange_Gfy(real *array) { exchange_face(array, BBPCG_GFY); }
 extern "C" void mpi_cuda_exchange_Gfz(real *array) { exchange_face(array, BBPCG_GFZ); }
 
-/* ---- solve prologue: src/bluebottle.c:221, src/cuda_bluebottle.cu:2313-2492 ---- */
+/* ---- solve prologue: src/bluebottle.c:220, src/cuda_bluebottle.cu:2313-2492 ---- */
 extern "C" void cuda_solvability(void)
 {
   cudaDeviceSynchronize();

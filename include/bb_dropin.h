@@ -11,7 +11,7 @@
  *   cuda_PP_cg_timed                     src/bluebottle.h:3098, no caller in the reference
  *   mpi_cuda_exchange_Gcc(real *array)   src/mpi_comm.h:318, 19 call sites outside the solver
  *   mpi_cuda_exchange_Gfx/_Gfy/_Gfz(real *array)   src/mpi_comm.h:335,352,369; 24 call sites in src/bluebottle.c
- *   cuda_solvability                     src/cuda_bluebottle.cu:2313, called src/bluebottle.c:221 (reads the global out_plane)
+ *   cuda_solvability                     src/cuda_bluebottle.cu:2313, called src/bluebottle.c:220 (reads the global out_plane)
  * and, for the solve epilogue (link instead of the same-named functions of cuda_bluebottle.o):
  *   cuda_dom_BC_p(real *array)           src/cuda_bluebottle.cu:2536, called src/bluebottle.c:234,255
  *   cuda_project                         src/cuda_bluebottle.cu:2495, called src/bluebottle.c:237

@@ -82,8 +82,8 @@ int  bb_domain_write_decomp(const char *path, const dom_struct *DOM, const dom_s
 void bb_domain_free(dom_struct *dom);
 
 /* ---- restart files as fixtures (no GPU needed) ---------------------------------------------
- * Reader for the per-rank binary `restart.config-<rank>` files Bluebottle writes (out_restart, src/domain.c:3005-3085;
- * read back by in_restart, :3087-3180), so that the state of a production run -- u*, v*, w*, flags, phase, phi, p, p0 --
+ * Reader for the per-rank binary `restart.config-<rank>` files Bluebottle writes (out_restart, src/domain.c:3005-3092;
+ * read back by in_restart, :3094-3260), so that the state of a production run -- u*, v*, w*, flags, phase, phi, p, p0 --
  * can be replayed through this library without MPI.  Layout (sequential fwrite's, no padding): ttime, dt0, dt (real),
  * stepnum, rec_vtk_stepnum_out (int), three output times (real); then u, u0, diff0_u, conv0_u, diff_u, conv_u, u_star on
  * Gfx s3b, the same seven for v (Gfy) and w (Gfz); p, phi, p0 (real) and phase, phase_shell (int) on Gcc s3b; flag_u,

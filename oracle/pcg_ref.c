@@ -42,7 +42,7 @@ typedef struct bbo_block {
   real *rhs_p, *phi, *pb_q;            /* Gcc s3b                (bluebottle.h:974-1013)   */
   real *invM, *r_q, *z_q, *p_q, *Apb_q;/* Gcc s3                                          */
   real *send[6], *recv[6];             /* e,w,n,s,t,b packing buffers (cuda_bluebottle.cu:255-319) */
-  real *u, *v, *w;                     /* Gfx/Gfy/Gfz s3b: projected velocity (bluebottle.h:1137-1161) */
+  real *u, *v, *w;                     /* Gfx/Gfy/Gfz s3b: projected velocity (bluebottle.h:1137,1186,1235) */
   real *p0, *p;                        /* Gcc s3b: previous / updated pressure (bluebottle.h:961,1037)  */
 } bbo_block;
 

@@ -222,7 +222,7 @@ def test_face_exchange_three_way(bc):
 
 
 def test_replay_from_a_restart_file(tmp_path):
-    """a Bluebottle restart file (out_restart, src/domain.c:3005-3085) replayed through the library:
+    """a Bluebottle restart file (out_restart, src/domain.c:3005-3092) replayed through the library:
     flags, phase and u* come from the file; the solve and the epilogue equal the run fed from the arrays directly"""
     import bbpcg
     from gpu_util import Product

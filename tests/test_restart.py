@@ -1,5 +1,5 @@
 """Restart files as fixtures: bb_restart_read parses the per-rank binary file Bluebottle's
-out_restart writes (src/domain.c:3005-3085).  The test writes files in that byte layout with numpy -- header scalars,
+out_restart writes (src/domain.c:3005-3092).  The test writes files in that byte layout with numpy -- header scalars,
 seven arrays per velocity component, p/phi/p0, phase/phase_shell, the three flag arrays, nparts_subdom, then trailing
 bytes standing in for the particle structs -- and reads them back through the C ABI.  CPU only; the GPU replay test
 (solve from a restart file == solve from the arrays) is in tests/test_gpu_epilogue.py."""
