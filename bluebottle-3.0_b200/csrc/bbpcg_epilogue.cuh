@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256, 3) k_epilogue(const __grid_constant__ Dev
     }
   }
   if (UPDATE_P) {
-    /* mean pressure: thrust::reduce + MPI_Allreduce of cuda_bluebottle.cu:2524-2527, kept on the device */
+    /* mean pressure: thrust::reduce + MPI_Allreduce of cuda_bluebottle.cu:2526-2529, kept on the device */
     double v[1] = { psum }, tot[1];
     if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, false)) {
       rank_allreduce(d, tot, 1, false);

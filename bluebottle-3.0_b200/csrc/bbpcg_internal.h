@@ -132,7 +132,7 @@ struct Scal {
   int comm_timeout;     /* set if a peer never showed up                  */
   int pad0, pad1;
   unsigned long long seq;   /* publish counter, never reset               */
-  double p_sum;         /* epilogue: sum of p over all ranks' interior cells (cuda_bluebottle.cu:2524-2527) */
+  double p_sum;         /* epilogue: sum of p over all ranks' interior cells (cuda_bluebottle.cu:2526-2529) */
   double eps[3];        /* solvability: net outflow per axis over all ranks (cuda_bluebottle.cu:2414-2420) */
 };
 

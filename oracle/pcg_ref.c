@@ -606,8 +606,8 @@ void bbo_exchange_Gcc(bbo_state *s, int array_id)
 /* ------------------------------------------------------------------------------------ */
 /* mpi_cuda_exchange_Gfx / _Gfy / _Gfz, src/mpi_comm.c:317-405, pack/unpack kernels src/bluebottle_kernel.cu:782-1081,
  * 1179-1466.  Same scheme as the Gcc exchange with the grid's own extents and index macro; along the grid's own normal
- * the block-boundary face is shared with the neighbour, so the planes _ie-1 / _is+1 are sent (:795,:812 for Gfx,
- * :926,:943 for Gfy, :1059,:1076 for Gfz) into the ghosts _isb / _ieb. */
+ * the block-boundary face is shared with the neighbour, so the planes _ie-1 / _is+1 are sent (:793,:811 for Gfx,
+ * :927,:944 for Gfy, :1059,:1077 for Gfz) into the ghosts _isb / _ieb. */
 static real *blk_face_array(bbo_block *b, int id, int *grid)
 {
   switch (id) {
