@@ -60,9 +60,8 @@ def parse():
     ap.add_argument("--bc", default="duct")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--blocks", default="", help="In,Jn,Kn override")
-    ap.add_argument("--tile", type=int, default=-1)
-    ap.add_argument("--kc", type=int, default=-1)
-    ap.add_argument("--resid-blocks", type=int, default=-1)
+    ap.add_argument("--ty", type=int, default=-1, help="tile rows of the iteration kernels (default: planner)")
+    ap.add_argument("--kc", type=int, default=-1, help="planes per z-chunk (default: planner)")
     ap.add_argument("--fixed-iters", type=int, default=0, help=">0: fixed iteration count per step, no stop test")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -239,7 +238,7 @@ def run_bbpcg(args):
     s = bbpcg.PoissonSolver(dec, w.rank, device=w.local)
     if w.size > 1:
         s.comm_init_torch()
-    for key, val in (("tile", args.tile), ("kc", args.kc), ("resid_blocks", args.resid_blocks)):
+    for key, val in (("ty", args.ty), ("kc", args.kc)):
         if val >= 0:
             s.set_option(key, val)
     for kv in args.opt:
@@ -257,7 +256,7 @@ def run_bbpcg(args):
 
     for _ in range(args.warmup):
         r = s.PP_cg_noparts(u, v, wz, rhs, phi, **kw)
-    recompute = int(s.info("recompute"))
+    recompute = 1
     bytes_search = BYTES_SEARCH[recompute]
     clocks = ClockSampler(w.local) if w.rank == 0 else None
     w.barrier()

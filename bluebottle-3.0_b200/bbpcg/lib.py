@@ -38,7 +38,7 @@ class SolveArgs(C.Structure):
                 ("rhs_p", C.c_void_p), ("phi", C.c_void_p), ("phase", C.c_void_p), ("phase_shell", C.c_void_p),
                 ("rho_f", C.c_double), ("dt", C.c_double), ("pp_residual", C.c_double),
                 ("pp_max_iter", C.c_int), ("use_phase", C.c_int), ("fixed_iters", C.c_int),
-                ("part_bc", PART_BC_FN)]
+                ("part_bc", PART_BC_FN), ("no_refine", C.c_int)]
 
 
 class EpilogueArgs(C.Structure):

@@ -223,3 +223,102 @@ def flags_noparts_torch(dom, DOM, bc, device):
         if dom.K == DOM.Ke:
             fw[dom.Gfz.get("_ke")] = 0
     return fu, fv, fw
+
+
+def cages_torch(dom, DOM, bc, parts, device):
+    """phase, phase_shell (int32, Gcc s3b) and flag_u, flag_v, flag_w (int32, Gfx/Gfy/Gfz s3b) of one block for a list of
+    spheres parts = (x, y, z, r) in global coordinates: cuda_build_cages (src/cuda_particle.cu:1516-1646) with cage_setup
+    (src/particle_kernel.cu:135-146), build_phase (:148-253), build_phase_shell (:255-426), cage_flag_u/v/w (:482-540) and
+    the external-wall flags (:542-576), evaluated with torch on `device` (bench.py builds the 1000-sphere case of
+    BASELINE configs[3] on the GPU with it; tests/test_domain.py holds it to the CPU oracle bit for bit).
+    The same IEEE operations in the same order as the reference's expressions, so floor(d / r) < 1 agrees on every cell."""
+    import math
+    import torch
+    px, py, pz, pr = [np.asarray(v, dtype=np.float64) for v in parts]
+    g = dom.Gcc
+    knb, jnb, inb = g.get("knb"), g.get("jnb"), g.get("inb")
+    phase = torch.full((knb, jnb, inb), -1, dtype=torch.int32, device=device)
+    shell = torch.ones((knb, jnb, inb), dtype=torch.int32, device=device)
+    S = [g.get("_is") if (dom.I == DOM.Is and bc.pW != PERIODIC) else g.get("_isb"),
+         g.get("_js") if (dom.J == DOM.Js and bc.pS != PERIODIC) else g.get("_jsb"),
+         g.get("_ks") if (dom.K == DOM.Ks and bc.pB != PERIODIC) else g.get("_ksb")]
+    E = [g.get("_ie") if (dom.I == DOM.Ie and bc.pE != PERIODIC) else g.get("_ieb"),
+         g.get("_je") if (dom.J == DOM.Je and bc.pN != PERIODIC) else g.get("_jeb"),
+         g.get("_ke") if (dom.K == DOM.Ke and bc.pT != PERIODIC) else g.get("_keb")]
+    dd = (dom.dx, dom.dy, dom.dz)
+    ss = (dom.xs, dom.ys, dom.zs)
+    nn = (dom.xn, dom.yn, dom.zn)
+
+    def c_round(v):                                   # C round(): half away from zero
+        return math.floor(v + 0.5) if v >= 0 else -math.floor(-v + 0.5)
+
+    def cage(n):
+        lo, hi = [0, 0, 0], [0, 0, 0]
+        for a, pc in enumerate((px[n], py[n], pz[n])):
+            cg = int(2. * math.ceil(pr[n] / dd[a])) + 2 - (nn[a] % 2)
+            lo[a] = int(c_round((pc - ss[a]) * (1. / dd[a])) - 0.5 * cg + DOM_BUF_)
+            hi[a] = lo[a] + cg
+            lo[a] = min(max(lo[a], S[a]), E[a])
+            hi[a] = min(max(hi[a], S[a]), E[a])
+            if lo[a] == hi[a]:
+                return None
+        return lo, hi
+
+    def axis(lo, hi, a, pc, off=0):
+        l = torch.arange(lo, hi + 1, dtype=torch.float64, device=device)
+        return (l + off - 0.5) * dd[a] - (pc - ss[a])
+
+    cages = [cage(n) for n in range(len(pr))]
+    for n, cg in enumerate(cages):                    # build_phase
+        if cg is None:
+            continue
+        lo, hi = cg
+        xx, yy, zz = axis(lo[0], hi[0], 0, px[n]), axis(lo[1], hi[1], 1, py[n]), axis(lo[2], hi[2], 2, pz[n])
+        d2 = (xx * xx)[None, None, :] + (yy * yy)[None, :, None] + (zz * zz)[:, None, None]
+        inside = torch.floor(torch.sqrt(d2) * (1. / pr[n])) < 1
+        sub = phase[lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1]
+        sub[inside] = n
+    for n, cg in enumerate(cages):                    # build_phase_shell
+        if cg is None:
+            continue
+        lo, hi = cg
+        ax = [[axis(lo[a], hi[a], a, pc, off) for off in (-1, 0, 1)] for a, pc in enumerate((px[n], py[n], pz[n]))]
+        sq = [[v * v for v in row] for row in ax]
+
+        def outside(ox, oy, oz):
+            d2 = sq[0][ox + 1][None, None, :] + sq[1][oy + 1][None, :, None] + sq[2][oz + 1][:, None, None]
+            return ~(torch.floor(torch.sqrt(d2) * (1. / pr[n])) < 1)
+        any_out = outside(-1, 0, 0) | outside(1, 0, 0) | outside(0, -1, 0) | outside(0, 1, 0) | outside(0, 0, -1) | outside(0, 0, 1)
+        sub_p = phase[lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1]
+        sub_s = shell[lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1]
+        sub_s[(sub_p == n) & any_out] = 0
+
+    def face_flag(lo_p, hi_p, lo_s, hi_s):
+        cut = ((lo_p < 0) & (hi_p > -1)) | ((lo_p > -1) & (hi_p < 0)) | ((hi_s < 1) & (lo_s < 1))
+        return (1 - 2 * cut.to(torch.int32))
+    fu = torch.ones(grid_shape(dom, "Gfx"), dtype=torch.int32, device=device)   # [i, k, j]
+    fv = torch.ones(grid_shape(dom, "Gfy"), dtype=torch.int32, device=device)   # [j, i, k]
+    fw = torch.ones(grid_shape(dom, "Gfz"), dtype=torch.int32, device=device)   # [k, j, i]
+    # faces _is.._ie = 1..n+1 between cells i-1 and i; phase is [k, j, i]
+    fu[1:-1] = face_flag(phase[:, :, :-1], phase[:, :, 1:], shell[:, :, :-1], shell[:, :, 1:]).permute(2, 0, 1)
+    fv[1:-1] = face_flag(phase[:, :-1, :], phase[:, 1:, :], shell[:, :-1, :], shell[:, 1:, :]).permute(1, 2, 0)
+    fw[1:-1] = face_flag(phase[:-1], phase[1:], shell[:-1], shell[1:])
+    if bc.pW != PERIODIC and bc.pE != PERIODIC:
+        if dom.I == DOM.Is:
+            fu[dom.Gfx.get("_is")] = 0
+        if dom.I == DOM.Ie:
+            fu[dom.Gfx.get("_ie")] = 0
+    if bc.pS != PERIODIC and bc.pN != PERIODIC:
+        if dom.J == DOM.Js:
+            fv[dom.Gfy.get("_js")] = 0
+        if dom.J == DOM.Je:
+            fv[dom.Gfy.get("_je")] = 0
+    if bc.pB != PERIODIC and bc.pT != PERIODIC:
+        if dom.K == DOM.Ks:
+            fw[dom.Gfz.get("_ks")] = 0
+        if dom.K == DOM.Ke:
+            fw[dom.Gfz.get("_ke")] = 0
+    return phase, shell, fu, fv, fw
+
+
+DOM_BUF_ = 1                                          # src/bluebottle.h:141

@@ -74,7 +74,7 @@ static void run(int use_phase)
   a.rho_f = rho_f; a.dt = dt; a.pp_residual = pp_residual; a.pp_max_iter = pp_max_iter;
   a.use_phase = use_phase;
   a.part_bc = (use_phase && nparts > 0) ? cuda_part_BC_p : NULL;     /* :130-132 */
-  if (use_phase && nparts <= 0) a.phase_shell = NULL;                /* no patch on particle-free ranks */
+  if (use_phase && nparts <= 0) { a.phase_shell = NULL; a.no_refine = 1; }   /* no patch, no coeffs_refine on particle-free ranks (:130-142) */
   cudaDeviceSynchronize();          /* the caller's default-stream work on u*, flags is complete */
   if (bbpcg_solve(solver(), &a, &res)) die("bbpcg_solve");
   gettimeofday(&te, 0);
@@ -87,6 +87,13 @@ static void run(int use_phase)
       break;
     case BBPCG_CONVERGED:                                  /* :235-241 */
       recorder_PP(rname, res.niter, res.resid, etime);
+      if (res.niter > pp_max_iter) {                       /* converged on iteration pp_max_iter + 1: the reference records the line,
+                                                              breaks, and still fails its `q > pp_max_iter` test (:271-279) */
+        printf("N%d >> The pressure-Poisson equation did not converge.\n", rank);
+        printf("N%d >> (rhs, rhs) is %e\n", rank, res.sp_rhs);
+        printf("N%d >> Residual at iteration %d is %lf\n", rank, res.niter, res.resid);
+        exit(EXIT_FAILURE);
+      }
       break;
     case BBPCG_NAN:                                        /* :245-251 */
       if (rank == 0) {

@@ -1,13 +1,13 @@
 /* bbpcg_internal.h -- device-side data layout shared by the kernels and the host driver.
  *
- * PRIVATE PADDED LAYOUT ("P-layout") of the solver's own vectors (r, p0, p1, q, x) and byte
+ * PRIVATE PADDED LAYOUT ("P-layout") of the solver's own vectors (r, p0, p1, x) and byte
  * masks.  Same logical extent as the reference's ghosted Gcc grid -- (in+2)(jn+2)(kn+2), one
  * ghost layer, interior 1..n (src/domain.c:1262-1289) -- but every x-row is padded so that
  * interior cell i = 1 starts on a 128-byte boundary:
  *
  *     offset(i,j,k) = (i + 15) + j*px + k*ps,   px = roundup(in + 17, 16),  ps = px*(jn+2)
  *
- * ghost i = 0 sits at 15, interior at 16..16+in-1, ghost i = in+1 at 16+in.  All five vectors
+ * ghost i = 0 sits at 15, interior at 16..16+in-1, ghost i = in+1 at 16+in.  All four vectors
  * and the masks share one index, so one offset addresses a cell in every array.
  */
 #ifndef BBPCG_INTERNAL_H
@@ -23,7 +23,7 @@
 #define BB_GROUP 64                /* CTAs per first-level reduction group */
 #define BB_MAXGROUPS (BB_MAXBLOCKS / BB_GROUP)
 #define BB_FLAT_MAX 1024           /* grids up to this many CTAs reduce in ONE level (a single group) */
-#define BB_MAXZ 1024               /* max z-chunks of the search kernel */
+#define BB_MAXZ 1024               /* max z-chunks of the iteration kernels */
 
 /* coefficient mask bits (fmask): squared face flags, src/solver_kernel.cu:824-829 */
 #define FM_E 1u
@@ -70,7 +70,7 @@ static inline Layout make_layout(int in, int jn, int kn)
 /* byte offsets of everything inside a rank's single device allocation ("arena").  A pure
  * function of (in,jn,kn), so a peer can address a neighbour's arrays from its dimensions. */
 struct ArenaMap {
-  size_t r, p0, p1, q, x;          /* doubles[L.n] */
+  size_t r, p0, p1, x;             /* doubles[L.n] */
   size_t fmask, pmask;             /* bytes[L.n]   */
   size_t recv[2][6];               /* doubles, generic exchange staging (double-buffered) */
   size_t partials;                 /* doubles[4*BB_MAXBLOCKS]: up to 4 values per CTA */
@@ -93,7 +93,7 @@ static inline ArenaMap make_arena_map(const Layout &L)
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
   size_t vec = (size_t)L.n * sizeof(double);
-  m.r = take(vec); m.p0 = take(vec); m.p1 = take(vec); m.q = take(vec); m.x = take(vec);
+  m.r = take(vec); m.p0 = take(vec); m.p1 = take(vec); m.x = take(vec);
   m.fmask = take((size_t)L.n); m.pmask = take((size_t)L.n);
   /* staging faces sized for the largest of the four grids (a face grid is one entry longer along its normal) */
   size_t fi = (size_t)(L.jn + 1) * (L.kn + 1), fj = (size_t)(L.in + 1) * (L.kn + 1), fk = (size_t)(L.in + 1) * (L.jn + 1);
@@ -149,14 +149,15 @@ struct Halo { NbrFace f[6]; };     /* 0:E 1:W 2:N 3:S 4:T 5:B */
 
 struct Comm {
   int rank, nranks;
-  long long timeout_cycles;                   /* spin limit of the in-kernel all-reduce */
+  long long timeout_cycles;                   /* spin limit of the in-kernel all-reduce; <= 0: wait for ever (as MPI does) */
+  int *host_flag;                             /* pinned host word, set when a wait timed out: every entry point reads it after its stream sync */
   unsigned long long *mbox[BB_MAXR];          /* rank p's mailbox (mapped) */
 };
 
 /* everything a kernel needs about this rank, passed by value */
 struct Dev {
   Layout L;
-  double *r, *P[2], *q, *x;
+  double *r, *P[2], *x;
   unsigned char *fmask, *pmask;
   double *recv[2][6];
   double *partials, *gpartials;

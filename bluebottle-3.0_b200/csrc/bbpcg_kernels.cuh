@@ -1,20 +1,20 @@
-/* bbpcg_kernels.cuh -- hand-written sm_100a kernels of the pressure-Poisson PCG path.
+/* bbpcg_kernels.cuh -- shared device code of the pressure-Poisson PCG path (hand-written sm_100a): the operator,
+ * the deterministic grid reduction, the in-kernel rank all-reduce, and every kernel that is not one of the two
+ * iteration kernels (those live in bbpcg_search_tma.cuh / bbpcg_resid_tma.cuh).
  *
- * One PCG iteration is TWO kernels (the reference uses 3 kernels + 2 Thrust reductions + 12
- * pack/unpack kernels + 4 host syncs, src/cuda_solver.cu:196-263):
+ * One PCG iteration is TWO kernels (the reference uses 3 kernels + 2 Thrust reductions + 12 pack/unpack kernels +
+ * 4 host syncs, src/cuda_solver.cu:196-263):
  *
- *   k_search_spmv   p = z + beta p  (z = r*invM recomputed from the 1-byte mask)   [PP_update_search]
+ *   k_search_tma    p = z + beta p  (z = r*invM recomputed from the 1-byte mask)   [PP_update_search]
  *                   x += alpha_prev p_prev   (lazy phi update)                      [PP_update_soln_resid, phi part]
- *                   q = -A p  (7-point, flag^2 / phase coefficients)                [PP_spmv_shared_load(_noparts)]
- *                   (p,q) partial -> last CTA: rank-ordered all-reduce, alpha        [inner_product + MPI_Allreduce]
- *   k_resid         r -= alpha q ; (r, r*invM) partial ; boundary r values are stored
- *                   straight into the neighbour's ghost cells over NVLink peer memory
- *                   [PP_update_soln_resid r/z part, inner_product, MPI_Allreduce, mpi_cuda_exchange_Gcc]
- *                   last CTA: all-reduce, stop test, beta.
+ *                   q = -A p  (7-point, flag^2 / phase coefficients), (p,q) partial [PP_spmv_shared_load(_noparts)]
+ *                   last CTA: rank-ordered all-reduce, alpha                        [inner_product + MPI_Allreduce]
+ *   k_resid_tma     q re-applied to the p just written; r -= alpha q; (r, r*invM) partial
+ *                   [PP_update_soln_resid r/z part, inner_product, MPI_Allreduce]; last CTA: stop test, beta.
  *
- * Algorithmic traffic: 48 B + 24 B = 72 B per cell per iteration (+2 mask bytes).
- * All scalars live in device memory (struct Scal); a finished solve turns every later launch
- * into a no-op through Scal::done.
+ * Traffic actually moved: 40 B + 24 B = 64 B per cell per iteration (+2 mask bytes); the committed model every
+ * roofline figure is scored against is 72 B (docs/bytes_model.md).  All scalars live in device memory
+ * (struct Scal); a finished solve turns every later launch into a no-op through Scal::done.
  */
 #ifndef BBPCG_KERNELS_CUH
 #define BBPCG_KERNELS_CUH
@@ -47,33 +47,50 @@ __device__ __forceinline__ void fill_invM_table(double *tab, const Dev &d)
   for (int m = threadIdx.x; m < 128; m += blockDim.x) tab[m] = __ldg(d.invM_tab + m);
 }
 
-/* -A p at one cell, noparts operator: src/solver_kernel.cu:824-829 (same association) */
+/* -A p at one cell.  The three axis terms  X = fE^2 (pE - pC) - fW^2 (pC - pW), Y, Z  are formed per path and combined at
+ * ONE code site with explicit roundings, so that the search kernel and the residual kernel (which re-applies the operator
+ * instead of reading a stored q) produce the same bits whatever the compiler would have contracted:
+ *     -A p = -idx2 X - idy2 Y - idz2 Z                                  src/solver_kernel.cu:824-829 */
+__device__ __forceinline__ double stencil_combine(const Dev &d, double X, double Y, double Z)
+{
+  return __fma_rn(-d.idz2, Z, __fma_rn(-d.idy2, Y, __dmul_rn(-d.idx2, X)));
+}
+
+/* every flag of the cell is 1 (the common case away from walls and particles): multiplying by 1.0 is exact, so these
+ * plain differences equal the flagged forms below bit for bit */
+__device__ __forceinline__ double stencil_plain(const Dev &d, double pC, double pE, double pW, double pN, double pS, double pT, double pB)
+{
+  return stencil_combine(d, __dsub_rn(__dsub_rn(pE, pC), __dsub_rn(pC, pW)), __dsub_rn(__dsub_rn(pN, pC), __dsub_rn(pC, pS)),
+                         __dsub_rn(__dsub_rn(pT, pC), __dsub_rn(pC, pB)));
+}
+
+/* noparts operator: src/solver_kernel.cu:824-829 (same association; f in {0,1}, so f * difference is exact) */
 __device__ __forceinline__ double stencil_noparts(const Dev &d, unsigned m, double pC, double pE, double pW,
                                                   double pN, double pS, double pT, double pB)
 {
-  double fe = (m & FM_E) ? 1. : 0., fw = (m & FM_W) ? 1. : 0., fn = (m & FM_N) ? 1. : 0.,
-         fs = (m & FM_S) ? 1. : 0., ft = (m & FM_T) ? 1. : 0., fb = (m & FM_B) ? 1. : 0.;
-  return -d.idx2 * (fe * (pE - pC) - fw * (pC - pW))
-         - d.idy2 * (fn * (pN - pC) - fs * (pC - pS))
-         - d.idz2 * (ft * (pT - pC) - fb * (pC - pB));
+  const double fe = (m & FM_E) ? 1. : 0., fw = (m & FM_W) ? 1. : 0., fn = (m & FM_N) ? 1. : 0.,
+               fs = (m & FM_S) ? 1. : 0., ft = (m & FM_T) ? 1. : 0., fb = (m & FM_B) ? 1. : 0.;
+  return stencil_combine(d, __dsub_rn(__dmul_rn(fe, __dsub_rn(pE, pC)), __dmul_rn(fw, __dsub_rn(pC, pW))),
+                         __dsub_rn(__dmul_rn(fn, __dsub_rn(pN, pC)), __dmul_rn(fs, __dsub_rn(pC, pS))),
+                         __dsub_rn(__dmul_rn(ft, __dsub_rn(pT, pC)), __dmul_rn(fb, __dsub_rn(pC, pB))));
 }
 
-/* -A p at one cell with particle masking: src/solver_kernel.cu:683-707 */
+/* with particle masking: src/solver_kernel.cu:683-707.  pm == 0 (fluid cell, no solid neighbour) reduces to the noparts form. */
 __device__ __forceinline__ double stencil_parts(const Dev &d, unsigned m, unsigned pm, double pC, double pE,
                                                 double pW, double pN, double pS, double pT, double pB)
 {
-  double fe = (m & FM_E) ? 1. : 0., fw = (m & FM_W) ? 1. : 0., fn = (m & FM_N) ? 1. : 0.,
-         fs = (m & FM_S) ? 1. : 0., ft = (m & FM_T) ? 1. : 0., fb = (m & FM_B) ? 1. : 0.;
-  bool solid = (pm & PM_C) != 0;
-  double pfx = solid ? -d.dx2_6 : 1., pfy = solid ? -d.dy2_6 : 1., pfz = solid ? -d.dz2_6 : 1.;
-  double pfe = (!solid && !(pm & PM_E)) ? 1. : 0., pfw = (!solid && !(pm & PM_W)) ? 1. : 0.;
-  double pfn = (!solid && !(pm & PM_N)) ? 1. : 0., pfs = (!solid && !(pm & PM_S)) ? 1. : 0.;
-  double pft = (!solid && !(pm & PM_T)) ? 1. : 0., pfb = (!solid && !(pm & PM_B)) ? 1. : 0.;
-  double a;
-  a = -d.idx2 * (fe * (pE * pfe - pfx * pC) - fw * (pC * pfx - pfw * pW));
-  a += -d.idy2 * (fn * (pN * pfn - pfy * pC) - fs * (pC * pfy - pfs * pS));
-  a += -d.idz2 * (ft * (pT * pft - pfz * pC) - fb * (pC * pfz - pfb * pB));
-  return a;
+  const double fe = (m & FM_E) ? 1. : 0., fw = (m & FM_W) ? 1. : 0., fn = (m & FM_N) ? 1. : 0.,
+               fs = (m & FM_S) ? 1. : 0., ft = (m & FM_T) ? 1. : 0., fb = (m & FM_B) ? 1. : 0.;
+  const bool solid = (pm & PM_C) != 0;
+  const double pfx = solid ? -d.dx2_6 : 1., pfy = solid ? -d.dy2_6 : 1., pfz = solid ? -d.dz2_6 : 1.;
+  const double pfe = (!solid && !(pm & PM_E)) ? 1. : 0., pfw = (!solid && !(pm & PM_W)) ? 1. : 0.;
+  const double pfn = (!solid && !(pm & PM_N)) ? 1. : 0., pfs = (!solid && !(pm & PM_S)) ? 1. : 0.;
+  const double pft = (!solid && !(pm & PM_T)) ? 1. : 0., pfb = (!solid && !(pm & PM_B)) ? 1. : 0.;
+  const double cx = __dmul_rn(pfx, pC), cy = __dmul_rn(pfy, pC), cz = __dmul_rn(pfz, pC);
+  const double X = __dsub_rn(__dmul_rn(fe, __dsub_rn(__dmul_rn(pE, pfe), cx)), __dmul_rn(fw, __dsub_rn(cx, __dmul_rn(pfw, pW))));
+  const double Y = __dsub_rn(__dmul_rn(fn, __dsub_rn(__dmul_rn(pN, pfn), cy)), __dmul_rn(fs, __dsub_rn(cy, __dmul_rn(pfs, pS))));
+  const double Z = __dsub_rn(__dmul_rn(ft, __dsub_rn(__dmul_rn(pT, pft), cz)), __dmul_rn(fb, __dsub_rn(cz, __dmul_rn(pfb, pB))));
+  return stencil_combine(d, X, Y, Z);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -227,11 +244,11 @@ __device__ __forceinline__ void rank_allreduce(const Dev &d, double *v /* thread
     for (;;) {
       w0 = ld_relaxed_sys(src); w1 = ld_relaxed_sys(src + 1); w2 = ld_relaxed_sys(src + 2); w3 = ld_relaxed_sys(src + 3);
       if ((w0 >> 32) == tag && (w1 >> 32) == tag && (w2 >> 32) == tag && (w3 >> 32) == tag) break;
-      if (clock64() - t0 > c.timeout_cycles) { ok = false; break; }            /* a peer is gone */
+      if (c.timeout_cycles > 0 && clock64() - t0 > c.timeout_cycles) { ok = false; break; }      /* a peer is gone */
     }
     s_in[t][0] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
     s_in[t][1] = __longlong_as_double((long long)((w2 & 0xffffffffull) | (w3 << 32)));
-    if (!ok) d.sc->comm_timeout = 1;
+    if (!ok) { d.sc->comm_timeout = 1; *c.host_flag = 1; }    /* sticky: the ranks now disagree, the solver object is dead */
     fence_acq_rel_sys();             /* acquire side: peers' released data is read by LATER kernels */
   }
   __syncthreads();
@@ -284,185 +301,17 @@ __device__ __forceinline__ long long j_px_fix(const Layout &L, const Layout &N, 
   return (long long)j * (L.px - N.px);
 }
 
-/* ------------------------------------------------------------------------------------ */
-/* k_search_spmv: see file header.  CTA tile TX x TY owned cells, marching KC planes in k.
- * Phase A (plane kk): every thread computes p_new on the halo'd tile (TX+2)x(TY+2) from
- * r, p_prev and the mask (values prefetched into registers one plane ahead), stores it into
- * a 4-slot shared-memory ring, writes p_new / updates x for the cells this CTA owns and keeps
- * the block's ghost copies of p current.  Phase B (plane kk-1): 7-point operator from the
- * ring, q store, (p,q) partial.  One __syncthreads per plane. */
+/* launch arguments of the two iteration kernels (bbpcg_search_tma.cuh, bbpcg_resid_tma.cuh) */
 struct SearchArgs {
-  int nbx, nby, nbz;   /* z-chunk c owns planes d.ztab[c]+1 .. d.ztab[c+1] */
-  int store_q;         /* 0: recompute variant, k_resid_tma re-applies the operator instead of reading q */
+  int nbx, nby, nbz;   /* tiles in x, y; z-chunks: chunk c owns planes d.ztab[c]+1 .. d.ztab[c+1] */
+  int ty;              /* owned rows per tile (1..8): chosen by the host planner so that the CTA count fills the SM slots */
   const double *rhs;   /* refresh form of k_resid_tma only: the caller's right-hand side (Gcc s3b) and its strides */
   int s1b, s2b;
 };
 
-template <int TX, int TY, int NT, int MINB, bool PARTS>
-__global__ void __launch_bounds__(NT, MINB) k_search_spmv(const Dev d, const SearchArgs a)
-{
-  Scal *sc = d.sc;
-  if (sc->done) return;
-  constexpr int HX = TX + 2, HY = TY + 2, NITEM = HX * HY;
-  constexpr int IPT = (NITEM + NT - 1) / NT;
-  constexpr int NB = TX * TY;
-  static_assert(NB % NT == 0, "tile must be a multiple of the CTA size");
-  constexpr int BPT = NB / NT;
-
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *sp = reinterpret_cast<double *>(smem_raw);            /* [4][NITEM] */
-  double *tab = sp + 4 * NITEM;                                 /* [128]      */
-  u8 *sm = reinterpret_cast<u8 *>(tab + 128);                   /* [4][NITEM] */
-
-  const Layout L = d.L;
-  const int q = sc->q;
-  const double beta = sc->beta, ax = sc->alpha_x;
-  const double *__restrict__ r = d.r;
-  const double *__restrict__ pprev = d.P[q & 1];
-  double *__restrict__ pnew = d.P[(q + 1) & 1];
-  double *__restrict__ x = d.x;
-  double *__restrict__ qv = d.q;
-  const u8 *__restrict__ fmask = d.fmask;
-
-  fill_invM_table(tab, d);
-
-  const int tid = threadIdx.x;
-  const int i0 = blockIdx.x * TX + 1, j0 = blockIdx.y * TY + 1;
-  const int k0 = __ldg(d.ztab + blockIdx.z) + 1;
-  const int k1 = __ldg(d.ztab + blockIdx.z + 1);
-  const int ilast = min(i0 + TX - 1, L.in), jlast = min(j0 + TY - 1, L.jn);
-
-  /* per-thread item geometry, fixed across planes */
-  int goff[IPT];                 /* in-plane offset of the item, -1: not a cell */
-  unsigned role[IPT];            /* bit0 owned (x,y)   bit1 in-plane ghost this CTA maintains */
-  int gsrc[IPT], noff[IPT];      /* x/y ghost: face it is pulled from (-1 none) and in-plane offset there */
-  bool zint[IPT];                /* (i,j) inside the block: pulled from the T/B neighbour on ghost planes */
-#pragma unroll
-  for (int n = 0; n < IPT; n++) {
-    int idx = tid + n * NT;
-    int hx = idx % HX, hy = idx / HX;
-    int i = i0 - 1 + hx, j = j0 - 1 + hy;
-    bool valid = idx < NITEM && i <= L.in + 1 && j <= L.jn + 1;
-    bool ox = i >= i0 && i <= ilast, oy = j >= j0 && j <= jlast;
-    bool gx = (i == 0 || i == L.in + 1), gy = (j == 0 || j == L.jn + 1);
-    /* a ghost in x next to a cell we own (hx = 0 or the column right of ilast), same in y */
-    bool mx = gx && oy && ((i == 0 && i0 == 1) || (i == L.in + 1 && ilast == L.in));
-    bool my = gy && ox && ((j == 0 && j0 == 1) || (j == L.jn + 1 && jlast == L.jn));
-    goff[n] = valid ? (i + BB_XOFF) + j * L.px : -1;
-    role[n] = (ox && oy ? 1u : 0u) | ((mx || my) ? 2u : 0u);
-    /* PULL model: the r value of a ghost cell is read straight from the neighbour's r array
-     * (peer memory over NVLink, or this block itself for a periodic self-wrap) -- faces only */
-    gsrc[n] = -1; noff[n] = 0;
-    if (valid && (gx != gy)) {
-      const int f = gx ? (i == 0 ? 1 : 0) : (j == 0 ? 3 : 2);
-      const NbrFace &nf = d.halo.f[f];
-      if (nf.r && (gx ? (j >= 1 && j <= L.jn) : (i >= 1 && i <= L.in))) {
-        const int ii = gx ? (i == 0 ? nf.L.in : 1) : i, jn_ = gx ? j : (j == 0 ? nf.L.jn : 1);
-        gsrc[n] = f; noff[n] = (ii + BB_XOFF) + jn_ * nf.L.px;
-      }
-    }
-    zint[n] = valid && i >= 1 && i <= L.in && j >= 1 && j <= L.jn;
-  }
-
-  double rr[IPT], pp[IPT], xx[IPT];
-  unsigned mm[IPT];
-
-  auto prefetch = [&](int kk) {
-    const long long pb = (long long)kk * L.ps;
-    const bool plane_owned = kk >= k0 && kk <= k1;
-#pragma unroll
-    for (int n = 0; n < IPT; n++) {
-      rr[n] = 0.; pp[n] = 0.; xx[n] = 0.; mm[n] = FM_DEAD;
-      if (goff[n] >= 0) {
-        const long long g = pb + goff[n];
-        const double *rp = r + g;
-        if (kk == 0 || kk == L.kn + 1) {
-          const NbrFace &nz = d.halo.f[kk == 0 ? 5 : 4];
-          if (nz.r && zint[n]) rp = nz.r + goff[n] - j_px_fix(L, nz.L, goff[n]) + (long long)(kk == 0 ? nz.L.kn : 1) * nz.L.ps;
-        } else if (gsrc[n] >= 0) {
-          const NbrFace &nf = d.halo.f[gsrc[n]];
-          rp = nf.r + noff[n] + (long long)kk * nf.L.ps;
-        }
-        rr[n] = __ldg(rp);
-        pp[n] = __ldg(pprev + g);
-        mm[n] = __ldg(fmask + g);
-        if (plane_owned && (role[n] & 1u)) xx[n] = x[g];
-      }
-    }
-  };
-
-  double dot = 0.;
-  prefetch(k0 - 1);
-  __syncthreads();          /* invM table ready */
-
-  for (int kk = k0 - 1; kk <= k1 + 1; kk++) {
-    const int slot = kk & 3;
-    const long long pb = (long long)kk * L.ps;
-    const bool plane_owned = kk >= k0 && kk <= k1;
-    const bool plane_ghost = (kk == 0 || kk == L.kn + 1);
-    /* ---- phase A: p_new on the halo'd tile of plane kk ---- */
-#pragma unroll
-    for (int n = 0; n < IPT; n++) {
-      int idx = tid + n * NT;
-      if (idx < NITEM) {
-        double z = rr[n] * tab[mm[n] & 127u];
-        double pn = z + beta * pp[n];                     /* PP_update_search, solver_kernel.cu:921 */
-        sp[slot * NITEM + idx] = pn;
-        sm[slot * NITEM + idx] = (u8)mm[n];
-        if (goff[n] >= 0) {
-          const long long g = pb + goff[n];
-          if (plane_owned) {
-            if (role[n] & 1u) { pnew[g] = pn; x[g] = xx[n] + ax * pp[n]; }   /* phi += alpha p, :852 */
-            else if (role[n] & 2u) pnew[g] = pn;
-          } else if (plane_ghost && (role[n] & 1u)) pnew[g] = pn;
-        }
-      }
-    }
-    if (kk + 1 <= k1 + 1) prefetch(kk + 1);
-    __syncthreads();
-    /* ---- phase B: q = -A p on plane kk-1 ---- */
-    const int kc = kk - 1;
-    if (kc >= k0) {
-      const double *S0 = sp + ((kc - 1) & 3) * NITEM, *S1 = sp + (kc & 3) * NITEM, *S2 = sp + ((kc + 1) & 3) * NITEM;
-      const u8 *M1 = sm + (kc & 3) * NITEM;
-      const long long pc = (long long)kc * L.ps;
-#pragma unroll
-      for (int m = 0; m < BPT; m++) {
-        int idx = tid + m * NT;
-        int tx = idx % TX, ty = idx / TX;
-        int i = i0 + tx, j = j0 + ty;
-        if (i <= L.in && j <= L.jn) {
-          int c = (ty + 1) * HX + (tx + 1);
-          double pC = S1[c];
-          const long long g = pc + (i + BB_XOFF) + (long long)j * L.px;
-          double Ap;
-          if (PARTS) Ap = stencil_parts(d, M1[c], __ldg(d.pmask + g), pC, S1[c + 1], S1[c - 1], S1[c + HX], S1[c - HX], S2[c], S0[c]);
-          else Ap = stencil_noparts(d, M1[c], pC, S1[c + 1], S1[c - 1], S1[c + HX], S1[c - HX], S2[c], S0[c]);
-          qv[g] = Ap;
-          dot += pC * Ap;
-        }
-      }
-    }
-  }
-
-  /* ---- (p,q): grid reduction, rank all-reduce, alpha (cuda_solver.cu:204-206) ---- */
-  double v[1] = { dot }, tot[1];
-  const int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-  const int nblocks = gridDim.x * gridDim.y * gridDim.z;
-  if (grid_reduce<1>(d, v, bid, nblocks, tot, false)) {
-    rank_allreduce(d, tot, 1, false);         /* this kernel writes nothing a peer reads */
-    if (threadIdx.x == 0) {
-      sc->pAp = tot[0];
-      sc->alpha = sc->rz / tot[0];
-    }
-  }
-}
-
 /* ------------------------------------------------------------------------------------ */
-/* k_resid: r -= alpha q; (r, z); halo push of r; stop test + beta in the last CTA.
- * One CTA-iteration = ROWS x-rows; thread = VEC consecutive cells.
- * Follows PP_update_soln_resid (r/z part, src/solver_kernel.cu:855-858) and the host logic
- * of src/cuda_solver.cu:231-267. */
+/* end of an iteration, run by ONE thread once the global (r,z) is known: the host logic of src/cuda_solver.cu:231-267
+ * (history, stop test, NaN test, iteration bound, beta) on the device-resident scalars */
 __device__ __forceinline__ void finish_iteration(const Dev &d, double rz_new, bool refreshed)
 {
   Scal *sc = d.sc;
@@ -470,7 +319,7 @@ __device__ __forceinline__ void finish_iteration(const Dev &d, double rz_new, bo
   sc->q = qn;
   if (qn < BB_HIST_CAP) d.history[qn] = rz_new;
   sc->alpha_x = refreshed ? 0. : sc->alpha;
-  if (sc->comm_timeout) { sc->done = 1; sc->status = 4; sc->resid = sqrt(rz_new) / sqrt(sc->bb); return; }
+  if (sc->comm_timeout) { sc->done = 1; sc->status = BBPCG_COMM_TIMEOUT; sc->resid = sqrt(rz_new) / sqrt(sc->bb); return; }
   if (!sc->fixed && rz_new <= sc->tol2 * sc->bb) {               /* :235 */
     sc->done = 1; sc->status = BBPCG_CONVERGED; sc->resid = sqrt(rz_new) / sqrt(sc->bb);
   } else if (!sc->fixed && isnan(rz_new)) {                      /* :245 */
@@ -502,114 +351,14 @@ __device__ __forceinline__ void st256(double *p, const d4 &v)
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.a), "d"(v.b), "d"(v.c), "d"(v.d) : "memory");
 }
 
-/* Many TINY CTAs (B200 streams best that way: measured 7.0 TB/s for this access pattern with
- * 128-thread CTAs of one batch each, scratch/kb/triad.cu): CTA = 128 threads = XT chunk columns x
- * YT rows, one pass = YT*UNR rows x XT chunks; every load of the pass -- r, q, mask and the
- * scalars alpha / done -- is issued before the first use. */
-struct ResidArgs { int cpr; int ncb; int npass; int ppc; };   /* chunks per row, column blocks, passes, passes per CTA */
-
-template <int XT, int UNR>
-__global__ void __launch_bounds__(128, 4) k_resid(const __grid_constant__ Dev d, const ResidArgs a)
-{
-  constexpr int NT = 128, YT = NT / XT;
-  __shared__ double tab[128];
-  const Layout L = d.L;
-  Scal *sc = d.sc;
-  double *__restrict__ r = d.r;
-  const double *__restrict__ qv = d.q;
-  const u8 *__restrict__ fmask = d.fmask;
-  const unsigned nrows = (unsigned)L.jn * (unsigned)L.kn;
-  const int tx = threadIdx.x % XT, ty = threadIdx.x / XT;
-  double dot = 0.;
-  const int pass0 = blockIdx.x * a.ppc, pass1 = min(pass0 + a.ppc, a.npass);
-  pdl_wait();                                   /* q and alpha come from the search kernel before us */
-  for (int pass = pass0; pass < pass1; pass++) {
-    const int cb = pass % a.ncb, rg = pass / a.ncb;
-    const int c = cb * XT + tx;
-    const unsigned row0 = (unsigned)rg * (YT * UNR) + ty;
-    d4 rv[UNR], qq[UNR];
-    unsigned mk[UNR];
-    long long g[UNR];
-    int jj[UNR], kk[UNR];
-#pragma unroll
-    for (int u = 0; u < UNR; u++) {
-      const unsigned row = row0 + u * YT;
-      const unsigned k0 = row / (unsigned)L.jn;
-      jj[u] = (int)(row - k0 * (unsigned)L.jn) + 1; kk[u] = (int)k0 + 1;
-      g[u] = (long long)kk[u] * L.ps + (long long)jj[u] * L.px + (BB_XOFF + 1) + 4 * c;
-      if (row < nrows && c < a.cpr) {
-        rv[u] = ld256(r + g[u]);
-        qq[u] = ld256_stream(qv + g[u]);
-        mk[u] = __ldg(reinterpret_cast<const unsigned *>(fmask + g[u]));
-      } else { kk[u] = -1; }
-    }
-    const double alpha = sc->alpha;
-    const int done = sc->done;
-    if (pass == pass0) { tab[threadIdx.x] = __ldg(d.invM_tab + threadIdx.x); __syncthreads(); }
-    if (done) return;                                                     /* uniform: a finished solve */
-    const int nv = min(4, L.in - 4 * c);                                  /* cells of this chunk inside the block */
-#pragma unroll
-    for (int u = 0; u < UNR; u++) {
-      if (kk[u] < 0) continue;
-      d4 v = rv[u];
-      v.a -= alpha * qq[u].a; v.b -= alpha * qq[u].b; v.c -= alpha * qq[u].c; v.d -= alpha * qq[u].d;   /* solver_kernel.cu:855 */
-      const double za = v.a * tab[mk[u] & 127u], zb = v.b * tab[(mk[u] >> 8) & 127u],
-                   zc = v.c * tab[(mk[u] >> 16) & 127u], zd = v.d * tab[(mk[u] >> 24) & 127u];          /* :858 */
-      if (nv == 4) {
-        dot += v.a * za; dot += v.b * zb; dot += v.c * zc; dot += v.d * zd;
-        st256(r + g[u], v);
-      } else {                                                            /* ragged row end: never touch the E ghost */
-        double *rp = r + g[u];
-        dot += v.a * za; rp[0] = v.a;
-        if (nv > 1) { dot += v.b * zb; rp[1] = v.b; }
-        if (nv > 2) { dot += v.c * zc; rp[2] = v.c; }
-      }
-      if (c == 0) store_xface(d, 1, jj[u], kk[u], v.a);
-      if (4 * c + nv == L.in && L.in > 1) store_xface(d, L.in, jj[u], kk[u], nv == 4 ? v.d : nv == 3 ? v.c : nv == 2 ? v.b : v.a);
-    }
-  }
-  pdl_launch_dependents();
-  double v[1] = { dot }, tot[1];
-  if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, false)) {
-    rank_allreduce(d, tot, 1, true);          /* peers pull the r written here */
-    if (threadIdx.x == 0) finish_iteration(d, tot[0], false);
-  }
-}
+struct ResidArgs { int cpr; int ncb; int npass; int ppc; };   /* k_refresh_x4: chunks per row, column blocks, passes, passes per CTA */
 
 /* ------------------------------------------------------------------------------------ */
 /* Every-50th-iteration true-residual refresh, src/cuda_solver.cu:209-223:
- * k_refresh_x : phi += alpha p (PP_update_solution, solver_kernel.cu:864-881) + halo of phi
- * k_refresh_r : r = b - (-A)phi ; z ; (r,z)  (SpMV + PP_update_residual, :883-904) + halo of r */
-template <int NT>
-__global__ void __launch_bounds__(NT) k_refresh_x(const Dev d)
-{
-  Scal *sc = d.sc;
-  if (sc->done) return;
-  const Layout L = d.L;
-  const double alpha = sc->alpha, ax = sc->alpha_x;
-  const double *__restrict__ pcur = d.P[(sc->q + 1) & 1];     /* p of the iteration in flight */
-  const double *__restrict__ pprev = d.P[sc->q & 1];
-  (void)pprev; (void)ax;
-  double *__restrict__ x = d.x;
-  const long long nrows = (long long)L.jn * L.kn;
-  bool pushed = false;
-  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
-    const int j = (int)(row % L.jn) + 1, k = (int)(row / L.jn) + 1;
-    const long long base = pidx(L, 1, j, k);
-    for (int i = threadIdx.x + 1; i <= L.in; i += NT) {
-      const long long g = base + (i - 1);
-      /* x already holds phi_{q-1} (k_search_spmv applied alpha_{q-1} p_{q-1}); add this step */
-      double xv = x[g] + alpha * pcur[g];
-      x[g] = xv;
-      if (j == 1 || j == L.jn || k == 1 || k == L.kn || i == 1 || i == L.in) pushed |= push_halo(d, 1, i, j, k, xv);
-    }
-  }
-  double v[1] = { 0. }, tot[1];
-  if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) rank_allreduce(d, tot, 0, true);   /* barrier */
-}
-
-/* k_refresh_x in the streaming form of k_resid: 256-bit accesses, tiny CTAs; only boundary cells take the
- * (possibly remote) halo-push path */
+ * k_refresh_x4 : phi += alpha p (PP_update_solution, solver_kernel.cu:864-881) + halo of phi
+ * then the REFRESH form of k_resid_tma: r = b - (-A)phi ; z ; (r,z)  (SpMV + PP_update_residual, :883-904) */
+/* phi += alpha p as a streaming kernel: many tiny CTAs, 256-bit accesses, every load of a pass issued before its first
+ * use; only boundary cells take the (possibly remote) halo-push path */
 template <int XT, int UNR>
 __global__ void __launch_bounds__(128, 4) k_refresh_x4(const __grid_constant__ Dev d, const ResidArgs a)
 {
@@ -662,47 +411,10 @@ __global__ void __launch_bounds__(128, 4) k_refresh_x4(const __grid_constant__ D
   if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) rank_allreduce(d, tot, 0, true);   /* barrier */
 }
 
-template <int NT, bool PARTS>
-__global__ void __launch_bounds__(NT) k_refresh_r(const Dev d, const double *__restrict__ rhs_s3b, int s1b, int s2b)
-{
-  Scal *sc = d.sc;
-  if (sc->done) return;
-  __shared__ double tab[128];
-  fill_invM_table(tab, d);
-  __syncthreads();
-  const Layout L = d.L;
-  const double *__restrict__ x = d.x;
-  double *__restrict__ r = d.r;
-  const long long nrows = (long long)L.jn * L.kn;
-  double dot = 0.;
-  bool pushed = false;
-  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
-    const int j = (int)(row % L.jn) + 1, k = (int)(row / L.jn) + 1;
-    const long long base = pidx(L, 1, j, k);
-    for (int i = threadIdx.x + 1; i <= L.in; i += NT) {
-      const long long g = base + (i - 1);
-      const unsigned m = d.fmask[g];
-      double Ap;
-      if (PARTS) Ap = stencil_parts(d, m, d.pmask[g], x[g], x[g + 1], x[g - 1], x[g + L.px], x[g - L.px], x[g + L.ps], x[g - L.ps]);
-      else Ap = stencil_noparts(d, m, x[g], x[g + 1], x[g - 1], x[g + L.px], x[g - L.px], x[g + L.ps], x[g - L.ps]);
-      double rv = rhs_s3b[i + (long long)j * s1b + (long long)k * s2b] - Ap;    /* solver_kernel.cu:897 */
-      double z = rv * tab[m & 127u];
-      dot += rv * z;
-      r[g] = rv;
-      store_xface(d, i, j, k, rv);
-    }
-  }
-  double v[1] = { dot }, tot[1];
-  if (grid_reduce<1>(d, v, blockIdx.x, gridDim.x, tot, pushed)) {
-    rank_allreduce(d, tot, 1, true);
-    if (threadIdx.x == 0) finish_iteration(d, tot[0], true);
-  }
-}
-
 /* ------------------------------------------------------------------------------------ */
 /* Set-up: r = b, x = 0, (b,b), (r,z) -- PP_cg_init (src/solver_kernel.cu:258-283) and the two
  * inner products of src/cuda_solver.cu:151,169.  p buffers are zeroed by the host (memset), so
- * the first k_search_spmv computes p = z + 0*0. */
+ * the first k_search_tma computes p = z + 0*0. */
 template <int NT>
 __global__ void __launch_bounds__(NT) k_init(const Dev d, const double *__restrict__ rhs_s3b, int s1b, int s2b,
                                              double tol2, int max_q, int fixed)
@@ -739,7 +451,7 @@ __global__ void __launch_bounds__(NT) k_init(const Dev d, const double *__restri
       const double RHS_TOL = 1.e-8;                                          /* cuda_solver.cu:176 */
       if (!fixed && tot[0] < RHS_TOL * RHS_TOL) { sc->done = 1; sc->status = BBPCG_TINY_RHS; }
       else sc->done = sc->comm_timeout ? 1 : 0;
-      if (sc->comm_timeout) sc->status = 4;
+      if (sc->comm_timeout) sc->status = BBPCG_COMM_TIMEOUT;
     }
   }
 }

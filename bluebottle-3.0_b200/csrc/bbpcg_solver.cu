@@ -59,39 +59,31 @@ struct bbpcg_solver {
   int has_phase;                    /* set_coefficients was given a phase array */
   int coeffs_set;
   /* launch configuration */
-  int tile;                         /* k_search_spmv variant */
-  int kc;                           /* planes per CTA */
-  int resid_blocks, stream_blocks, resid_ppc;
+  int opt_ty, opt_kc;               /* user overrides of the plan (0 = automatic) */
+  int stream_blocks;
   int check_every;                  /* iterations per polling batch */
   int sm_count;
   /* pinned poll words + host-mode buffers */
   int *h_poll;
   Scal *h_scal;
   double *hb_u, *hb_v, *hb_w, *hb_rhs, *hb_phi;
-  int *hb_dummy;
   long long launches;
   unsigned exchange_count;
-  /* optional per-kernel timing (bench.py's roofline leg): events around every launch of the
-   * iteration loop, on the solver's own stream */
-  int last_search_grid, last_search_kc;
-  /* z-chunk plan of the search kernel (device table Dev::ztab) */
+  /* tile / z-chunk plan of the two iteration kernels (device table Dev::ztab) */
   int *h_ztab;                      /* pinned [BB_MAXZ + 1] */
-  int zt_cols, zt_kc, zt_g10, zt_min, zt_nbz;   /* what the uploaded table was built for */
-  int taper_g10, taper_min;         /* guided chunking: t = remaining*columns*10 / (g10*slots), >= taper_min */
+  int plan_ok;                      /* the plan below, the uploaded table and the tensor maps are current */
+  int plan_ty, plan_nbx, plan_nby, plan_nbz, plan_kc;
   int pdl;                          /* programmatic dependent launch of the two iteration kernels: 0 off, 1 on, 2 auto */
-  int resid_mb, resid_d;            /* k_resid_tma: CTAs per SM the register budget is compiled for (2 or 3); TMA planes in flight */
-  int fast_refresh;                 /* q%50 refresh through k_refresh_x4 + the refresh form of k_resid_tma */
   int rhs_tiled;                    /* PP_rhs through shared-memory transposes (default) or the row-walking kernel */
-  int recompute;                    /* 64-B iteration: k_resid_tma re-applies the operator, q is never stored */
   int shared_device;                /* some peer rank lives on this same GPU (single-process harness) */
-  SearchMaps maps[2];               /* tensor maps of k_search_tma for TY = 8 / TY = 4 */
-  int maps_ok;
+  SearchMaps maps;                  /* tensor maps of the iteration kernels for the planned tile height */
   int kernel_timing;
   cudaEvent_t *kev;                 /* [2*BB_KT_CAP+1] */
   double kt_search_ms, kt_resid_ms, kt_refresh_ms;
   int kt_search_n, kt_resid_n, kt_refresh_n;
 };
 #define BB_KT_CAP 4096
+#define BB_POLL_COMM 8                /* int index inside h_poll of the comm-timeout word the device sets */
 
 static int preload_kernels();
 
@@ -106,7 +98,7 @@ static void point_dev_at_arena(bbpcg_solver *s)
   char *a = s->arena;
   const ArenaMap &m = s->amap;
   d.r = (double *)(a + m.r); d.P[0] = (double *)(a + m.p0); d.P[1] = (double *)(a + m.p1);
-  d.q = (double *)(a + m.q); d.x = (double *)(a + m.x);
+  d.x = (double *)(a + m.x);
   d.fmask = (u8 *)(a + m.fmask); d.pmask = (u8 *)(a + m.pmask);
   for (int b = 0; b < 2; b++) for (int f = 0; f < 6; f++) d.recv[b][f] = (double *)(a + m.recv[b][f]);
   d.partials = (double *)(a + m.partials); d.gpartials = (double *)(a + m.gpartials); d.counter = (unsigned *)(a + m.counter);
@@ -162,37 +154,30 @@ static int make_map2(CUtensorMap *m, void *base, const Layout &L, int by)
   return BBPCG_OK;
 }
 
-template <int TY>
-static int build_search_maps_t(bbpcg_solver *s, SearchMaps *M)
+/* boxes follow the planned tile height ty: halo'd tiles (TX+4) x (ty+2), owned tiles TX x ty */
+static int build_search_maps(bbpcg_solver *s, int ty)
 {
-  typedef SearchGeom<TY, true> G;
+  typedef SearchGeom<true> G;
   const Dev &d = s->dev;
+  SearchMaps *M = &s->maps;
+  const int hy = ty + 2;
   int rc = 0;
   memset(M, 0, sizeof(*M));
-  if (!rc) rc = make_map(&M->r, d.r, d.L, false, G::HXP, G::HY);
-  if (!rc) rc = make_map(&M->p[0], d.P[0], d.L, false, G::HXP, G::HY);
-  if (!rc) rc = make_map(&M->p[1], d.P[1], d.L, false, G::HXP, G::HY);
-  if (!rc) rc = make_map(&M->fm, d.fmask, d.L, true, G::MXP, G::HY);
-  if (!rc) rc = make_map(&M->pm, d.pmask, d.L, true, G::TX, TY);
-  if (!rc) rc = make_map(&M->xo, d.x, d.L, false, G::TX, TY);
-  if (!rc) rc = make_map(&M->ro, d.r, d.L, false, G::TX, TY);
-  if (!rc) rc = make_map(&M->xh, d.x, d.L, false, G::HXP, G::HY);
+  if (!rc) rc = make_map(&M->r, d.r, d.L, false, G::HXP, hy);
+  if (!rc) rc = make_map(&M->p[0], d.P[0], d.L, false, G::HXP, hy);
+  if (!rc) rc = make_map(&M->p[1], d.P[1], d.L, false, G::HXP, hy);
+  if (!rc) rc = make_map(&M->fm, d.fmask, d.L, true, G::MXP, hy);
+  if (!rc) rc = make_map(&M->pm, d.pmask, d.L, true, G::TX, ty);
+  if (!rc) rc = make_map(&M->xo, d.x, d.L, false, G::TX, ty);
+  if (!rc) rc = make_map(&M->ro, d.r, d.L, false, G::TX, ty);
+  if (!rc) rc = make_map(&M->xh, d.x, d.L, false, G::HXP, hy);
   for (int f = 0; f < 6 && !rc; f++) {
     const NbrFace &nf = d.halo.f[f];
     if (!nf.r) { M->nb[f] = M->r; continue; }            /* never used: keeps the parameter well formed */
-    if (f < 2) rc = make_map2(&M->nb[f], nf.xf, nf.L, G::HY);
+    if (f < 2) rc = make_map2(&M->nb[f], nf.xf, nf.L, G::GXN);             /* fixed even run: a box starts and ends on 16-byte boundaries */
     else if (f < 4) rc = make_map(&M->nb[f], nf.r, nf.L, false, G::HXP, 1);
-    else rc = make_map(&M->nb[f], nf.r, nf.L, false, G::HXP, G::HY);
+    else rc = make_map(&M->nb[f], nf.r, nf.L, false, G::HXP, hy);
   }
-  return rc;
-}
-
-static int build_search_maps(bbpcg_solver *s)
-{
-  s->maps_ok = 0;
-  int rc = build_search_maps_t<8>(s, &s->maps[0]);
-  if (!rc) rc = build_search_maps_t<4>(s, &s->maps[1]);
-  if (!rc) s->maps_ok = 1;
   return rc;
 }
 
@@ -222,13 +207,64 @@ static void build_halo(bbpcg_solver *s, const int (*dims)[3])
   d.xf[0] = d.halo.f[1].r ? (double *)(s->arena + s->amap.xface[0]) : NULL;
   d.xf[1] = d.halo.f[0].r ? (double *)(s->arena + s->amap.xface[1]) : NULL;
   d.comm.rank = s->dom.rank; d.comm.nranks = s->nranks;
-  if (d.comm.timeout_cycles <= 0) d.comm.timeout_cycles = 1ll << 34;       /* ~8 s */
+  if (d.comm.timeout_cycles == 0) d.comm.timeout_cycles = 1ll << 37;       /* ~70 s default: far above any start-up or I/O skew; option comm_timeout_ms (0 = wait for ever) */
   for (int p = 0; p < BB_MAXR; p++) d.comm.mbox[p] = NULL;
   for (int p = 0; p < s->nranks; p++) {
     Layout L = make_layout(dims[p][0], dims[p][1], dims[p][2]);
     ArenaMap m = make_arena_map(L);
     d.comm.mbox[p] = (unsigned long long *)(s->peer_arena[p] + m.mbox);
   }
+}
+
+/* everything of bbpcg_create that can fail after the object exists; on failure the caller destroys the half-built
+ * object (bbpcg_destroy tolerates missing pieces), so no error path leaks the arena, events or pinned buffers */
+static int create_impl(bbpcg_solver *s, const dom_struct *dom_rank, const dom_struct *DOM)
+{
+  const grid_info &g = dom_rank->Gcc;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, s->device));
+  s->sm_count = prop.multiProcessorCount;
+  Dev &d = s->dev;
+  d.L = make_layout(g.in, g.jn, g.kn);
+  s->amap = make_arena_map(d.L);
+  if (cudaMalloc(&s->arena, s->amap.total) != cudaSuccess) {
+    bbpcg_set_error("bbpcg_create: cudaMalloc of %zu bytes failed", s->amap.total); cudaGetLastError(); s->arena = NULL; return BBPCG_ENOMEM;
+  }
+  CU(cudaMemset(s->arena, 0, s->amap.total));
+  point_dev_at_arena(s);
+  CU(cudaMemset(d.fmask, FM_DEAD, (size_t)d.L.n));          /* ghosts behind walls stay dead forever */
+  d.idx2 = 1. / (dom_rank->dx * dom_rank->dx); d.idy2 = 1. / (dom_rank->dy * dom_rank->dy); d.idz2 = 1. / (dom_rank->dz * dom_rank->dz);
+  d.dx2_6 = (dom_rank->dx * dom_rank->dx) / 6.; d.dy2_6 = (dom_rank->dy * dom_rank->dy) / 6.; d.dz2_6 = (dom_rank->dz * dom_rank->dz) / 6.;
+  s->fst.us1b = dom_rank->Gfx.s1b; s->fst.us2b = dom_rank->Gfx.s2b;
+  s->fst.vs1b = dom_rank->Gfy.s1b; s->fst.vs2b = dom_rank->Gfy.s2b;
+  s->fst.ws1b = dom_rank->Gfz.s1b; s->fst.ws2b = dom_rank->Gfz.s2b;
+  s->fst.cs1b = g.s1b; s->fst.cs2b = g.s2b;
+  { int rc = preload_kernels(); if (rc) return rc; }
+  k_build_tab<<<1, 128>>>((double *)(s->arena + s->amap.invM_tab), d.idx2, d.idy2, d.idz2);
+  CU(cudaDeviceSynchronize());
+  CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; i++) CU(cudaEventCreate(&s->ev[i]));
+  for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&s->ev_poll[i], cudaEventDisableTiming));
+  CU(cudaHostAlloc(&s->h_poll, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+  memset(s->h_poll, 0, 64);
+  CU(cudaHostGetDevicePointer((void **)&d.comm.host_flag, (void *)&s->h_poll[BB_POLL_COMM], 0));
+  CU(cudaHostAlloc(&s->h_scal, sizeof(Scal), cudaHostAllocDefault));
+  CU(cudaHostAlloc(&s->h_ztab, sizeof(int) * (BB_MAXZ + 1), cudaHostAllocDefault));
+  s->pdl = 2; s->rhs_tiled = 1;
+  /* single rank: neighbours are this block itself (periodic wrap) or nothing */
+  s->nranks = 1;
+  for (int p = 0; p < BB_MAXR; p++) { s->peer_arena[p] = NULL; s->peer_opened[p] = false; }
+  if (DOM->In * DOM->Jn * DOM->Kn == 1) {
+    s->peer_arena[0] = s->arena;
+    int dims[1][3] = { { g.in, g.jn, g.kn } };
+    build_halo(s, dims);
+  } else {
+    memset(&d.halo, 0, sizeof(d.halo));     /* until bbpcg_comm_import */
+    d.comm.rank = dom_rank->rank; d.comm.nranks = 1;
+  }
+  s->stream_blocks = s->sm_count * 8;
+  s->check_every = 10;
+  return BBPCG_OK;
 }
 
 extern "C" int bbpcg_create(bbpcg_solver **out, const dom_struct *dom_rank, const dom_struct *DOM,
@@ -241,57 +277,15 @@ extern "C" int bbpcg_create(bbpcg_solver **out, const dom_struct *dom_rank, cons
   }
   if (device < 0) CU(cudaGetDevice(&device));
   CU(cudaSetDevice(device));
+  const grid_info &g = dom_rank->Gcc;
+  if (g.in < 1 || g.jn < 1 || g.kn < 1 || g.s1b != g.in + 2 || g.s2b != g.s1b * (g.jn + 2)) {
+    bbpcg_set_error("bbpcg_create: dom_struct is not filled (run bb_domain_fill)"); return BBPCG_EINVAL;
+  }
   bbpcg_solver *s = new bbpcg_solver();
   memset(s, 0, sizeof(*s));
   s->dom = *dom_rank; s->DOM = *DOM; s->bc = *bc; s->device = device;
-  const grid_info &g = dom_rank->Gcc;
-  if (g.in < 1 || g.jn < 1 || g.kn < 1 || g.s1b != g.in + 2 || g.s2b != g.s1b * (g.jn + 2)) {
-    bbpcg_set_error("bbpcg_create: dom_struct is not filled (run bb_domain_fill)"); delete s; return BBPCG_EINVAL;
-  }
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, device));
-  s->sm_count = prop.multiProcessorCount;
-  Dev &d = s->dev;
-  d.L = make_layout(g.in, g.jn, g.kn);
-  s->amap = make_arena_map(d.L);
-  if (cudaMalloc(&s->arena, s->amap.total) != cudaSuccess) {
-    bbpcg_set_error("bbpcg_create: cudaMalloc of %zu bytes failed", s->amap.total); cudaGetLastError(); delete s; return BBPCG_ENOMEM;
-  }
-  CU(cudaMemset(s->arena, 0, s->amap.total));
-  point_dev_at_arena(s);
-  CU(cudaMemset(d.fmask, FM_DEAD, (size_t)d.L.n));          /* ghosts behind walls stay dead forever */
-  d.idx2 = 1. / (dom_rank->dx * dom_rank->dx); d.idy2 = 1. / (dom_rank->dy * dom_rank->dy); d.idz2 = 1. / (dom_rank->dz * dom_rank->dz);
-  d.dx2_6 = (dom_rank->dx * dom_rank->dx) / 6.; d.dy2_6 = (dom_rank->dy * dom_rank->dy) / 6.; d.dz2_6 = (dom_rank->dz * dom_rank->dz) / 6.;
-  s->fst.us1b = dom_rank->Gfx.s1b; s->fst.us2b = dom_rank->Gfx.s2b;
-  s->fst.vs1b = dom_rank->Gfy.s1b; s->fst.vs2b = dom_rank->Gfy.s2b;
-  s->fst.ws1b = dom_rank->Gfz.s1b; s->fst.ws2b = dom_rank->Gfz.s2b;
-  s->fst.cs1b = g.s1b; s->fst.cs2b = g.s2b;
-  { int rc = preload_kernels(); if (rc) { cudaFree(s->arena); delete s; return rc; } }
-  k_build_tab<<<1, 128>>>((double *)(s->arena + s->amap.invM_tab), d.idx2, d.idy2, d.idz2);
-  CU(cudaDeviceSynchronize());
-  CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 4; i++) CU(cudaEventCreate(&s->ev[i]));
-  for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&s->ev_poll[i], cudaEventDisableTiming));
-  CU(cudaHostAlloc(&s->h_poll, 64, cudaHostAllocDefault));
-  CU(cudaHostAlloc(&s->h_scal, sizeof(Scal), cudaHostAllocDefault));
-  CU(cudaHostAlloc(&s->h_ztab, sizeof(int) * (BB_MAXZ + 1), cudaHostAllocDefault));
-  s->zt_cols = -1; s->taper_g10 = 0; s->taper_min = 8; s->pdl = 2; s->recompute = 1; s->rhs_tiled = 1; s->fast_refresh = 1; s->resid_mb = 2; s->resid_d = 2;
-  /* single rank: neighbours are this block itself (periodic wrap) or nothing */
-  s->nranks = 1;
-  for (int p = 0; p < BB_MAXR; p++) { s->peer_arena[p] = NULL; s->peer_opened[p] = false; }
-  if (DOM->In * DOM->Jn * DOM->Kn == 1) {
-    s->peer_arena[0] = s->arena;
-    int dims[1][3] = { { g.in, g.jn, g.kn } };
-    build_halo(s, dims);
-    { int rc = build_search_maps(s); if (rc) { cudaFree(s->arena); delete s; return rc; } }
-  } else {
-    memset(&d.halo, 0, sizeof(d.halo));     /* until bbpcg_comm_import */
-    d.comm.rank = dom_rank->rank; d.comm.nranks = 1;
-  }
-  s->tile = 0; s->kc = 0;
-  s->resid_blocks = s->sm_count * 12;
-  s->stream_blocks = s->sm_count * 8;
-  s->check_every = 10;
+  const int rc = create_impl(s, dom_rank, DOM);
+  if (rc) { bbpcg_destroy(s); return rc; }
   *out = s;
   return BBPCG_OK;
 }
@@ -300,15 +294,18 @@ extern "C" void bbpcg_destroy(bbpcg_solver *s)
 {
   if (!s) return;
   cudaSetDevice(s->device);
-  cudaStreamSynchronize(s->stream);
+  if (s->stream) cudaStreamSynchronize(s->stream);
   for (int p = 0; p < BB_MAXR; p++) if (s->peer_opened[p]) cudaIpcCloseMemHandle(s->peer_arena[p]);
-  cudaFree(s->arena);
+  if (s->arena) cudaFree(s->arena);
   cudaFree(s->hb_u); cudaFree(s->hb_v); cudaFree(s->hb_w); cudaFree(s->hb_rhs); cudaFree(s->hb_phi);
-  cudaFreeHost(s->h_poll); cudaFreeHost(s->h_scal); cudaFreeHost(s->h_ztab);
-  if (s->kev) { for (int i = 0; i <= 2 * BB_KT_CAP; i++) cudaEventDestroy(s->kev[i]); free(s->kev); }
-  for (int i = 0; i < 4; i++) cudaEventDestroy(s->ev[i]);
-  for (int i = 0; i < 2; i++) cudaEventDestroy(s->ev_poll[i]);
-  cudaStreamDestroy(s->stream);
+  if (s->h_poll) cudaFreeHost(s->h_poll);
+  if (s->h_scal) cudaFreeHost(s->h_scal);
+  if (s->h_ztab) cudaFreeHost(s->h_ztab);
+  if (s->kev) { for (int i = 0; i <= 2 * BB_KT_CAP; i++) if (s->kev[i]) cudaEventDestroy(s->kev[i]); free(s->kev); }
+  for (int i = 0; i < 4; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+  for (int i = 0; i < 2; i++) if (s->ev_poll[i]) cudaEventDestroy(s->ev_poll[i]);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  cudaGetLastError();
   delete s;
 }
 
@@ -341,6 +338,7 @@ extern "C" int bbpcg_comm_import(bbpcg_solver *s, const void *all_blobs, int nra
     if (b.magic != BB_MAGIC || b.rank != p) { bbpcg_set_error("bbpcg_comm_import: record %d is not rank %d's export", p, p); return BBPCG_ECOMM; }
     dims[p][0] = b.in; dims[p][1] = b.jn; dims[p][2] = b.kn;
     if (p == s->dom.rank) { s->peer_arena[p] = s->arena; continue; }
+    if (s->peer_opened[p]) continue;                       /* a repeated import: this peer's mapping is still open */
     if (b.pid == mypid && b.device == s->device) s->shared_device = 1;
     if (b.pid == mypid) {
       /* same process (several ranks driven from one process): the pointer is directly usable;
@@ -357,77 +355,72 @@ extern "C" int bbpcg_comm_import(bbpcg_solver *s, const void *all_blobs, int nra
     } else {
       void *ptr = NULL;
       cudaError_t e = cudaIpcOpenMemHandle(&ptr, b.handle, cudaIpcMemLazyEnablePeerAccess);
-      if (e != cudaSuccess) { bbpcg_set_error("cudaIpcOpenMemHandle(rank %d): %s", p, cudaGetErrorString(e)); cudaGetLastError(); return BBPCG_ECOMM; }
+      if (e != cudaSuccess) {
+        bbpcg_set_error("cudaIpcOpenMemHandle(rank %d): %s", p, cudaGetErrorString(e)); cudaGetLastError();
+        for (int o = 0; o < p; o++) if (s->peer_opened[o]) { cudaIpcCloseMemHandle(s->peer_arena[o]); s->peer_opened[o] = false; s->peer_arena[o] = NULL; }
+        return BBPCG_ECOMM;
+      }
       s->peer_arena[p] = (char *)ptr; s->peer_opened[p] = true;
     }
   }
   s->nranks = nranks;
   build_halo(s, dims);
-  return build_search_maps(s);
+  s->plan_ok = 0;                   /* the neighbour tensor maps are part of the plan */
+  return BBPCG_OK;
 }
 
 /* ---- launch helpers ------------------------------------------------------------------------ */
-struct TileCfg { int tx, ty, nt; };
-static const TileCfg k_tiles[] = { { 128, 8, 256 }, { 128, 4, 256 }, { 128, 8, 256 }, { 128, 4, 256 }, { 64, 8, 256 }, { 128, 8, 512 },
-                                   { 32, 8, 128 }, { 256, 4, 256 }, { 128, 8, 256 }, { 128, 4, 256 } };
-static const int k_ntiles = sizeof(k_tiles) / sizeof(k_tiles[0]);
-static bool tile_is_tma(int t) { return t == 0 || t == 1 || t == 8 || t == 9; }
-static bool recompute_active(const bbpcg_solver *s) { return s->recompute && tile_is_tma(s->tile); }
-
-/* z-chunk plan of the search kernel.  The grid is (x-tiles, y-tiles, z-chunks); CTAs are dispatched
- * z-chunk-major, so y/x neighbours of one chunk run together (their halo rows hit L2).  kc > 0: uniform
- * chunks of kc planes.  kc <= 0: GUIDED chunks -- each slab takes remaining*columns/(g*slots) planes
- * (>= taper_min), i.e. long chunks first (few re-read halo planes) and short ones last, so the
- * final partial wave of the `slots` resident CTAs is short whatever the block size.  Uploads the prefix
- * table to Dev::ztab when the plan changed; returns nbz. */
-static int plan_zchunks(bbpcg_solver *s, int columns, int slots, int *nbz_out)
+/* Tile / z-chunk plan of the two iteration kernels.  The grid is (x-tiles of 128, y-tiles of ty rows, z-chunks); CTAs are
+ * dispatched z-chunk-major, so the y/x neighbours of one chunk run together and their halo rows hit L2.  2 CTAs are
+ * resident per SM: `slots` = 2 x SM count.  Measured (scripts/sweep.py; profiles/r02b_sweep*.jsonl):
+ *   - many waves (512^3: 256 columns): ~24-plane chunks win (1519 us/iteration); ONE wave of 296 long CTAs (ty 7, 512
+ *     planes each) loses 16 % although it re-reads no halo plane and fills every slot: the long CTAs drift out of lock
+ *     step, the halo rows their y neighbours fetched have left L2 (+10 % DRAM bytes, ncu) and nothing rebalances the tail;
+ *   - few waves (256^3 block, the 8-GPU share of 512^3): 256..300 CTAs of ~64..86 planes, every (ty, chunk) pair between
+ *     6 x 86 and 8 x 32 lands within 2 % (212-221 us): the wave count decides, so minimise ceil(CTAs/slots) x (planes + 6).
+ * Tile height: 8 rows (fewest halo-row re-reads) unless option `ty` says otherwise; the kernels take any 1..8.
+ * Options `ty` / `kc` override either choice.  Uploads the chunk table (Dev::ztab) and rebuilds the tensor maps. */
+static int make_plan(bbpcg_solver *s)
 {
-  const int kn = s->dev.L.kn;
-  if (s->zt_cols == columns && s->zt_kc == s->kc && s->zt_g10 == s->taper_g10 && s->zt_min == s->taper_min) { *nbz_out = s->zt_nbz; return BBPCG_OK; }
-  std::vector<int> sz;
-  if (s->kc > 0) {
-    for (int r = kn; r > 0; r -= s->kc) sz.push_back(r < s->kc ? r : s->kc);
-  } else if (s->taper_g10 > 0) {
-    const int tmin = s->taper_min < 1 ? 1 : s->taper_min;
-    int r = kn;
-    while (r > 0) {
-      long long t = ((long long)r * columns * 10 + (long long)s->taper_g10 * slots - 1) / ((long long)s->taper_g10 * slots);
-      if (t < tmin) t = tmin;
-      if (t > r || r - t < (tmin + 1) / 2) t = r;
-      sz.push_back((int)t); r -= (int)t;
-    }
-  } else {
-    /* default, from the measured sweeps: with many waves of resident CTAs the best chunk
-     * is ~24 planes (>= 7 waves: the ragged last wave is short, the two re-read halo planes stay cheap);
-     * with few waves what matters is the wave count itself: minimise ceil(CTAs/slots) * (kc + 6). */
-    int nz = (kn + 23) / 24;
-    if ((long long)columns * nz < 7ll * slots) {
-      long long best = -1;
-      const int nzmax = kn >= 16 ? kn / 8 : 1;
-      for (int c = 1; c <= nzmax; c++) {
-        const long long waves = ((long long)columns * c + slots - 1) / slots;
-        const long long cost = waves * ((kn + c - 1) / c + 6);    /* +6: two halo planes + pipeline fill/drain */
-        if (best < 0 || cost < best) { best = cost; nz = c; }
+  if (s->plan_ok) return BBPCG_OK;
+  const Layout &L = s->dev.L;
+  const int slots = s->sm_count * 2;
+  const int nbx = (L.in + 127) / 128;
+  const int best_ty = s->opt_ty > 0 ? s->opt_ty : BB_TYMAX;
+  const int cols = nbx * ((L.jn + best_ty - 1) / best_ty);
+  int best_nz = 1;
+  double best = -1.;
+  if (s->opt_kc > 0) { best_nz = (L.kn + s->opt_kc - 1) / s->opt_kc; best = 0.; }
+  else {
+    best_nz = (L.kn + 23) / 24; best = 0.;
+    if ((long long)cols * best_nz < 7ll * slots) {
+      best = -1.;
+      const int nz_hi = L.kn >= 16 ? L.kn / 8 : 1;
+      for (int nz = 1; nz <= nz_hi && nz <= BB_MAXZ; nz++) {
+        const long long ctas = (long long)cols * nz;
+        if (ctas > BB_MAXBLOCKS) break;
+        const long long waves = (ctas + slots - 1) / slots;
+        const double cost = (double)waves * ((L.kn + nz - 1) / nz + 6);        /* +6: two halo planes + pipeline fill/drain */
+        if (best < 0. || cost < best) { best = cost; best_nz = nz; }
       }
     }
-    const int kc = (kn + nz - 1) / nz;
-    for (int r = kn; r > 0; r -= kc) sz.push_back(r < kc ? r : kc);
   }
-  if ((int)sz.size() > BB_MAXZ || (long long)sz.size() * columns > BB_MAXBLOCKS) {
-    /* fall back to the shortest uniform chunks that fit the workspace */
-    int nz = BB_MAXBLOCKS / columns; if (nz > BB_MAXZ) nz = BB_MAXZ;
-    if (nz < 1) { bbpcg_set_error("grid too large for the reduction workspace"); return BBPCG_EINVAL; }
-    const int kc = (kn + nz - 1) / nz;
-    sz.clear();
-    for (int r = kn; r > 0; r -= kc) sz.push_back(r < kc ? r : kc);
-  }
+  if (best_nz > BB_MAXZ) best_nz = BB_MAXZ;
+  if ((long long)cols * best_nz > BB_MAXBLOCKS) best_nz = BB_MAXBLOCKS / cols;     /* the shortest chunks the reduction workspace allows */
+  if (best_nz < 1) best = -1.;
+  if (best < 0.) { bbpcg_set_error("grid too large for the reduction workspace"); return BBPCG_EINVAL; }
+  const int kc = (L.kn + best_nz - 1) / best_nz;
+  std::vector<int> sz;
+  for (int r = L.kn; r > 0; r -= kc) sz.push_back(r < kc ? r : kc);
   /* the copy source must stay valid until the copy ran: it is only rewritten after a stream sync */
   CU(cudaStreamSynchronize(s->stream));
   s->h_ztab[0] = 0;
   for (size_t i = 0; i < sz.size(); i++) s->h_ztab[i + 1] = s->h_ztab[i] + sz[i];
   CU(cudaMemcpyAsync((void *)s->dev.ztab, s->h_ztab, sizeof(int) * (sz.size() + 1), cudaMemcpyHostToDevice, s->stream));
-  s->zt_cols = columns; s->zt_kc = s->kc; s->zt_g10 = s->taper_g10; s->zt_min = s->taper_min; s->zt_nbz = (int)sz.size();
-  *nbz_out = s->zt_nbz;
+  s->plan_ty = best_ty; s->plan_nbx = nbx; s->plan_nby = (L.jn + best_ty - 1) / best_ty; s->plan_nbz = (int)sz.size(); s->plan_kc = kc;
+  int rc = build_search_maps(s, best_ty);
+  if (rc) return rc;
+  s->plan_ok = 1;
   return BBPCG_OK;
 }
 
@@ -459,87 +452,46 @@ static cudaError_t launch_k(bbpcg_solver *s, void (*kernel)(KArgs...), dim3 grid
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-template <int TX, int TY, int NT, int MINB>
-static int launch_search_t(bbpcg_solver *s, bool parts)
+static SearchArgs plan_args(const bbpcg_solver *s)
 {
-  const Layout &L = s->dev.L;
-  constexpr int NITEM = (TX + 2) * (TY + 2);
-  const size_t smem = (size_t)(4 * NITEM + 128) * sizeof(double) + 4 * NITEM;
   SearchArgs a;
-  a.nbx = (L.in + TX - 1) / TX; a.nby = (L.jn + TY - 1) / TY;
-  int rc = plan_zchunks(s, a.nbx * a.nby, s->sm_count * MINB, &a.nbz);
-  if (rc) return rc;
-  a.store_q = 1;
-  dim3 grid(a.nbx, a.nby, a.nbz);
-  s->last_search_grid = a.nbx * a.nby * a.nbz; s->last_search_kc = s->h_ztab[1];
-  if (parts) {
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_search_spmv<TX, TY, NT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_search_spmv<TX, TY, NT, MINB, true><<<grid, NT, smem, s->stream>>>(s->dev, a);
-  } else {
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_search_spmv<TX, TY, NT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_search_spmv<TX, TY, NT, MINB, false><<<grid, NT, smem, s->stream>>>(s->dev, a);
-  }
-  s->launches++;
-  return BBPCG_OK;
+  memset(&a, 0, sizeof(a));
+  a.nbx = s->plan_nbx; a.nby = s->plan_nby; a.nbz = s->plan_nbz; a.ty = s->plan_ty;
+  return a;
 }
 
-/* the TMA-fed kernel (bbpcg_search_tma.cuh) */
-template <int TY, bool PARTS, int DD>
-static int launch_search_tma_t(bbpcg_solver *s, const SearchMaps &M)
+/* k_search_tma (bbpcg_search_tma.cuh) */
+static int launch_search(bbpcg_solver *s, bool parts)
 {
-  typedef SearchGeom<TY, PARTS, DD> G;
   static_assert(sizeof(Dev) + sizeof(SearchMaps) + sizeof(SearchArgs) + 192 <= 4096, "kernel parameters exceed 4 KB");
-  const Layout &L = s->dev.L;
-  if (!s->maps_ok) { bbpcg_set_error("tensor maps not built"); return BBPCG_EINVAL; }
-  SearchArgs a;
-  a.nbx = (L.in + G::TX - 1) / G::TX; a.nby = (L.jn + TY - 1) / TY;
-  int rc = plan_zchunks(s, a.nbx * a.nby, s->sm_count * 2, &a.nbz);
+  int rc = make_plan(s);
   if (rc) return rc;
-  a.store_q = recompute_active(s) ? 0 : 1;
-  dim3 grid(a.nbx, a.nby, a.nbz);
-  s->last_search_grid = a.nbx * a.nby * a.nbz; s->last_search_kc = s->h_ztab[1];
-  CU(launch_k(s, k_search_tma<TY, PARTS, DD>, grid, G::NT, G::SMEM, true, s->dev, M, a));
+  const SearchArgs a = plan_args(s);
+  const dim3 grid(a.nbx, a.nby, a.nbz);
+  if (parts) CU(launch_k(s, k_search_tma<true, 2>, grid, 256, SearchGeom<true, 2>::SMEM, true, s->dev, s->maps, a));
+  else CU(launch_k(s, k_search_tma<false, 2>, grid, 256, SearchGeom<false, 2>::SMEM, true, s->dev, s->maps, a));
   s->launches++;
   return BBPCG_OK;
 }
 
-/* the residual half of the recompute variant (bbpcg_resid_tma.cuh): same tiles and z-chunks as the search kernel */
-template <int TY, bool PARTS, int MB, int DD, bool REFRESH>
-static int launch_resid_tma_t(bbpcg_solver *s, const SearchMaps &M, const real *rhs)
+/* k_resid_tma (bbpcg_resid_tma.cuh): same tiles and z-chunks as the search kernel.  rhs != NULL: the true-residual
+ * refresh form r = b - (-A x) */
+static int launch_resid(bbpcg_solver *s, bool parts, const real *rhs)
 {
-  typedef ResidGeom<TY, PARTS, DD> G;
-  const Layout &L = s->dev.L;
-  SearchArgs a;
-  a.nbx = (L.in + G::TX - 1) / G::TX; a.nby = (L.jn + TY - 1) / TY;
-  int rc = plan_zchunks(s, a.nbx * a.nby, s->sm_count * 2, &a.nbz);
+  int rc = make_plan(s);
   if (rc) return rc;
-  a.store_q = 0; a.rhs = rhs; a.s1b = s->fst.cs1b; a.s2b = s->fst.cs2b;
-  CU(launch_k(s, k_resid_tma<TY, PARTS, MB, DD, REFRESH>, dim3(a.nbx, a.nby, a.nbz), G::NT, G::SMEM, !REFRESH, s->dev, M, a));
-  s->launches++;
-  return BBPCG_OK;
-}
-
-static int launch_resid_tma(bbpcg_solver *s, bool parts)
-{
-  const bool t8 = k_tiles[s->tile].ty == 8;
-  const SearchMaps &M = s->maps[t8 ? 0 : 1];
-  if (parts) return t8 ? launch_resid_tma_t<8, true, 2, 2, false>(s, M, NULL) : launch_resid_tma_t<4, true, 2, 2, false>(s, M, NULL);
-  if (!t8) return launch_resid_tma_t<4, false, 3, 2, false>(s, M, NULL);
-  switch (s->resid_mb * 10 + s->resid_d) {
-    case 23: return launch_resid_tma_t<8, false, 2, 3, false>(s, M, NULL);
-    case 32: return launch_resid_tma_t<8, false, 3, 2, false>(s, M, NULL);
-    case 33: return launch_resid_tma_t<8, false, 3, 3, false>(s, M, NULL);
-    default: return launch_resid_tma_t<8, false, 2, 2, false>(s, M, NULL);
+  SearchArgs a = plan_args(s);
+  a.rhs = rhs; a.s1b = s->fst.cs1b; a.s2b = s->fst.cs2b;
+  const dim3 grid(a.nbx, a.nby, a.nbz);
+  if (rhs) {
+    if (parts) CU(launch_k(s, k_resid_tma<true, 2, true>, grid, 256, ResidGeom<true, 2>::SMEM, false, s->dev, s->maps, a));
+    else CU(launch_k(s, k_resid_tma<false, 2, true>, grid, 256, ResidGeom<false, 2>::SMEM, false, s->dev, s->maps, a));
+  } else {
+    if (parts) CU(launch_k(s, k_resid_tma<true, 2, false>, grid, 256, ResidGeom<true, 2>::SMEM, true, s->dev, s->maps, a));
+    else CU(launch_k(s, k_resid_tma<false, 2, false>, grid, 256, ResidGeom<false, 2>::SMEM, true, s->dev, s->maps, a));
   }
-}
-
-/* true-residual refresh with the same tiles: r = b - (-A x) */
-static int launch_refresh_r_tma(bbpcg_solver *s, bool parts, const real *rhs)
-{
-  const bool t8 = k_tiles[s->tile].ty == 8;
-  const SearchMaps &M = s->maps[t8 ? 0 : 1];
-  if (parts) return t8 ? launch_resid_tma_t<8, true, 2, 2, true>(s, M, rhs) : launch_resid_tma_t<4, true, 2, 2, true>(s, M, rhs);
-  return t8 ? launch_resid_tma_t<8, false, 2, 2, true>(s, M, rhs) : launch_resid_tma_t<4, false, 2, 2, true>(s, M, rhs);
+  s->launches++;
+  return BBPCG_OK;
 }
 
 template <int XT, int UNR>
@@ -569,24 +521,6 @@ static int launch_refresh_x4(bbpcg_solver *s)
   return launch_refresh_x4_t<32, 4>(s);
 }
 
-static int launch_search(bbpcg_solver *s, bool parts)
-{
-  switch (s->tile) {
-    case 0: return parts ? launch_search_tma_t<8, true, 2>(s, s->maps[0]) : launch_search_tma_t<8, false, 2>(s, s->maps[0]);
-    case 1: return parts ? launch_search_tma_t<4, true, 2>(s, s->maps[1]) : launch_search_tma_t<4, false, 2>(s, s->maps[1]);
-    case 2: return launch_search_t<128, 8, 256, 2>(s, parts);
-    case 3: return launch_search_t<128, 4, 256, 3>(s, parts);
-    case 4: return launch_search_t<64, 8, 256, 3>(s, parts);
-    case 5: return launch_search_t<128, 8, 512, 2>(s, parts);
-    case 6: return launch_search_t<32, 8, 128, 4>(s, parts);
-    case 7: return launch_search_t<256, 4, 256, 2>(s, parts);
-    case 8: return parts ? launch_search_tma_t<8, true, 3>(s, s->maps[0]) : launch_search_tma_t<8, false, 3>(s, s->maps[0]);
-    case 9: return parts ? launch_search_tma_t<4, true, 3>(s, s->maps[1]) : launch_search_tma_t<4, false, 3>(s, s->maps[1]);
-  }
-  bbpcg_set_error("unknown tile variant %d", s->tile);
-  return BBPCG_EINVAL;
-}
-
 /* Load every kernel of the library NOW.  CUDA loads device functions lazily at their first
  * launch, and that load takes a context-wide lock; when several ranks share one context (the
  * single-process test harness) a first launch on one rank's host thread would block the other
@@ -600,73 +534,38 @@ template <typename K> static int preload_one(K kernel, int dyn_smem = 0)
   if (dyn_smem > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
   return BBPCG_OK;
 }
-template <int TY, bool PARTS, int DD> static int preload_search_tma() { return preload_one(k_search_tma<TY, PARTS, DD>, SearchGeom<TY, PARTS, DD>::SMEM); }
-template <int TY, bool PARTS, int MB, int DD, bool REFRESH> static int preload_resid_tma() { return preload_one(k_resid_tma<TY, PARTS, MB, DD, REFRESH>, ResidGeom<TY, PARTS, DD>::SMEM); }
-template <int TX, int TY, int NT, int MINB> static int preload_search()
-{
-  int rc = preload_one(k_search_spmv<TX, TY, NT, MINB, false>);
-  if (!rc) rc = preload_one(k_search_spmv<TX, TY, NT, MINB, true>);
-  return rc;
-}
 static int preload_kernels()
 {
   int rc = 0;
 #define PL(...) if (!rc) rc = preload_one(__VA_ARGS__)
-#define PS(...) if (!rc) rc = preload_search_tma<__VA_ARGS__>()
-#define PR(...) if (!rc) rc = preload_resid_tma<__VA_ARGS__>()
-  PS(8, false, 2); PS(8, true, 2); PS(4, false, 2); PS(4, true, 2); PS(8, false, 3); PS(8, true, 3); PS(4, false, 3); PS(4, true, 3);
-  if (!rc) rc = preload_search<128, 8, 256, 2>();
-  if (!rc) rc = preload_search<128, 4, 256, 3>();
-  if (!rc) rc = preload_search<64, 8, 256, 3>();
-  if (!rc) rc = preload_search<128, 8, 512, 2>();
-  if (!rc) rc = preload_search<32, 8, 128, 4>();
-  if (!rc) rc = preload_search<256, 4, 256, 2>();
-  PR(8, true, 2, 2, false); PR(4, true, 2, 2, false); PR(4, false, 3, 2, false);
-  PR(8, false, 2, 2, false); PR(8, false, 2, 3, false); PR(8, false, 3, 2, false); PR(8, false, 3, 3, false);
-  PR(8, true, 2, 2, true); PR(4, true, 2, 2, true); PR(8, false, 2, 2, true); PR(4, false, 2, 2, true);
-#undef PS
-#undef PR
+  PL(k_search_tma<false, 2>, SearchGeom<false, 2>::SMEM); PL(k_search_tma<true, 2>, SearchGeom<true, 2>::SMEM);
+  PL(k_resid_tma<false, 2, false>, ResidGeom<false, 2>::SMEM); PL(k_resid_tma<true, 2, false>, ResidGeom<true, 2>::SMEM);
+  PL(k_resid_tma<false, 2, true>, ResidGeom<false, 2>::SMEM); PL(k_resid_tma<true, 2, true>, ResidGeom<true, 2>::SMEM);
   PL(k_refresh_x4<128, 4>); PL(k_refresh_x4<64, 4>); PL(k_refresh_x4<32, 4>);
-  PL(k_resid<128, 4>); PL(k_resid<64, 4>); PL(k_resid<32, 4>); PL(k_refresh_x<256>); PL(k_refresh_r<256, false>); PL(k_refresh_r<256, true>);
   PL(k_build_tab); PL(k_init<256>); PL(k_finish<256>); PL(k_rhs<256>); PL(k_rhs_tiled); PL(k_masks<256>); PL(k_part_rhs_net);
   PL(k_coeffs_refine<256>); PL(k_zero_ghosts); PL(k_xchg_send); PL(k_xchg_recv);
   PL(k_spmv_s3b<256, false>); PL(k_spmv_s3b<256, true>);
   PL(k_solv_sum); PL(k_solv_apply);
   PL(k_bc_p); PL(k_sub_mean);
-  if (!rc) rc = preload_one(k_epilogue<true, true>, EPI_SMEM);
-  if (!rc) rc = preload_one(k_epilogue<true, false>, EPI_SMEM);
-  if (!rc) rc = preload_one(k_epilogue<false, true>, EPI_SMEM);
+  PL(k_epilogue<true, true>, EPI_SMEM); PL(k_epilogue<true, false>, EPI_SMEM); PL(k_epilogue<false, true>, EPI_SMEM);
 #undef PL
   return rc;
 }
 
 static int clampi(long long v, int lo, int hi) { return (int)(v < lo ? lo : v > hi ? hi : v); }
 
-template <int XT, int UNR>
-static int launch_resid_t(bbpcg_solver *s)
+/* The in-kernel collectives give up after Comm::timeout_cycles instead of hanging (the reference's MPI calls block for
+ * ever).  A time-out leaves the ranks with different sums and ghosts, so it is FATAL for the solver objects of all ranks:
+ * the device sets a pinned host word, every collective entry point reads it after its stream sync (and on entry) and
+ * returns BBPCG_ECOMM from then on; destroy and re-create the solvers to recover. */
+static int comm_check(const bbpcg_solver *s, const char *who)
 {
-  const Layout &L = s->dev.L;
-  constexpr int YT = 128 / XT;
-  ResidArgs a;
-  a.cpr = (L.in + 3) / 4;
-  a.ncb = (a.cpr + XT - 1) / XT;
-  const long long nrows = (long long)L.jn * L.kn;
-  const long long npass = (nrows + YT * UNR - 1) / (YT * UNR) * a.ncb;
-  if (npass > 0x7fffffffll) { bbpcg_set_error("block too large"); return BBPCG_EINVAL; }
-  a.npass = (int)npass;
-  a.ppc = s->resid_ppc > 0 ? s->resid_ppc : 1;
-  if ((a.npass + a.ppc - 1) / a.ppc > BB_MAXBLOCKS) a.ppc = (a.npass + BB_MAXBLOCKS - 1) / BB_MAXBLOCKS;
-  CU(launch_k(s, k_resid<XT, UNR>, dim3((a.npass + a.ppc - 1) / a.ppc), 128, 0, true, s->dev, a));
-  s->launches++;
+  if (((volatile int *)s->h_poll)[BB_POLL_COMM]) {
+    bbpcg_set_error("%s: a peer rank did not arrive within the collective time-out (option comm_timeout_ms); ghosts and sums are "
+                    "inconsistent across ranks -- destroy and re-create the solver on every rank", who);
+    return BBPCG_ECOMM;
+  }
   return BBPCG_OK;
-}
-
-static int launch_resid(bbpcg_solver *s)
-{
-  const int cpr = (s->dev.L.in + 3) / 4;
-  if (cpr > 64) return launch_resid_t<128, 4>(s);
-  if (cpr > 32) return launch_resid_t<64, 4>(s);
-  return launch_resid_t<32, 4>(s);
 }
 
 /* ---- coefficients -------------------------------------------------------------------------- */
@@ -680,6 +579,7 @@ extern "C" int bbpcg_set_coefficients(bbpcg_solver *s, const int *flag_u, const 
   s->launches++;
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(s->stream));
+  if (comm_check(s, "bbpcg_set_coefficients")) return BBPCG_ECOMM;
   s->has_phase = phase != NULL;
   s->coeffs_set = 1;
   return BBPCG_OK;
@@ -748,11 +648,12 @@ extern "C" int bbpcg_exchange(bbpcg_solver *s, real *array, int grid)
   if (grid < BBPCG_GCC || grid > BBPCG_GFZ) { bbpcg_set_error("bbpcg_exchange: grid must be BBPCG_GCC/GFX/GFY/GFZ"); return BBPCG_EINVAL; }
   if (s->nranks == 1 && s->DOM.In * s->DOM.Jn * s->DOM.Kn != 1) { bbpcg_set_error("decomposition has %d blocks: call bbpcg_comm_import first", s->DOM.In * s->DOM.Jn * s->DOM.Kn); return BBPCG_ECOMM; }
   CU(cudaSetDevice(s->device));
+  if (comm_check(s, "bbpcg_exchange")) return BBPCG_ECOMM;
   int rc = enqueue_exchange(s, array, grid);
   if (rc) return rc;
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(s->stream));
-  return BBPCG_OK;
+  return comm_check(s, "bbpcg_exchange");
 }
 
 extern "C" int bbpcg_exchange_Gcc(bbpcg_solver *s, real *array) { return bbpcg_exchange(s, array, BBPCG_GCC); }
@@ -848,7 +749,7 @@ extern "C" int bbpcg_epilogue(bbpcg_solver *s, const bbpcg_epilogue_args *a, dou
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(s->stream));
   if (ms_out) { float ms = 0.f; cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]); *ms_out = ms; }
-  return BBPCG_OK;
+  return comm_check(s, "bbpcg_epilogue");
 }
 
 /* ---- solve prologue: cuda_solvability (bbpcg_epilogue.cuh) -------------------------------------------------- */
@@ -877,34 +778,22 @@ extern "C" int bbpcg_solvability(bbpcg_solver *s, real *u_star, real *v_star, re
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(s->stream));
   if (eps_out) { eps_out[0] = s->h_scal->eps[0]; eps_out[1] = s->h_scal->eps[1]; eps_out[2] = s->h_scal->eps[2]; }
-  return BBPCG_OK;
+  return comm_check(s, "bbpcg_solvability");
 }
 
 /* ---- the solve ----------------------------------------------------------------------------- */
 static int enqueue_iteration(bbpcg_solver *s, int it, bool parts, const real *rhs)
 {
-  const long long nrows = (long long)s->dev.L.jn * s->dev.L.kn;
   const bool kt = s->kernel_timing && it <= BB_KT_CAP;
   if (kt && it == 1) CU(cudaEventRecord(s->kev[0], s->stream));
   int rc = launch_search(s, parts);
   if (rc) return rc;
   if (kt) CU(cudaEventRecord(s->kev[2 * it - 1], s->stream));
   if (it % 50 == 0) {                                     /* cuda_solver.cu:209-223 */
-    if (recompute_active(s) && s->fast_refresh) {
-      rc = launch_refresh_x4(s);
-      if (!rc) rc = launch_refresh_r_tma(s, parts, rhs);
-      if (rc) return rc;
-    } else {
-      const int nb = clampi(nrows, 1, s->stream_blocks);
-      k_refresh_x<256><<<nb, 256, 0, s->stream>>>(s->dev);
-      if (parts) k_refresh_r<256, true><<<nb, 256, 0, s->stream>>>(s->dev, rhs, s->fst.cs1b, s->fst.cs2b);
-      else k_refresh_r<256, false><<<nb, 256, 0, s->stream>>>(s->dev, rhs, s->fst.cs1b, s->fst.cs2b);
-      s->launches += 2;
-    }
-  } else {
-    rc = recompute_active(s) ? launch_resid_tma(s, parts) : launch_resid(s);
-    if (rc) return rc;
-  }
+    rc = launch_refresh_x4(s);
+    if (!rc) rc = launch_resid(s, parts, rhs);
+  } else rc = launch_resid(s, parts, NULL);
+  if (rc) return rc;
   if (kt) CU(cudaEventRecord(s->kev[2 * it], s->stream));
   return BBPCG_OK;
 }
@@ -938,9 +827,12 @@ extern "C" int bbpcg_solve(bbpcg_solver *s, const bbpcg_solve_args *a, bbpcg_res
     }
     rc = enqueue_exchange(s, a->rhs_p);
     if (rc) return rc;
-    k_coeffs_refine<256><<<nbs, 256, 0, s->stream>>>(g.in, g.jn, g.kn, g.s1b, g.s2b, a->rhs_p, a->phase, s->dev.idx2, s->dev.idy2, s->dev.idz2);
+    if (!a->no_refine) {                                   /* :139-142, guarded by the rank-local nparts > 0 in the reference */
+      k_coeffs_refine<256><<<nbs, 256, 0, s->stream>>>(g.in, g.jn, g.kn, g.s1b, g.s2b, a->rhs_p, a->phase, s->dev.idx2, s->dev.idy2, s->dev.idz2);
+      s->launches++;
+    }
     k_zero_ghosts<<<s->sm_count * 4, 256, 0, s->stream>>>(a->rhs_p, g.inb, g.jnb, g.knb);
-    s->launches += 2;
+    s->launches++;
   }
   CU(cudaMemsetAsync(s->dev.x, 0, sizeof(double) * (size_t)L.n, s->stream));
   CU(cudaMemsetAsync(s->dev.P[0], 0, sizeof(double) * (size_t)L.n, s->stream));
@@ -958,7 +850,11 @@ extern "C" int bbpcg_solve(bbpcg_solver *s, const bbpcg_solve_args *a, bbpcg_res
   poll[0] = poll[16 / 4] = 0;
   while (!finished && it < max_q) {
     const int upto = (it + s->check_every < max_q) ? it + s->check_every : max_q;
-    while (it < upto) { ++it; rc = enqueue_iteration(s, it, parts, a->rhs_p); if (rc) return rc; }
+    while (it < upto) {
+      ++it;
+      rc = enqueue_iteration(s, it, parts, a->rhs_p);
+      if (rc) { cudaStreamSynchronize(s->stream); return rc; }     /* nothing of this solve stays enqueued behind an error */
+    }
     const int slot = nbatch & 1;
     CU(cudaMemcpyAsync((void *)&s->h_poll[slot * 4], &s->dev.sc->done, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaEventRecord(s->ev_poll[slot], s->stream));
@@ -997,7 +893,8 @@ extern "C" int bbpcg_solve(bbpcg_solver *s, const bbpcg_solve_args *a, bbpcg_res
     cudaEventElapsedTime(&ms, s->ev[0], s->ev[3]); res->ms_total = ms;
     res->launches = s->launches - launches0;
   }
-  if (sc.status == 4) { bbpcg_set_error("bbpcg_solve: a peer rank never arrived (in-kernel all-reduce timed out)"); return BBPCG_ECOMM; }
+  if (sc.status == BBPCG_COMM_TIMEOUT) s->h_poll[BB_POLL_COMM] = 1;
+  if (comm_check(s, "bbpcg_solve")) return BBPCG_ECOMM;
   return BBPCG_OK;
 }
 
@@ -1041,21 +938,19 @@ extern "C" int bbpcg_history(bbpcg_solver *s, double *out, int cap)
 extern "C" int bbpcg_set_option(bbpcg_solver *s, const char *key, long long value)
 {
   if (!s || !key) return BBPCG_EINVAL;
-  if (!strcmp(key, "tile")) { if (value < 0 || value >= k_ntiles) { bbpcg_set_error("tile must be 0..%d", k_ntiles - 1); return BBPCG_EINVAL; } s->tile = (int)value; }
-  else if (!strcmp(key, "kc")) s->kc = (int)value;
-  else if (!strcmp(key, "taper_g10")) s->taper_g10 = clampi(value, 0, 1000);
-  else if (!strcmp(key, "taper_min")) s->taper_min = clampi(value, 1, 4096);
+  if (!strcmp(key, "ty")) { if (value < 0 || value > BB_TYMAX) { bbpcg_set_error("ty must be 0 (automatic) .. %d", BB_TYMAX); return BBPCG_EINVAL; } s->opt_ty = (int)value; s->plan_ok = 0; }
+  else if (!strcmp(key, "kc")) { s->opt_kc = value > 0 ? (int)value : 0; s->plan_ok = 0; }
   else if (!strcmp(key, "pdl")) s->pdl = clampi(value, 0, 2);
-  else if (!strcmp(key, "recompute")) s->recompute = value != 0;
   else if (!strcmp(key, "rhs_tiled")) s->rhs_tiled = value != 0;
-  else if (!strcmp(key, "fast_refresh")) s->fast_refresh = value != 0;
-  else if (!strcmp(key, "resid_mb")) s->resid_mb = value == 2 ? 2 : 3;
-  else if (!strcmp(key, "resid_d")) s->resid_d = clampi(value, 2, 3);
-  else if (!strcmp(key, "resid_blocks")) s->resid_blocks = clampi(value, 1, BB_MAXBLOCKS);
-  else if (!strcmp(key, "resid_ppc")) s->resid_ppc = clampi(value, 0, 1 << 20);
   else if (!strcmp(key, "stream_blocks")) s->stream_blocks = clampi(value, 1, BB_MAXBLOCKS);
   else if (!strcmp(key, "check_every")) s->check_every = clampi(value, 1, 1000);
-  else if (!strcmp(key, "comm_timeout_ms")) s->dev.comm.timeout_cycles = value * 2000000ll;   /* ~2 GHz */
+  else if (!strcmp(key, "comm_timeout_ms")) s->dev.comm.timeout_cycles = value > 0 ? value * 2000000ll : -1;   /* ~2 GHz; <= 0: wait for ever, like MPI */
+  else if (!strcmp(key, "comm_reset")) {                    /* tests only: clear a recorded time-out (all ranks must do it together) */
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaMemset(&s->dev.sc->comm_timeout, 0, sizeof(int)));
+    s->h_poll[BB_POLL_COMM] = 0;
+  }
   else if (!strcmp(key, "kernel_timing")) {
     s->kernel_timing = value != 0;
     if (s->kernel_timing && !s->kev) {
@@ -1076,8 +971,8 @@ extern "C" long long bbpcg_get_info(bbpcg_solver *s, const char *key)
   if (!strcmp(key, "pitch")) return s->dev.L.px;
   if (!strcmp(key, "sm_count")) return s->sm_count;
   if (!strcmp(key, "nranks")) return s->nranks;
-  if (!strcmp(key, "tile_tx")) return k_tiles[s->tile].tx;
-  if (!strcmp(key, "tile_ty")) return k_tiles[s->tile].ty;
+  if (!strcmp(key, "tile_tx")) return 128;
+  if (!strcmp(key, "tile_ty") || !strcmp(key, "search_ty")) return make_plan(s) ? -1 : s->plan_ty;
   /* per-kernel device time of the last solve (kernel_timing = 1), nanoseconds / launch counts */
   if (!strcmp(key, "kt_search_ns")) return (long long)(s->kt_search_ms * 1e6);
   if (!strcmp(key, "kt_resid_ns")) return (long long)(s->kt_resid_ms * 1e6);
@@ -1085,10 +980,10 @@ extern "C" long long bbpcg_get_info(bbpcg_solver *s, const char *key)
   if (!strcmp(key, "kt_search_n")) return s->kt_search_n;
   if (!strcmp(key, "kt_resid_n")) return s->kt_resid_n;
   if (!strcmp(key, "kt_refresh_n")) return s->kt_refresh_n;
-  if (!strcmp(key, "search_grid")) return s->last_search_grid;
-  if (!strcmp(key, "search_kc")) return s->last_search_kc;
-  if (!strcmp(key, "search_nbz")) return s->zt_nbz;
+  if (!strcmp(key, "search_grid")) return make_plan(s) ? -1 : (long long)s->plan_nbx * s->plan_nby * s->plan_nbz;
+  if (!strcmp(key, "search_kc")) return make_plan(s) ? -1 : s->plan_kc;
+  if (!strcmp(key, "search_nbz")) return make_plan(s) ? -1 : s->plan_nbz;
   if (!strcmp(key, "pdl")) return pdl_active(s);
-  if (!strcmp(key, "recompute")) return recompute_active(s);
+  if (!strcmp(key, "comm_timeout")) return s->h_poll ? s->h_poll[BB_POLL_COMM] : 0;
   return -1;
 }

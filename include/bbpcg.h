@@ -42,6 +42,8 @@ extern "C" {
 #define BBPCG_TINY_RHS    1   /* (b,b) < (1e-8)^2: phi = 0, 0 iterations                    */
 #define BBPCG_MAXITER     2   /* pp_max_iter+1 iterations without convergence (reference: exit) */
 #define BBPCG_NAN         3   /* (r,z) is NaN (reference: exit)                             */
+#define BBPCG_COMM_TIMEOUT 4  /* a peer rank never arrived in an in-kernel collective: the call returns BBPCG_ECOMM and
+                                 the solver objects of ALL ranks are dead (destroy + re-create); see option comm_timeout_ms */
 
 #define BBPCG_MAX_RANKS 16
 #define BBPCG_BLOB_BYTES 256  /* size of one rank's bbpcg_comm_export() record */
@@ -147,6 +149,9 @@ typedef struct bbpcg_solve_args {
   int         fixed_iters;                 /* >0: run exactly this many iterations, no stop
                                               test (benchmark mode; status CONVERGED)        */
   bbpcg_part_bc_fn part_bc;                /* may be NULL                                    */
+  int         no_refine;                   /* 1: skip coeffs_refine, as the reference does on a rank
+                                              that holds no particle (nparts == 0 while NPARTS > 0,
+                                              src/cuda_solver.cu:139-142)                    */
 } bbpcg_solve_args;
 
 int  bbpcg_solve(bbpcg_solver *s, const bbpcg_solve_args *args, bbpcg_result *res);

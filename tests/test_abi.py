@@ -129,7 +129,7 @@ def test_ctypes_mirrors_match_the_c_structs(tmp_path):
         "bbpcg_result": (L.Result, ["status", "niter", "resid", "sp_rhs", "sp_rq0", "ms_setup", "ms_iter", "ms_total", "launches"]),
         "bb_flow_params": (L.FlowParams, ["rho_f", "pp_residual", "pp_max_iter"]),
         "bbpcg_solve_args": (L.SolveArgs, ["u_star", "v_star", "w_star", "rhs_p", "phi", "phase", "phase_shell", "rho_f", "dt",
-                                           "pp_residual", "pp_max_iter", "use_phase", "fixed_iters", "part_bc"]),
+                                           "pp_residual", "pp_max_iter", "use_phase", "fixed_iters", "part_bc", "no_refine"]),
         "bbpcg_epilogue_args": (L.EpilogueArgs, ["u_star", "v_star", "w_star", "flag_u", "flag_v", "flag_w", "phi", "u", "v", "w",
                                                  "p0", "phase", "p", "rho_f", "dt", "phi_ghosts_valid"]),
         "bb_restart": (L.Restart, ["ttime", "dt0", "dt", "stepnum", "rec_vtk_stepnum_out", "rec_cgns_flow_ttime_out",

@@ -111,34 +111,51 @@ def test_solve_noparts_all_bc_sets(bc):
     p.close()
 
 
-@pytest.mark.parametrize("tile", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
-def test_solve_every_tile_variant(tile):
-    case = Case((40, 24, 36), bc="duct")      # ragged: not a multiple of any tile
-    p = _product(case, options={"tile": tile})
+@pytest.mark.parametrize("ty", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_solve_every_tile_height(ty):
+    """the tile height of the two iteration kernels is a run-time argument picked by the planner (fills the SM slots)"""
+    case = Case((40, 24, 36), bc="duct")      # ragged: not a multiple of any tile (general form of the plane loop)
+    p = _product(case, options={"ty": ty})
+    assert p.solvers[0].info("search_ty") == ty
     _check_solve(case, p)
     p.close()
 
 
-@pytest.mark.parametrize("recompute,tile", [(0, 0), (1, 0), (0, 1), (1, 1), (1, 8)])
-@pytest.mark.parametrize("blocks,parts", [((1, 1, 1), False), ((2, 1, 2), False), ((1, 1, 1), True), ((1, 2, 1), True)])
-def test_recompute_variant_matches_stored_q(recompute, tile, blocks, parts):
-    """64-B iteration (k_resid_tma re-applies the operator) vs the 72-B one (q stored and re-read):
-    both against the oracle, on ragged sizes, decomposed, and with particles."""
+@pytest.mark.parametrize("ty,kc", [(0, 0), (7, 9), (5, 11), (8, 1000)])
+@pytest.mark.parametrize("cells,blocks,parts", [((128, 28, 44), (1, 1, 1), False), ((256, 20, 24), (2, 1, 2), False),
+                                                ((128, 36, 28), (1, 1, 1), True), ((128, 36, 28), (1, 2, 1), True),
+                                                ((36, 28, 44), (2, 1, 2), False), ((36, 28, 44), (1, 2, 1), True)])
+def test_full_and_ragged_tiles(ty, kc, cells, blocks, parts):
+    """in a multiple of 128: the predicate-free XFULL form of both plane loops (with its all-ones-mask fast path next to
+    walls and particles, where it must fall back per warp); other sizes: the general form.  Decomposed and with particles."""
     kw = dict(nparts=3, radius=2.5) if parts else {}
-    case = Case((36, 28, 44), blocks=blocks, bc="sedimentation" if parts else "channel", **kw)
-    p = _product(case, options={"tile": tile, "recompute": recompute, "kc": 9})
-    assert p.solvers[0].info("recompute") == recompute
+    ext = tuple(v for n in cells for v in (0., n / 3.))          # dx = 1/3 in every direction: a sphere is 7.5 cells in radius
+    case = Case(cells, blocks=blocks, bc="sedimentation" if parts else "channel", extent=ext, **kw)
+    p = _product(case, options={"ty": ty, "kc": kc})
     _check_solve(case, p, parts=parts)
     p.close()
 
 
-@pytest.mark.parametrize("opts", [{"taper_g10": 20, "taper_min": 4}, {"taper_g10": 10, "taper_min": 8}, {"kc": 1}, {"kc": 1000}, {"pdl": 0},
-                                  {"fast_refresh": 0}, {"rhs_tiled": 0}, {"fast_refresh": 0, "recompute": 0}])
+@pytest.mark.parametrize("opts", [{"kc": 1}, {"kc": 3, "ty": 4}, {"kc": 1000}, {"pdl": 0}, {"pdl": 1}, {"rhs_tiled": 0}])
 def test_zchunk_plans(opts):
     case = Case((24, 20, 52), bc="cavity")      # > 100 iterations: two true-residual refreshes
     p = _product(case, options=opts)
     _check_solve(case, p)
     p.close()
+
+
+def test_plan_fills_the_sm_slots():
+    """the planner's CTA count for the benchmarked block shapes is a whole number of waves of the 2 x SM-count slots"""
+    import bbpcg
+    from bbpcg.grid import BC_SETS
+    for cells in ((256, 256, 256), (512, 256, 256), (512, 512, 256)):
+        dec = bbpcg.Decomposition.uniform((0., 12., 0., 12., 0., 12.), cells, (1, 1, 1), BC_SETS["duct"])
+        s = bbpcg.PoissonSolver(dec, 0)
+        slots = 2 * s.info("sm_count")
+        grid, ty = s.info("search_grid"), s.info("search_ty")
+        assert 4 <= ty <= 8
+        assert grid % slots == 0 or grid > 6 * slots, (cells, grid, ty, slots)
+        s.close()
 
 
 @pytest.mark.parametrize("cells", [(33, 17, 9), (7, 5, 3), (130, 9, 18), (16, 16, 130)])
