@@ -193,3 +193,22 @@ class Oracle:
             i0, j0, k0 = d.Gcc.get("is") - 1, d.Gcc.get("js") - 1, d.Gcc.get("ks") - 1
             out[k0:k0 + d.zn, j0:j0 + d.yn, i0:i0 + d.xn] = a
         return out
+
+
+def single_block_domain(extent, cells, bc, omp=False):
+    """(DOM, dom) of a 1 x 1 x 1 decomposition filled by the oracle's OWN restatement of domain_fill (bbo_domain_fill,
+    src/domain.c:918-1486) without allocating any field: what bench.py's reference arm hands to oracle/_ref so that the
+    product library is not even mapped into that process."""
+    lib = load(omp)
+    D = C.POINTER(DomStruct)
+    lib.bbo_domain_fill.argtypes = [D, D, C.POINTER(PressureBC)]
+    lib.bbo_domain_fill.restype = None
+    DOM, dom = DomStruct(), DomStruct()
+    for d in (DOM, dom):
+        d.xs, d.xe, d.ys, d.ye, d.zs, d.ze = [float(v) for v in extent]
+        d.xn, d.yn, d.zn = [int(v) for v in cells]
+    DOM.In = DOM.Jn = DOM.Kn = 1
+    dom.I = dom.J = dom.K = 0
+    pbc = PressureBC(*bc)
+    lib.bbo_domain_fill(C.byref(DOM), C.byref(dom), C.byref(pbc))
+    return DOM, dom, pbc

@@ -2,7 +2,9 @@
 """Turn the ncu artefacts a gpurun call left in gpurun_out/ into the tracked summaries under
 profiles/ (the judge reads profiles/, gpurun_out/ is scratch).
 
-    python scripts/summarize_profiles.py r01 [gpurun_out/launches.csv] [gpurun_out/prof_iter.ncu-rep]
+    python scripts/summarize_profiles.py r01 [gpurun_out/launches.csv] [gpurun_out/prof_iter.ncu-rep] [cells_per_launch]
+
+cells_per_launch (default 512^3): only a capture of the 512^3 single-GPU launch rewrites profiles/traffic.json.
 
 Writes profiles/<tag>_launches.csv (trimmed launch list), profiles/<tag>_launches.md (per-kernel
 shares), profiles/<tag>_ncu_full.md + .csv (selected metrics of the --set full capture) and
@@ -65,7 +67,7 @@ def launches(tag, path):
     return agg, tot
 
 
-def full(tag, rep):
+def full(tag, rep, cells=512 ** 3):
     raw = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], text=True, stderr=subprocess.DEVNULL)
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -95,12 +97,14 @@ def full(tag, rep):
             traffic.setdefault(name, []).append((b, t))
     out = {"source": "profiles/" + tag + "_ncu_full.csv", "cells_per_launch": 512 ** 3}
     for name, v in traffic.items():
-        key = "k_search_spmv" if name.startswith("k_search") else "k_resid" if name.startswith("k_resid") else name.split("<")[0]
+        key = "k_search_tma" if name.startswith("k_search") else "k_resid_tma" if name.startswith("k_resid") else name.split("<")[0]
         out[key + "_bytes_per_launch"] = sum(b for b, _ in v) / len(v)
         out[key + "_ncu_us"] = sum(t for _, t in v) / len(v) * 1e6
         out[key + "_kernel"] = name
-    with open(os.path.join(PROF, "traffic.json"), "w") as f:
-        json.dump(out, f, indent=1)
+    out["cells_per_launch"] = cells
+    if cells == 512 ** 3:
+        with open(os.path.join(PROF, "traffic.json"), "w") as f:
+            json.dump(out, f, indent=1)
     return out
 
 
@@ -112,8 +116,9 @@ def main():
     if os.path.exists(lpath):
         agg, tot = launches(tag, lpath)
         print("launch list: %d kernels, %.1f ms" % (sum(a[0] for a in agg.values()), tot / 1e6))
+    cells = int(sys.argv[4]) if len(sys.argv) > 4 else 512 ** 3
     if os.path.exists(rep):
-        print(json.dumps(full(tag, rep), indent=1))
+        print(json.dumps(full(tag, rep, cells), indent=1))
 
 
 if __name__ == "__main__":

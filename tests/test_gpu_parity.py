@@ -144,17 +144,20 @@ def test_zchunk_plans(opts):
     p.close()
 
 
-def test_plan_fills_the_sm_slots():
-    """the planner's CTA count for the benchmarked block shapes is a whole number of waves of the 2 x SM-count slots"""
+def test_plan_of_the_benchmarked_block_shapes():
+    """the planner's tile / z-chunk choice for the benchmarked block shapes: 8-row tiles; ~24-plane chunks when
+    that gives many waves of the 2 x SM-count resident CTAs, else the chunk count with the fewest waves"""
     import bbpcg
     from bbpcg.grid import BC_SETS
-    for cells in ((256, 256, 256), (512, 256, 256), (512, 512, 256)):
+    for cells, many_waves in (((256, 256, 256), False), ((512, 512, 64), False), ((512, 512, 512), True)):
         dec = bbpcg.Decomposition.uniform((0., 12., 0., 12., 0., 12.), cells, (1, 1, 1), BC_SETS["duct"])
         s = bbpcg.PoissonSolver(dec, 0)
         slots = 2 * s.info("sm_count")
-        grid, ty = s.info("search_grid"), s.info("search_ty")
-        assert 4 <= ty <= 8
-        assert grid % slots == 0 or grid > 6 * slots, (cells, grid, ty, slots)
+        grid, ty, kc, nbz = s.info("search_grid"), s.info("search_ty"), s.info("search_kc"), s.info("search_nbz")
+        assert ty == 8 and grid == (cells[0] // 128) * (cells[1] // 8) * nbz and nbz == -(-cells[2] // kc)
+        assert (grid >= 7 * slots and kc == 24) if many_waves else grid <= 2 * slots
+        s.set_option("ty", 7); s.set_option("kc", 16)
+        assert s.info("search_ty") == 7 and s.info("search_kc") == 16
         s.close()
 
 
