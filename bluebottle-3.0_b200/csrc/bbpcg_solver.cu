@@ -38,6 +38,7 @@ struct ExportBlob {                 /* one rank's record for bbpcg_comm_import (
   unsigned long long arena_ptr;     /* valid inside the exporting process */
   unsigned long long arena_bytes;
   cudaIpcMemHandle_t handle;
+  unsigned char uuid[16];           /* of the exporting GPU: two PROCESSES on one GPU must be recognised as sharing it */
 };
 static_assert(sizeof(ExportBlob) <= BBPCG_BLOB_BYTES, "blob too large");
 #define BB_MAGIC 0xbb9c6001u
@@ -75,7 +76,8 @@ struct bbpcg_solver {
   int plan_ty, plan_nbx, plan_nby, plan_nbz, plan_kc;
   int pdl;                          /* programmatic dependent launch of the two iteration kernels: 0 off, 1 on, 2 auto */
   int rhs_tiled;                    /* PP_rhs through shared-memory transposes (default) or the row-walking kernel */
-  int shared_device;                /* some peer rank lives on this same GPU (single-process harness) */
+  int shared_device;                /* some peer rank lives on this same GPU (single-process harness, or two processes on one GPU) */
+  unsigned char uuid[16];
   SearchMaps maps;                  /* tensor maps of the iteration kernels for the planned tile height */
   int kernel_timing;
   cudaEvent_t *kev;                 /* [2*BB_KT_CAP+1] */
@@ -224,6 +226,7 @@ static int create_impl(bbpcg_solver *s, const dom_struct *dom_rank, const dom_st
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, s->device));
   s->sm_count = prop.multiProcessorCount;
+  memcpy(s->uuid, &prop.uuid, 16);
   Dev &d = s->dev;
   d.L = make_layout(g.in, g.jn, g.kn);
   s->amap = make_arena_map(d.L);
@@ -320,6 +323,7 @@ extern "C" int bbpcg_comm_export(bbpcg_solver *s, void *blob)
   b.device = s->device; b.pid = (long long)getpid();
   b.arena_ptr = (unsigned long long)(uintptr_t)s->arena; b.arena_bytes = s->amap.total;
   CU(cudaIpcGetMemHandle(&b.handle, s->arena));
+  memcpy(b.uuid, s->uuid, 16);
   memset(blob, 0, BBPCG_BLOB_BYTES);
   memcpy(blob, &b, sizeof(b));
   return BBPCG_OK;
@@ -339,7 +343,7 @@ extern "C" int bbpcg_comm_import(bbpcg_solver *s, const void *all_blobs, int nra
     dims[p][0] = b.in; dims[p][1] = b.jn; dims[p][2] = b.kn;
     if (p == s->dom.rank) { s->peer_arena[p] = s->arena; continue; }
     if (s->peer_opened[p]) continue;                       /* a repeated import: this peer's mapping is still open */
-    if (b.pid == mypid && b.device == s->device) s->shared_device = 1;
+    if ((b.pid == mypid && b.device == s->device) || !memcmp(b.uuid, s->uuid, 16)) s->shared_device = 1;
     if (b.pid == mypid) {
       /* same process (several ranks driven from one process): the pointer is directly usable;
        * a different device needs peer access */

@@ -10,7 +10,12 @@
  *
  * with `void f(void)` signatures.  recorder_PP() and cuda_part_BC_p() -- callees the library calls back -- are
  * this file's own small stand-ins (same signature; recorder_PP writes the solver_expd.rec line in the column
- * format of src/recorder.c:190-221).  TEST CODE: built and run by tests/test_gpu_dropin.py; single rank.
+ * format of src/recorder.c:190-221).  TEST CODE: built and run by tests/test_dropin.py.
+ *
+ * Multi-rank: one process per rank, as Bluebottle runs under mpirun.  The environment stands in for the launcher:
+ * BB_RANK / BB_NPROCS (OMPI_COMM_WORLD_RANK / _SIZE) and BB_RDV, a directory through which bb_dropin_allgather() -- the
+ * three-line MPI_Allgather hook of INTEGRATION.md -- exchanges the ranks' attach records as files.  Rank r uses GPU
+ * r mod (device count), reads <inputs.bin>.<r> and writes <phi_out.bin>.<r>.
  *
  *   dropin_host <flow.config> <decomp.config> <inputs.bin> <phi_out.bin> <record_dir> <noparts|parts> [pp_max_iter [epilogue_out.bin]]
  *
@@ -23,7 +28,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
+#include <unistd.h>
 #include <cuda_runtime.h>
 
 #include "../include/bbpcg.h"
@@ -48,7 +55,8 @@ static char g_record_dir[1024] = ".";
 void recorder_PP(char *name, int niter, real resid, real etime)
 {
   char path[2048];
-  snprintf(path, sizeof(path), "%s/%s", g_record_dir, name);
+  if (nprocs > 1) snprintf(path, sizeof(path), "%s/%s.%d", g_record_dir, name, rank);   /* the reference's rank 0 writes one line after an MPI_Allreduce */
+  else snprintf(path, sizeof(path), "%s/%s", g_record_dir, name);
   FILE *rec = fopen(path, "a");
   if (!rec) { fprintf(stderr, "cannot open %s\n", path); exit(EXIT_FAILURE); }
   fprintf(rec, "\n");
@@ -60,6 +68,30 @@ void recorder_PP(char *name, int niter, real resid, real etime)
   fprintf(rec, "%-15e", etime);
   fclose(rec);
 }
+}
+
+/* the multi-rank bootstrap hook (include/bb_dropin.h): MPI_Allgather in Bluebottle, files in a rendezvous directory here */
+extern "C" int bb_dropin_allgather(const void *send, void *recv, int bytes_per_rank)
+{
+  static int seq = 0;
+  const char *rdv = getenv("BB_RDV");
+  if (!rdv) return -1;
+  char path[2048], tmp[2048];
+  snprintf(path, sizeof(path), "%s/gather.%d.%d", rdv, seq, rank);
+  snprintf(tmp, sizeof(tmp), "%s.tmp", path);
+  FILE *f = fopen(tmp, "wb");
+  if (!f || fwrite(send, 1, bytes_per_rank, f) != (size_t)bytes_per_rank) return -1;
+  fclose(f);
+  if (rename(tmp, path)) return -1;
+  for (int r = 0; r < nprocs; r++) {
+    snprintf(path, sizeof(path), "%s/gather.%d.%d", rdv, seq, r);
+    FILE *g = NULL;
+    for (int tries = 0; tries < 60000 && !(g = fopen(path, "rb")); tries++) usleep(1000);      /* <= 60 s */
+    if (!g || fread((char *)recv + (size_t)r * bytes_per_rank, 1, bytes_per_rank, g) != (size_t)bytes_per_rank) return -1;
+    fclose(g);
+  }
+  seq++;
+  return 0;
 }
 
 /* stand-in for cuda_part_BC_p (src/cuda_particle.cu:1680): the net effect of part_BC_p on rhs
@@ -92,16 +124,20 @@ int main(int argc, char **argv)
   if (argc < 7) { fprintf(stderr, "usage: %s flow.config decomp.config inputs.bin phi_out.bin record_dir noparts|parts [pp_max_iter]\n", argv[0]); return 2; }
   bb_flow_params fp;
   if (bb_domain_read(argv[1], argv[2], &DOM, &dom, &bc, &fp)) { fprintf(stderr, "%s\n", bbpcg_last_error()); return 2; }
-  if (DOM.In * DOM.Jn * DOM.Kn != 1) { fprintf(stderr, "this miniature host is single rank\n"); return 2; }
+  if (getenv("BB_RANK")) { rank = atoi(getenv("BB_RANK")); nprocs = atoi(getenv("BB_NPROCS")); }
+  if (DOM.In * DOM.Jn * DOM.Kn != nprocs) { fprintf(stderr, "decomposition has %d blocks but BB_NPROCS = %d\n", DOM.In * DOM.Jn * DOM.Kn, nprocs); return 2; }
   rho_f = fp.rho_f; pp_residual = fp.pp_residual; pp_max_iter = argc > 7 ? atoi(argv[7]) : fp.pp_max_iter;
   snprintf(g_record_dir, sizeof(g_record_dir), "%s", argv[5]);
   const bool parts = strcmp(argv[6], "parts") == 0;
   NPARTS = nparts = parts ? 1 : 0;
   int ndev = 0;
   const bool have_gpu = cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0;
+  if (have_gpu) cudaSetDevice(rank % ndev);             /* the reference selects the device before MPI_Init (src/mpi_comm.c:42-63) */
   const dom_struct *d = &dom[rank];
-  FILE *f = fopen(argv[3], "rb");
-  if (!f) { fprintf(stderr, "cannot open %s\n", argv[3]); return 2; }
+  const std::string sfx = nprocs > 1 ? "." + std::to_string(rank) : "";
+  const std::string in_path = argv[3] + sfx, out_path = argv[4] + sfx;
+  FILE *f = fopen(in_path.c_str(), "rb");
+  if (!f) { fprintf(stderr, "cannot open %s\n", in_path.c_str()); return 2; }
   _flag_u = upload<int>(f, d->Gfx.s3b, have_gpu); _flag_v = upload<int>(f, d->Gfy.s3b, have_gpu); _flag_w = upload<int>(f, d->Gfz.s3b, have_gpu);
   _phase = upload<int>(f, d->Gcc.s3b, have_gpu); _phase_shell = upload<int>(f, d->Gcc.s3b, have_gpu);
   _u_star = upload<real>(f, d->Gfx.s3b, have_gpu); _v_star = upload<real>(f, d->Gfy.s3b, have_gpu); _w_star = upload<real>(f, d->Gfz.s3b, have_gpu);
@@ -138,7 +174,7 @@ int main(int argc, char **argv)
   }
   std::vector<real> phi(d->Gcc.s3b);
   cudaMemcpy(phi.data(), _phi, sizeof(real) * phi.size(), cudaMemcpyDeviceToHost);
-  FILE *o = fopen(argv[4], "wb");
+  FILE *o = fopen(out_path.c_str(), "wb");
   fwrite(phi.data(), sizeof(real), phi.size(), o);
   fclose(o);
   bbpcg_dropin_finalize();

@@ -83,3 +83,63 @@ class Product:
     def close(self):
         for s in self.solvers:
             s.close()
+
+
+class TorchProduct:
+    """Like Product, but every input is built on the GPU with bbpcg.synth's torch builders (bit-identical to the numpy
+    ones), so grids of the BENCHMARKED sizes (256^3, 512x256x256, ...) need no host-side oracle state.  All ranks of the
+    decomposition share one process and one GPU."""
+
+    def __init__(self, extent, cells, blocks, bcname, nparts=0, radius=1.0, options=None):
+        import torch
+        from bbpcg import synth
+        from bbpcg.grid import grid_shape
+        self.torch = torch
+        self.dec = bbpcg.Decomposition.uniform(extent, cells, blocks, BC_SETS[bcname])
+        self.n, self.nparts = self.dec.nranks, nparts
+        self.solvers = [bbpcg.PoissonSolver(self.dec, r) for r in range(self.n)]
+        if self.n > 1:
+            blobs = [s.comm_export() for s in self.solvers]
+            for s in self.solvers:
+                s.comm_import(blobs)
+        self.dev = []
+        parts = synth.random_spheres(self.dec.DOM, nparts, radius) if nparts else None
+        for r, s in enumerate(self.solvers):
+            s.set_option("comm_timeout_ms", 20000)
+            for k, v in (options or {}).items():
+                s.set_option(k, v)
+            dom, dv = self.dec.doms[r], s.device
+            d = {}
+            if nparts:
+                d["phase"], d["phase_shell"], d["flag_u"], d["flag_v"], d["flag_w"] = synth.cages_torch(dom, self.dec.DOM, self.dec.bc, parts, dv)
+            else:
+                d["flag_u"], d["flag_v"], d["flag_w"] = synth.flags_noparts_torch(dom, self.dec.DOM, self.dec.bc, dv)
+                d["phase"] = torch.full(grid_shape(dom, "Gcc"), -1, dtype=torch.int32, device=dv)
+                d["phase_shell"] = d["phase"]
+            d["u_star"], d["v_star"], d["w_star"] = synth.velocity_star_torch(dom, self.dec.DOM, self.dec.bc, dv)
+            d["rhs_p"], d["phi"] = s.empty("Gcc"), s.empty("Gcc")
+            self.dev.append(d)
+
+    each = Product.each
+
+    def set_coefficients(self):
+        self.each(lambda r, s, d: s.init_jacobi_preconditioner(d["flag_u"], d["flag_v"], d["flag_w"], d["phase"] if self.nparts else None))
+
+    def solve(self, **kw):
+        if self.nparts:
+            return self.each(lambda r, s, d: s.PP_cg(d["u_star"], d["v_star"], d["w_star"], d["rhs_p"], d["phi"], d["phase"], d["phase_shell"], **kw))
+        return self.each(lambda r, s, d: s.PP_cg_noparts(d["u_star"], d["v_star"], d["w_star"], d["rhs_p"], d["phi"], **kw))
+
+    def gather(self, key):
+        """global interior field (Nz, Ny, Nx) as a torch tensor on the GPU"""
+        D = self.dec.DOM
+        out = self.torch.zeros((D.zn, D.yn, D.xn), dtype=self.torch.float64, device=self.solvers[0].device)
+        for r in range(self.n):
+            d = self.dec.doms[r]
+            i0, j0, k0 = d.Gcc.get("is") - 1, d.Gcc.get("js") - 1, d.Gcc.get("ks") - 1
+            out[k0:k0 + d.zn, j0:j0 + d.yn, i0:i0 + d.xn] = self.dev[r][key][1:-1, 1:-1, 1:-1]
+        return out
+
+    def close(self):
+        for s in self.solvers:
+            s.close()

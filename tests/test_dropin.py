@@ -45,6 +45,23 @@ def _write_case(tmp, case, blocks=(1, 1, 1)):
     return flow, dec, inp
 
 
+def _write_case_ranks(tmp, case, blocks):
+    """flow.config / decomp.config of the decomposition + one inputs.bin.<rank> per block"""
+    flow, dec, inp = _write_case(tmp, case, blocks)
+    os.remove(inp)
+    for r in range(case.o.nblocks):
+        a = case.inputs(r)
+        with open("%s.%d" % (inp, r), "wb") as f:
+            for k in ("flag_u", "flag_v", "flag_w", "phase", "phase_shell", "u_star", "v_star", "w_star"):
+                f.write(np.ascontiguousarray(a[k]).tobytes())
+    return flow, dec, inp
+
+
+def _gpu_count():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
 def _no_gpu():
     import torch
     return not torch.cuda.is_available()
@@ -124,3 +141,70 @@ def test_dropin_epilogue_matches_oracle(tmp_path, bc):
         # phi comes from two different solvers (1e-10 relative L2): compare at the solve's accuracy
         assert np.abs(got - ref)[1:-1, 1:-1, 1:-1].max() <= 1e-8 * np.abs(ref).max(), aid
     assert off == raw.size
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("blocks", [(1, 1, 2), (2, 1, 1)])
+def test_dropin_two_processes_bootstrap_through_the_allgather_hook(tmp_path, blocks):
+    """One process per rank, as under mpirun: each defines the reference's globals, the first entry point bootstraps the
+    peer mapping through bb_dropin_allgather() (bbpcg_dropin.cu:46-54; MPI_Allgather in Bluebottle, files here), the solve
+    and mpi_cuda_exchange_Gcc(_phi) then run over peer memory.  phi of both ranks against the oracle's decomposed solve."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs (two processes time-slicing ONE GPU would spin against each other)")
+    exe = _build()
+    case = Case((32, 28, 36), blocks=blocks, bc="duct")
+    flow, dec, inp = _write_case_ranks(tmp_path, case, blocks)
+    rdv = tmp_path / "rdv"
+    rdv.mkdir()
+    out = str(tmp_path / "phi.bin")
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, BB_RANK=str(r), BB_NPROCS="2", BB_RDV=str(rdv))
+        procs.append(subprocess.Popen([exe, flow, dec, inp, out, str(tmp_path / "record"), "noparts"], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    logs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    ores, _ = case.solve_oracle()
+    case.o.exchange_Gcc(ob.PHI)
+    for r in range(2):
+        g = case.o.dom(r).Gcc
+        phi = np.fromfile("%s.%d" % (out, r), dtype=np.float64).reshape(g.get("knb"), g.get("jnb"), g.get("inb"))
+        ophi = case.o.array(r, ob.PHI)
+        assert rel_l2(phi[1:-1, 1:-1, 1:-1], ophi[1:-1, 1:-1, 1:-1]) < 1e-10
+        # ghosts from the NEIGHBOUR RANK's process (the exchange after the solve, src/bluebottle.c:233)
+        for sl in ((slice(1, -1), slice(1, -1), 0), (slice(1, -1), slice(1, -1), -1), (0, slice(1, -1), slice(1, -1)), (-1, slice(1, -1), slice(1, -1))):
+            assert np.allclose(phi[sl], ophi[sl], rtol=0, atol=1e-10 * np.abs(ophi).max())
+        rec = open(tmp_path / "record" / ("solver_expd.rec.%d" % r)).read().split()
+        assert int(rec[3]) == ores.niter
+
+
+@pytest.mark.gpu
+def test_dropin_nan_prints_and_exits(tmp_path):
+    """src/cuda_solver.cu:245-251: two printf lines naming the iteration and exit(EXIT_FAILURE)"""
+    exe = _build()
+    case = Case((24, 24, 24), bc="periodic")
+    case.o.array(0, ob.U_STAR)[4, 5, 6] = np.nan
+    flow, dec, inp = _write_case(tmp_path, case)
+    p = subprocess.run([exe, flow, dec, inp, str(tmp_path / "phi.bin"), str(tmp_path / "record"), "noparts"], capture_output=True, text=True)
+    assert p.returncode == 1
+    assert "The PP equation did not converge." in p.stdout and "The residual at iteration 1 is nan" in p.stdout
+    assert not os.path.exists(tmp_path / "phi.bin")
+
+
+@pytest.mark.gpu
+def test_dropin_converging_on_the_last_allowed_iteration_still_exits(tmp_path):
+    """src/cuda_solver.cu:192,235-241,271-279: the loop runs q = 1 .. pp_max_iter + 1; converging ON iteration pp_max_iter + 1
+    records the line, breaks, and still fails the `q > pp_max_iter` test"""
+    exe = _build()
+    case = Case((24, 24, 24), bc="periodic")
+    ores, _ = case.solve_oracle()
+    flow, dec, inp = _write_case(tmp_path, case)
+    p = subprocess.run([exe, flow, dec, inp, str(tmp_path / "phi.bin"), str(tmp_path / "record"), "noparts", str(ores.niter - 1)],
+                       capture_output=True, text=True)
+    assert p.returncode == 1 and "The pressure-Poisson equation did not converge." in p.stdout
+    assert "Residual at iteration %d is" % ores.niter in p.stdout
+    rec = open(tmp_path / "record" / "solver_expd.rec").read().split()
+    assert int(rec[3]) == ores.niter                           # recorder_PP was still called (:239)
+    p = subprocess.run([exe, flow, dec, inp, str(tmp_path / "phi.bin"), str(tmp_path / "record"), "noparts", str(ores.niter)],
+                       capture_output=True, text=True)
+    assert p.returncode == 0                                   # one more allowed iteration: a normal convergence
