@@ -64,6 +64,7 @@ class Restart(C.Structure):
 SYMBOLS = [
     "bb_domain_read", "bb_domain_fill", "bb_domain_split", "bb_domain_write_decomp", "bb_domain_free",
     "bb_restart_path", "bb_restart_read", "bb_restart_free",
+    "bb_recorder_PP_init", "bb_recorder_PP", "bb_recorder_PP_init_timed", "bb_recorder_PP_timed",
     "bbpcg_create", "bbpcg_destroy", "bbpcg_comm_export", "bbpcg_comm_import", "bbpcg_set_coefficients",
     "bbpcg_solve", "bbpcg_solve_host", "bbpcg_history", "bbpcg_exchange_Gcc", "bbpcg_rhs", "bbpcg_spmv",
     "bbpcg_set_option", "bbpcg_get_info", "bbpcg_last_error", "bbpcg_version",
@@ -96,6 +97,10 @@ def load_library():
     lib.bb_restart_read.argtypes = [C.c_char_p, D, C.POINTER(Restart)]
     lib.bb_restart_free.argtypes = [C.POINTER(Restart)]
     lib.bb_restart_free.restype = None
+    lib.bb_recorder_PP_init.argtypes = [C.c_char_p, C.c_char_p]
+    lib.bb_recorder_PP_init_timed.argtypes = [C.c_char_p, C.c_char_p]
+    lib.bb_recorder_PP.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]
+    lib.bb_recorder_PP_timed.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, dp]
     lib.bbpcg_create.argtypes = [C.POINTER(vp), D, D, C.POINTER(PressureBC), C.c_int]
     lib.bbpcg_destroy.argtypes = [vp]
     lib.bbpcg_destroy.restype = None

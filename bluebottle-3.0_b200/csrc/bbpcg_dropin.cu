@@ -27,6 +27,10 @@ extern int *_flag_u, *_flag_v, *_flag_w, *_phase, *_phase_shell;
 extern int out_plane;                         /* src/bluebottle.h:650 (solvability) */
 void cuda_part_BC_p(void);                    /* src/cuda_particle.cu:1680 */
 void recorder_PP(char *name, int niter, real resid, real etime);   /* src/recorder.c:190 */
+/* cuda_PP_cg_timed's log (src/recorder.c:223-336); weak: a host linked without recorder.o's timed pair still loads */
+void recorder_PP_init_timed(char *name) __attribute__((weak));
+void recorder_PP_timed(char *name, int niter, real resid, real etime, real etime_spmv, real etime_ip1, real etime_AR1,
+                       real etime_up1, real etime_ip2, real etime_AR2, real etime_up2, real etime_mpi) __attribute__((weak));
 int bb_dropin_allgather(const void *send, void *recv, int bytes_per_rank) __attribute__((weak));
 }
 
@@ -62,10 +66,25 @@ extern "C" void cuda_PP_init_jacobi_preconditioner(void)
   if (bbpcg_set_coefficients(solver(), _flag_u, _flag_v, _flag_w, NPARTS > 0 ? _phase : NULL)) die("bbpcg_set_coefficients");
 }
 
-static void run(int use_phase)
+/* The reference's eight wall-clock segments (src/cuda_solver.cu:372-390) do not exist as separate steps here: an iteration
+ * is two fused kernels with the reductions, the all-reduces and the halo pull inside them.  The columns are filled with
+ * what can be measured (CUDA events around every launch, option kernel_timing):
+ *   spmv  <- k_search_tma  (PP_update_search + SpMV + (p,Ap) + its all-reduce + the halo pull of the NEXT search direction)
+ *   up1   <- k_resid_tma   (PP_update_soln_resid + (r,z) + its all-reduce), incl. the every-50th refresh pair
+ *   ip1, ar1, ip2, ar2, up2, mpi <- 0 (fused into the two above) */
+struct timed_segments { real spmv, up1; };
+
+static void record(char *rname, int timed, int niter, real resid, real etime, const timed_segments &t)
+{
+  if (timed && recorder_PP_timed) recorder_PP_timed(rname, niter, resid, etime, t.spmv, 0., 0., t.up1, 0., 0., 0., 0.);
+  else recorder_PP(rname, niter, resid, etime);
+}
+
+static void run(int use_phase, int timed = 0)
 {
   struct timeval ts, te;
   gettimeofday(&ts, 0);                                     /* src/cuda_solver.cu:42-43 */
+  if (timed) bbpcg_set_option(solver(), "kernel_timing", 1);
   bbpcg_solve_args a;
   bbpcg_result res;
   memset(&a, 0, sizeof(a));
@@ -79,14 +98,22 @@ static void run(int use_phase)
   if (bbpcg_solve(solver(), &a, &res)) die("bbpcg_solve");
   gettimeofday(&te, 0);
   real etime = (te.tv_sec - ts.tv_sec) + (te.tv_usec - ts.tv_usec) * 1.e-6;
-  char rname[] = "solver_expd.rec";
+  char rname_plain[] = "solver_expd.rec", rname_timed[] = "solver_expd_timed.rec";      /* :174, :367 */
+  char *rname = (timed && recorder_PP_timed) ? rname_timed : rname_plain;
+  timed_segments seg = { 0., 0. };
+  if (timed) {
+    seg.spmv = bbpcg_get_info(solver(), "kt_search_ns") * 1.e-9;
+    seg.up1 = (bbpcg_get_info(solver(), "kt_resid_ns") + bbpcg_get_info(solver(), "kt_refresh_ns")) * 1.e-9;
+    bbpcg_set_option(solver(), "kernel_timing", 0);
+    if (stepnum == 1 && recorder_PP_init_timed) recorder_PP_init_timed(rname);          /* :392-394 */
+  }
   switch (res.status) {
     case BBPCG_TINY_RHS:                                   /* :178-189 */
-      recorder_PP(rname, 0, 0., etime);
+      record(rname, timed, 0, 0., etime, seg);
       if (rank == 0) printf("N%d >> Norm of the rhs is less than %.1e, exiting solver\n", rank, 1.e-8);
       break;
     case BBPCG_CONVERGED:                                  /* :235-241 */
-      recorder_PP(rname, res.niter, res.resid, etime);
+      record(rname, timed, res.niter, res.resid, etime, seg);
       if (res.niter > pp_max_iter) {                       /* converged on iteration pp_max_iter + 1: the reference records the line,
                                                               breaks, and still fails its `q > pp_max_iter` test (:271-279) */
         printf("N%d >> The pressure-Poisson equation did not converge.\n", rank);
@@ -111,7 +138,7 @@ static void run(int use_phase)
 
 extern "C" void cuda_PP_cg(void) { run(NPARTS > 0 ? 1 : 0); }          /* the phase-aware operator equals the plain one when phase == -1 everywhere */
 extern "C" void cuda_PP_cg_noparts(void) { run(0); }
-extern "C" void cuda_PP_cg_timed(void) { run(0); }                     /* reference: noparts variant + segment timers, no caller */
+extern "C" void cuda_PP_cg_timed(void) { run(0, 1); }                  /* reference: noparts variant + segment timers -> solver_expd_timed.rec (:302-571), no caller */
 
 extern "C" void mpi_cuda_exchange_Gcc(real *array)
 {

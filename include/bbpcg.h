@@ -108,6 +108,18 @@ int  bb_restart_path(char *out, size_t cap, const char *dir, int rank, int S3);
 int  bb_restart_read(const char *path, const dom_struct *dom_rank, bb_restart *out);
 void bb_restart_free(bb_restart *r);
 
+/* ---- record files (no GPU needed) ----------------------------------------------------------
+ * Writers of the per-solve record lines, byte-compatible with recorder_PP_init / recorder_PP (src/recorder.c:157-221:
+ * <root_dir>/record/solver_expd.rec) and recorder_PP_init_timed / recorder_PP_timed (:223-336: solver_expd_timed.rec with
+ * the eight segment columns spmv, ip1, ar1, up1, ip2, ar2, up2, mpi).  The reference averages the times over the ranks
+ * (MPI_Allreduce, :193-194) before rank 0 writes: pass averaged values and call on rank 0 only.  A missing file is
+ * created with its header first (:201-204); a line is "\n" + fields, so the file never ends in a newline. */
+int  bb_recorder_PP_init(const char *root_dir, const char *name);
+int  bb_recorder_PP(const char *root_dir, const char *name, int stepnum, real ttime, real dt, int niter, real resid, real etime);
+int  bb_recorder_PP_init_timed(const char *root_dir, const char *name);
+int  bb_recorder_PP_timed(const char *root_dir, const char *name, int stepnum, real ttime, real dt, int niter, real resid,
+                          real etime, const real seg[8]);
+
 /* ---- solver object ------------------------------------------------------------------------ */
 /* dom_rank: this rank's filled block; DOM: the global domain; bc: pressure BC types.
  * device: CUDA ordinal, or -1 for the current device.  Allocates the private workspace

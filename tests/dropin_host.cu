@@ -9,15 +9,15 @@
  *     cuda_dom_BC_p(_phi); cuda_project(); cuda_update_p();   // src/bluebottle.c:234,237,250 (when an epilogue file is asked for)
  *
  * with `void f(void)` signatures.  recorder_PP() and cuda_part_BC_p() -- callees the library calls back -- are
- * this file's own small stand-ins (same signature; recorder_PP writes the solver_expd.rec line in the column
- * format of src/recorder.c:190-221).  TEST CODE: built and run by tests/test_dropin.py.
+ * this file's own small stand-ins (same signature; recorder_PP / recorder_PP_timed write the record lines through the
+ * product's bb_recorder_PP* writers).  TEST CODE: built and run by tests/test_dropin.py.
  *
  * Multi-rank: one process per rank, as Bluebottle runs under mpirun.  The environment stands in for the launcher:
  * BB_RANK / BB_NPROCS (OMPI_COMM_WORLD_RANK / _SIZE) and BB_RDV, a directory through which bb_dropin_allgather() -- the
  * three-line MPI_Allgather hook of INTEGRATION.md -- exchanges the ranks' attach records as files.  Rank r uses GPU
  * r mod (device count), reads <inputs.bin>.<r> and writes <phi_out.bin>.<r>.
  *
- *   dropin_host <flow.config> <decomp.config> <inputs.bin> <phi_out.bin> <record_dir> <noparts|parts> [pp_max_iter [epilogue_out.bin]]
+ *   dropin_host <flow.config> <decomp.config> <inputs.bin> <phi_out.bin> <root>/record <noparts|parts|timed> [pp_max_iter [epilogue_out.bin]]
  *
  * epilogue_out.bin: u, v, w (float64, Gfx/Gfy/Gfz s3b) and p (Gcc s3b) after the epilogue with the previous pressure
  *             p0[C] = ((C * 2654435761 mod 2^32) >> 8) / 2^24 - 0.5 (exactly reproducible in numpy).
@@ -49,24 +49,32 @@ int out_plane = 10;                     /* HOMOGENEOUS, src/bluebottle.h:353 */
 real *_u_star = NULL, *_v_star = NULL, *_w_star = NULL, *_rhs_p = NULL, *_phi = NULL;
 real *_u = NULL, *_v = NULL, *_w = NULL, *_p = NULL, *_p0 = NULL;
 int *_flag_u = NULL, *_flag_v = NULL, *_flag_w = NULL, *_phase = NULL, *_phase_shell = NULL;
-static char g_record_dir[1024] = ".";
+static char g_record_dir[1024] = ".";      /* the reference's ROOT_DIR: records go to <ROOT_DIR>/record/ */
 
-/* stand-in for src/recorder.c:190-221 (same columns, single rank: no MPI average) */
+/* src/recorder.c:190-221 and :259-336 through the PRODUCT's record writers (bb_recorder_PP*, include/bbpcg.h): the header
+ * is created on the first line, the columns are the reference's.  Multi-rank: the reference's rank 0 writes one line after
+ * an MPI_Allreduce of the elapsed time; here every rank writes its own <name>.<rank> so that the test sees all of them. */
+static const char *rec_name(char *buf, size_t cap, const char *name)
+{
+  if (nprocs > 1) { snprintf(buf, cap, "%s.%d", name, rank); return buf; }
+  return name;
+}
 void recorder_PP(char *name, int niter, real resid, real etime)
 {
-  char path[2048];
-  if (nprocs > 1) snprintf(path, sizeof(path), "%s/%s.%d", g_record_dir, name, rank);   /* the reference's rank 0 writes one line after an MPI_Allreduce */
-  else snprintf(path, sizeof(path), "%s/%s", g_record_dir, name);
-  FILE *rec = fopen(path, "a");
-  if (!rec) { fprintf(stderr, "cannot open %s\n", path); exit(EXIT_FAILURE); }
-  fprintf(rec, "\n");
-  fprintf(rec, "%-12d", stepnum);
-  fprintf(rec, "%-15e", ttime);
-  fprintf(rec, "%-15e", dt);
-  fprintf(rec, "%-8d", niter);
-  fprintf(rec, "%-15e", resid);
-  fprintf(rec, "%-15e", etime);
-  fclose(rec);
+  char nm[256];
+  if (bb_recorder_PP(g_record_dir, rec_name(nm, sizeof(nm), name), stepnum, ttime, dt, niter, resid, etime)) { fprintf(stderr, "%s\n", bbpcg_last_error()); exit(EXIT_FAILURE); }
+}
+void recorder_PP_init_timed(char *name)
+{
+  char nm[256];
+  if (bb_recorder_PP_init_timed(g_record_dir, rec_name(nm, sizeof(nm), name))) { fprintf(stderr, "%s\n", bbpcg_last_error()); exit(EXIT_FAILURE); }
+}
+void recorder_PP_timed(char *name, int niter, real resid, real etime, real etime_spmv, real etime_ip1, real etime_AR1,
+                       real etime_up1, real etime_ip2, real etime_AR2, real etime_up2, real etime_mpi)
+{
+  char nm[256];
+  const real seg[8] = { etime_spmv, etime_ip1, etime_AR1, etime_up1, etime_ip2, etime_AR2, etime_up2, etime_mpi };
+  if (bb_recorder_PP_timed(g_record_dir, rec_name(nm, sizeof(nm), name), stepnum, ttime, dt, niter, resid, etime, seg)) { fprintf(stderr, "%s\n", bbpcg_last_error()); exit(EXIT_FAILURE); }
 }
 }
 
@@ -128,7 +136,12 @@ int main(int argc, char **argv)
   if (DOM.In * DOM.Jn * DOM.Kn != nprocs) { fprintf(stderr, "decomposition has %d blocks but BB_NPROCS = %d\n", DOM.In * DOM.Jn * DOM.Kn, nprocs); return 2; }
   rho_f = fp.rho_f; pp_residual = fp.pp_residual; pp_max_iter = argc > 7 ? atoi(argv[7]) : fp.pp_max_iter;
   snprintf(g_record_dir, sizeof(g_record_dir), "%s", argv[5]);
-  const bool parts = strcmp(argv[6], "parts") == 0;
+  {                                                     /* <root>/record is what the command line names; keep <root> */
+    size_t n = strlen(g_record_dir);
+    while (n > 1 && g_record_dir[n - 1] == '/') g_record_dir[--n] = 0;
+    if (n >= 7 && !strcmp(g_record_dir + n - 7, "/record")) g_record_dir[n - 7] = 0;
+  }
+  const bool parts = strcmp(argv[6], "parts") == 0, timed = strcmp(argv[6], "timed") == 0;
   NPARTS = nparts = parts ? 1 : 0;
   int ndev = 0;
   const bool have_gpu = cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0;
@@ -149,7 +162,7 @@ int main(int argc, char **argv)
   /* ---- what src/bluebottle.c does ---- */
   cuda_PP_init_jacobi_preconditioner();                 /* :139 -- without a GPU this prints and exits(EXIT_FAILURE) */
   stepnum = 1; ttime = dt;
-  if (parts) cuda_PP_cg(); else cuda_PP_cg_noparts();   /* :228-232 */
+  if (parts) cuda_PP_cg(); else if (timed) cuda_PP_cg_timed(); else cuda_PP_cg_noparts();   /* :228-232 */
   mpi_cuda_exchange_Gcc(_phi);                          /* :233 */
   if (argc > 8) {                                       /* the solve epilogue, src/bluebottle.c:234-250 */
     std::vector<real> p0(d->Gcc.s3b);

@@ -18,6 +18,12 @@ BUILD = os.path.join(ROOT, "tests", "_build")
 EXE = os.path.join(BUILD, "dropin_host")
 
 
+
+def _rec_lines(path):
+    """(header tokens, tokens of the LAST line) of a record file written in the column format of src/recorder.c:157-221"""
+    lines = open(path).read().split("\n")
+    return lines[0].split(), lines[-1].split()
+
 def _build():
     os.makedirs(BUILD, exist_ok=True)
     src = os.path.join(ROOT, "tests", "dropin_host.cu")
@@ -98,7 +104,8 @@ def test_dropin_solve_matches_oracle(tmp_path, bc, parts):
                (slice(1, -1), -1, slice(1, -1)), (0, slice(1, -1), slice(1, -1)), (-1, slice(1, -1), slice(1, -1))):
         assert np.allclose(phi[sl], ophi[sl], rtol=0, atol=1e-10 * np.abs(ophi).max())
     # recorder_PP received (niter, resid): one line in the reference's column format (src/recorder.c:190-221)
-    rec = open(tmp_path / "record" / "solver_expd.rec").read().split()
+    head, rec = _rec_lines(tmp_path / "record" / "solver_expd.rec")
+    assert head == ["stepnum", "ttime", "dt", "niter", "resid", "time", "(s)"]
     assert int(rec[0]) == 1 and int(rec[3]) == ores.niter and abs(float(rec[4]) - ores.resid) <= 1e-5 * ores.resid
 
 
@@ -174,7 +181,7 @@ def test_dropin_two_processes_bootstrap_through_the_allgather_hook(tmp_path, blo
         # ghosts from the NEIGHBOUR RANK's process (the exchange after the solve, src/bluebottle.c:233)
         for sl in ((slice(1, -1), slice(1, -1), 0), (slice(1, -1), slice(1, -1), -1), (0, slice(1, -1), slice(1, -1)), (-1, slice(1, -1), slice(1, -1))):
             assert np.allclose(phi[sl], ophi[sl], rtol=0, atol=1e-10 * np.abs(ophi).max())
-        rec = open(tmp_path / "record" / ("solver_expd.rec.%d" % r)).read().split()
+        rec = _rec_lines(tmp_path / "record" / ("solver_expd.rec.%d" % r))[1]
         assert int(rec[3]) == ores.niter
 
 
@@ -203,8 +210,31 @@ def test_dropin_converging_on_the_last_allowed_iteration_still_exits(tmp_path):
                        capture_output=True, text=True)
     assert p.returncode == 1 and "The pressure-Poisson equation did not converge." in p.stdout
     assert "Residual at iteration %d is" % ores.niter in p.stdout
-    rec = open(tmp_path / "record" / "solver_expd.rec").read().split()
+    rec = _rec_lines(tmp_path / "record" / "solver_expd.rec")[1]
     assert int(rec[3]) == ores.niter                           # recorder_PP was still called (:239)
     p = subprocess.run([exe, flow, dec, inp, str(tmp_path / "phi.bin"), str(tmp_path / "record"), "noparts", str(ores.niter)],
                        capture_output=True, text=True)
     assert p.returncode == 0                                   # one more allowed iteration: a normal convergence
+
+
+@pytest.mark.gpu
+def test_dropin_timed_entry_point_writes_the_segment_log(tmp_path):
+    """cuda_PP_cg_timed (src/cuda_solver.cu:302-571): same solve as cuda_PP_cg_noparts, logged to solver_expd_timed.rec with
+    the eight segment columns of recorder_PP_timed (src/recorder.c:259-336); the fused kernels fill spmv and up1"""
+    exe = _build()
+    case = Case((32, 24, 40), bc="duct")
+    ores, _ = case.solve_oracle()
+    flow, dec, inp = _write_case(tmp_path, case)
+    out = str(tmp_path / "phi.bin")
+    p = subprocess.run([exe, flow, dec, inp, out, str(tmp_path / "record"), "timed"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    g = case.o.dom(0).Gcc
+    phi = np.fromfile(out, dtype=np.float64).reshape(g.get("knb"), g.get("jnb"), g.get("inb"))
+    assert rel_l2(phi[1:-1, 1:-1, 1:-1], case.o.array(0, ob.PHI)[1:-1, 1:-1, 1:-1]) < 1e-10
+    lines = open(tmp_path / "record" / "solver_expd_timed.rec").read().split("\n")
+    assert lines[0].split()[:5] == ["stepnum", "ttime", "dt", "niter", "resid"] and "spmv time (s)" in lines[0] and "mpi time (s)" in lines[0]
+    rec = lines[-1].split()
+    assert len(rec) == 14 and int(rec[3]) == ores.niter
+    total, spmv, up1 = float(rec[5]), float(rec[6]), float(rec[9])
+    assert spmv > 0. and up1 > 0. and spmv + up1 <= total          # device time of the two kernels inside the wall time of the call
+    assert all(float(rec[i]) == 0. for i in (7, 8, 10, 11, 12, 13))
