@@ -49,6 +49,28 @@ class EpilogueArgs(C.Structure):
                 ("rho_f", C.c_double), ("dt", C.c_double), ("phi_ghosts_valid", C.c_int)]
 
 
+class VelocityBC(C.Structure):
+    """bb_velocity_bc: type[c][f], val[c][f]; component c = u, v, w; face f = W, E, S, N, B, T (the reference's order)"""
+    _fields_ = [("type", (C.c_int * 6) * 3), ("val", (C.c_double * 6) * 3)]
+
+    FACES = ("W", "E", "S", "N", "B", "T")
+
+    @classmethod
+    def make(cls, spec):
+        """spec: {"uW": ("D", 1.5), "vN": "N", ...}; everything not named is PERIODIC (no action)"""
+        out = cls()
+        codes = {"P": 0, "D": 1, "N": 2, "PRECURSOR": 3}
+        for key, v in (spec or {}).items():
+            c, f = "uvw".index(key[0]), cls.FACES.index(key[1])
+            kind, val = (v, 0.) if isinstance(v, str) else v
+            out.type[c][f] = codes[kind]
+            out.val[c][f] = float(val)
+        return out
+
+    def flat(self):
+        return [self.type[c][f] for c in range(3) for f in range(6)], [self.val[c][f] for c in range(3) for f in range(6)]
+
+
 class Restart(C.Structure):
     _fields_ = [("ttime", C.c_double), ("dt0", C.c_double), ("dt", C.c_double), ("stepnum", C.c_int),
                 ("rec_vtk_stepnum_out", C.c_int), ("rec_cgns_flow_ttime_out", C.c_double),
@@ -68,10 +90,10 @@ SYMBOLS = [
     "bbpcg_create", "bbpcg_destroy", "bbpcg_comm_export", "bbpcg_comm_import", "bbpcg_set_coefficients",
     "bbpcg_solve", "bbpcg_solve_host", "bbpcg_history", "bbpcg_exchange_Gcc", "bbpcg_rhs", "bbpcg_spmv",
     "bbpcg_set_option", "bbpcg_get_info", "bbpcg_last_error", "bbpcg_version",
-    "bbpcg_dom_BC_p", "bbpcg_epilogue", "bbpcg_exchange", "bbpcg_solvability",
+    "bbpcg_dom_BC_p", "bbpcg_epilogue", "bbpcg_exchange", "bbpcg_solvability", "bbpcg_dom_BC_star", "bbpcg_prologue",
 ]
 DROPIN_SYMBOLS = ["cuda_PP_init_jacobi_preconditioner", "cuda_PP_cg", "cuda_PP_cg_noparts", "cuda_PP_cg_timed",
-                  "mpi_cuda_exchange_Gcc", "mpi_cuda_exchange_Gfx", "mpi_cuda_exchange_Gfy", "mpi_cuda_exchange_Gfz", "cuda_solvability", "cuda_dom_BC_p", "cuda_project", "cuda_update_p", "bbpcg_dropin_finalize"]
+                  "mpi_cuda_exchange_Gcc", "mpi_cuda_exchange_Gfx", "mpi_cuda_exchange_Gfy", "mpi_cuda_exchange_Gfz", "cuda_solvability", "cuda_dom_BC_star", "cuda_dom_BC_p", "cuda_project", "cuda_update_p", "bbpcg_dropin_finalize"]
 
 _lib = None
 
@@ -116,6 +138,8 @@ def load_library():
     lib.bbpcg_exchange.argtypes = [vp, vp, C.c_int]
     lib.bbpcg_solvability.argtypes = [vp, vp, vp, vp, C.c_int, dp]
     lib.bbpcg_dom_BC_p.argtypes = [vp, vp]
+    lib.bbpcg_dom_BC_star.argtypes = [vp, vp, vp, vp, C.POINTER(VelocityBC)]
+    lib.bbpcg_prologue.argtypes = [vp, vp, vp, vp, C.POINTER(VelocityBC), C.c_int, dp]
     lib.bbpcg_epilogue.argtypes = [vp, C.POINTER(EpilogueArgs), dp]
     lib.bbpcg_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
     lib.bbpcg_get_info.argtypes = [vp, C.c_char_p]

@@ -280,6 +280,23 @@ class PoissonSolver:
                 "bbpcg_solvability")
         return [eps[0], eps[1], eps[2]]
 
+    def dom_BC_star(self, u_star, v_star, w_star, vbc):
+        """cuda_dom_BC_star(): the velocity BC table on u*, v*, w* (in place); vbc: lib.VelocityBC or the dict its make() takes"""
+        if not isinstance(vbc, L.VelocityBC):
+            vbc = L.VelocityBC.make(vbc)
+        self._sync_caller_stream()
+        L.check(self.lib.bbpcg_dom_BC_star(self.h, _ptr(u_star), _ptr(v_star), _ptr(w_star), C.byref(vbc)), "bbpcg_dom_BC_star")
+
+    def prologue(self, u_star, v_star, w_star, vbc, out_plane="HOMOGENEOUS"):
+        """src/bluebottle.c:213-225 without particles: BC_star, exchanges, solvability, BC_star, exchanges; returns device ms"""
+        if not isinstance(vbc, L.VelocityBC):
+            vbc = L.VelocityBC.make(vbc)
+        ms = C.c_double()
+        self._sync_caller_stream()
+        L.check(self.lib.bbpcg_prologue(self.h, _ptr(u_star), _ptr(v_star), _ptr(w_star), C.byref(vbc), L.OUT_PLANE[out_plane], C.byref(ms)),
+                "bbpcg_prologue")
+        return ms.value
+
     def dom_BC_p(self, array):
         self._sync_caller_stream()
         L.check(self.lib.bbpcg_dom_BC_p(self.h, _ptr(array)), "bbpcg_dom_BC_p")

@@ -17,7 +17,7 @@ extern "C" {
 extern dom_struct *dom;                       /* src/bluebottle.h:511 */
 extern dom_struct DOM;                        /* src/bluebottle.h:487 */
 extern int rank, nprocs;                      /* src/mpi_comm.h:218-230 */
-extern struct bb_pressure_bc bc;              /* first six ints of BC, src/bluebottle.h:663-668 */
+extern bb_BC bc;                              /* the reference's BC struct, src/bluebottle.h:662-747 (mirrored field for field) */
 extern real rho_f, dt, pp_residual, ttime;    /* src/bluebottle.h:524,560,572,2439 */
 extern int pp_max_iter, stepnum;              /* src/bluebottle.h:2389,2487 */
 extern int NPARTS, nparts;                    /* src/particle.h:319,331 */
@@ -46,7 +46,7 @@ static bbpcg_solver *solver(void)
 {
   if (g_solver) return g_solver;
   /* the reference selects the device before MPI_Init (src/mpi_comm.c:42-63); use it as is */
-  if (bbpcg_create(&g_solver, &dom[rank], &DOM, &bc, -1)) die("bbpcg_create");
+  if (bbpcg_create(&g_solver, &dom[rank], &DOM, (const bb_pressure_bc *)&bc, -1)) die("bbpcg_create");   /* BC opens with the six pressure types */
   if (nprocs > 1) {
     if (!bb_dropin_allgather) { fprintf(stderr, "N%d >> bbpcg: nprocs = %d but the host program does not define bb_dropin_allgather()\n", rank, nprocs); exit(EXIT_FAILURE); }
     char mine[BBPCG_BLOB_BYTES];
@@ -161,6 +161,16 @@ extern "C" void cuda_solvability(void)
 {
   cudaDeviceSynchronize();
   if (bbpcg_solvability(solver(), _u_star, _v_star, _w_star, out_plane, NULL)) die("bbpcg_solvability");
+}
+
+/* src/bluebottle.c:214,222; src/cuda_bluebottle.cu:2111-2311: reads the types and the CURRENT Dirichlet values of bc */
+extern "C" void cuda_dom_BC_star(void)
+{
+  bb_velocity_bc vbc;
+  const bb_bc_entry *comp[3] = { bc.u, bc.v, bc.w };
+  for (int c = 0; c < 3; c++) for (int f = 0; f < 6; f++) { vbc.type[c][f] = comp[c][f].type; vbc.val[c][f] = comp[c][f].D; }
+  cudaDeviceSynchronize();
+  if (bbpcg_dom_BC_star(solver(), _u_star, _v_star, _w_star, &vbc)) die("bbpcg_dom_BC_star");
 }
 
 /* ---- solve epilogue, src/bluebottle.c:233-256 ---- */

@@ -282,4 +282,54 @@ __global__ void __launch_bounds__(256) k_solv_apply(const __grid_constant__ Dev 
   }
 }
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * cuda_dom_BC_star (src/cuda_bluebottle.cu:2111-2311): the velocity boundary-condition table applied to u*, v*, w* on every
+ * face of this block that has no neighbour -- 36 kernels BC_{u,v,w}_{W,E,S,N,B,T}_{D,N} (src/bluebottle_kernel.cu:104-598),
+ * up to 18 launches per call.  Here ONE launch per axis (W/E, S/N, B/T): a thread owns one boundary line of one component
+ * and applies the low face, then the high face -- the reference's order, which matters when a block is 1 cell thick.  The
+ * three axis launches stay separate because a later face reads what an earlier one wrote (BC_u_S_D reads u on the plane
+ * i = _is that BC_u_W_D just set to the wall value).
+ *   normal component, DIRICHLET:   ghost = 2 bc - a(one face in);  wall face = bc                 (:104-132, 300-328, 492-520)
+ *   tangential,      DIRICHLET:   ghost = 8/3 bc - 2 a(first) + 1/3 a(second)                    (:134-190, 270-298, ...)
+ *   NEUMANN (both):               ghost = a(first)                                               (:192-268, 358-434, 522-598)
+ * PERIODIC / PRECURSOR: no action (the switch has no such case). */
+struct BcStarArgs {
+  double *arr[3];          /* u*, v*, w* (Gfx / Gfy / Gfz s3b) */
+  int n[3][3];             /* n[c][axis]: in, jn, kn of component c's grid */
+  int st[3][3];            /* st[c][axis]: element stride of i, j, k in that grid (index macros, src/bluebottle.h:70-73) */
+  int type[3][2];          /* [c][low / high face of this launch's axis]: 0 = leave alone, BB_DIRICHLET, BB_NEUMANN */
+  double val[3][2];
+  int axis;                /* 0: W/E   1: S/N   2: B/T */
+  int a1[3], a2[3];        /* per component: the two tangential axes, a1 the one with the smaller stride */
+};
+
+__global__ void __launch_bounds__(256) k_bc_star(const BcStarArgs a)
+{
+  long long cnt[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) cnt[c] = (a.type[c][0] || a.type[c][1]) ? (long long)a.n[c][a.a1[c]] * a.n[c][a.a2[c]] : 0;
+  const long long total = cnt[0] + cnt[1] + cnt[2];
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    long long u = t;
+    int c = 0;
+    if (u >= cnt[0]) { u -= cnt[0]; c = 1; if (u >= cnt[1]) { u -= cnt[1]; c = 2; } }
+    const int n1 = a.n[c][a.a1[c]];
+    const long long base = (long long)((int)(u % n1) + 1) * a.st[c][a.a1[c]] + (long long)((int)(u / n1) + 1) * a.st[c][a.a2[c]];
+    double *__restrict__ f = a.arr[c] + base;
+    const long long sN = a.st[c][a.axis];
+    const int N = a.n[c][a.axis];             /* _is = 1, _ie = N, _isb = 0, _ieb = N + 1 along the normal */
+    const bool normal = c == a.axis;
+    if (a.type[c][0] == BB_DIRICHLET) {
+      const double bc = a.val[c][0];
+      if (normal) { f[0] = 2. * bc - f[2 * sN]; f[sN] = bc; }
+      else f[0] = 8. / 3. * bc - 2. * f[sN] + 1. / 3. * f[2 * sN];
+    } else if (a.type[c][0] == BB_NEUMANN) f[0] = f[sN];
+    if (a.type[c][1] == BB_DIRICHLET) {
+      const double bc = a.val[c][1];
+      if (normal) { f[(N + 1) * sN] = 2. * bc - f[(N - 1) * sN]; f[N * sN] = bc; }
+      else f[(N + 1) * sN] = 8. / 3. * bc - 2. * f[N * sN] + 1. / 3. * f[(N - 1) * sN];
+    } else if (a.type[c][1] == BB_NEUMANN) f[(N + 1) * sN] = f[N * sN];
+  }
+}
+
 #endif

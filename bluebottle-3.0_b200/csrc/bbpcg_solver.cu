@@ -549,7 +549,7 @@ static int preload_kernels()
   PL(k_build_tab); PL(k_init<256>); PL(k_finish<256>); PL(k_rhs<256>); PL(k_rhs_tiled); PL(k_masks<256>); PL(k_part_rhs_net);
   PL(k_coeffs_refine<256>); PL(k_zero_ghosts); PL(k_xchg_send); PL(k_xchg_recv);
   PL(k_spmv_s3b<256, false>); PL(k_spmv_s3b<256, true>);
-  PL(k_solv_sum); PL(k_solv_apply);
+  PL(k_solv_sum); PL(k_solv_apply); PL(k_bc_star);
   PL(k_bc_p); PL(k_sub_mean);
   PL(k_epilogue<true, true>, EPI_SMEM); PL(k_epilogue<true, false>, EPI_SMEM); PL(k_epilogue<false, true>, EPI_SMEM);
 #undef PL
@@ -757,12 +757,8 @@ extern "C" int bbpcg_epilogue(bbpcg_solver *s, const bbpcg_epilogue_args *a, dou
 }
 
 /* ---- solve prologue: cuda_solvability (bbpcg_epilogue.cuh) -------------------------------------------------- */
-extern "C" int bbpcg_solvability(bbpcg_solver *s, real *u_star, real *v_star, real *w_star, int out_plane, real *eps_out)
+static int enqueue_solvability(bbpcg_solver *s, real *u_star, real *v_star, real *w_star, int out_plane)
 {
-  if (!s || !u_star || !v_star || !w_star) { bbpcg_set_error("bbpcg_solvability: NULL argument"); return BBPCG_EINVAL; }
-  if (!((out_plane >= 0 && out_plane <= 5) || out_plane == 10)) { bbpcg_set_error("bbpcg_solvability: out_plane must be WEST 0 .. TOP 5 or HOMOGENEOUS 10"); return BBPCG_EINVAL; }
-  if (s->nranks == 1 && s->DOM.In * s->DOM.Jn * s->DOM.Kn != 1) { bbpcg_set_error("decomposition has %d blocks: call bbpcg_comm_import first", s->DOM.In * s->DOM.Jn * s->DOM.Kn); return BBPCG_ECOMM; }
-  CU(cudaSetDevice(s->device));
   const dom_struct &d = s->dom;
   SolvArgs a;
   a.u = u_star; a.v = v_star; a.w = w_star; a.out_plane = out_plane;
@@ -778,11 +774,102 @@ extern "C" int bbpcg_solvability(bbpcg_solver *s, real *u_star, real *v_star, re
   k_solv_sum<<<nb, 256, 0, s->stream>>>(s->dev, s->fst, a);
   k_solv_apply<<<nb, 256, 0, s->stream>>>(s->dev, s->fst, a);
   s->launches += 2;
+  return BBPCG_OK;
+}
+
+static int check_out_plane(int out_plane, const char *who)
+{
+  if (!((out_plane >= 0 && out_plane <= 5) || out_plane == 10)) { bbpcg_set_error("%s: out_plane must be WEST 0 .. TOP 5 or HOMOGENEOUS 10", who); return BBPCG_EINVAL; }
+  return BBPCG_OK;
+}
+
+extern "C" int bbpcg_solvability(bbpcg_solver *s, real *u_star, real *v_star, real *w_star, int out_plane, real *eps_out)
+{
+  if (!s || !u_star || !v_star || !w_star) { bbpcg_set_error("bbpcg_solvability: NULL argument"); return BBPCG_EINVAL; }
+  if (check_out_plane(out_plane, "bbpcg_solvability")) return BBPCG_EINVAL;
+  if (s->nranks == 1 && s->DOM.In * s->DOM.Jn * s->DOM.Kn != 1) { bbpcg_set_error("decomposition has %d blocks: call bbpcg_comm_import first", s->DOM.In * s->DOM.Jn * s->DOM.Kn); return BBPCG_ECOMM; }
+  CU(cudaSetDevice(s->device));
+  int rc = enqueue_solvability(s, u_star, v_star, w_star, out_plane);
+  if (rc) return rc;
   if (eps_out) CU(cudaMemcpyAsync(s->h_scal, s->dev.sc, sizeof(Scal), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(s->stream));
   if (eps_out) { eps_out[0] = s->h_scal->eps[0]; eps_out[1] = s->h_scal->eps[1]; eps_out[2] = s->h_scal->eps[2]; }
   return comm_check(s, "bbpcg_solvability");
+}
+
+/* ---- solve prologue: cuda_dom_BC_star (bbpcg_epilogue.cuh) -------------------------------------------------- */
+/* one launch per axis whose faces carry a DIRICHLET / NEUMANN entry on a side without a neighbour
+ * (`dom[rank].w == MPI_PROC_NULL`, cuda_bluebottle.cu:2114 ...) */
+static int enqueue_bc_star(bbpcg_solver *s, real *u_star, real *v_star, real *w_star, const bb_velocity_bc *vbc)
+{
+  const dom_struct &d = s->dom;
+  const grid_info *g[3] = { &d.Gfx, &d.Gfy, &d.Gfz };
+  const int nbr[6] = { d.w, d.e, d.s, d.n, d.b, d.t };           /* the reference's face order W, E, S, N, B, T */
+  BcStarArgs a;
+  memset(&a, 0, sizeof(a));
+  a.arr[0] = u_star; a.arr[1] = v_star; a.arr[2] = w_star;
+  for (int c = 0; c < 3; c++) { a.n[c][0] = g[c]->in; a.n[c][1] = g[c]->jn; a.n[c][2] = g[c]->kn; }
+  /* index macros, src/bluebottle.h:70-73 */
+  a.st[0][0] = d.Gfx.s2b; a.st[0][1] = 1;         a.st[0][2] = d.Gfx.s1b;
+  a.st[1][0] = d.Gfy.s1b; a.st[1][1] = d.Gfy.s2b; a.st[1][2] = 1;
+  a.st[2][0] = 1;         a.st[2][1] = d.Gfz.s1b; a.st[2][2] = d.Gfz.s2b;
+  for (int axis = 0; axis < 3; axis++) {
+    a.axis = axis;
+    long long work = 0;
+    for (int c = 0; c < 3; c++) {
+      int t1 = (axis + 1) % 3, t2 = (axis + 2) % 3;
+      if (a.st[c][t1] > a.st[c][t2]) { int t = t1; t1 = t2; t2 = t; }
+      a.a1[c] = t1; a.a2[c] = t2;
+      for (int side = 0; side < 2; side++) {
+        const int f = 2 * axis + side;
+        const int ty = vbc->type[c][f];
+        a.type[c][side] = (nbr[f] < 0 && (ty == BB_DIRICHLET || ty == BB_NEUMANN)) ? ty : 0;
+        a.val[c][side] = vbc->val[c][f];
+      }
+      if (a.type[c][0] || a.type[c][1]) work += (long long)a.n[c][t1] * a.n[c][t2];
+    }
+    if (!work) continue;
+    k_bc_star<<<clampi((work + 255) / 256, 1, s->sm_count * 8), 256, 0, s->stream>>>(a);
+    s->launches++;
+  }
+  return BBPCG_OK;
+}
+
+extern "C" int bbpcg_dom_BC_star(bbpcg_solver *s, real *u_star, real *v_star, real *w_star, const bb_velocity_bc *vbc)
+{
+  if (!s || !u_star || !v_star || !w_star || !vbc) { bbpcg_set_error("bbpcg_dom_BC_star: NULL argument"); return BBPCG_EINVAL; }
+  CU(cudaSetDevice(s->device));
+  int rc = enqueue_bc_star(s, u_star, v_star, w_star, vbc);
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  return BBPCG_OK;
+}
+
+/* the whole particle-free prologue of src/bluebottle.c:213-225 enqueued back to back, one host synchronisation at the end */
+extern "C" int bbpcg_prologue(bbpcg_solver *s, real *u_star, real *v_star, real *w_star, const bb_velocity_bc *vbc, int out_plane, double *ms_out)
+{
+  if (!s || !u_star || !v_star || !w_star || !vbc) { bbpcg_set_error("bbpcg_prologue: NULL argument"); return BBPCG_EINVAL; }
+  if (check_out_plane(out_plane, "bbpcg_prologue")) return BBPCG_EINVAL;
+  if (s->nranks == 1 && s->DOM.In * s->DOM.Jn * s->DOM.Kn != 1) { bbpcg_set_error("decomposition has %d blocks: call bbpcg_comm_import first", s->DOM.In * s->DOM.Jn * s->DOM.Kn); return BBPCG_ECOMM; }
+  CU(cudaSetDevice(s->device));
+  if (comm_check(s, "bbpcg_prologue")) return BBPCG_ECOMM;
+  CU(cudaEventRecord(s->ev[0], s->stream));
+  int rc = 0;
+  for (int pass = 0; pass < 2 && !rc; pass++) {
+    if (pass == 1) rc = enqueue_solvability(s, u_star, v_star, w_star, out_plane);             /* bluebottle.c:220 */
+    if (!rc) rc = enqueue_bc_star(s, u_star, v_star, w_star, vbc);                            /* :214, :222 */
+    if (!rc) rc = enqueue_exchange(s, u_star, BBPCG_GFX);                                     /* :215-217, :223-225 */
+    if (!rc) rc = enqueue_exchange(s, v_star, BBPCG_GFY);
+    if (!rc) rc = enqueue_exchange(s, w_star, BBPCG_GFZ);
+  }
+  if (rc) { cudaStreamSynchronize(s->stream); return rc; }
+  CU(cudaEventRecord(s->ev[1], s->stream));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  if (ms_out) { float ms = 0.f; cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]); *ms_out = ms; }
+  return comm_check(s, "bbpcg_prologue");
 }
 
 /* ---- the solve ----------------------------------------------------------------------------- */

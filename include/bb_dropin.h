@@ -12,6 +12,7 @@
  *   mpi_cuda_exchange_Gcc(real *array)   src/mpi_comm.h:318, 19 call sites outside the solver
  *   mpi_cuda_exchange_Gfx/_Gfy/_Gfz(real *array)   src/mpi_comm.h:335,352,369; 24 call sites in src/bluebottle.c
  *   cuda_solvability                     src/cuda_bluebottle.cu:2313, called src/bluebottle.c:220 (reads the global out_plane)
+ *   cuda_dom_BC_star                     src/cuda_bluebottle.cu:2111, called src/bluebottle.c:214,222 (reads the velocity entries of bc)
  * and, for the solve epilogue (link instead of the same-named functions of cuda_bluebottle.o):
  *   cuda_dom_BC_p(real *array)           src/cuda_bluebottle.cu:2536, called src/bluebottle.c:234,255
  *   cuda_project                         src/cuda_bluebottle.cu:2495, called src/bluebottle.c:237
@@ -46,6 +47,7 @@ void mpi_cuda_exchange_Gfx(real *array);
 void mpi_cuda_exchange_Gfy(real *array);
 void mpi_cuda_exchange_Gfz(real *array);
 void cuda_solvability(void);
+void cuda_dom_BC_star(void);
 void cuda_dom_BC_p(real *array);
 void cuda_project(void);
 void cuda_update_p(void);

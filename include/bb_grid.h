@@ -4,7 +4,7 @@
  * bbpcg library.  They restate, field for field and in the same order, the reference's
  *   grid_info   (src/domain.h:52-95)
  *   dom_struct  (src/domain.h:168-210)
- *   BC          (src/bluebottle.h:662-747; only the six pressure entries are read here)
+ *   BC          (src/bluebottle.h:662-747; the pressure types and, for cuda_dom_BC_star, the velocity types/values)
  * and the four index macros (src/bluebottle.h:70-73).  sizeof(dom_struct) must be 880
  * bytes (0x370) -- checked by a static assertion below -- so that a `dom_struct *dom`
  * owned by the reference host program can be handed to this library unchanged.
@@ -73,6 +73,34 @@ typedef struct dom_struct {     /* src/domain.h:168-210 */
 typedef struct bb_pressure_bc {
   int pW, pE, pS, pN, pB, pT;
 } bb_pressure_bc;
+
+/* One velocity entry of the reference's BC struct (src/bluebottle.h:669-740): the type, then the maximum, the current
+ * and the acceleration of the DIRICHLET value.  cuda_dom_BC_star reads the type and the current value. */
+#define BB_PRECURSOR 3          /* src/bluebottle.h:254: no action in cuda_dom_BC_star's switch */
+typedef struct bb_bc_entry { int type; real Dm, D, Da; } bb_bc_entry;
+
+/* The whole BC struct, field for field (src/bluebottle.h:662-747): six pressure types, then u, v, w on W, E, S, N, B, T,
+ * then the six screen offsets.  The reference's global `bc` can be read through a `const bb_BC *`. */
+typedef struct bb_BC {
+  int pW, pE, pS, pN, pB, pT;
+  bb_bc_entry u[6], v[6], w[6];                 /* [W, E, S, N, B, T] */
+  real dsW, dsE, dsS, dsN, dsB, dsT;
+} bb_BC;
+
+/* Explicit-argument form of what cuda_dom_BC_star reads: type[c][f] / val[c][f] of component c (0 u, 1 v, 2 w) on face f
+ * (0 W, 1 E, 2 S, 3 N, 4 B, 5 T -- the reference's order). */
+typedef struct bb_velocity_bc {
+  int  type[3][6];
+  real val[3][6];
+} bb_velocity_bc;
+
+#if defined(__cplusplus)
+static_assert(sizeof(bb_bc_entry) == 32, "BC entry layout (int + pad + 3 reals)");
+static_assert(sizeof(bb_BC) == 24 + 18 * 32 + 48, "BC must match the reference (648 bytes)");
+#else
+_Static_assert(sizeof(bb_bc_entry) == 32, "BC entry layout (int + pad + 3 reals)");
+_Static_assert(sizeof(bb_BC) == 24 + 18 * 32 + 48, "BC must match the reference (648 bytes)");
+#endif
 
 #if defined(__cplusplus)
 static_assert(sizeof(grid_info) == 42 * sizeof(int), "grid_info layout");

@@ -229,6 +229,19 @@ int  bbpcg_epilogue(bbpcg_solver *s, const bbpcg_epilogue_args *args, double *ms
 #define BBPCG_HOMOGENEOUS 10
 int  bbpcg_solvability(bbpcg_solver *s, real *u_star, real *v_star, real *w_star, int out_plane, real *eps_out);
 
+/* = cuda_dom_BC_star() (src/cuda_bluebottle.cu:2111-2311): the velocity boundary-condition table on u*, v*, w* -- on every
+ * face of this block without a neighbour, per component: DIRICHLET (wall-normal component: ghost = 2 bc - inner face, wall
+ * face = bc; tangential: ghost = 8/3 bc - 2 a1 + 1/3 a2) or NEUMANN (ghost = first value); PERIODIC / PRECURSOR entries are
+ * left alone, faces only (BC_{u,v,w}_{W,E,S,N,B,T}_{D,N}, src/bluebottle_kernel.cu:104-598).  Three launches (one per
+ * axis, W before E etc. inside a thread) instead of up to 18.  Not collective. */
+int  bbpcg_dom_BC_star(bbpcg_solver *s, real *u_star, real *v_star, real *w_star, const bb_velocity_bc *vbc);
+
+/* The particle-free prologue of the pressure solve, src/bluebottle.c:213-225, in ONE call with one host synchronisation:
+ *   cuda_dom_BC_star; exchange Gfx/Gfy/Gfz;  cuda_solvability;  cuda_dom_BC_star; exchange Gfx/Gfy/Gfz
+ * (with particles the caller interleaves cuda_part_BC_star and uses the separate entry points).  COLLECTIVE.
+ * ms_out (may be NULL): device time of the call. */
+int  bbpcg_prologue(bbpcg_solver *s, real *u_star, real *v_star, real *w_star, const bb_velocity_bc *vbc, int out_plane, double *ms_out);
+
 /* Unit entry points used by the parity tests (same kernels the solve uses). */
 int  bbpcg_rhs(bbpcg_solver *s, const real *u_star, const real *v_star, const real *w_star,
                real rho_f, real dt, real *rhs_p);

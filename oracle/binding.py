@@ -72,6 +72,7 @@ def load(omp=False):
     lib.bbo_exchange.argtypes = [C.c_void_p, C.c_int]
     lib.bbo_solvability.argtypes = [C.c_void_p, C.c_int, dp]
     lib.bbo_dom_BC_p.argtypes = [C.c_void_p, C.c_int]
+    lib.bbo_dom_BC_star.argtypes = [C.c_void_p, ip, dp]
     lib.bbo_project.argtypes = [C.c_void_p, C.c_double, C.c_double]
     lib.bbo_update_p.argtypes = [C.c_void_p]
     lib.bbo_update_p.restype = C.c_double
@@ -159,6 +160,11 @@ class Oracle:
 
     def dom_BC_p(self, aid):
         self.lib.bbo_dom_BC_p(self.h, aid)
+
+    def dom_BC_star(self, types, vals):
+        """cuda_dom_BC_star on the oracle's u_star / v_star / w_star (in place); 18 types + 18 values, component-major
+        (u on W,E,S,N,B,T, then v, then w)"""
+        self.lib.bbo_dom_BC_star(self.h, _arr([int(t) for t in types], C.c_int), _arr([float(v) for v in vals], C.c_double))
 
     def project(self, rho_f=1.0, dt=1e-3):
         self.lib.bbo_project(self.h, rho_f, dt)

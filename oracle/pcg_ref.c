@@ -730,6 +730,64 @@ void bbo_solvability(bbo_state *s, int out_plane, real eps[3])
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* cuda_dom_BC_star, src/cuda_bluebottle.cu:2111-2311: on every side of a block that has no neighbour (MPI_PROC_NULL),
+ * faces in the order W, E, S, N, B, T and components u, v, w inside a face, a switch on the velocity BC type launches
+ * BC_{u,v,w}_{face}_D(array, value) or BC_{u,v,w}_{face}_N(array) (src/bluebottle_kernel.c:104-598); PERIODIC and
+ * PRECURSOR fall through.  The later faces read what the earlier ones wrote, so the order is kept.
+ *   DIRICHLET, wall-normal component (BC_u_W_D :104-117, BC_u_E_D :119-132, BC_v_S_D :300-313, BC_v_N_D :315-328,
+ *     BC_w_B_D :492-505, BC_w_T_D :507-520):   ghost = 2.*bc - a[one face inside the wall face];  a[wall face] = bc
+ *   DIRICHLET, tangential (e.g. BC_u_N_D :134-147, BC_v_W_D :270-283):
+ *     ghost = 8./3.*bc - 2.*a[first interior] + 1./3.*a[second interior]
+ *   NEUMANN (e.g. BC_u_W_N :192-203):          ghost = a[first: the wall face for the normal component]
+ * Index ranges: the grid's own in / jn / kn of the two tangential directions (1..n), no edges.
+ * type / val: 18 entries, component-major: u on W,E,S,N,B,T, then v, then w. */
+static size_t comp_loc(int comp, const grid_info *g, int i, int j, int k)
+{
+  return comp == 0 ? (size_t)GFX_LOC(i, j, k, g->s1b, g->s2b) : comp == 1 ? (size_t)GFY_LOC(i, j, k, g->s1b, g->s2b)
+                                                                            : (size_t)GFZ_LOC(i, j, k, g->s1b, g->s2b);
+}
+
+static void bc_star_face(real *a, int comp, const grid_info *g, int face, int type, real bc)
+{
+  const int axis = face / 2, high = face & 1;
+  const int n[3] = { g->in, g->jn, g->kn };
+  const int t1 = (axis + 1) % 3, t2 = (axis + 2) % 3;
+  /* along the normal: _s = 1, _e = n, _sb = 0, _eb = n + 1 (src/domain.c:1262-1478) */
+  const int gh = high ? n[axis] + 1 : 0, first = high ? n[axis] : 1, second = high ? n[axis] - 1 : 2;
+  int p, q;
+  if (type != BB_DIRICHLET && type != BB_NEUMANN) return;
+  for (q = 1; q <= n[t2]; q++) for (p = 1; p <= n[t1]; p++) {
+    int c[3], cg[3], c1[3], c2[3];
+    c[t1] = p; c[t2] = q;
+    memcpy(cg, c, sizeof(c)); memcpy(c1, c, sizeof(c)); memcpy(c2, c, sizeof(c));
+    cg[axis] = gh; c1[axis] = first; c2[axis] = second;
+    {
+      const size_t G = comp_loc(comp, g, cg[0], cg[1], cg[2]), F = comp_loc(comp, g, c1[0], c1[1], c1[2]),
+                   S = comp_loc(comp, g, c2[0], c2[1], c2[2]);
+      if (type == BB_NEUMANN) a[G] = a[F];
+      else if (comp == axis) { a[G] = 2. * bc - a[S]; a[F] = bc; }
+      else a[G] = 8. / 3. * bc - 2. * a[F] + 1. / 3. * a[S];
+    }
+  }
+}
+
+void bbo_dom_BC_star(bbo_state *s, const int *type, const real *val)
+{
+  int c, face, comp;
+  for (c = 0; c < s->nblocks; c++) {
+    const dom_struct *d = &s->dom[c];
+    bbo_block *b = &s->blk[c];
+    const int nbr[6] = { d->w, d->e, d->s, d->n, d->b, d->t };
+    real *arr[3] = { b->u_star, b->v_star, b->w_star };
+    const grid_info *g[3] = { &d->Gfx, &d->Gfy, &d->Gfz };
+    for (face = 0; face < 6; face++) {
+      if (nbr[face] >= 0) continue;                        /* dom[rank].w == MPI_PROC_NULL, :2114 ... */
+      for (comp = 0; comp < 3; comp++) bc_star_face(arr[comp], comp, g[comp], face, type[comp * 6 + face], val[comp * 6 + face]);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* The solve epilogue, src/bluebottle.c:233-256.
  *
  * cuda_dom_BC_p, src/cuda_bluebottle.cu:2536-2589 with BC_p_{W,E,S,N,B,T}_N, src/bluebottle_kernel.cu:26-102:

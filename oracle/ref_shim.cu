@@ -449,6 +449,44 @@ int bbref_solvability(real *u_h, real *v_h, real *w_h, int out_plane_, real *eps
   return 0;
 }
 
+/* cuda_dom_BC_star (cuda_bluebottle.cu:2111-2311; its translation unit is not linked -- it drags in the whole flow
+ * solver): the host switch table restated, every KERNEL the reference's own BC_{u,v,w}_{W,E,S,N,B,T}_{D,N}
+ * (bluebottle_kernel.cu:104-598) with the reference's launch shapes (blocks.Gf?.num_in / _jn / _kn). */
+#define SHIM_BC_COMP(C, G, ARR, F, SHAPE)                                                                             \
+  switch (bc.C##F) {                                                                                                  \
+    case DIRICHLET: BC_##C##_##F##_D<<<blocks.G.num_##SHAPE, blocks.G.dim_##SHAPE>>>(ARR, bc.C##F##D); break;         \
+    case NEUMANN:   BC_##C##_##F##_N<<<blocks.G.num_##SHAPE, blocks.G.dim_##SHAPE>>>(ARR); break;                     \
+  }
+#define SHIM_BC_FACE(NBR, F, SHAPE)                                                                                   \
+  if (dom[rank].NBR == MPI_PROC_NULL) {                                                                               \
+    SHIM_BC_COMP(u, Gfx, _u_star, F, SHAPE) SHIM_BC_COMP(v, Gfy, _v_star, F, SHAPE) SHIM_BC_COMP(w, Gfz, _w_star, F, SHAPE) \
+  }
+static void shim_dom_BC_star(void)
+{
+  SHIM_BC_FACE(w, W, in) SHIM_BC_FACE(e, E, in) SHIM_BC_FACE(s, S, jn) SHIM_BC_FACE(n, N, jn) SHIM_BC_FACE(b, B, kn) SHIM_BC_FACE(t, T, kn)
+}
+
+/* type / val: 18 entries, component-major (u on W,E,S,N,B,T, then v, then w); arrays are host, in place */
+int bbref_dom_BC_star(real *u_h, real *v_h, real *w_h, const int *type, const real *val)
+{
+  const dom_struct *d = &dom[rank];
+  int *ty[18] = { &bc.uW, &bc.uE, &bc.uS, &bc.uN, &bc.uB, &bc.uT, &bc.vW, &bc.vE, &bc.vS, &bc.vN, &bc.vB, &bc.vT,
+                  &bc.wW, &bc.wE, &bc.wS, &bc.wN, &bc.wB, &bc.wT };
+  real *vl[18] = { &bc.uWD, &bc.uED, &bc.uSD, &bc.uND, &bc.uBD, &bc.uTD, &bc.vWD, &bc.vED, &bc.vSD, &bc.vND, &bc.vBD, &bc.vTD,
+                   &bc.wWD, &bc.wED, &bc.wSD, &bc.wND, &bc.wBD, &bc.wTD };
+  for (int e = 0; e < 18; e++) { *ty[e] = type[e]; *vl[e] = val[e]; }
+  CK(cudaMemcpy(_u_star, u_h, (size_t)d->Gfx.s3b * sizeof(real), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(_v_star, v_h, (size_t)d->Gfy.s3b * sizeof(real), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(_w_star, w_h, (size_t)d->Gfz.s3b * sizeof(real), cudaMemcpyHostToDevice));
+  shim_dom_BC_star();
+  CK(cudaDeviceSynchronize());
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(u_h, _u_star, (size_t)d->Gfx.s3b * sizeof(real), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(v_h, _v_star, (size_t)d->Gfy.s3b * sizeof(real), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(w_h, _w_star, (size_t)d->Gfz.s3b * sizeof(real), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 /* device pointers of the reference's arrays, for the benchmark's device-resident leg: 0 phi, 1 p0, 2 p */
 void *bbref_dev_ptr(int which) { return which == 0 ? (void *)_phi : which == 1 ? (void *)_p0 : (void *)_p; }
 

@@ -83,6 +83,7 @@ def load_ref():
     lib.bbref_epilogue.argtypes = [vp, vp, vp, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
     lib.bbref_exchange_face.argtypes = [vp, C.c_int]
     lib.bbref_solvability.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_double)]
+    lib.bbref_dom_BC_star.argtypes = [vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_double)]
     lib.bbref_dev_ptr.argtypes = [C.c_int]
     lib.bbref_dev_ptr.restype = C.c_void_p
     return lib
@@ -116,3 +117,34 @@ def face_exchange_inputs(case, rank, seed):
     d = case.o.dom(rank)
     rng = np.random.default_rng(seed + 1000 * rank)
     return {k: (rng.standard_normal(grid_shape(d, g)), code) for k, g, code in (("u", "Gfx", 1), ("v", "Gfy", 2), ("w", "Gfz", 3))}
+
+
+# ---- cuda_dom_BC_star: velocity BC tables, 18 (type, value) pairs, component-major (u on W,E,S,N,B,T, then v, then w) ----
+_P, _D, _N, _PRE = 0, 1, 2, 3        # PERIODIC, DIRICHLET, NEUMANN, PRECURSOR (src/bluebottle.h:218-254)
+BC_STAR_TABLES = {
+    "dirichlet": ([_D] * 18, [0.1 * (e + 1) * (-1) ** e for e in range(18)]),
+    "neumann": ([_N] * 18, [0.0] * 18),
+    # no-slip walls with a lid: u = 1 on the NORTH wall, everything else 0 (the pattern of examples/lid-driven-cavity)
+    "cavity_lid": ([_D] * 18, [0., 0., 0., 1., 0., 0.] + [0.] * 12),
+    "mixed": ([_D, _N, _D, _D, _P, _PRE, _N, _D, _N, _D, _D, _N, _PRE, _P, _D, _N, _D, _D],
+              [1.5, 9., -0.25, 0., 7., 7., 9., 0.75, 9., -1.25, 2., 9., 7., 7., 0.5, 9., -0.125, 3.]),
+}
+
+
+def velocity_bc(table):
+    """lib.VelocityBC of a BC_STAR_TABLES entry"""
+    from bbpcg.lib import VelocityBC
+    types, vals = BC_STAR_TABLES[table] if isinstance(table, str) else table
+    out = VelocityBC()
+    for e in range(18):
+        out.type[e // 6][e % 6] = types[e]
+        out.val[e // 6][e % 6] = vals[e]
+    return out
+
+
+def ref_dom_BC_star(lib, case, arrs, table):
+    """the reference's own BC_* kernels (O1) on host copies of one block's u*, v*, w* (in place)"""
+    types, vals = BC_STAR_TABLES[table] if isinstance(table, str) else table
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    assert lib.bbref_dom_BC_star(P(arrs["u"]), P(arrs["v"]), P(arrs["w"]), (C.c_int * 18)(*types), (C.c_double * 18)(*vals)) == 0
+    return arrs

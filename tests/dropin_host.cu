@@ -41,7 +41,7 @@ extern "C" {
 dom_struct *dom = NULL;
 dom_struct DOM;
 int rank = 0, nprocs = 1;
-bb_pressure_bc bc;                      /* the reference's BC struct opens with these six ints */
+bb_BC bc;                               /* the reference's BC struct (include/bb_grid.h mirrors it field for field) */
 real rho_f = 1., dt = 1e-3, pp_residual = 1e-6, ttime = 0.;
 int pp_max_iter = 2000, stepnum = 0;
 int NPARTS = 0, nparts = 0;
@@ -131,7 +131,7 @@ int main(int argc, char **argv)
 {
   if (argc < 7) { fprintf(stderr, "usage: %s flow.config decomp.config inputs.bin phi_out.bin record_dir noparts|parts [pp_max_iter]\n", argv[0]); return 2; }
   bb_flow_params fp;
-  if (bb_domain_read(argv[1], argv[2], &DOM, &dom, &bc, &fp)) { fprintf(stderr, "%s\n", bbpcg_last_error()); return 2; }
+  if (bb_domain_read(argv[1], argv[2], &DOM, &dom, (bb_pressure_bc *)&bc, &fp)) { fprintf(stderr, "%s\n", bbpcg_last_error()); return 2; }
   if (getenv("BB_RANK")) { rank = atoi(getenv("BB_RANK")); nprocs = atoi(getenv("BB_NPROCS")); }
   if (DOM.In * DOM.Jn * DOM.Kn != nprocs) { fprintf(stderr, "decomposition has %d blocks but BB_NPROCS = %d\n", DOM.In * DOM.Jn * DOM.Kn, nprocs); return 2; }
   rho_f = fp.rho_f; pp_residual = fp.pp_residual; pp_max_iter = argc > 7 ? atoi(argv[7]) : fp.pp_max_iter;
