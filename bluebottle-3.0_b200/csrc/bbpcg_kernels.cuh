@@ -64,33 +64,36 @@ __device__ __forceinline__ double stencil_plain(const Dev &d, double pC, double 
                          __dsub_rn(__dsub_rn(pT, pC), __dsub_rn(pC, pB)));
 }
 
-/* noparts operator: src/solver_kernel.cu:824-829 (same association; f in {0,1}, so f * difference is exact) */
+/* A flag^2 in {0,1} times a difference: 1 * x is x and 0 * x is a zero, so a SELECT gives the product's value without an
+ * FP64 multiply (the sign of a zero is the only thing that can differ, and it never reaches a stored value: a zero term
+ * changes neither q = -A p, nor the dot products, nor r -= alpha q). */
+__device__ __forceinline__ double flagged(unsigned bit, double x) { return bit ? x : 0.; }
+
+/* noparts operator: src/solver_kernel.cu:824-829 (same association) */
 __device__ __forceinline__ double stencil_noparts(const Dev &d, unsigned m, double pC, double pE, double pW,
                                                   double pN, double pS, double pT, double pB)
 {
-  const double fe = (m & FM_E) ? 1. : 0., fw = (m & FM_W) ? 1. : 0., fn = (m & FM_N) ? 1. : 0.,
-               fs = (m & FM_S) ? 1. : 0., ft = (m & FM_T) ? 1. : 0., fb = (m & FM_B) ? 1. : 0.;
-  return stencil_combine(d, __dsub_rn(__dmul_rn(fe, __dsub_rn(pE, pC)), __dmul_rn(fw, __dsub_rn(pC, pW))),
-                         __dsub_rn(__dmul_rn(fn, __dsub_rn(pN, pC)), __dmul_rn(fs, __dsub_rn(pC, pS))),
-                         __dsub_rn(__dmul_rn(ft, __dsub_rn(pT, pC)), __dmul_rn(fb, __dsub_rn(pC, pB))));
+  return stencil_combine(d, __dsub_rn(flagged(m & FM_E, __dsub_rn(pE, pC)), flagged(m & FM_W, __dsub_rn(pC, pW))),
+                         __dsub_rn(flagged(m & FM_N, __dsub_rn(pN, pC)), flagged(m & FM_S, __dsub_rn(pC, pS))),
+                         __dsub_rn(flagged(m & FM_T, __dsub_rn(pT, pC)), flagged(m & FM_B, __dsub_rn(pC, pB))));
 }
 
-/* with particle masking: src/solver_kernel.cu:683-707.  pm == 0 (fluid cell, no solid neighbour) reduces to the noparts form. */
+/* with particle masking: src/solver_kernel.cu:683-707.  The reference multiplies the centre value by pf{x,y,z} (1 in a
+ * fluid cell, -d?^2/6 in a solid one) and every neighbour value by pf{e,w,n,s,t,b} in {0,1} (0 toward a solid neighbour and
+ * on every coupling of a solid row): one rounded product for the centre of a solid cell, selects for everything else.
+ * pm == 0 (fluid cell, no solid neighbour) reduces to the noparts form bit for bit. */
 __device__ __forceinline__ double stencil_parts(const Dev &d, unsigned m, unsigned pm, double pC, double pE,
                                                 double pW, double pN, double pS, double pT, double pB)
 {
-  const double fe = (m & FM_E) ? 1. : 0., fw = (m & FM_W) ? 1. : 0., fn = (m & FM_N) ? 1. : 0.,
-               fs = (m & FM_S) ? 1. : 0., ft = (m & FM_T) ? 1. : 0., fb = (m & FM_B) ? 1. : 0.;
   const bool solid = (pm & PM_C) != 0;
-  const double pfx = solid ? -d.dx2_6 : 1., pfy = solid ? -d.dy2_6 : 1., pfz = solid ? -d.dz2_6 : 1.;
-  const double pfe = (!solid && !(pm & PM_E)) ? 1. : 0., pfw = (!solid && !(pm & PM_W)) ? 1. : 0.;
-  const double pfn = (!solid && !(pm & PM_N)) ? 1. : 0., pfs = (!solid && !(pm & PM_S)) ? 1. : 0.;
-  const double pft = (!solid && !(pm & PM_T)) ? 1. : 0., pfb = (!solid && !(pm & PM_B)) ? 1. : 0.;
-  const double cx = __dmul_rn(pfx, pC), cy = __dmul_rn(pfy, pC), cz = __dmul_rn(pfz, pC);
-  const double X = __dsub_rn(__dmul_rn(fe, __dsub_rn(__dmul_rn(pE, pfe), cx)), __dmul_rn(fw, __dsub_rn(cx, __dmul_rn(pfw, pW))));
-  const double Y = __dsub_rn(__dmul_rn(fn, __dsub_rn(__dmul_rn(pN, pfn), cy)), __dmul_rn(fs, __dsub_rn(cy, __dmul_rn(pfs, pS))));
-  const double Z = __dsub_rn(__dmul_rn(ft, __dsub_rn(__dmul_rn(pT, pft), cz)), __dmul_rn(fb, __dsub_rn(cz, __dmul_rn(pfb, pB))));
-  return stencil_combine(d, X, Y, Z);
+  const double cx = solid ? __dmul_rn(-d.dx2_6, pC) : pC, cy = solid ? __dmul_rn(-d.dy2_6, pC) : pC,
+               cz = solid ? __dmul_rn(-d.dz2_6, pC) : pC;
+  const double zE = (pm & (PM_C | PM_E)) ? 0. : pE, zW = (pm & (PM_C | PM_W)) ? 0. : pW;
+  const double zN = (pm & (PM_C | PM_N)) ? 0. : pN, zS = (pm & (PM_C | PM_S)) ? 0. : pS;
+  const double zT = (pm & (PM_C | PM_T)) ? 0. : pT, zB = (pm & (PM_C | PM_B)) ? 0. : pB;
+  return stencil_combine(d, __dsub_rn(flagged(m & FM_E, __dsub_rn(zE, cx)), flagged(m & FM_W, __dsub_rn(cx, zW))),
+                         __dsub_rn(flagged(m & FM_N, __dsub_rn(zN, cy)), flagged(m & FM_S, __dsub_rn(cy, zS))),
+                         __dsub_rn(flagged(m & FM_T, __dsub_rn(zT, cz)), flagged(m & FM_B, __dsub_rn(cz, zB))));
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -307,6 +310,7 @@ struct SearchArgs {
   int ty;              /* owned rows per tile (1..8): chosen by the host planner so that the CTA count fills the SM slots */
   const double *rhs;   /* refresh form of k_resid_tma only: the caller's right-hand side (Gcc s3b) and its strides */
   int s1b, s2b;
+  int producer;        /* the thread that issues the TMA loads: BB_PRODUCER (lane 0 of the 9th warp; default) or 0 (option tma_warp 0) */
 };
 
 /* ------------------------------------------------------------------------------------ */

@@ -10,7 +10,7 @@
  * The iteration moves 40 + 24 = 64 B per cell instead of the 72 of a stored-q scheme (the q write and the q read are
  * gone; p is read here instead of q).
  *
- * CTA = 256 threads, tile 128 x ty owned cells of one k-plane (same run-time ty and z-chunks as the search kernel).
+ * CTA = 256 consumer threads + one producer warp (BB_NT_ITER), tile 128 x ty owned cells of one k-plane (same run-time ty and z-chunks as the search kernel).
  * The halo'd p tile and the mask tile arrive through TMA (cp.async.bulk.tensor.3d) into a shared-memory ring, D = 2
  * planes ahead; p ghost cells are already current in HBM (the search kernel keeps them so), so this kernel reads NO peer
  * memory.  Each thread owns the same (x,y) cells on every plane: p(k-1), p(k), p(k+1) of its cells stay in registers,
@@ -107,7 +107,7 @@ __device__ __forceinline__ double resid_planes(const Dev &d, const SearchMaps &t
     tma::load3d(st, &tm.fm, x0 - G::MX0, y0, pi, bar);
     if (PARTS && inner) tma::load3d(st + G::MT, &tm.pm, BB_XOFF + 1 + bx * TX, j0, pi, bar);
   };
-  if (tid == 0) {
+  if (tid == a.producer) {
 #pragma unroll
     for (int l = 0; l < G::D; l++) if (l < nplanes) issue(l);
   }
@@ -115,13 +115,14 @@ __device__ __forceinline__ double resid_planes(const Dev &d, const SearchMaps &t
   done = sc->done;
   double *__restrict__ r = d.r;
   if (done) {                       /* a finished solve: drain the loads already issued, then leave */
-    if (tid == 0) {
+    if (tid == a.producer) {
 #pragma unroll
       for (int l = 0; l < G::D; l++) if (l < nplanes) tma::mbar_wait(bar0 + 8 * l, 0);
     }
     return 0.;
   }
   const double c63 = __ldg(d.invM_tab + 63);
+  const bool consumer = tid < BB_PRODUCER;              /* warp-uniform; the producer warp only issues loads */
 
   double2 pB[NO], pC[NO], bn[NO];                       /* bn: refresh form, b of the NEXT plane to be computed */
 #pragma unroll
@@ -131,8 +132,9 @@ __device__ __forceinline__ double resid_planes(const Dev &d, const SearchMaps &t
   for (int lp = 0; lp < nplanes; lp++) {
     const int pi = k0 - 1 + lp;
     const int ms = lp % G::NMS, ps = lp % G::NPS;
-    if (tid == 0 && lp + G::D < nplanes) issue(lp + G::D);
+    if (tid == a.producer && lp + G::D < nplanes) issue(lp + G::D);
     const bool plane_owned = pi >= k0 && pi <= k1;
+    if (consumer) {
     double2 bc[NO];
     if (REFRESH) {                                      /* b(kc) was requested one iteration ago; request b(kc+1) = b(pi) now */
 #pragma unroll
@@ -202,13 +204,14 @@ __device__ __forceinline__ double resid_planes(const Dev &d, const SearchMaps &t
     }
 #pragma unroll
     for (int o = 0; o < NO; o++) { pB[o] = pC[o]; pC[o] = pT[o]; }
+    }                                 /* consumer */
     __syncthreads();                  /* every thread is done with the slots the next issue overwrites */
   }
   return dot;
 }
 
 template <bool PARTS, int DD, bool REFRESH>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(BB_NT_ITER, 2)
 k_resid_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps tm, const SearchArgs a)
 {
   typedef ResidGeom<PARTS, DD> G;

@@ -5,7 +5,7 @@
  *   q = -A p  (7-point, flag^2 / phase coefficients) PP_spmv_shared_load(_noparts) src/solver_kernel.cu:528-836
  *   (p,q) partial -> last CTA: rank-ordered all-reduce, alpha     src/cuda_solver.cu:204-206
  *
- * CTA = 256 threads, tile TX = 128 x ty owned cells of one k-plane (ty <= 8 is a RUN-TIME argument: the host planner
+ * CTA = 256 consumer threads + one producer warp (BB_NT_ITER = 288), tile TX = 128 x ty owned cells of one k-plane (ty <= 8 is a RUN-TIME argument: the host planner
  * picks the tile height and the z-chunk count whose CTA count fills the 2 x 148 resident slots, e.g. 7 rows x 4 chunks
  * = 296 CTAs for a 256^3 block, 7 rows x 1 chunk = 296 CTAs at 512^3), marching its z-chunk in k.
  * All plane inputs arrive through TMA (cp.async.bulk.tensor.3d, SASS UTMALDG) into a shared-memory ring, issued D planes
@@ -74,6 +74,12 @@ __device__ __forceinline__ void stg128(double *p, double a, double b)
 
 /* geometry shared with the host (tensor-map boxes, dynamic shared memory size): sized for the tallest tile, ty = 8 */
 #define BB_TYMAX 8
+/* CTA of the two iteration kernels: 8 consumer warps (threads 0..255 own the tile's cells) + 1 PRODUCER warp whose lane 0
+ * (thread 256) issues every TMA load, D planes ahead.  With the issue on thread 0 the whole CTA waited at the per-plane
+ * barrier for warp 0's serial expect_tx + 4..9 UTMALDG instructions; the producer warp issues plane lp + D while the
+ * consumers compute plane lp and meets them at the same barrier. */
+#define BB_NT_ITER 288
+#define BB_PRODUCER 256
 template <bool PARTS, int DD = 2>
 struct SearchGeom {
   static constexpr int TX = 128, NT = 256, HXP = TX + 4, HYMAX = BB_TYMAX + 2;
@@ -193,7 +199,7 @@ __device__ __forceinline__ double search_planes(const Dev &d, const SearchMaps &
       if (PARTS) tma::load3d(st + G::RT + G::MT + G::GY + G::GX, &tm.pm, BB_XOFF + 1 + bx * TX, j0, pi, bar);
     }
   };
-  if (tid == 0) {
+  if (tid == a.producer) {
 #pragma unroll
     for (int l = 0; l < G::D; l++) if (l < nplanes) issue(l);
   }
@@ -204,13 +210,14 @@ __device__ __forceinline__ double search_planes(const Dev &d, const SearchMaps &
   double *__restrict__ x = d.x;
   if (tid < 128) tab[tid] = __ldg(d.invM_tab + tid);
   if (done) {                       /* a finished solve: drain the loads already issued, then leave */
-    if (tid == 0) {
+    if (tid == a.producer) {
 #pragma unroll
       for (int l = 0; l < G::D; l++) if (l < nplanes) tma::mbar_wait(bar0 + 8 * l, 0);
     }
     return 0.;
   }
   const double c63 = __ldg(d.invM_tab + 63);            /* Jacobi diagonal of a cell with all six flags set */
+  const bool consumer = tid < BB_PRODUCER;              /* warp-uniform */
 
   /* register pipeline of the owned cells: p(kc-1), p(kc), masks of kc */
   double2 pB[NO], pC[NO];
@@ -229,9 +236,10 @@ __device__ __forceinline__ double search_planes(const Dev &d, const SearchMaps &
   for (int lp = 0; lp < nplanes; lp++) {
     const int pi = k0 - 1 + lp;
     const int rs = lp % G::NRS, ps = lp % G::NPS;
-    if (tid == 0 && lp + G::D < nplanes) issue(lp + G::D);
+    if (tid == a.producer && lp + G::D < nplanes) issue(lp + G::D);
     const bool plane_owned = pi >= k0 && pi <= k1;
     const bool plane_ghost = (pi == 0 || pi == L.kn + 1);
+    if (consumer) {
     tma::mbar_wait(bar0 + 8 * rs, (lp / G::NRS) & 1);
 
     double *Pt = reinterpret_cast<double *>(smem + ps * G::RT);
@@ -343,13 +351,14 @@ __device__ __forceinline__ double search_planes(const Dev &d, const SearchMaps &
 #pragma unroll
     for (int o = 0; o < NO; o++) { pB[o] = pC[o]; pC[o] = pT[o]; mC[o] = mT[o]; if (PARTS) pmC[o] = pmT[o]; }
     tma::fence_proxy_async();
+    }                                 /* consumer */
     __syncthreads();
   }
   return dot;
 }
 
 template <bool PARTS, int DD>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(BB_NT_ITER, 2)
 k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps tm, const SearchArgs a)
 {
   typedef SearchGeom<PARTS, DD> G;

@@ -75,6 +75,7 @@ struct bbpcg_solver {
   int plan_ok;                      /* the plan below, the uploaded table and the tensor maps are current */
   int plan_ty, plan_nbx, plan_nby, plan_nbz, plan_kc;
   int pdl;                          /* programmatic dependent launch of the two iteration kernels: 0 off, 1 on, 2 auto */
+  int tma_warp;                     /* 1 (default): a dedicated producer warp issues the iteration kernels' TMA loads; 0: thread 0 does */
   int rhs_tiled;                    /* PP_rhs through shared-memory transposes (default) or the row-walking kernel */
   int shared_device;                /* some peer rank lives on this same GPU (single-process harness, or two processes on one GPU) */
   unsigned char uuid[16];
@@ -253,7 +254,7 @@ static int create_impl(bbpcg_solver *s, const dom_struct *dom_rank, const dom_st
   CU(cudaHostGetDevicePointer((void **)&d.comm.host_flag, (void *)&s->h_poll[BB_POLL_COMM], 0));
   CU(cudaHostAlloc(&s->h_scal, sizeof(Scal), cudaHostAllocDefault));
   CU(cudaHostAlloc(&s->h_ztab, sizeof(int) * (BB_MAXZ + 1), cudaHostAllocDefault));
-  s->pdl = 2; s->rhs_tiled = 1;
+  s->pdl = 2; s->rhs_tiled = 1; s->tma_warp = 1;
   /* single rank: neighbours are this block itself (periodic wrap) or nothing */
   s->nranks = 1;
   for (int p = 0; p < BB_MAXR; p++) { s->peer_arena[p] = NULL; s->peer_opened[p] = false; }
@@ -461,6 +462,7 @@ static SearchArgs plan_args(const bbpcg_solver *s)
   SearchArgs a;
   memset(&a, 0, sizeof(a));
   a.nbx = s->plan_nbx; a.nby = s->plan_nby; a.nbz = s->plan_nbz; a.ty = s->plan_ty;
+  a.producer = s->tma_warp ? BB_PRODUCER : 0;
   return a;
 }
 
@@ -472,8 +474,8 @@ static int launch_search(bbpcg_solver *s, bool parts)
   if (rc) return rc;
   const SearchArgs a = plan_args(s);
   const dim3 grid(a.nbx, a.nby, a.nbz);
-  if (parts) CU(launch_k(s, k_search_tma<true, 2>, grid, 256, SearchGeom<true, 2>::SMEM, true, s->dev, s->maps, a));
-  else CU(launch_k(s, k_search_tma<false, 2>, grid, 256, SearchGeom<false, 2>::SMEM, true, s->dev, s->maps, a));
+  if (parts) CU(launch_k(s, k_search_tma<true, 2>, grid, BB_NT_ITER, SearchGeom<true, 2>::SMEM, true, s->dev, s->maps, a));
+  else CU(launch_k(s, k_search_tma<false, 2>, grid, BB_NT_ITER, SearchGeom<false, 2>::SMEM, true, s->dev, s->maps, a));
   s->launches++;
   return BBPCG_OK;
 }
@@ -488,11 +490,11 @@ static int launch_resid(bbpcg_solver *s, bool parts, const real *rhs)
   a.rhs = rhs; a.s1b = s->fst.cs1b; a.s2b = s->fst.cs2b;
   const dim3 grid(a.nbx, a.nby, a.nbz);
   if (rhs) {
-    if (parts) CU(launch_k(s, k_resid_tma<true, 2, true>, grid, 256, ResidGeom<true, 2>::SMEM, false, s->dev, s->maps, a));
-    else CU(launch_k(s, k_resid_tma<false, 2, true>, grid, 256, ResidGeom<false, 2>::SMEM, false, s->dev, s->maps, a));
+    if (parts) CU(launch_k(s, k_resid_tma<true, 2, true>, grid, BB_NT_ITER, ResidGeom<true, 2>::SMEM, false, s->dev, s->maps, a));
+    else CU(launch_k(s, k_resid_tma<false, 2, true>, grid, BB_NT_ITER, ResidGeom<false, 2>::SMEM, false, s->dev, s->maps, a));
   } else {
-    if (parts) CU(launch_k(s, k_resid_tma<true, 2, false>, grid, 256, ResidGeom<true, 2>::SMEM, true, s->dev, s->maps, a));
-    else CU(launch_k(s, k_resid_tma<false, 2, false>, grid, 256, ResidGeom<false, 2>::SMEM, true, s->dev, s->maps, a));
+    if (parts) CU(launch_k(s, k_resid_tma<true, 2, false>, grid, BB_NT_ITER, ResidGeom<true, 2>::SMEM, true, s->dev, s->maps, a));
+    else CU(launch_k(s, k_resid_tma<false, 2, false>, grid, BB_NT_ITER, ResidGeom<false, 2>::SMEM, true, s->dev, s->maps, a));
   }
   s->launches++;
   return BBPCG_OK;
@@ -1033,6 +1035,7 @@ extern "C" int bbpcg_set_option(bbpcg_solver *s, const char *key, long long valu
   else if (!strcmp(key, "kc")) { s->opt_kc = value > 0 ? (int)value : 0; s->plan_ok = 0; }
   else if (!strcmp(key, "pdl")) s->pdl = clampi(value, 0, 2);
   else if (!strcmp(key, "rhs_tiled")) s->rhs_tiled = value != 0;
+  else if (!strcmp(key, "tma_warp")) s->tma_warp = value != 0;
   else if (!strcmp(key, "stream_blocks")) s->stream_blocks = clampi(value, 1, BB_MAXBLOCKS);
   else if (!strcmp(key, "check_every")) s->check_every = clampi(value, 1, 1000);
   else if (!strcmp(key, "comm_timeout_ms")) s->dev.comm.timeout_cycles = value > 0 ? value * 2000000ll : -1;   /* ~2 GHz; <= 0: wait for ever, like MPI */

@@ -21,6 +21,7 @@
 
 #include "cuda_solver.h"      /* reference header (from -I $(REF)/src): types + kernel prototypes */
 #include "cuda_bluebottle.h"  /* pack/unpack kernel prototypes */
+#include "cuda_particle.h"    /* cage-building kernel prototypes, part_struct */
 
 /* ---- globals the reference objects link against --------------------------------------- */
 __constant__ dom_struct _dom;            /* cuda_bluebottle.cu:34 */
@@ -118,11 +119,15 @@ static void shim_blocks_init(const dom_struct *d)
   blocks.G.num_in = dim3(by, bz); blocks.G.num_jn = dim3(bz, bx); blocks.G.num_kn = dim3(bx, by);
   SHIM_FACE_BLOCKS(Gfx) SHIM_FACE_BLOCKS(Gfy) SHIM_FACE_BLOCKS(Gfz)
 #undef SHIM_FACE_BLOCKS
-  /* ghost-inclusive shapes used by zero_rhs_ghost_{i,j,k} (cuda_bluebottle.cu:545-560) */
-  tx = thr(d->Gcc.inb); ty = thr(d->Gcc.jnb); tz = thr(d->Gcc.knb);
-  bx = nblk(d->Gcc.inb, tx); by = nblk(d->Gcc.jnb, ty); bz = nblk(d->Gcc.knb, tz);
-  blocks.Gcc.dim_inb = dim3(ty, tz); blocks.Gcc.dim_jnb = dim3(tz, tx); blocks.Gcc.dim_knb = dim3(tx, ty);
-  blocks.Gcc.num_inb = dim3(by, bz); blocks.Gcc.num_jnb = dim3(bz, bx); blocks.Gcc.num_knb = dim3(bx, by);
+  /* ghost-inclusive shapes (cuda_bluebottle.cu:762-790 Gcc, :822-850 Gfx, :882-910 Gfy, :942-970 Gfz): zero_rhs_ghost_{i,j,k},
+   * reset_flag_*, reset_phases, cage_flag_*, flag_external_* */
+#define SHIM_GHOST_BLOCKS(G)                                                                             \
+  tx = thr(d->G.inb); ty = thr(d->G.jnb); tz = thr(d->G.knb);                                            \
+  bx = nblk(d->G.inb, tx); by = nblk(d->G.jnb, ty); bz = nblk(d->G.knb, tz);                             \
+  blocks.G.dim_inb = dim3(ty, tz); blocks.G.dim_jnb = dim3(tz, tx); blocks.G.dim_knb = dim3(tx, ty);     \
+  blocks.G.num_inb = dim3(by, bz); blocks.G.num_jnb = dim3(bz, bx); blocks.G.num_knb = dim3(bx, by);
+  SHIM_GHOST_BLOCKS(Gcc) SHIM_GHOST_BLOCKS(Gfx) SHIM_GHOST_BLOCKS(Gfy) SHIM_GHOST_BLOCKS(Gfz)
+#undef SHIM_GHOST_BLOCKS
 }
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "bbref: %s -> %s\n", #x, cudaGetErrorString(e_)); return -1; } } while (0)
@@ -484,6 +489,74 @@ int bbref_dom_BC_star(real *u_h, real *v_h, real *w_h, const int *type, const re
   CK(cudaMemcpy(u_h, _u_star, (size_t)d->Gfx.s3b * sizeof(real), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(v_h, _v_star, (size_t)d->Gfy.s3b * sizeof(real), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(w_h, _w_star, (size_t)d->Gfz.s3b * sizeof(real), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+/* cuda_build_cages (cuda_particle.cu:1516-1646; its translation unit is not linked): the host sequence restated, every
+ * KERNEL the reference's own (particle_kernel.cu:79-576): reset_flag_*, reset_phases, per particle cage_setup + build_phase,
+ * then cage_setup + build_phase_shell, cage_flag_*, flag_external_*.  nparts_ = this rank's particle count (the reference's
+ * `nparts`, ghost particles included); NPARTS > 0 selects the particle branch (:1524).  Outputs are host arrays (s3b). */
+int bbref_build_cages(int NPARTS_, int nparts_, const real *px, const real *py, const real *pz, const real *pr, const int *pbc,
+                      int *flag_u_h, int *flag_v_h, int *flag_w_h, int *phase_h, int *phase_shell_h)
+{
+  const dom_struct *d = &dom[rank];
+  NPARTS = NPARTS_; nparts = nparts_;
+  bc.pW = pbc[0]; bc.pE = pbc[1]; bc.pS = pbc[2]; bc.pN = pbc[3]; bc.pB = pbc[4]; bc.pT = pbc[5];
+  part_struct *parts_h = (part_struct *)calloc(nparts_ > 0 ? nparts_ : 1, sizeof(part_struct));
+  for (int n = 0; n < nparts_; n++) { parts_h[n].x = px[n]; parts_h[n].y = py[n]; parts_h[n].z = pz[n]; parts_h[n].r = pr[n]; }
+  part_struct *_parts_d = NULL; dom_struct *_DOM_d = NULL; BC *_bc_d = NULL;
+  CK(cudaMalloc(&_parts_d, (nparts_ > 0 ? nparts_ : 1) * sizeof(part_struct)));
+  CK(cudaMemcpy(_parts_d, parts_h, (nparts_ > 0 ? nparts_ : 1) * sizeof(part_struct), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&_DOM_d, sizeof(dom_struct))); CK(cudaMemcpy(_DOM_d, &DOM, sizeof(dom_struct), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&_bc_d, sizeof(BC))); CK(cudaMemcpy(_bc_d, &bc, sizeof(BC), cudaMemcpyHostToDevice));
+
+  reset_flag_u<<<blocks.Gfx.num_inb, blocks.Gfx.dim_inb>>>(_flag_u);                    /* :1520-1522 */
+  reset_flag_v<<<blocks.Gfy.num_jnb, blocks.Gfy.dim_jnb>>>(_flag_v);
+  reset_flag_w<<<blocks.Gfz.num_knb, blocks.Gfz.dim_knb>>>(_flag_w);
+  if (NPARTS > 0) {
+    reset_phases<<<blocks.Gcc.num_knb, blocks.Gcc.dim_knb>>>(_phase, _phase_shell);     /* :1526 */
+    int tx = 0.5 * MAX_THREADS_DIM, ty = 0.5 * MAX_THREADS_DIM, tz = 0.5 * MAX_THREADS_DIM;
+    real itx = 1. / tx, ity = 1. / ty, itz = 1. / tz;
+    int cage_dim[3], *_cage_dim;
+    CK(cudaMalloc(&_cage_dim, 3 * sizeof(int)));
+    for (int pass = 0; pass < 2; pass++) {                                              /* :1541-1584: phase, then phase_shell */
+      for (int n = 0; n < nparts; n++) {
+        cage_setup<<<1, 1>>>(_parts_d, n, _cage_dim);
+        CK(cudaMemcpy(cage_dim, _cage_dim, 3 * sizeof(int), cudaMemcpyDeviceToHost));
+        int bx = (int)ceil((real)cage_dim[0] * itx), by = (int)ceil((real)cage_dim[1] * ity), bz = (int)ceil((real)cage_dim[2] * itz);
+        dim3 dimb_3(tx, ty, tz), numb_3(bx, by, bz);
+        if (bx > 0 && by > 0 && bz > 0) {
+          if (pass == 0) build_phase<<<numb_3, dimb_3>>>(_parts_d, n, _cage_dim, _phase, _phase_shell, _DOM_d, _bc_d);
+          else build_phase_shell<<<numb_3, dimb_3>>>(_parts_d, n, _cage_dim, _phase, _phase_shell, _DOM_d, _bc_d);
+        }
+      }
+    }
+    CK(cudaFree(_cage_dim));
+    cage_flag_u<<<blocks.Gfx.num_inb, blocks.Gfx.dim_inb>>>(_flag_u, _phase, _phase_shell);   /* :1595-1597 */
+    cage_flag_v<<<blocks.Gfy.num_jnb, blocks.Gfy.dim_jnb>>>(_flag_v, _phase, _phase_shell);
+    cage_flag_w<<<blocks.Gfz.num_knb, blocks.Gfz.dim_knb>>>(_flag_w, _phase, _phase_shell);
+  }
+  if (bc.pW != PERIODIC && bc.pE != PERIODIC) {                                         /* :1605-1639 */
+    if (d->I == DOM.Is) flag_external_u<<<blocks.Gfx.num_inb, blocks.Gfx.dim_inb>>>(_flag_u, d->Gfx._is);
+    if (d->I == DOM.Ie) flag_external_u<<<blocks.Gfx.num_inb, blocks.Gfx.dim_inb>>>(_flag_u, d->Gfx._ie);
+  }
+  if (bc.pS != PERIODIC && bc.pN != PERIODIC) {
+    if (d->J == DOM.Js) flag_external_v<<<blocks.Gfy.num_jnb, blocks.Gfy.dim_jnb>>>(_flag_v, d->Gfy._js);
+    if (d->J == DOM.Je) flag_external_v<<<blocks.Gfy.num_jnb, blocks.Gfy.dim_jnb>>>(_flag_v, d->Gfy._je);
+  }
+  if (bc.pB != PERIODIC && bc.pT != PERIODIC) {
+    if (d->K == DOM.Ks) flag_external_w<<<blocks.Gfz.num_knb, blocks.Gfz.dim_knb>>>(_flag_w, d->Gfz._ks);
+    if (d->K == DOM.Ke) flag_external_w<<<blocks.Gfz.num_knb, blocks.Gfz.dim_knb>>>(_flag_w, d->Gfz._ke);
+  }
+  CK(cudaDeviceSynchronize());
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(flag_u_h, _flag_u, (size_t)d->Gfx.s3b * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(flag_v_h, _flag_v, (size_t)d->Gfy.s3b * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(flag_w_h, _flag_w, (size_t)d->Gfz.s3b * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(phase_h, _phase, (size_t)d->Gcc.s3b * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(phase_shell_h, _phase_shell, (size_t)d->Gcc.s3b * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaFree(_parts_d)); CK(cudaFree(_DOM_d)); CK(cudaFree(_bc_d));
+  free(parts_h);
   return 0;
 }
 
