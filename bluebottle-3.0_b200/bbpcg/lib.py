@@ -6,7 +6,7 @@ from .grid import DomStruct, PressureBC
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(os.path.dirname(_HERE), "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libbbpcg.so")
+LIB_PATH = os.environ.get("BBPCG_LIB_PATH") or os.path.join(LIB_DIR, "libbbpcg.so")   # BBPCG_LIB_PATH: a debug build of the SAME library (make trace)
 DROPIN_PATH = os.path.join(LIB_DIR, "libbbpcg_dropin.so")
 
 BLOB_BYTES = 256
@@ -47,6 +47,12 @@ class EpilogueArgs(C.Structure):
                 ("phi", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("w", C.c_void_p),
                 ("p0", C.c_void_p), ("phase", C.c_void_p), ("p", C.c_void_p),
                 ("rho_f", C.c_double), ("dt", C.c_double), ("phi_ghosts_valid", C.c_int)]
+
+
+class PartsView(C.Structure):
+    """bbpcg_parts_view: a strided view of the rank's particle list (device memory)"""
+    _fields_ = [("base", C.c_void_p), ("stride", C.c_size_t), ("off_x", C.c_size_t), ("off_y", C.c_size_t),
+                ("off_z", C.c_size_t), ("off_r", C.c_size_t)]
 
 
 class VelocityBC(C.Structure):
@@ -90,10 +96,10 @@ SYMBOLS = [
     "bbpcg_create", "bbpcg_destroy", "bbpcg_comm_export", "bbpcg_comm_import", "bbpcg_set_coefficients",
     "bbpcg_solve", "bbpcg_solve_host", "bbpcg_history", "bbpcg_exchange_Gcc", "bbpcg_rhs", "bbpcg_spmv",
     "bbpcg_set_option", "bbpcg_get_info", "bbpcg_last_error", "bbpcg_version",
-    "bbpcg_dom_BC_p", "bbpcg_epilogue", "bbpcg_exchange", "bbpcg_solvability", "bbpcg_dom_BC_star", "bbpcg_prologue",
+    "bbpcg_dom_BC_p", "bbpcg_epilogue", "bbpcg_exchange", "bbpcg_solvability", "bbpcg_dom_BC_star", "bbpcg_prologue", "bbpcg_build_cages",
 ]
 DROPIN_SYMBOLS = ["cuda_PP_init_jacobi_preconditioner", "cuda_PP_cg", "cuda_PP_cg_noparts", "cuda_PP_cg_timed",
-                  "mpi_cuda_exchange_Gcc", "mpi_cuda_exchange_Gfx", "mpi_cuda_exchange_Gfy", "mpi_cuda_exchange_Gfz", "cuda_solvability", "cuda_dom_BC_star", "cuda_dom_BC_p", "cuda_project", "cuda_update_p", "bbpcg_dropin_finalize"]
+                  "mpi_cuda_exchange_Gcc", "mpi_cuda_exchange_Gfx", "mpi_cuda_exchange_Gfy", "mpi_cuda_exchange_Gfz", "cuda_solvability", "cuda_dom_BC_star", "cuda_build_cages", "cuda_dom_BC_p", "cuda_project", "cuda_update_p", "bbpcg_dropin_finalize"]
 
 _lib = None
 
@@ -138,6 +144,7 @@ def load_library():
     lib.bbpcg_exchange.argtypes = [vp, vp, C.c_int]
     lib.bbpcg_solvability.argtypes = [vp, vp, vp, vp, C.c_int, dp]
     lib.bbpcg_dom_BC_p.argtypes = [vp, vp]
+    lib.bbpcg_build_cages.argtypes = [vp, C.c_int, C.c_int, C.POINTER(PartsView), vp, vp, vp, vp, vp]
     lib.bbpcg_dom_BC_star.argtypes = [vp, vp, vp, vp, C.POINTER(VelocityBC)]
     lib.bbpcg_prologue.argtypes = [vp, vp, vp, vp, C.POINTER(VelocityBC), C.c_int, dp]
     lib.bbpcg_epilogue.argtypes = [vp, C.POINTER(EpilogueArgs), dp]

@@ -216,6 +216,22 @@ class PoissonSolver:
         L.check(self.lib.bbpcg_set_coefficients(self.h, _ptr(flag_u), _ptr(flag_v), _ptr(flag_w), _ptr(phase)),
                 "bbpcg_set_coefficients")
 
+    def build_cages(self, parts_xyzr, flag_u, flag_v, flag_w, phase=None, phase_shell=None, NPARTS=None):
+        """cuda_build_cages() + the mask digestion of cuda_PP_init_jacobi_preconditioner(): parts_xyzr is a device tensor
+        [nparts, 4] of (x, y, z, r) -- or None -- in global coordinates; fills the five int arrays and the solver's masks"""
+        n = 0 if parts_xyzr is None else int(parts_xyzr.shape[0])
+        NPARTS = n if NPARTS is None else NPARTS
+        view = L.PartsView()
+        if n:
+            assert parts_xyzr.dtype == self.torch.float64 and parts_xyzr.is_contiguous() and parts_xyzr.shape[1] == 4
+            view.base, view.stride = parts_xyzr.data_ptr(), 32
+            view.off_x, view.off_y, view.off_z, view.off_r = 0, 8, 16, 24
+        self._sync_caller_stream()
+        L.check(self.lib.bbpcg_build_cages(self.h, NPARTS, n, C.byref(view), _ptr(flag_u), _ptr(flag_v), _ptr(flag_w),
+                                           _ptr(phase) if phase is not None else None,
+                                           _ptr(phase_shell) if phase_shell is not None else None), "bbpcg_build_cages")
+        self._has_phase = NPARTS > 0
+
     def _solve(self, u_star, v_star, w_star, rhs_p, phi, rho_f, dt, pp_residual, pp_max_iter, use_phase,
                phase=None, phase_shell=None, fixed_iters=0):
         a = L.SolveArgs()

@@ -25,6 +25,7 @@ extern real *_u_star, *_v_star, *_w_star, *_rhs_p, *_phi;
 extern real *_u, *_v, *_w, *_p, *_p0;         /* src/bluebottle.h:961,1037,1137,1186,1235 (epilogue) */
 extern int *_flag_u, *_flag_v, *_flag_w, *_phase, *_phase_shell;
 extern int out_plane;                         /* src/bluebottle.h:650 (solvability) */
+extern void *_parts;                          /* part_struct *_parts, src/particle.h:692: this rank's particles on the device */
 void cuda_part_BC_p(void);                    /* src/cuda_particle.cu:1680 */
 void recorder_PP(char *name, int niter, real resid, real etime);   /* src/recorder.c:190 */
 /* cuda_PP_cg_timed's log (src/recorder.c:223-336); weak: a host linked without recorder.o's timed pair still loads */
@@ -57,6 +58,25 @@ static bbpcg_solver *solver(void)
     free(all);
   }
   return g_solver;
+}
+
+/* Layout of the reference's part_struct (src/particle.h:343-...) with -DDOUBLE: `int N; real r; real x; real y; real z; ...`,
+ * sizeof 3128.  Only these four fields are read.  tests/test_abi.py re-derives the numbers from the reference header
+ * whenever /root/reference is present; INTEGRATION.md shows the static_assert a maintainer adds on the Bluebottle side. */
+#define BB_PART_STRIDE 3128
+#define BB_PART_OFF_R 8
+#define BB_PART_OFF_X 16
+#define BB_PART_OFF_Y 24
+#define BB_PART_OFF_Z 32
+
+/* src/bluebottle.c:389 (+ :392-394: the preconditioner re-initialisation that follows it is folded in) */
+extern "C" void cuda_build_cages(void)
+{
+  bbpcg_parts_view pv;
+  pv.base = _parts; pv.stride = BB_PART_STRIDE;
+  pv.off_x = BB_PART_OFF_X; pv.off_y = BB_PART_OFF_Y; pv.off_z = BB_PART_OFF_Z; pv.off_r = BB_PART_OFF_R;
+  cudaDeviceSynchronize();
+  if (bbpcg_build_cages(solver(), NPARTS, nparts, &pv, _flag_u, _flag_v, _flag_w, _phase, _phase_shell)) die("bbpcg_build_cages");
 }
 
 extern "C" void cuda_PP_init_jacobi_preconditioner(void)

@@ -174,6 +174,16 @@ struct Dev {
   Halo halo;
   Comm comm;
   int any_nbr;                    /* some face has a neighbour (another rank or a periodic self-wrap) */
+#ifdef BB_TRACE
+  unsigned long long *trace;      /* debug build only (make trace): per-CTA globaltimer stamps of the iteration kernels */
+#endif
 };
+
+/* ---- optional per-CTA time line of the two iteration kernels (libbbpcg_trace.so, scripts/trace_timeline.py) ---- */
+#ifdef BB_TRACE
+#define BB_TRACE_EV 8
+#define BB_TRACE_LAUNCHES 64
+#define BB_TRACE_CTAS 4096
+#endif
 
 #endif

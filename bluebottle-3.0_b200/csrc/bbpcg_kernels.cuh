@@ -310,8 +310,20 @@ struct SearchArgs {
   int ty;              /* owned rows per tile (1..8): chosen by the host planner so that the CTA count fills the SM slots */
   const double *rhs;   /* refresh form of k_resid_tma only: the caller's right-hand side (Gcc s3b) and its strides */
   int s1b, s2b;
+  int launch;          /* trace build: running launch number */
   int producer;        /* the thread that issues the TMA loads: BB_PRODUCER (lane 0 of the 9th warp; default) or 0 (option tma_warp 0) */
 };
+
+#ifdef BB_TRACE
+__device__ __forceinline__ unsigned long long bb_gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned bb_smid() { unsigned v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
+#define BB_TRACE_AT(d, a, ev, val) do { if (threadIdx.x == 0 && (d).trace) { const int bid_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); \
+  if (bid_ < BB_TRACE_CTAS) (d).trace[((size_t)((a).launch % BB_TRACE_LAUNCHES) * BB_TRACE_CTAS + bid_) * BB_TRACE_EV + (ev)] = (val); } } while (0)
+#define BB_STAMP(d, a, ev) BB_TRACE_AT(d, a, ev, bb_gtimer())
+#else
+#define BB_TRACE_AT(d, a, ev, val) do { } while (0)
+#define BB_STAMP(d, a, ev) do { } while (0)
+#endif
 
 /* ------------------------------------------------------------------------------------ */
 /* end of an iteration, run by ONE thread once the global (r,z) is known: the host logic of src/cuda_solver.cu:231-267

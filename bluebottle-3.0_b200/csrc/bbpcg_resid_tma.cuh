@@ -89,7 +89,9 @@ __device__ __forceinline__ double resid_planes(const Dev &d, const SearchMaps &t
   const bool xf_e0 = d.xf[1] != nullptr && iA == L.in, xf_e1 = d.xf[1] != nullptr && iA + 1 == L.in;
 
   /* ---- from here on we read what the search kernel wrote ---- */
+  BB_STAMP(d, a, 0);
   pdl_wait();
+  BB_STAMP(d, a, 1);
   const int q = sc->q;
   auto issue = [&](int lp) {
     const int pi = k0 - 1 + lp;
@@ -148,6 +150,7 @@ __device__ __forceinline__ double resid_planes(const Dev &d, const SearchMaps &t
       }
     }
     tma::mbar_wait(bar0 + 8 * ms, (lp / G::NMS) & 1);
+    if (lp == 0) BB_STAMP(d, a, 2);
 
     const double *Pt = reinterpret_cast<const double *>(smem + ps * G::RT);
     double2 pT[NO];
@@ -227,15 +230,21 @@ k_resid_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps tm
   int done;
   const double dot = xfull ? resid_planes<PARTS, DD, REFRESH, true>(d, tm, a, smem, done) : resid_planes<PARTS, DD, REFRESH, false>(d, tm, a, smem, done);
   if (done) return;                 /* a finished solve: every later launch is a no-op */
+  BB_STAMP(d, a, 3);
+  BB_TRACE_AT(d, a, 6, (unsigned long long)bb_smid());
+  BB_TRACE_AT(d, a, 7, 2ull | ((unsigned long long)a.launch << 8));
 
   pdl_launch_dependents();
   /* ---- (r,z): grid reduction, rank all-reduce, stop test, beta (cuda_solver.cu:231-267) ---- */
   double v[1] = { dot }, tot[1];
   const int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
   const int nblocks = gridDim.x * gridDim.y * gridDim.z;
-  if (grid_reduce<1>(d, v, bid, nblocks, tot, false)) {
+  const bool last = grid_reduce<1>(d, v, bid, nblocks, tot, false);
+  BB_STAMP(d, a, 4);
+  if (last) {
     rank_allreduce(d, tot, 1, true);          /* peers pull the r written here */
     if (threadIdx.x == 0) finish_iteration(d, tot[0], REFRESH);
+    BB_STAMP(d, a, 5);
   }
 }
 

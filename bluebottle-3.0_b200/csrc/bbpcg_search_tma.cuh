@@ -165,7 +165,9 @@ __device__ __forceinline__ double search_planes(const Dev &d, const SearchMaps &
   const bool s_store = s_ok && (s_i == 0 || s_i == L.in + 1) && s_j >= 1 && s_j <= L.jn;   /* x-ghost p kept current */
 
   /* ---- everything above is independent of the previous kernels; from here on we read what they wrote ---- */
+  BB_STAMP(d, a, 0);
   pdl_wait();
+  BB_STAMP(d, a, 1);
   const int q = sc->q;
   /* one thread issues every TMA load of plane lp (local index; global plane pi = k0-1+lp) */
   auto issue = [&](int lp) {
@@ -241,6 +243,7 @@ __device__ __forceinline__ double search_planes(const Dev &d, const SearchMaps &
     const bool plane_ghost = (pi == 0 || pi == L.kn + 1);
     if (consumer) {
     tma::mbar_wait(bar0 + 8 * rs, (lp / G::NRS) & 1);
+    if (lp == 0) BB_STAMP(d, a, 2);
 
     double *Pt = reinterpret_cast<double *>(smem + ps * G::RT);
     const unsigned char *St = smem + G::OFF_STAGE + rs * G::STAGE;
@@ -373,18 +376,24 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
   int done;
   const double dot = xfull ? search_planes<PARTS, DD, true>(d, tm, a, smem, done) : search_planes<PARTS, DD, false>(d, tm, a, smem, done);
   if (done) return;                 /* a finished solve: every later launch is a no-op */
+  BB_STAMP(d, a, 3);
+  BB_TRACE_AT(d, a, 6, (unsigned long long)bb_smid());
+  BB_TRACE_AT(d, a, 7, 1ull | ((unsigned long long)a.launch << 8));
 
   pdl_launch_dependents();          /* k_resid_tma may be scheduled behind our tail; it blocks in pdl_wait() until alpha is final */
   /* ---- (p,q): grid reduction, rank all-reduce, alpha (cuda_solver.cu:204-206) ---- */
   double v[1] = { dot }, tot[1];
   const int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
   const int nblocks = gridDim.x * gridDim.y * gridDim.z;
-  if (grid_reduce<1>(d, v, bid, nblocks, tot, false)) {
+  const bool last = grid_reduce<1>(d, v, bid, nblocks, tot, false);
+  BB_STAMP(d, a, 4);
+  if (last) {
     rank_allreduce(d, tot, 1, false);         /* this kernel writes nothing a peer reads */
     if (threadIdx.x == 0) {
       d.sc->pAp = tot[0];
       d.sc->alpha = d.sc->rz / tot[0];
     }
+    BB_STAMP(d, a, 5);
   }
 }
 

@@ -17,6 +17,7 @@
 #include "bbpcg_search_tma.cuh"
 #include "bbpcg_resid_tma.cuh"
 #include "bbpcg_epilogue.cuh"
+#include "bbpcg_cages.cuh"
 
 /* ---- error plumbing ---------------------------------------------------------------------- */
 static thread_local char g_err[512] = "";
@@ -268,6 +269,10 @@ static int create_impl(bbpcg_solver *s, const dom_struct *dom_rank, const dom_st
   }
   s->stream_blocks = s->sm_count * 8;
   s->check_every = 10;
+#ifdef BB_TRACE
+  CU(cudaMalloc(&d.trace, (size_t)BB_TRACE_LAUNCHES * BB_TRACE_CTAS * BB_TRACE_EV * 8));
+  CU(cudaMemset(d.trace, 0, (size_t)BB_TRACE_LAUNCHES * BB_TRACE_CTAS * BB_TRACE_EV * 8));
+#endif
   return BBPCG_OK;
 }
 
@@ -463,6 +468,7 @@ static SearchArgs plan_args(const bbpcg_solver *s)
   memset(&a, 0, sizeof(a));
   a.nbx = s->plan_nbx; a.nby = s->plan_nby; a.nbz = s->plan_nbz; a.ty = s->plan_ty;
   a.producer = s->tma_warp ? BB_PRODUCER : 0;
+  a.launch = (int)(s->launches & 0x7fffffff);
   return a;
 }
 
@@ -552,6 +558,7 @@ static int preload_kernels()
   PL(k_coeffs_refine<256>); PL(k_zero_ghosts); PL(k_xchg_send); PL(k_xchg_recv);
   PL(k_spmv_s3b<256, false>); PL(k_spmv_s3b<256, true>);
   PL(k_solv_sum); PL(k_solv_apply); PL(k_bc_star);
+  PL(k_cage_reset); PL(k_cage<false>); PL(k_cage<true>); PL(k_cage_flags<256>);
   PL(k_bc_p); PL(k_sub_mean);
   PL(k_epilogue<true, true>, EPI_SMEM); PL(k_epilogue<true, false>, EPI_SMEM); PL(k_epilogue<false, true>, EPI_SMEM);
 #undef PL
@@ -587,6 +594,60 @@ extern "C" int bbpcg_set_coefficients(bbpcg_solver *s, const int *flag_u, const 
   CU(cudaStreamSynchronize(s->stream));
   if (comm_check(s, "bbpcg_set_coefficients")) return BBPCG_ECOMM;
   s->has_phase = phase != NULL;
+  s->coeffs_set = 1;
+  return BBPCG_OK;
+}
+
+/* ---- coefficient producers: cuda_build_cages (+ the mask digestion of cuda_PP_init_jacobi_preconditioner), bbpcg_cages.cuh ---- */
+extern "C" int bbpcg_build_cages(bbpcg_solver *s, int NPARTS, int nparts, const bbpcg_parts_view *parts,
+                                 int *flag_u, int *flag_v, int *flag_w, int *phase, int *phase_shell)
+{
+  if (!s || !flag_u || !flag_v || !flag_w) { bbpcg_set_error("bbpcg_build_cages: NULL flag array"); return BBPCG_EINVAL; }
+  if (NPARTS > 0 && (!phase || !phase_shell)) { bbpcg_set_error("bbpcg_build_cages: NPARTS > 0 needs phase and phase_shell"); return BBPCG_EINVAL; }
+  if (NPARTS > 0 && nparts > 0 && (!parts || !parts->base)) { bbpcg_set_error("bbpcg_build_cages: nparts > 0 needs the particle view"); return BBPCG_EINVAL; }
+  if (nparts < 0) { bbpcg_set_error("bbpcg_build_cages: nparts < 0"); return BBPCG_EINVAL; }
+  if (s->nranks == 1 && s->DOM.In * s->DOM.Jn * s->DOM.Kn != 1) { bbpcg_set_error("decomposition has %d blocks: call bbpcg_comm_import first", s->DOM.In * s->DOM.Jn * s->DOM.Kn); return BBPCG_ECOMM; }
+  CU(cudaSetDevice(s->device));
+  if (comm_check(s, "bbpcg_build_cages")) return BBPCG_ECOMM;
+  const dom_struct &d = s->dom;
+  const dom_struct &D = s->DOM;
+  const grid_info &g = d.Gcc;
+  if (NPARTS > 0) {                                                        /* cuda_particle.cu:1524-1598 */
+    k_cage_reset<<<clampi(((long long)g.s3b + 255) / 256, 1, s->sm_count * 16), 256, 0, s->stream>>>(phase, phase_shell, (long long)g.s3b);
+    s->launches++;
+    if (nparts > 0) {
+      CageArgs a;
+      memset(&a, 0, sizeof(a));
+      a.parts = (const char *)parts->base; a.stride = parts->stride; a.ox = parts->off_x; a.oy = parts->off_y; a.oz = parts->off_z; a.orad = parts->off_r;
+      a.nparts = nparts;
+      a.xs = d.xs; a.ys = d.ys; a.zs = d.zs; a.dx = d.dx; a.dy = d.dy; a.dz = d.dz;
+      a.xn = d.xn; a.yn = d.yn; a.zn = d.zn;
+      /* a cage is clipped to _is.._ie on a non-periodic edge of the GLOBAL domain, to _isb.._ieb elsewhere (particle_kernel.cu:177-211) */
+      a.S[0] = (d.I == D.Is && s->bc.pW != BB_PERIODIC) ? g._is : g._isb;  a.E[0] = (d.I == D.Ie && s->bc.pE != BB_PERIODIC) ? g._ie : g._ieb;
+      a.S[1] = (d.J == D.Js && s->bc.pS != BB_PERIODIC) ? g._js : g._jsb;  a.E[1] = (d.J == D.Je && s->bc.pN != BB_PERIODIC) ? g._je : g._jeb;
+      a.S[2] = (d.K == D.Ks && s->bc.pB != BB_PERIODIC) ? g._ks : g._ksb;  a.E[2] = (d.K == D.Ke && s->bc.pT != BB_PERIODIC) ? g._ke : g._keb;
+      a.s1b = g.s1b; a.s2b = g.s2b;
+      a.phase = phase; a.phase_shell = phase_shell;
+      k_cage<false><<<nparts, 256, 0, s->stream>>>(a);                    /* every build_phase before any build_phase_shell (:1541-1584) */
+      k_cage<true><<<nparts, 256, 0, s->stream>>>(a);
+      s->launches += 2;
+    }
+  }
+  CageFlagArgs f;
+  f.flag_u = flag_u; f.flag_v = flag_v; f.flag_w = flag_w;
+  f.phase = NPARTS > 0 ? phase : NULL; f.phase_shell = NPARTS > 0 ? phase_shell : NULL;
+  /* flag_external_*: only when neither side of the axis is periodic and the block touches the global face (cuda_particle.cu:1605-1639) */
+  f.ext = 0;
+  if (s->bc.pW != BB_PERIODIC && s->bc.pE != BB_PERIODIC) f.ext |= (d.I == D.Is ? 1u : 0u) | (d.I == D.Ie ? 2u : 0u);
+  if (s->bc.pS != BB_PERIODIC && s->bc.pN != BB_PERIODIC) f.ext |= (d.J == D.Js ? 4u : 0u) | (d.J == D.Je ? 8u : 0u);
+  if (s->bc.pB != BB_PERIODIC && s->bc.pT != BB_PERIODIC) f.ext |= (d.K == D.Ks ? 16u : 0u) | (d.K == D.Ke ? 32u : 0u);
+  const long long nrows = (long long)(s->dev.L.jn + 2) * (s->dev.L.kn + 2);
+  k_cage_flags<256><<<clampi(nrows, 1, s->stream_blocks), 256, 0, s->stream>>>(s->dev, s->fst, f);
+  s->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  if (comm_check(s, "bbpcg_build_cages")) return BBPCG_ECOMM;
+  s->has_phase = NPARTS > 0;
   s->coeffs_set = 1;
   return BBPCG_OK;
 }
@@ -1056,6 +1117,23 @@ extern "C" int bbpcg_set_option(bbpcg_solver *s, const char *key, long long valu
   else { bbpcg_set_error("unknown option %s", key); return BBPCG_EINVAL; }
   return BBPCG_OK;
 }
+
+#ifdef BB_TRACE
+/* debug build only: the stamps of the last BB_TRACE_LAUNCHES launches of the iteration kernels, raw u64 */
+extern "C" int bbpcg_trace_dump(bbpcg_solver *s, const char *path)
+{
+  if (!s || !path || !s->dev.trace) return BBPCG_EINVAL;
+  CU(cudaSetDevice(s->device));
+  const size_t n = (size_t)BB_TRACE_LAUNCHES * BB_TRACE_CTAS * BB_TRACE_EV;
+  std::vector<unsigned long long> h(n);
+  CU(cudaMemcpy(h.data(), s->dev.trace, n * 8, cudaMemcpyDeviceToHost));
+  FILE *f = fopen(path, "wb");
+  if (!f) return BBPCG_EIO;
+  const long long hdr[4] = { BB_TRACE_LAUNCHES, BB_TRACE_CTAS, BB_TRACE_EV, s->launches };
+  fwrite(hdr, 8, 4, f); fwrite(h.data(), 8, n, f); fclose(f);
+  return BBPCG_OK;
+}
+#endif
 
 extern "C" long long bbpcg_get_info(bbpcg_solver *s, const char *key)
 {

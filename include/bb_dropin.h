@@ -13,6 +13,7 @@
  *   mpi_cuda_exchange_Gfx/_Gfy/_Gfz(real *array)   src/mpi_comm.h:335,352,369; 24 call sites in src/bluebottle.c
  *   cuda_solvability                     src/cuda_bluebottle.cu:2313, called src/bluebottle.c:220 (reads the global out_plane)
  *   cuda_dom_BC_star                     src/cuda_bluebottle.cu:2111, called src/bluebottle.c:214,222 (reads the velocity entries of bc)
+ *   cuda_build_cages                     src/cuda_particle.cu:1516, called src/bluebottle.c:389 (+ domain / restart set-up); reads _parts
  * and, for the solve epilogue (link instead of the same-named functions of cuda_bluebottle.o):
  *   cuda_dom_BC_p(real *array)           src/cuda_bluebottle.cu:2536, called src/bluebottle.c:234,255
  *   cuda_project                         src/cuda_bluebottle.cu:2495, called src/bluebottle.c:237
@@ -22,7 +23,7 @@
  * src/mpi_comm.c:26-27, src/particle.c:27-28):
  *   dom, DOM, rank, nprocs, bc, rho_f, dt, pp_residual, pp_max_iter, stepnum, ttime,
  *   NPARTS, nparts, _u_star, _v_star, _w_star, _flag_u, _flag_v, _flag_w, _phase,
- *   _phase_shell, _rhs_p, _phi, and for the epilogue _u, _v, _w, _p, _p0
+ *   _phase_shell, _rhs_p, _phi, _parts, out_plane, and for the epilogue _u, _v, _w, _p, _p0
  * and call back into reference code at: cuda_part_BC_p() (src/cuda_particle.cu:1680) and
  * recorder_PP() (src/recorder.c:190).  `_invM,_r_q,_z_q,_p_q,_pb_q,_Apb_q` are NOT used: the
  * library keeps its own padded workspace.
@@ -48,6 +49,7 @@ void mpi_cuda_exchange_Gfy(real *array);
 void mpi_cuda_exchange_Gfz(real *array);
 void cuda_solvability(void);
 void cuda_dom_BC_star(void);
+void cuda_build_cages(void);
 void cuda_dom_BC_p(real *array);
 void cuda_project(void);
 void cuda_update_p(void);

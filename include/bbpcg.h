@@ -143,6 +143,25 @@ int  bbpcg_comm_import(bbpcg_solver *s, const void *all_blobs, int nranks);
 int  bbpcg_set_coefficients(bbpcg_solver *s, const int *flag_u, const int *flag_v,
                             const int *flag_w, const int *phase);
 
+/* ---- coefficient producers ---------------------------------------------------------------------
+ * = cuda_build_cages() (src/cuda_particle.cu:1516-1646) FUSED with the mask digestion of cuda_PP_init_jacobi_preconditioner:
+ * from this rank's particle list (centres and radii in global coordinates; the reference's `_parts`, ghost particles
+ * included) it fills phase / phase_shell (Gcc s3b ints: local particle index or -1; 0 on a particle's surface shell, else 1)
+ * and flag_u / flag_v / flag_w (Gfx / Gfy / Gfz s3b ints: 1, -1 on cage faces, 0 on external walls) EXACTLY as the reference
+ * does -- its other kernels read them -- and writes the solver's own 1-byte coefficient masks in the same pass, so no
+ * bbpcg_set_coefficients call is needed afterwards.  NPARTS == 0 (no particle anywhere): phase arrays are not touched, flags
+ * are 1 except on external walls.  4 launches, no host round trip (reference: 4 nparts + ~12 launches and 2 nparts blocking
+ * copies).  COLLECTIVE.  All arrays are DEVICE pointers; the particle list is addressed through a strided view so that an
+ * array of the reference's part_struct can be passed as is (stride sizeof(part_struct), offsets of x, y, z, r). */
+typedef struct bbpcg_parts_view {
+  const void *base;                 /* device */
+  size_t stride;                    /* bytes between particles */
+  size_t off_x, off_y, off_z, off_r;/* byte offsets of the `real` fields inside one particle */
+} bbpcg_parts_view;
+
+int  bbpcg_build_cages(bbpcg_solver *s, int NPARTS, int nparts, const bbpcg_parts_view *parts,
+                       int *flag_u, int *flag_v, int *flag_w, int *phase, int *phase_shell);
+
 /* Optional callback = the reference's cuda_part_BC_p() (src/cuda_particle.cu:1680), invoked
  * after PP_rhs when use_phase != 0 (src/cuda_solver.cu:128-132).  When NULL and phase_shell !=
  * NULL the library applies that kernel's net effect on rhs (rhs *= (phase<0 && phase_shell),

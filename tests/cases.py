@@ -84,6 +84,7 @@ def load_ref():
     lib.bbref_exchange_face.argtypes = [vp, C.c_int]
     lib.bbref_solvability.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_double)]
     lib.bbref_dom_BC_star.argtypes = [vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    lib.bbref_build_cages.argtypes = [C.c_int, C.c_int] + [vp] * 10
     lib.bbref_dev_ptr.argtypes = [C.c_int]
     lib.bbref_dev_ptr.restype = C.c_void_p
     return lib
@@ -148,3 +149,36 @@ def ref_dom_BC_star(lib, case, arrs, table):
     P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
     assert lib.bbref_dom_BC_star(P(arrs["u"]), P(arrs["v"]), P(arrs["w"]), (C.c_int * 18)(*types), (C.c_double * 18)(*vals)) == 0
     return arrs
+
+
+# ---- cuda_build_cages: particle lists (global coordinates) chosen to hit the corner cases of the cage logic ----
+def cage_particles(case_name, extent, cells):
+    """(x, y, z, r) arrays.  dx = extent / cells; radii are a few cells."""
+    xs, xe, ys, ye, zs, ze = extent
+    dx = (xe - xs) / cells[0]
+    L = np.array([xe - xs, ye - ys, ze - zs])
+    o = np.array([xs, ys, zs])
+    frac = {
+        # well inside; two spheres OVERLAPPING (the later index wins the shared cells); one tiny (r < dx)
+        "inside": [(0.30, 0.35, 0.40, 3.3), (0.62, 0.55, 0.52, 2.6), (0.70, 0.60, 0.55, 2.2), (0.2, 0.75, 0.8, 0.7)],
+        # cages cut by the domain faces: lower corner, upper face, one centred exactly on a face, one outside the block
+        "faces": [(0.04, 0.05, 0.06, 2.9), (0.5, 0.97, 0.5, 2.4), (1.0, 0.5, 0.3, 2.0), (0.5, 0.5, -0.4, 1.5), (0.93, 0.08, 0.95, 3.1)],
+        "single": [(0.5, 0.5, 0.5, 3.0)],
+    }[case_name]
+    a = np.array([[o[0] + f[0] * L[0], o[1] + f[1] * L[1], o[2] + f[2] * L[2], f[3] * dx] for f in frac])
+    return a[:, 0].copy(), a[:, 1].copy(), a[:, 2].copy(), a[:, 3].copy()
+
+
+def ref_build_cages(lib, case, parts, NPARTS=None):
+    """the reference's own cage kernels (O1) on one block: returns flag_u, flag_v, flag_w, phase, phase_shell"""
+    from bbpcg.grid import BC_SETS, grid_shape
+    d = case.o.dom(0)
+    px, py, pz, pr = [np.ascontiguousarray(v, dtype=np.float64) for v in parts]
+    n = len(px)
+    out = {k: np.full(grid_shape(d, g), 7, dtype=np.int32) for k, g in (("flag_u", "Gfx"), ("flag_v", "Gfy"), ("flag_w", "Gfz"),
+                                                                          ("phase", "Gcc"), ("phase_shell", "Gcc"))}
+    pbc = (C.c_int * 6)(*BC_SETS[case.bcname])
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    assert lib.bbref_build_cages(n if NPARTS is None else NPARTS, n, P(px), P(py), P(pz), P(pr), C.cast(pbc, C.c_void_p),
+                                 P(out["flag_u"]), P(out["flag_v"]), P(out["flag_w"]), P(out["phase"]), P(out["phase_shell"])) == 0
+    return out

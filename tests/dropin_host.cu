@@ -46,6 +46,7 @@ real rho_f = 1., dt = 1e-3, pp_residual = 1e-6, ttime = 0.;
 int pp_max_iter = 2000, stepnum = 0;
 int NPARTS = 0, nparts = 0;
 int out_plane = 10;                     /* HOMOGENEOUS, src/bluebottle.h:353 */
+void *_parts = NULL;                    /* part_struct *_parts (src/particle.h:692); only cuda_build_cages reads it */
 real *_u_star = NULL, *_v_star = NULL, *_w_star = NULL, *_rhs_p = NULL, *_phi = NULL;
 real *_u = NULL, *_v = NULL, *_w = NULL, *_p = NULL, *_p0 = NULL;
 int *_flag_u = NULL, *_flag_v = NULL, *_flag_w = NULL, *_phase = NULL, *_phase_shell = NULL;

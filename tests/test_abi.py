@@ -61,7 +61,7 @@ def test_dropin_exports_the_reference_entry_points_and_imports_its_globals():
     for g in ("dom", "DOM", "rank", "nprocs", "bc", "rho_f", "dt", "pp_residual", "pp_max_iter", "NPARTS", "nparts",
               "_u_star", "_v_star", "_w_star", "_flag_u", "_flag_v", "_flag_w", "_phase", "_phase_shell", "_rhs_p", "_phi",
               "cuda_part_BC_p", "recorder_PP",
-              "_u", "_v", "_w", "_p", "_p0", "out_plane"):            # epilogue / solvability entry points
+              "_u", "_v", "_w", "_p", "_p0", "out_plane", "_parts"):  # epilogue / solvability / cage entry points
         assert g in und, g
     # private scratch of the reference solver is NOT touched
     for g in ("_invM", "_r_q", "_z_q", "_p_q", "_pb_q", "_Apb_q", "_dom"):
@@ -82,6 +82,25 @@ def test_product_does_not_link_or_import_the_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 for needle in ("import oracle", "from oracle", "liboracle", "libbbref", "pcg_ref", "oracle/"):
                     assert needle not in txt, (os.path.join(dp, f), needle)
+
+
+def test_part_struct_view_matches_the_reference_header(tmp_path):
+    """the drop-in's cuda_build_cages reads x, y, z, r of the reference's part_struct through fixed offsets: re-derive them
+    from the reference's own header whenever it is available (the authoring container)"""
+    ref = "/root/reference/src"
+    if not os.path.exists(os.path.join(ref, "particle.h")):
+        pytest.skip("reference tree not present")
+    src = tmp_path / "po.cu"
+    src.write_text('#include <cstdio>\n#include <cstddef>\n#include "bluebottle.h"\n#include "particle.h"\n'
+                   'int main(){ printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(part_struct), offsetof(part_struct, r), offsetof(part_struct, x), '
+                   'offsetof(part_struct, y), offsetof(part_struct, z), sizeof(BC)); }\n')
+    exe = str(tmp_path / "po")
+    subprocess.check_call(["nvcc", "-DDOUBLE", "-w", "-I", os.path.join(ROOT, "oracle", "stubs"), "-I", ref, "-o", exe, str(src)])
+    size, off_r, off_x, off_y, off_z, size_bc = [int(v) for v in subprocess.check_output([exe], text=True).split()]
+    txt = open(os.path.join(ROOT, "bluebottle-3.0_b200", "csrc", "bbpcg_dropin.cu")).read()
+    got = {k: int(re.search(r"#define %s (\d+)" % k, txt).group(1)) for k in ("BB_PART_STRIDE", "BB_PART_OFF_R", "BB_PART_OFF_X", "BB_PART_OFF_Y", "BB_PART_OFF_Z")}
+    assert got == {"BB_PART_STRIDE": size, "BB_PART_OFF_R": off_r, "BB_PART_OFF_X": off_x, "BB_PART_OFF_Y": off_y, "BB_PART_OFF_Z": off_z}
+    assert size_bc == 648                       # include/bb_grid.h: bb_BC mirrors the reference's BC
 
 
 def test_grid_contract_sizes():

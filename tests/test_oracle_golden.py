@@ -35,7 +35,7 @@ def _load(name):
 
 
 def test_manifest_lists_every_fixture():
-    files = sorted(f[:-4] for f in os.listdir(GOLD) if f.endswith(".npz") and not f.startswith("epi_"))   # epi_*: EPILOGUE_MANIFEST.json
+    files = sorted(f[:-4] for f in os.listdir(GOLD) if f.endswith(".npz") and not f.startswith(("epi_", "bcs_", "cage_")))   # epi_*: EPILOGUE_MANIFEST.json, bcs_*: BCSTAR_MANIFEST.json, cage_*: CAGES_MANIFEST.json
     assert files == sorted(CASES)
     assert MANIFEST["solve"] == {"rho_f": 1.0, "dt": 1e-3, "pp_residual": 1e-6, "pp_max_iter": 2000}
 
