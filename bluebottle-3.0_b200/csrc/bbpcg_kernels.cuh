@@ -311,6 +311,7 @@ struct SearchArgs {
   const double *rhs;   /* refresh form of k_resid_tma only: the caller's right-hand side (Gcc s3b) and its strides */
   int s1b, s2b;
   int launch;          /* trace build: running launch number */
+  int zshift;          /* experiment: CTA blockIdx.z owns z-chunk (blockIdx.z + zshift) % nbz */
   int producer;        /* the thread that issues the TMA loads: BB_PRODUCER (lane 0 of the 9th warp; default) or 0 (option tma_warp 0) */
 };
 

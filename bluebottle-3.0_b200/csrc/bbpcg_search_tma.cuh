@@ -120,8 +120,9 @@ __device__ __forceinline__ double search_planes(const Dev &d, const SearchMaps &
   const int ty = a.ty, hy = ty + 2;
   const int i0 = bx * TX + 1, j0 = by * ty + 1;
   const int tyc = min(ty, L.jn - j0 + 1);               /* owned rows of THIS tile (the last tile of a column may be short) */
-  const int k0 = __ldg(d.ztab + blockIdx.z) + 1;        /* host-written table: safe before pdl_wait() */
-  const int k1 = __ldg(d.ztab + blockIdx.z + 1);
+  const int cz = (blockIdx.z + a.zshift) % a.nbz;     /* which z-chunk this CTA owns */
+  const int k0 = __ldg(d.ztab + cz) + 1;        /* host-written table: safe before pdl_wait() */
+  const int k1 = __ldg(d.ztab + cz + 1);
   const int nplanes = k1 - k0 + 3;                      /* planes k0-1 .. k1+1 */
   const int x0 = BB_XOFF + 1 + bx * TX - 2;             /* array x index of tile column 0 */
   const int y0 = j0 - 1;

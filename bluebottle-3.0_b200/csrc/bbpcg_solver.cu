@@ -76,6 +76,7 @@ struct bbpcg_solver {
   int plan_ok;                      /* the plan below, the uploaded table and the tensor maps are current */
   int plan_ty, plan_nbx, plan_nby, plan_nbz, plan_kc;
   int pdl;                          /* programmatic dependent launch of the two iteration kernels: 0 off, 1 on, 2 auto */
+  int zshift;                       /* experiment (option zshift): rotate the CTA -> z-chunk map */
   int tma_warp;                     /* 1 (default): a dedicated producer warp issues the iteration kernels' TMA loads; 0: thread 0 does */
   int rhs_tiled;                    /* PP_rhs through shared-memory transposes (default) or the row-walking kernel */
   int shared_device;                /* some peer rank lives on this same GPU (single-process harness, or two processes on one GPU) */
@@ -469,6 +470,7 @@ static SearchArgs plan_args(const bbpcg_solver *s)
   a.nbx = s->plan_nbx; a.nby = s->plan_nby; a.nbz = s->plan_nbz; a.ty = s->plan_ty;
   a.producer = s->tma_warp ? BB_PRODUCER : 0;
   a.launch = (int)(s->launches & 0x7fffffff);
+  a.zshift = s->zshift;
   return a;
 }
 
@@ -1097,6 +1099,7 @@ extern "C" int bbpcg_set_option(bbpcg_solver *s, const char *key, long long valu
   else if (!strcmp(key, "pdl")) s->pdl = clampi(value, 0, 2);
   else if (!strcmp(key, "rhs_tiled")) s->rhs_tiled = value != 0;
   else if (!strcmp(key, "tma_warp")) s->tma_warp = value != 0;
+  else if (!strcmp(key, "zshift")) s->zshift = value > 0 ? (int)value : 0;
   else if (!strcmp(key, "stream_blocks")) s->stream_blocks = clampi(value, 1, BB_MAXBLOCKS);
   else if (!strcmp(key, "check_every")) s->check_every = clampi(value, 1, 1000);
   else if (!strcmp(key, "comm_timeout_ms")) s->dev.comm.timeout_cycles = value > 0 ? value * 2000000ll : -1;   /* ~2 GHz; <= 0: wait for ever, like MPI */

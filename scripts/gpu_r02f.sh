@@ -1,0 +1,9 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+rm -f gpurun_out/r02f_trace.json
+for o in "--opt ty=8 --opt kc=64" "--opt ty=8 --opt kc=32" "--opt ty=6 --opt kc=86"; do
+  BBPCG_LIB_PATH=$PWD/bluebottle-3.0_b200/lib/libbbpcg_trace.so timeout 200 python scripts/trace_timeline.py --grid 256 $o --out gpurun_out/r02f_trace.json 2>> gpurun_out/r02f_trace.err | cut -c1-300
+done
+BBPCG_LIB_PATH=$PWD/bluebottle-3.0_b200/lib/libbbpcg_trace.so timeout 200 python scripts/trace_timeline.py --grid 256 --bc periodic --opt ty=8 --opt kc=64 --out gpurun_out/r02f_trace.json 2>> gpurun_out/r02f_trace.err | cut -c1-300
+tail -3 gpurun_out/r02f_trace.err

@@ -94,7 +94,15 @@ def main():
     solo = np.array([per_sm[int(s_)] == 1 for s_ in last["sm"]])
     out["loop_us_solo_sm"] = float(np.median(dur[solo])) if solo.any() else None
     out["loop_us_shared_sm"] = float(np.median(dur[~solo])) if (~solo).any() else None
-    print(json.dumps(out))
+    # per-CTA detail of that launch: where are the slow CTAs? (block index -> bx, by, bz; SM id; loop duration)
+    nbx = (cells[0] + 127) // 128
+    ty = s.info("search_ty")
+    nby = (cells[1] + ty - 1) // ty
+    bid = np.nonzero(t[[i for i in range(nl) if (t[i, :, 7].max() >> 8) == last["launch"]][0], :, 3] > 0)[0]
+    out["per_cta"] = {"bx": (bid % nbx).tolist(), "by": ((bid // nbx) % nby).tolist(), "bz": (bid // (nbx * nby)).tolist(),
+                      "sm": last["sm"].tolist(), "loop_us": [round(float(v), 2) for v in dur],
+                      "start_us": [round(float(v), 2) for v in (last["first"] - last["entry"].min()) / 1e3]}
+    print(json.dumps({k: v for k, v in out.items() if k != "per_cta"}))
     with open(a.out, "a") as f:
         f.write(json.dumps(out) + "\n")
     os.remove(path)
