@@ -311,9 +311,67 @@ struct SearchArgs {
   const double *rhs;   /* refresh form of k_resid_tma only: the caller's right-hand side (Gcc s3b) and its strides */
   int s1b, s2b;
   int launch;          /* trace build: running launch number */
-  int zshift;          /* experiment: CTA blockIdx.z owns z-chunk (blockIdx.z + zshift) % nbz */
+  int nitems;          /* nbx * nby * nbz work items, claimed dynamically by the resident CTAs */
   int producer;        /* the thread that issues the TMA loads: BB_PRODUCER (lane 0 of the 9th warp; default) or 0 (option tma_warp 0) */
 };
+
+/* ---- persistent, dynamically balanced work distribution of the two iteration kernels -------------------------------
+ * A WORK ITEM is one (x-tile, y-tile, z-chunk): item = bx + nbx (by + nby cz).  The kernels run as ONE wave of resident
+ * CTAs; a CTA's first item is its block index, every further one is claimed from an atomic counter in item order, and the
+ * TMA producer keeps its D-plane lead ACROSS item boundaries, so a CTA streams without a pipeline refill.  Why: with a
+ * static one-wave partition the 256^3 block of an 8-GPU run straggled -- identical CTAs took 84 .. 135 us depending on the
+ * SM group they landed on (profiles/r02fg_trace_per_cta.jsonl: the two CTAs of an SM finish together, SM groups differ by
+ * 40 %), the kernel ended with the slowest CTA and HBM idled behind it; hardware-scheduled small CTAs pay a launch + ramp
+ * per CTA instead.  Dot products stay bit-reproducible under any assignment: every item stores ITS partial in its own
+ * slot and the last CTA adds the slots in item order. */
+#define BB_CLAIM_SEARCH 1          /* Dev::counter[1], [2]: claim counters of the two kernels; [3]: finished CTAs */
+#define BB_CLAIM_RESID 2
+#define BB_CLAIM_DONE 3
+#define BB_QN 4                    /* item queue between the producer thread and the consumers (the producer is <= 2 items ahead) */
+
+struct ItemGeom { int bx, by, k0, k1, nplanes; };
+
+__device__ __forceinline__ ItemGeom decode_item(const Dev &d, const SearchArgs &a, int item)
+{
+  ItemGeom g;
+  g.bx = item % a.nbx;
+  const int t = item / a.nbx;
+  g.by = t % a.nby;
+  const int cz = t / a.nby;
+  g.k0 = __ldg(d.ztab + cz) + 1;                        /* host-written table: safe before pdl_wait() */
+  g.k1 = __ldg(d.ztab + cz + 1);
+  g.nplanes = g.k1 - g.k0 + 3;                          /* planes k0-1 .. k1+1 */
+  return g;
+}
+
+/* next item of this CTA (-1: none left) */
+__device__ __forceinline__ int claim_item(const Dev &d, const SearchArgs &a, int which)
+{
+  const int item = (int)gridDim.x + (int)atomicAdd(d.counter + which, 1u);
+  return item < a.nitems ? item : -1;
+}
+
+/* End of a persistent kernel: the LAST CTA to arrive adds the per-item partials in item order (bit-identical whatever CTA
+ * computed which item) and re-arms the counters.  Returns true (all threads) in that CTA only; tot valid in thread 0. */
+__device__ bool items_reduce(const Dev &d, int nitems, int which, double &tot)
+{
+  __shared__ double sh[32];
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();                                    /* this CTA's item partials (and its stores to r / p / x) before the count */
+    const unsigned t = atomicAdd(d.counter + BB_CLAIM_DONE, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  double s = 0.;
+  for (int i = threadIdx.x; i < nitems; i += blockDim.x) s += __ldcg(&d.partials[i]);
+  tot = block_sum<1>(s, sh);
+  if (threadIdx.x == 0) { d.counter[BB_CLAIM_DONE] = 0u; d.counter[which] = 0u; }
+  return true;
+}
 
 #ifdef BB_TRACE
 __device__ __forceinline__ unsigned long long bb_gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }

@@ -47,8 +47,39 @@ struct ResidGeom {
 /* REFRESH = true is the every-50th-iteration true-residual form (src/cuda_solver.cu:209-223, PP_update_residual
  * src/solver_kernel.cu:883-904): the operator is applied to x (whose ghosts k_refresh_x4 just made current)
  * instead of p, and r = b - (-A x) with b read from the caller's right-hand side array. */
+template <bool PARTS, int DD, bool REFRESH>
+__device__ __forceinline__ void resid_issue(const Dev &d, const SearchMaps &tm, const SearchArgs &a, unsigned char *smem, const ProdCursor &c, int q)
+{
+  typedef ResidGeom<PARTS, DD> G;
+  constexpr int TX = G::TX, HXP = G::HXP;
+  const Layout &L = d.L;
+  const int ty = a.ty, hy = ty + 2;
+  const int bx = c.ig.bx, k0 = c.ig.k0, k1 = c.ig.k1;
+  const int j0 = c.ig.by * ty + 1;
+  const int x0 = BB_XOFF + 1 + bx * TX - 2;             /* array x index of tile column 0 */
+  const int y0 = j0 - 1;
+  const unsigned bar0 = tma::smem_u32(smem + G::OFF_BAR);
+  const unsigned sP = tma::smem_u32(smem), sS = tma::smem_u32(smem + G::OFF_STAGE);
+  const int pi = k0 - 1 + c.lp;
+  const int ms = c.g % G::NMS, ps = c.g % G::NPS;
+  const unsigned bar = bar0 + 8 * ms;
+  const unsigned st = sS + ms * G::STAGE;
+  const bool inner = pi >= 1 && pi <= L.kn;
+  unsigned bytes = HXP * hy * 8 + G::MXP * hy;
+  if (PARTS && inner) bytes += TX * ty;
+  const bool owned = !REFRESH && pi >= k0 && pi <= k1;
+  if (owned) bytes += TX * ty * 8;
+  tma::mbar_expect_tx(bar, bytes);
+  if (owned) tma::load3d(st + G::MT + G::PMT, &tm.ro, BB_XOFF + 1 + bx * TX, j0, pi, bar);
+  tma::load3d(sP + ps * G::RT, REFRESH ? &tm.xh : &tm.p[(q + 1) & 1], x0, y0, pi, bar);   /* p of the iteration in flight (ghosts current) / x */
+  tma::load3d(st, &tm.fm, x0 - G::MX0, y0, pi, bar);
+  if (PARTS && inner) tma::load3d(st + G::MT, &tm.pm, BB_XOFF + 1 + bx * TX, j0, pi, bar);
+}
+
+/* the plane loop of ONE item; see search_item (bbpcg_search_tma.cuh) for the roles of g, pc and queue */
 template <bool PARTS, int DD, bool REFRESH, bool XFULL>
-__device__ __forceinline__ double resid_planes(const Dev &d, const SearchMaps &tm, const SearchArgs &a, unsigned char *smem, int &done)
+__device__ __forceinline__ double resid_item(const Dev &d, const SearchMaps &tm, const SearchArgs &a, unsigned char *smem, const ItemGeom &ig,
+                                             int &g, ProdCursor &pc, int *queue, int q, double alpha, double c63)
 {
   typedef ResidGeom<PARTS, DD> G;
   constexpr int TX = G::TX, HXP = G::HXP, NO = G::NO;
@@ -56,20 +87,14 @@ __device__ __forceinline__ double resid_planes(const Dev &d, const SearchMaps &t
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + G::OFF_BAR);
 
   const Layout L = d.L;
-  Scal *sc = d.sc;
   const int tid = threadIdx.x;
-  const int bx = blockIdx.x, by = blockIdx.y;
-  const int ty = a.ty, hy = ty + 2;
+  const int bx = ig.bx, by = ig.by;
+  const int ty = a.ty;
   const int i0 = bx * TX + 1, j0 = by * ty + 1;
   const int tyc = min(ty, L.jn - j0 + 1);
-  const int cz = (blockIdx.z + a.zshift) % a.nbz;     /* which z-chunk this CTA owns */
-  const int k0 = __ldg(d.ztab + cz) + 1;
-  const int k1 = __ldg(d.ztab + cz + 1);
-  const int nplanes = k1 - k0 + 3;                      /* planes k0-1 .. k1+1 */
-  const int x0 = BB_XOFF + 1 + bx * TX - 2;             /* array x index of tile column 0 */
+  const int k0 = ig.k0, k1 = ig.k1, nplanes = ig.nplanes;
   const int y0 = j0 - 1;
   const unsigned bar0 = tma::smem_u32(bars);
-  const unsigned sP = tma::smem_u32(smem), sS = tma::smem_u32(smem + G::OFF_STAGE);
 
   /* per-thread geometry: two owned double2 items on tile rows rg+1, rg+5 */
   const int col2 = tid & 63, rg = tid >> 6;
@@ -89,42 +114,7 @@ __device__ __forceinline__ double resid_planes(const Dev &d, const SearchMaps &t
   const bool xf_w = d.xf[0] != nullptr && iA == 1;
   const bool xf_e0 = d.xf[1] != nullptr && iA == L.in, xf_e1 = d.xf[1] != nullptr && iA + 1 == L.in;
 
-  /* ---- from here on we read what the search kernel wrote ---- */
-  BB_STAMP(d, a, 0);
-  pdl_wait();
-  BB_STAMP(d, a, 1);
-  const int q = sc->q;
-  auto issue = [&](int lp) {
-    const int pi = k0 - 1 + lp;
-    const int ms = lp % G::NMS, ps = lp % G::NPS;
-    const unsigned bar = bar0 + 8 * ms;
-    const unsigned st = sS + ms * G::STAGE;
-    const bool inner = pi >= 1 && pi <= L.kn;
-    unsigned bytes = HXP * hy * 8 + G::MXP * hy;
-    if (PARTS && inner) bytes += TX * ty;
-    const bool owned = !REFRESH && pi >= k0 && pi <= k1;
-    if (owned) bytes += TX * ty * 8;
-    tma::mbar_expect_tx(bar, bytes);
-    if (owned) tma::load3d(st + G::MT + G::PMT, &tm.ro, BB_XOFF + 1 + bx * TX, j0, pi, bar);
-    tma::load3d(sP + ps * G::RT, REFRESH ? &tm.xh : &tm.p[(q + 1) & 1], x0, y0, pi, bar);   /* p of the iteration in flight (ghosts current) / x */
-    tma::load3d(st, &tm.fm, x0 - G::MX0, y0, pi, bar);
-    if (PARTS && inner) tma::load3d(st + G::MT, &tm.pm, BB_XOFF + 1 + bx * TX, j0, pi, bar);
-  };
-  if (tid == a.producer) {
-#pragma unroll
-    for (int l = 0; l < G::D; l++) if (l < nplanes) issue(l);
-  }
-  const double alpha = sc->alpha;
-  done = sc->done;
   double *__restrict__ r = d.r;
-  if (done) {                       /* a finished solve: drain the loads already issued, then leave */
-    if (tid == a.producer) {
-#pragma unroll
-      for (int l = 0; l < G::D; l++) if (l < nplanes) tma::mbar_wait(bar0 + 8 * l, 0);
-    }
-    return 0.;
-  }
-  const double c63 = __ldg(d.invM_tab + 63);
   const bool consumer = tid < BB_PRODUCER;              /* warp-uniform; the producer warp only issues loads */
 
   double2 pB[NO], pC[NO], bn[NO];                       /* bn: refresh form, b of the NEXT plane to be computed */
@@ -132,10 +122,10 @@ __device__ __forceinline__ double resid_planes(const Dev &d, const SearchMaps &t
   for (int o = 0; o < NO; o++) { pB[o] = make_double2(0., 0.); pC[o] = make_double2(0., 0.); bn[o] = make_double2(0., 0.); }
 
   double dot = 0.;
-  for (int lp = 0; lp < nplanes; lp++) {
+  for (int lp = 0; lp < nplanes; lp++, g++) {
     const int pi = k0 - 1 + lp;
-    const int ms = lp % G::NMS, ps = lp % G::NPS;
-    if (tid == a.producer && lp + G::D < nplanes) issue(lp + G::D);
+    const int ps = g % G::NPS;
+    if (tid == a.producer) producer_step(d, a, pc, queue, BB_CLAIM_RESID, [&](const ProdCursor &c) { resid_issue<PARTS, DD, REFRESH>(d, tm, a, smem, c, q); });
     const bool plane_owned = pi >= k0 && pi <= k1;
     if (consumer) {
     double2 bc[NO];
@@ -150,8 +140,8 @@ __device__ __forceinline__ double resid_planes(const Dev &d, const SearchMaps &t
         }
       }
     }
-    tma::mbar_wait(bar0 + 8 * ms, (lp / G::NMS) & 1);
-    if (lp == 0) BB_STAMP(d, a, 2);
+    tma::mbar_wait(bar0 + 8 * (g % G::NMS), (g / G::NMS) & 1);
+    if (g == 0) BB_STAMP(d, a, 2);
 
     const double *Pt = reinterpret_cast<const double *>(smem + ps * G::RT);
     double2 pT[NO];
@@ -161,8 +151,8 @@ __device__ __forceinline__ double resid_planes(const Dev &d, const SearchMaps &t
     /* ---- plane kc = pi-1: q = -A p from registers + the previous ring slot; r -= alpha q; (r, z) ---- */
     const int kc = pi - 1;
     if (kc >= k0) {
-      const double *Pc = reinterpret_cast<const double *>(smem + ((lp - 1) % G::NPS) * G::RT);
-      const unsigned char *Mc = smem + G::OFF_STAGE + ((lp - 1) % G::NMS) * G::STAGE;       /* mask, pmask, r of plane kc */
+      const double *Pc = reinterpret_cast<const double *>(smem + ((g - 1) % G::NPS) * G::RT);
+      const unsigned char *Mc = smem + G::OFF_STAGE + ((g - 1) % G::NMS) * G::STAGE;        /* mask, pmask, r of plane kc */
       const unsigned char *PMc = Mc + G::MT;
       const double *Rc = reinterpret_cast<const double *>(Mc + G::MT + G::PMT);
       double *r_pl = r + (long long)kc * L.ps;
@@ -220,27 +210,63 @@ k_resid_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps tm
 {
   typedef ResidGeom<PARTS, DD> G;
   extern __shared__ __align__(128) unsigned char smem[];
-  if (threadIdx.x == 0) {
+  __shared__ int queue[BB_QN];
+  __shared__ double sh_sum[32];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
     const unsigned bar0 = tma::smem_u32(smem + G::OFF_BAR);
     for (int s = 0; s < G::NMS; s++) tma::mbar_init(bar0 + 8 * s, 1);
     tma::fence_barrier_init();
   }
-  if (threadIdx.x < 128) reinterpret_cast<double *>(smem + G::OFF_TAB)[threadIdx.x] = __ldg(d.invM_tab + threadIdx.x);
+  if (tid < 128) reinterpret_cast<double *>(smem + G::OFF_TAB)[tid] = __ldg(d.invM_tab + tid);
+  ProdCursor pc;
+  pc.item = (int)blockIdx.x < a.nitems ? (int)blockIdx.x : -1; pc.lp = 0; pc.n = 0; pc.g = 0;
+  if (pc.item >= 0) pc.ig = decode_item(d, a, pc.item);
+  if (tid == a.producer) queue[0] = pc.item;
   __syncthreads();
-  const bool xfull = (blockIdx.x * G::TX + G::TX) <= d.L.in;
-  int done;
-  const double dot = xfull ? resid_planes<PARTS, DD, REFRESH, true>(d, tm, a, smem, done) : resid_planes<PARTS, DD, REFRESH, false>(d, tm, a, smem, done);
-  if (done) return;                 /* a finished solve: every later launch is a no-op */
+
+  /* ---- from here on we read what the search kernel wrote ---- */
+  BB_STAMP(d, a, 0);
+  pdl_wait();
+  BB_STAMP(d, a, 1);
+  Scal *sc = d.sc;
+  const int q = sc->q;
+  int issued = 0;
+  if (tid == a.producer) {
+#pragma unroll
+    for (int l = 0; l < G::D; l++) if (pc.item >= 0) { producer_step(d, a, pc, queue, BB_CLAIM_RESID, [&](const ProdCursor &c) { resid_issue<PARTS, DD, REFRESH>(d, tm, a, smem, c, q); }); issued++; }
+  }
+  const double alpha = sc->alpha;
+  const int done = sc->done;
+  if (done) {                       /* a finished solve: drain the loads already issued, then leave */
+    if (tid == a.producer) {
+      const unsigned bar0 = tma::smem_u32(smem + G::OFF_BAR);
+      for (int l = 0; l < issued; l++) tma::mbar_wait(bar0 + 8 * (l % G::NMS), (l / G::NMS) & 1);
+    }
+    return;
+  }
+  const double c63 = __ldg(d.invM_tab + 63);
+
+  int g = 0, n = 0;
+  int cur = queue[0];
+  while (cur >= 0) {
+    const ItemGeom ig = decode_item(d, a, cur);
+    const bool xfull = (ig.bx * G::TX + G::TX) <= d.L.in;
+    const double dot = xfull ? resid_item<PARTS, DD, REFRESH, true>(d, tm, a, smem, ig, g, pc, queue, q, alpha, c63)
+                             : resid_item<PARTS, DD, REFRESH, false>(d, tm, a, smem, ig, g, pc, queue, q, alpha, c63);
+    const double part = block_sum<1>(dot, sh_sum);      /* the item's (r,z) partial in the item's own slot */
+    if (tid == 0) d.partials[cur] = part;
+    n++;
+    cur = queue[n % BB_QN];
+  }
   BB_STAMP(d, a, 3);
-  BB_TRACE_AT(d, a, 6, (unsigned long long)bb_smid());
+  BB_TRACE_AT(d, a, 6, (unsigned long long)bb_smid() | ((unsigned long long)n << 32) | ((unsigned long long)g << 40));
   BB_TRACE_AT(d, a, 7, 2ull | ((unsigned long long)a.launch << 8));
 
   pdl_launch_dependents();
-  /* ---- (r,z): grid reduction, rank all-reduce, stop test, beta (cuda_solver.cu:231-267) ---- */
-  double v[1] = { dot }, tot[1];
-  const int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-  const int nblocks = gridDim.x * gridDim.y * gridDim.z;
-  const bool last = grid_reduce<1>(d, v, bid, nblocks, tot, false);
+  /* ---- (r,z): item partials in item order, rank all-reduce, stop test, beta (cuda_solver.cu:231-267) ---- */
+  double tot[1];
+  const bool last = items_reduce(d, a.nitems, BB_CLAIM_RESID, tot[0]);
   BB_STAMP(d, a, 4);
   if (last) {
     rank_allreduce(d, tot, 1, true);          /* peers pull the r written here */

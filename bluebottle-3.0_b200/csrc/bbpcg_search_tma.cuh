@@ -104,38 +104,114 @@ struct SearchGeom {
 
 #define BB_FULLMASK2 0x3f3fu        /* both cells of a double2 have all six flags set, neither is dead */
 
-/* The plane loop.  XFULL: columns i0 .. i0+127 are all interior columns of the block. */
-template <bool PARTS, int DD, bool XFULL>
-__device__ __forceinline__ double search_planes(const Dev &d, const SearchMaps &tm, const SearchArgs &a, unsigned char *smem, int &done)
+/* ---- the TMA producer: lane 0 of the 9th warp ------------------------------------------------------------------
+ * Its cursor (item, plane) runs D planes ahead of the consumers in the FLATTENED sequence of this CTA's items, so the
+ * ring never drains at an item boundary.  A newly claimed item is published in the small queue the consumers read when
+ * they get there (>= one CTA barrier later). */
+struct ProdCursor {
+  int item;            /* item being issued (-1: nothing left to issue) */
+  int lp;              /* next plane of it to issue */
+  int n;               /* sequence number of that item inside this CTA */
+  int g;               /* flattened plane number of the next issue: ring slot g % N, mbarrier parity (g / N) & 1 */
+  ItemGeom ig;
+};
+
+template <bool PARTS, int DD>
+__device__ __forceinline__ void search_issue(const Dev &d, const SearchMaps &tm, const SearchArgs &a, unsigned char *smem, const ProdCursor &c, int q)
 {
   typedef SearchGeom<PARTS, DD> G;
-  constexpr int TX = G::TX, HXP = G::HXP, NO = G::NO;
-  double *tab = reinterpret_cast<double *>(smem + G::OFF_TAB);
-  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + G::OFF_BAR);
-
-  const Layout L = d.L;
-  Scal *sc = d.sc;
-  const int tid = threadIdx.x;
-  const int bx = blockIdx.x, by = blockIdx.y;
+  constexpr int TX = G::TX, HXP = G::HXP;
+  const Layout &L = d.L;
   const int ty = a.ty, hy = ty + 2;
+  const int bx = c.ig.bx, by = c.ig.by, k0 = c.ig.k0, k1 = c.ig.k1;
   const int i0 = bx * TX + 1, j0 = by * ty + 1;
-  const int tyc = min(ty, L.jn - j0 + 1);               /* owned rows of THIS tile (the last tile of a column may be short) */
-  const int cz = (blockIdx.z + a.zshift) % a.nbz;     /* which z-chunk this CTA owns */
-  const int k0 = __ldg(d.ztab + cz) + 1;        /* host-written table: safe before pdl_wait() */
-  const int k1 = __ldg(d.ztab + cz + 1);
-  const int nplanes = k1 - k0 + 3;                      /* planes k0-1 .. k1+1 */
+  const int tyc = min(ty, L.jn - j0 + 1);
   const int x0 = BB_XOFF + 1 + bx * TX - 2;             /* array x index of tile column 0 */
   const int y0 = j0 - 1;
-  const int gxsh = y0 & 1;                              /* the x-ghost runs start at the even j at or below y0 */
-
-  /* which ghost buffers this tile needs (uniform per CTA) */
+  /* which ghost buffers this tile needs */
   const bool gy0 = (by == 0) && d.halo.f[3].r != nullptr;                    /* row 0 = j 0, from S      */
   const bool gy1 = (y0 + tyc + 1 == L.jn + 1) && d.halo.f[2].r != nullptr;   /* row tyc+1 = j jn+1, N    */
   const bool gx0 = (bx == 0) && d.halo.f[1].r != nullptr;                    /* column i = 0, from W     */
   const bool gx1 = (i0 + TX - 1 >= L.in) && d.halo.f[0].r != nullptr;        /* column i = in+1, from E  */
+  const unsigned bar0 = tma::smem_u32(smem + G::OFF_BAR);
+  const unsigned sP = tma::smem_u32(smem), sS = tma::smem_u32(smem + G::OFF_STAGE);
+  const int pi = k0 - 1 + c.lp;
+  const int rs = c.g % G::NRS, ps = c.g % G::NPS;
+  const unsigned bar = bar0 + 8 * rs;
+  const unsigned st = sS + rs * G::STAGE;
+  const bool inner = pi >= 1 && pi <= L.kn;
+  unsigned bytes = 2 * (HXP * hy * 8) + G::MXP * hy;
+  if (inner) {
+    if (gy0) bytes += HXP * 8;
+    if (gy1) bytes += HXP * 8;
+    if (gx0) bytes += G::GXN * 8;
+    if (gx1) bytes += G::GXN * 8;
+    if (PARTS) bytes += TX * ty;
+  }
+  const bool owned = pi >= k0 && pi <= k1;
+  if (owned) bytes += TX * ty * 8;
+  tma::mbar_expect_tx(bar, bytes);
+  if (owned) tma::load3d(st + G::RT + G::MT + G::GY + G::GX + G::PMT, &tm.xo, BB_XOFF + 1 + bx * TX, j0, pi, bar);
+  tma::load3d(sP + ps * G::RT, &tm.p[q & 1], x0, y0, pi, bar);
+  tma::load3d(st + G::RT, &tm.fm, x0 - G::MX0, y0, pi, bar);
+  if (pi == 0 && d.halo.f[5].r) tma::load3d(st, &tm.nb[5], x0, y0, d.halo.f[5].L.kn, bar);          /* B neighbour's top plane    */
+  else if (pi == L.kn + 1 && d.halo.f[4].r) tma::load3d(st, &tm.nb[4], x0, y0, 1, bar);            /* T neighbour's bottom plane */
+  else tma::load3d(st, &tm.r, x0, y0, pi, bar);
+  if (inner) {
+    if (gy0) tma::load3d(st + G::RT + G::MT, &tm.nb[3], x0, d.halo.f[3].L.jn, pi, bar);
+    if (gy1) tma::load3d(st + G::RT + G::MT + G::GYS, &tm.nb[2], x0, 1, pi, bar);
+    if (gx0) tma::load2d(st + G::RT + G::MT + G::GY, &tm.nb[1], y0 & ~1, pi, bar);          /* W neighbour's E face, j = (y0 & ~1) .. */
+    if (gx1) tma::load2d(st + G::RT + G::MT + G::GY + G::GXS, &tm.nb[0], y0 & ~1, pi, bar); /* E neighbour's W face                  */
+    if (PARTS) tma::load3d(st + G::RT + G::MT + G::GY + G::GX, &tm.pm, BB_XOFF + 1 + bx * TX, j0, pi, bar);
+  }
+}
+
+/* one step of the producer: issue the plane under the cursor, move on; at the end of an item claim the next one and
+ * publish it.  ISSUE is the kernel's issue function (search_issue / resid_issue). */
+template <typename ISSUE>
+__device__ __forceinline__ void producer_step(const Dev &d, const SearchArgs &a, ProdCursor &c, int *queue, int which, ISSUE issue)
+{
+  if (c.item < 0) return;
+  issue(c);
+  c.g++;
+  if (++c.lp == c.ig.nplanes) {
+    c.item = claim_item(d, a, which);
+    c.n++;
+    queue[c.n % BB_QN] = c.item;
+    c.lp = 0;
+    if (c.item >= 0) c.ig = decode_item(d, a, c.item);
+  }
+}
+
+/* The consumers' plane loop of ONE item (every thread of the CTA runs it: the producer warp follows the same control flow,
+ * its lane 0 issues the loads).  g: flattened plane counter of the CTA.  XFULL: the tile's 128 columns are all interior
+ * columns of the block.  Returns the thread's partial of (p, q) over the item. */
+template <bool PARTS, int DD, bool XFULL>
+__device__ __forceinline__ double search_item(const Dev &d, const SearchMaps &tm, const SearchArgs &a, unsigned char *smem, const ItemGeom &ig,
+                                              int &g, ProdCursor &pc, int *queue, int q, double beta, double ax, double c63)
+{
+  typedef SearchGeom<PARTS, DD> G;
+  constexpr int TX = G::TX, HXP = G::HXP, NO = G::NO;
+  const double *tab = reinterpret_cast<const double *>(smem + G::OFF_TAB);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + G::OFF_BAR);
+
+  const Layout L = d.L;
+  const int tid = threadIdx.x;
+  const int bx = ig.bx, by = ig.by;
+  const int ty = a.ty;
+  const int i0 = bx * TX + 1, j0 = by * ty + 1;
+  const int tyc = min(ty, L.jn - j0 + 1);               /* owned rows of THIS tile (the last tile of a column may be short) */
+  const int k0 = ig.k0, k1 = ig.k1, nplanes = ig.nplanes;
+  const int y0 = j0 - 1;
+  const int gxsh = y0 & 1;                              /* the x-ghost runs start at the even j at or below y0 */
+
+  /* which ghost buffers this tile needs (uniform per CTA) */
+  const bool gy0 = (by == 0) && d.halo.f[3].r != nullptr;
+  const bool gy1 = (y0 + tyc + 1 == L.jn + 1) && d.halo.f[2].r != nullptr;
+  const bool gx0 = (bx == 0) && d.halo.f[1].r != nullptr;
+  const bool gx1 = (i0 + TX - 1 >= L.in) && d.halo.f[0].r != nullptr;
 
   const unsigned bar0 = tma::smem_u32(bars);
-  const unsigned sP = tma::smem_u32(smem), sS = tma::smem_u32(smem + G::OFF_STAGE);
 
   /* ---- per-thread geometry: two owned-row items (tile rows rg+1, rg+5), one halo-row item for the row groups
    * rg = 0 (tile row 0) and rg = 1 (tile row tyc+1), and at most one single (W / E halo column) ---- */
@@ -165,61 +241,8 @@ __device__ __forceinline__ double search_planes(const Dev &d, const SearchMaps &
   const bool s_gx = s_ok && ((s_i == 0 && gx0) || (s_i == L.in + 1 && gx1));      /* r from the GX buffer */
   const bool s_store = s_ok && (s_i == 0 || s_i == L.in + 1) && s_j >= 1 && s_j <= L.jn;   /* x-ghost p kept current */
 
-  /* ---- everything above is independent of the previous kernels; from here on we read what they wrote ---- */
-  BB_STAMP(d, a, 0);
-  pdl_wait();
-  BB_STAMP(d, a, 1);
-  const int q = sc->q;
-  /* one thread issues every TMA load of plane lp (local index; global plane pi = k0-1+lp) */
-  auto issue = [&](int lp) {
-    const int pi = k0 - 1 + lp;
-    const int rs = lp % G::NRS, ps = lp % G::NPS;
-    const unsigned bar = bar0 + 8 * rs;
-    const unsigned st = sS + rs * G::STAGE;
-    const bool inner = pi >= 1 && pi <= L.kn;
-    unsigned bytes = 2 * (HXP * hy * 8) + G::MXP * hy;
-    if (inner) {
-      if (gy0) bytes += HXP * 8;
-      if (gy1) bytes += HXP * 8;
-      if (gx0) bytes += G::GXN * 8;
-      if (gx1) bytes += G::GXN * 8;
-      if (PARTS) bytes += TX * ty;
-    }
-    const bool owned = pi >= k0 && pi <= k1;
-    if (owned) bytes += TX * ty * 8;
-    tma::mbar_expect_tx(bar, bytes);
-    if (owned) tma::load3d(st + G::RT + G::MT + G::GY + G::GX + G::PMT, &tm.xo, BB_XOFF + 1 + bx * TX, j0, pi, bar);
-    tma::load3d(sP + ps * G::RT, &tm.p[q & 1], x0, y0, pi, bar);
-    tma::load3d(st + G::RT, &tm.fm, x0 - G::MX0, y0, pi, bar);
-    if (pi == 0 && d.halo.f[5].r) tma::load3d(st, &tm.nb[5], x0, y0, d.halo.f[5].L.kn, bar);          /* B neighbour's top plane    */
-    else if (pi == L.kn + 1 && d.halo.f[4].r) tma::load3d(st, &tm.nb[4], x0, y0, 1, bar);            /* T neighbour's bottom plane */
-    else tma::load3d(st, &tm.r, x0, y0, pi, bar);
-    if (inner) {
-      if (gy0) tma::load3d(st + G::RT + G::MT, &tm.nb[3], x0, d.halo.f[3].L.jn, pi, bar);
-      if (gy1) tma::load3d(st + G::RT + G::MT + G::GYS, &tm.nb[2], x0, 1, pi, bar);
-      if (gx0) tma::load2d(st + G::RT + G::MT + G::GY, &tm.nb[1], y0 & ~1, pi, bar);          /* W neighbour's E face, j = (y0 & ~1) .. */
-      if (gx1) tma::load2d(st + G::RT + G::MT + G::GY + G::GXS, &tm.nb[0], y0 & ~1, pi, bar); /* E neighbour's W face                  */
-      if (PARTS) tma::load3d(st + G::RT + G::MT + G::GY + G::GX, &tm.pm, BB_XOFF + 1 + bx * TX, j0, pi, bar);
-    }
-  };
-  if (tid == a.producer) {
-#pragma unroll
-    for (int l = 0; l < G::D; l++) if (l < nplanes) issue(l);
-  }
-
-  done = sc->done;
-  const double beta = sc->beta, ax = sc->alpha_x;
   double *__restrict__ pnew = d.P[(q + 1) & 1];
   double *__restrict__ x = d.x;
-  if (tid < 128) tab[tid] = __ldg(d.invM_tab + tid);
-  if (done) {                       /* a finished solve: drain the loads already issued, then leave */
-    if (tid == a.producer) {
-#pragma unroll
-      for (int l = 0; l < G::D; l++) if (l < nplanes) tma::mbar_wait(bar0 + 8 * l, 0);
-    }
-    return 0.;
-  }
-  const double c63 = __ldg(d.invM_tab + 63);            /* Jacobi diagonal of a cell with all six flags set */
   const bool consumer = tid < BB_PRODUCER;              /* warp-uniform */
 
   /* register pipeline of the owned cells: p(kc-1), p(kc), masks of kc */
@@ -234,17 +257,16 @@ __device__ __forceinline__ double search_planes(const Dev &d, const SearchMaps &
   const unsigned hgoff = (unsigned)(iA + BB_XOFF) + (unsigned)(y0 + hrow) * (unsigned)L.px;
 
   double dot = 0.;
-  __syncthreads();                                      /* table ready */
 
-  for (int lp = 0; lp < nplanes; lp++) {
+  for (int lp = 0; lp < nplanes; lp++, g++) {
     const int pi = k0 - 1 + lp;
-    const int rs = lp % G::NRS, ps = lp % G::NPS;
-    if (tid == a.producer && lp + G::D < nplanes) issue(lp + G::D);
+    const int rs = g % G::NRS, ps = g % G::NPS;
+    if (tid == a.producer) producer_step(d, a, pc, queue, BB_CLAIM_SEARCH, [&](const ProdCursor &c) { search_issue<PARTS, DD>(d, tm, a, smem, c, q); });
     const bool plane_owned = pi >= k0 && pi <= k1;
     const bool plane_ghost = (pi == 0 || pi == L.kn + 1);
     if (consumer) {
-    tma::mbar_wait(bar0 + 8 * rs, (lp / G::NRS) & 1);
-    if (lp == 0) BB_STAMP(d, a, 2);
+    tma::mbar_wait(bar0 + 8 * rs, (g / G::NRS) & 1);
+    if (g == 0) BB_STAMP(d, a, 2);
 
     double *Pt = reinterpret_cast<double *>(smem + ps * G::RT);
     const unsigned char *St = smem + G::OFF_STAGE + rs * G::STAGE;
@@ -326,7 +348,7 @@ __device__ __forceinline__ double search_planes(const Dev &d, const SearchMaps &
 
     /* ---- phase B: q = -A p on plane kc = pi-1 (centre plane in the previous P slot) ---- */
     if (pi - 1 >= k0) {
-      const double *Pc = reinterpret_cast<const double *>(smem + ((lp - 1) % G::NPS) * G::RT);
+      const double *Pc = reinterpret_cast<const double *>(smem + ((g - 1) % G::NPS) * G::RT);
 #pragma unroll
       for (int o = 0; o < NO; o++) {
         if (!own[o]) continue;
@@ -367,26 +389,64 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
 {
   typedef SearchGeom<PARTS, DD> G;
   extern __shared__ __align__(128) unsigned char smem[];     /* plain pointer arithmetic only: keeps LDS/STS (no generic LD/ST) */
-  if (threadIdx.x == 0) {
+  __shared__ int queue[BB_QN];
+  __shared__ double sh_sum[32];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
     const unsigned bar0 = tma::smem_u32(smem + G::OFF_BAR);
     for (int s = 0; s < G::NRS; s++) tma::mbar_init(bar0 + 8 * s, 1);
     tma::fence_barrier_init();
   }
+  if (tid < 128) reinterpret_cast<double *>(smem + G::OFF_TAB)[tid] = __ldg(d.invM_tab + tid);
+  /* the first item is the block index (no atomic, the initial wave keeps its neighbourly layout) */
+  ProdCursor pc;
+  pc.item = (int)blockIdx.x < a.nitems ? (int)blockIdx.x : -1; pc.lp = 0; pc.n = 0; pc.g = 0;
+  if (pc.item >= 0) pc.ig = decode_item(d, a, pc.item);
+  if (tid == a.producer) queue[0] = pc.item;
   __syncthreads();
-  const bool xfull = (blockIdx.x * G::TX + G::TX) <= d.L.in;
-  int done;
-  const double dot = xfull ? search_planes<PARTS, DD, true>(d, tm, a, smem, done) : search_planes<PARTS, DD, false>(d, tm, a, smem, done);
-  if (done) return;                 /* a finished solve: every later launch is a no-op */
+
+  /* ---- everything above is independent of the previous kernels; from here on we read what they wrote ---- */
+  BB_STAMP(d, a, 0);
+  pdl_wait();
+  BB_STAMP(d, a, 1);
+  Scal *sc = d.sc;
+  const int q = sc->q;
+  int issued = 0;
+  if (tid == a.producer) {
+#pragma unroll
+    for (int l = 0; l < G::D; l++) if (pc.item >= 0) { producer_step(d, a, pc, queue, BB_CLAIM_SEARCH, [&](const ProdCursor &c) { search_issue<PARTS, DD>(d, tm, a, smem, c, q); }); issued++; }
+  }
+  const int done = sc->done;
+  const double beta = sc->beta, ax = sc->alpha_x;
+  if (done) {                       /* a finished solve: drain the loads already issued (no item was claimed yet: an item has > D planes), then leave */
+    if (tid == a.producer) {
+      const unsigned bar0 = tma::smem_u32(smem + G::OFF_BAR);
+      for (int l = 0; l < issued; l++) tma::mbar_wait(bar0 + 8 * (l % G::NRS), (l / G::NRS) & 1);
+    }
+    return;
+  }
+  const double c63 = __ldg(d.invM_tab + 63);            /* Jacobi diagonal of a cell with all six flags set */
+
+  int g = 0, n = 0;
+  int cur = queue[0];
+  while (cur >= 0) {                /* uniform across the CTA: every thread reads the same queue entry after a barrier */
+    const ItemGeom ig = decode_item(d, a, cur);
+    const bool xfull = (ig.bx * G::TX + G::TX) <= d.L.in;
+    const double dot = xfull ? search_item<PARTS, DD, true>(d, tm, a, smem, ig, g, pc, queue, q, beta, ax, c63)
+                             : search_item<PARTS, DD, false>(d, tm, a, smem, ig, g, pc, queue, q, beta, ax, c63);
+    const double part = block_sum<1>(dot, sh_sum);      /* this ITEM's (p,q) partial in the item's own slot: the total does not depend on who computed what */
+    if (tid == 0) d.partials[cur] = part;
+    n++;
+    cur = queue[n % BB_QN];         /* published by the producer at least one barrier ago */
+  }
   BB_STAMP(d, a, 3);
-  BB_TRACE_AT(d, a, 6, (unsigned long long)bb_smid());
+  BB_TRACE_AT(d, a, 6, (unsigned long long)bb_smid() | ((unsigned long long)n << 32) | ((unsigned long long)g << 40));
   BB_TRACE_AT(d, a, 7, 1ull | ((unsigned long long)a.launch << 8));
 
   pdl_launch_dependents();          /* k_resid_tma may be scheduled behind our tail; it blocks in pdl_wait() until alpha is final */
-  /* ---- (p,q): grid reduction, rank all-reduce, alpha (cuda_solver.cu:204-206) ---- */
-  double v[1] = { dot }, tot[1];
-  const int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-  const int nblocks = gridDim.x * gridDim.y * gridDim.z;
-  const bool last = grid_reduce<1>(d, v, bid, nblocks, tot, false);
+  /* ---- (p,q): item partials in item order, rank all-reduce, alpha (cuda_solver.cu:204-206) ---- */
+  double tot[1];
+  const bool last = items_reduce(d, a.nitems, BB_CLAIM_SEARCH, tot[0]);
   BB_STAMP(d, a, 4);
   if (last) {
     rank_allreduce(d, tot, 1, false);         /* this kernel writes nothing a peer reads */

@@ -76,7 +76,7 @@ struct bbpcg_solver {
   int plan_ok;                      /* the plan below, the uploaded table and the tensor maps are current */
   int plan_ty, plan_nbx, plan_nby, plan_nbz, plan_kc;
   int pdl;                          /* programmatic dependent launch of the two iteration kernels: 0 off, 1 on, 2 auto */
-  int zshift;                       /* experiment (option zshift): rotate the CTA -> z-chunk map */
+  int guided, guided_pct, chunk_min; /* z-chunk plan of small blocks: decreasing chunk lengths (make_plan) */
   int tma_warp;                     /* 1 (default): a dedicated producer warp issues the iteration kernels' TMA loads; 0: thread 0 does */
   int rhs_tiled;                    /* PP_rhs through shared-memory transposes (default) or the row-walking kernel */
   int shared_device;                /* some peer rank lives on this same GPU (single-process harness, or two processes on one GPU) */
@@ -256,7 +256,7 @@ static int create_impl(bbpcg_solver *s, const dom_struct *dom_rank, const dom_st
   CU(cudaHostGetDevicePointer((void **)&d.comm.host_flag, (void *)&s->h_poll[BB_POLL_COMM], 0));
   CU(cudaHostAlloc(&s->h_scal, sizeof(Scal), cudaHostAllocDefault));
   CU(cudaHostAlloc(&s->h_ztab, sizeof(int) * (BB_MAXZ + 1), cudaHostAllocDefault));
-  s->pdl = 2; s->rhs_tiled = 1; s->tma_warp = 1;
+  s->pdl = 2; s->rhs_tiled = 1; s->tma_warp = 1; s->guided = 1; s->guided_pct = 100; s->chunk_min = 8;
   /* single rank: neighbours are this block itself (periodic wrap) or nothing */
   s->nranks = 1;
   for (int p = 0; p < BB_MAXR; p++) { s->peer_arena[p] = NULL; s->peer_opened[p] = false; }
@@ -381,54 +381,58 @@ extern "C" int bbpcg_comm_import(bbpcg_solver *s, const void *all_blobs, int nra
 }
 
 /* ---- launch helpers ------------------------------------------------------------------------ */
-/* Tile / z-chunk plan of the two iteration kernels.  The grid is (x-tiles of 128, y-tiles of ty rows, z-chunks); CTAs are
- * dispatched z-chunk-major, so the y/x neighbours of one chunk run together and their halo rows hit L2.  2 CTAs are
- * resident per SM: `slots` = 2 x SM count.  Measured (scripts/sweep.py; profiles/r02b_sweep*.jsonl):
- *   - many waves (512^3: 256 columns): ~24-plane chunks win (1519 us/iteration); ONE wave of 296 long CTAs (ty 7, 512
- *     planes each) loses 16 % although it re-reads no halo plane and fills every slot: the long CTAs drift out of lock
- *     step, the halo rows their y neighbours fetched have left L2 (+10 % DRAM bytes, ncu) and nothing rebalances the tail;
- *   - few waves (256^3 block, the 8-GPU share of 512^3): 256..300 CTAs of ~64..86 planes, every (ty, chunk) pair between
- *     6 x 86 and 8 x 32 lands within 2 % (212-221 us): the wave count decides, so minimise ceil(CTAs/slots) x (planes + 6).
+/* Tile / z-chunk plan of the two iteration kernels.  A work item is (x-tile of 128, y-tile of ty rows, z-chunk); the
+ * kernels run as ONE wave of resident CTAs (2 per SM) that claim items in index order -- x fastest, then y, then z-chunk,
+ * so the y/x neighbours of one chunk are in flight together and their halo rows hit L2.  Measured (scripts/sweep.py,
+ * scripts/trace_timeline.py; profiles/r02b_sweep*.jsonl, r02d_sweep*.jsonl, r02fg_trace_per_cta.jsonl):
+ *   - many items (512^3: 256 columns): uniform ~24-plane chunks (longer ones lose L2 hits on the halo rows their y
+ *     neighbours fetched, shorter ones re-read more halo planes);
+ *   - few items (256^3 block, the 8-GPU share of 512^3): identical CTAs of a static one-wave split finished between 84 and
+ *     135 us depending on the SM group they ran on, so the chunk lengths are GUIDED: every column is cut into chunks of
+ *     decreasing length (the first wave takes ~cols/slots of what is left per claim, never less than `chunk_min` = 8 planes:
+ *     12 already cost 35 % on a 256 x 128 x 128 block);
+ *     fast SMs claim more of the short tail chunks and all CTAs finish together.
  * Tile height: 8 rows (fewest halo-row re-reads) unless option `ty` says otherwise; the kernels take any 1..8.
- * Options `ty` / `kc` override either choice.  Uploads the chunk table (Dev::ztab) and rebuilds the tensor maps. */
+ * Option `kc` forces uniform chunks.  Uploads the chunk table (Dev::ztab) and rebuilds the tensor maps. */
 static int make_plan(bbpcg_solver *s)
 {
   if (s->plan_ok) return BBPCG_OK;
   const Layout &L = s->dev.L;
   const int slots = s->sm_count * 2;
   const int nbx = (L.in + 127) / 128;
-  const int best_ty = s->opt_ty > 0 ? s->opt_ty : BB_TYMAX;
+  const int kc_uniform = s->opt_kc > 0 ? s->opt_kc : 24;
+  const long long nz_uniform = (L.kn + kc_uniform - 1) / kc_uniform;
+  const bool uniform = s->opt_kc > 0 || !s->guided || (long long)nbx * ((L.jn + BB_TYMAX - 1) / BB_TYMAX) * nz_uniform >= 7ll * slots;
+  /* 8 rows: fewest halo-row re-reads.  In the guided regime 7 rows measured 1-3 % faster on the per-rank blocks of the 2-, 4- and
+   * 8-GPU runs (256^3: 209 vs 216 us, 512 x 256 x 256: 391 vs 400; profiles/r02k_sweep_shapes.jsonl) and within 1 % elsewhere */
+  const int best_ty = s->opt_ty > 0 ? s->opt_ty : uniform ? BB_TYMAX : 7;
   const int cols = nbx * ((L.jn + best_ty - 1) / best_ty);
-  int best_nz = 1;
-  double best = -1.;
-  if (s->opt_kc > 0) { best_nz = (L.kn + s->opt_kc - 1) / s->opt_kc; best = 0.; }
-  else {
-    best_nz = (L.kn + 23) / 24; best = 0.;
-    if ((long long)cols * best_nz < 7ll * slots) {
-      best = -1.;
-      const int nz_hi = L.kn >= 16 ? L.kn / 8 : 1;
-      for (int nz = 1; nz <= nz_hi && nz <= BB_MAXZ; nz++) {
-        const long long ctas = (long long)cols * nz;
-        if (ctas > BB_MAXBLOCKS) break;
-        const long long waves = (ctas + slots - 1) / slots;
-        const double cost = (double)waves * ((L.kn + nz - 1) / nz + 6);        /* +6: two halo planes + pipeline fill/drain */
-        if (best < 0. || cost < best) { best = cost; best_nz = nz; }
-      }
+  std::vector<int> sz;
+  if (uniform) {
+    int nz = (int)nz_uniform;
+    if (nz > BB_MAXZ) nz = BB_MAXZ;
+    if ((long long)cols * nz > BB_MAXBLOCKS) nz = BB_MAXBLOCKS / cols;       /* the shortest chunks the reduction workspace allows */
+    if (nz < 1) { bbpcg_set_error("grid too large for the reduction workspace"); return BBPCG_EINVAL; }
+    const int kc = (L.kn + nz - 1) / nz;
+    for (int r = L.kn; r > 0; r -= kc) sz.push_back(r < kc ? r : kc);
+  } else {
+    const int minc = s->chunk_min > 0 ? s->chunk_min : 8;
+    int r = L.kn;
+    while (r > 0) {
+      int c = (int)(((long long)r * cols * s->guided_pct / 100 + slots - 1) / slots);
+      if (c < minc) c = minc;
+      if (c > r || r - c < (minc + 1) / 2) c = r;
+      sz.push_back(c);
+      r -= c;
     }
   }
-  if (best_nz > BB_MAXZ) best_nz = BB_MAXZ;
-  if ((long long)cols * best_nz > BB_MAXBLOCKS) best_nz = BB_MAXBLOCKS / cols;     /* the shortest chunks the reduction workspace allows */
-  if (best_nz < 1) best = -1.;
-  if (best < 0.) { bbpcg_set_error("grid too large for the reduction workspace"); return BBPCG_EINVAL; }
-  const int kc = (L.kn + best_nz - 1) / best_nz;
-  std::vector<int> sz;
-  for (int r = L.kn; r > 0; r -= kc) sz.push_back(r < kc ? r : kc);
+  if (sz.size() > BB_MAXZ) { bbpcg_set_error("too many z-chunks"); return BBPCG_EINVAL; }
   /* the copy source must stay valid until the copy ran: it is only rewritten after a stream sync */
   CU(cudaStreamSynchronize(s->stream));
   s->h_ztab[0] = 0;
   for (size_t i = 0; i < sz.size(); i++) s->h_ztab[i + 1] = s->h_ztab[i] + sz[i];
   CU(cudaMemcpyAsync((void *)s->dev.ztab, s->h_ztab, sizeof(int) * (sz.size() + 1), cudaMemcpyHostToDevice, s->stream));
-  s->plan_ty = best_ty; s->plan_nbx = nbx; s->plan_nby = (L.jn + best_ty - 1) / best_ty; s->plan_nbz = (int)sz.size(); s->plan_kc = kc;
+  s->plan_ty = best_ty; s->plan_nbx = nbx; s->plan_nby = (L.jn + best_ty - 1) / best_ty; s->plan_nbz = (int)sz.size(); s->plan_kc = sz[0];
   int rc = build_search_maps(s, best_ty);
   if (rc) return rc;
   s->plan_ok = 1;
@@ -470,8 +474,15 @@ static SearchArgs plan_args(const bbpcg_solver *s)
   a.nbx = s->plan_nbx; a.nby = s->plan_nby; a.nbz = s->plan_nbz; a.ty = s->plan_ty;
   a.producer = s->tma_warp ? BB_PRODUCER : 0;
   a.launch = (int)(s->launches & 0x7fffffff);
-  a.zshift = s->zshift;
+  a.nitems = a.nbx * a.nby * a.nbz;
   return a;
+}
+
+/* one wave of resident CTAs (2 per SM, bounded by launch_bounds and the shared-memory size), never more than items */
+static unsigned iter_grid(const bbpcg_solver *s, const SearchArgs &a)
+{
+  const int slots = s->sm_count * 2;
+  return (unsigned)(a.nitems < slots ? a.nitems : slots);
 }
 
 /* k_search_tma (bbpcg_search_tma.cuh) */
@@ -481,7 +492,7 @@ static int launch_search(bbpcg_solver *s, bool parts)
   int rc = make_plan(s);
   if (rc) return rc;
   const SearchArgs a = plan_args(s);
-  const dim3 grid(a.nbx, a.nby, a.nbz);
+  const dim3 grid(iter_grid(s, a));
   if (parts) CU(launch_k(s, k_search_tma<true, 2>, grid, BB_NT_ITER, SearchGeom<true, 2>::SMEM, true, s->dev, s->maps, a));
   else CU(launch_k(s, k_search_tma<false, 2>, grid, BB_NT_ITER, SearchGeom<false, 2>::SMEM, true, s->dev, s->maps, a));
   s->launches++;
@@ -496,7 +507,7 @@ static int launch_resid(bbpcg_solver *s, bool parts, const real *rhs)
   if (rc) return rc;
   SearchArgs a = plan_args(s);
   a.rhs = rhs; a.s1b = s->fst.cs1b; a.s2b = s->fst.cs2b;
-  const dim3 grid(a.nbx, a.nby, a.nbz);
+  const dim3 grid(iter_grid(s, a));
   if (rhs) {
     if (parts) CU(launch_k(s, k_resid_tma<true, 2, true>, grid, BB_NT_ITER, ResidGeom<true, 2>::SMEM, false, s->dev, s->maps, a));
     else CU(launch_k(s, k_resid_tma<false, 2, true>, grid, BB_NT_ITER, ResidGeom<false, 2>::SMEM, false, s->dev, s->maps, a));
@@ -1099,7 +1110,9 @@ extern "C" int bbpcg_set_option(bbpcg_solver *s, const char *key, long long valu
   else if (!strcmp(key, "pdl")) s->pdl = clampi(value, 0, 2);
   else if (!strcmp(key, "rhs_tiled")) s->rhs_tiled = value != 0;
   else if (!strcmp(key, "tma_warp")) s->tma_warp = value != 0;
-  else if (!strcmp(key, "zshift")) s->zshift = value > 0 ? (int)value : 0;
+  else if (!strcmp(key, "guided")) { s->guided = value != 0; s->plan_ok = 0; }
+  else if (!strcmp(key, "guided_pct")) { s->guided_pct = clampi(value, 10, 400); s->plan_ok = 0; }
+  else if (!strcmp(key, "chunk_min")) { s->chunk_min = clampi(value, 2, 1024); s->plan_ok = 0; }
   else if (!strcmp(key, "stream_blocks")) s->stream_blocks = clampi(value, 1, BB_MAXBLOCKS);
   else if (!strcmp(key, "check_every")) s->check_every = clampi(value, 1, 1000);
   else if (!strcmp(key, "comm_timeout_ms")) s->dev.comm.timeout_cycles = value > 0 ? value * 2000000ll : -1;   /* ~2 GHz; <= 0: wait for ever, like MPI */
@@ -1155,7 +1168,8 @@ extern "C" long long bbpcg_get_info(bbpcg_solver *s, const char *key)
   if (!strcmp(key, "kt_search_n")) return s->kt_search_n;
   if (!strcmp(key, "kt_resid_n")) return s->kt_resid_n;
   if (!strcmp(key, "kt_refresh_n")) return s->kt_refresh_n;
-  if (!strcmp(key, "search_grid")) return make_plan(s) ? -1 : (long long)s->plan_nbx * s->plan_nby * s->plan_nbz;
+  if (!strcmp(key, "search_grid")) { if (make_plan(s)) return -1; const long long ni = (long long)s->plan_nbx * s->plan_nby * s->plan_nbz; return ni < 2 * s->sm_count ? ni : 2 * s->sm_count; }
+  if (!strcmp(key, "search_items")) return make_plan(s) ? -1 : (long long)s->plan_nbx * s->plan_nby * s->plan_nbz;
   if (!strcmp(key, "search_kc")) return make_plan(s) ? -1 : s->plan_kc;
   if (!strcmp(key, "search_nbz")) return make_plan(s) ? -1 : s->plan_nbz;
   if (!strcmp(key, "pdl")) return pdl_active(s);

@@ -60,7 +60,7 @@ def main():
         kind = int(e[0, 7] & 0xff)
         launch = int(e[0, 7] >> 8)
         recs.append(dict(launch=launch, kind=kind, nctas=int(used.sum()), entry=e[:, 0], waited=e[:, 1], first=e[:, 2], loop_end=e[:, 3],
-                         red=e[:, 4], end=int(e[:, 5].max()), sm=e[:, 6]))
+                         red=e[:, 4], end=int(e[:, 5].max()), sm=e[:, 6] & 0xffffffff, items=(e[:, 6] >> 32) & 0xff, planes=e[:, 6] >> 40))
     recs.sort(key=lambda x: x["launch"])
     recs = recs[2:-1]                                     # ring wrap: drop the partially overwritten oldest / the set-up neighbours
     out = {"cells": cells, "opts": a.opt, "us_per_iter": r.ms_iter * 1e3 / a.iters, "grid": s.info("search_grid"), "kc": s.info("search_kc"), "kernels": {}}
@@ -94,14 +94,8 @@ def main():
     solo = np.array([per_sm[int(s_)] == 1 for s_ in last["sm"]])
     out["loop_us_solo_sm"] = float(np.median(dur[solo])) if solo.any() else None
     out["loop_us_shared_sm"] = float(np.median(dur[~solo])) if (~solo).any() else None
-    # per-CTA detail of that launch: where are the slow CTAs? (block index -> bx, by, bz; SM id; loop duration)
-    nbx = (cells[0] + 127) // 128
-    ty = s.info("search_ty")
-    nby = (cells[1] + ty - 1) // ty
-    bid = np.nonzero(t[[i for i in range(nl) if (t[i, :, 7].max() >> 8) == last["launch"]][0], :, 3] > 0)[0]
-    out["per_cta"] = {"bx": (bid % nbx).tolist(), "by": ((bid // nbx) % nby).tolist(), "bz": (bid // (nbx * nby)).tolist(),
-                      "sm": last["sm"].tolist(), "loop_us": [round(float(v), 2) for v in dur],
-                      "start_us": [round(float(v), 2) for v in (last["first"] - last["entry"].min()) / 1e3]}
+    out["per_cta"] = {"sm": last["sm"].tolist(), "loop_us": [round(float(v), 2) for v in dur], "items": last["items"].tolist(), "planes": last["planes"].tolist(),
+                      "end_us": [round(float(v), 2) for v in (last["loop_end"] - last["entry"].min()) / 1e3]}
     print(json.dumps({k: v for k, v in out.items() if k != "per_cta"}))
     with open(a.out, "a") as f:
         f.write(json.dumps(out) + "\n")

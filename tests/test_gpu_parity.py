@@ -145,19 +145,23 @@ def test_zchunk_plans(opts):
 
 
 def test_plan_of_the_benchmarked_block_shapes():
-    """the planner's tile / z-chunk choice for the benchmarked block shapes: 8-row tiles; ~24-plane chunks when
-    that gives many waves of the 2 x SM-count resident CTAs, else the chunk count with the fewest waves"""
+    """the planner's tile / z-chunk choice for the benchmarked block shapes: 8-row tiles (7 for small blocks), ONE wave of resident
+    CTAs (2 per SM) claiming the work items; uniform ~24-plane chunks when there are many items, chunks of DECREASING length
+    (never below chunk_min) for the small blocks of an 8-GPU run"""
     import bbpcg
     from bbpcg.grid import BC_SETS
-    for cells, many_waves in (((256, 256, 256), False), ((512, 512, 64), False), ((512, 512, 512), True)):
+    for cells, many in (((256, 256, 256), False), ((512, 512, 64), False), ((512, 512, 512), True)):
         dec = bbpcg.Decomposition.uniform((0., 12., 0., 12., 0., 12.), cells, (1, 1, 1), BC_SETS["duct"])
         s = bbpcg.PoissonSolver(dec, 0)
         slots = 2 * s.info("sm_count")
-        grid, ty, kc, nbz = s.info("search_grid"), s.info("search_ty"), s.info("search_kc"), s.info("search_nbz")
-        assert ty == 8 and grid == (cells[0] // 128) * (cells[1] // 8) * nbz and nbz == -(-cells[2] // kc)
-        assert (grid >= 7 * slots and kc == 24) if many_waves else grid <= 2 * slots
+        grid, items, ty, kc, nbz = s.info("search_grid"), s.info("search_items"), s.info("search_ty"), s.info("search_kc"), s.info("search_nbz")
+        assert ty == (8 if many else 7) and items == (cells[0] // 128) * -(-cells[1] // ty) * nbz and grid == min(items, slots)
+        if many:
+            assert items >= 7 * slots and kc == 24 and nbz == -(-cells[2] // kc)
+        else:
+            assert kc > cells[2] // nbz and nbz >= 2          # guided: the first chunk is the longest
         s.set_option("ty", 7); s.set_option("kc", 16)
-        assert s.info("search_ty") == 7 and s.info("search_kc") == 16
+        assert s.info("search_ty") == 7 and s.info("search_kc") == 16 and s.info("search_nbz") == -(-cells[2] // 16)
         s.close()
 
 
