@@ -11,7 +11,7 @@
  * computed on the device by every CTA from the same expressions as cage_setup / build_phase, no host round trip -- and
  * k_cage_flags, one pass over the block that writes the three flag arrays (what the reference's other kernels read) AND the
  * solver's 1-byte masks directly (fmask depends on the external walls only, because a cage flag is +-1 and enters the
- * operator squared; pmask is phase > -1 of the cell and its six neighbours), pushes the boundary masks into the
+ * operator squared; the particle factors come from one more bit, phase > -1), pushes the boundary masks into the
  * neighbours' ghosts and runs the rank barrier: bbpcg_set_coefficients is not needed afterwards.
  *
  * Sequential semantics kept: build_phase applies `phase += cutoff (n - phase)` for n = 0, 1, ... in order, so the LAST
@@ -154,15 +154,12 @@ __global__ void __launch_bounds__(NT) k_cage_flags(const Dev d, const FaceStride
       /* ---- the solver's masks of an interior cell (what k_masks digests from the arrays above) ---- */
       const unsigned m = ((i == L.in && (a.ext & 2u)) ? 0u : FM_E) | ((i == 1 && (a.ext & 1u)) ? 0u : FM_W) |
                          ((j == L.jn && (a.ext & 8u)) ? 0u : FM_N) | ((j == 1 && (a.ext & 4u)) ? 0u : FM_S) |
-                         ((k == L.kn && (a.ext & 32u)) ? 0u : FM_T) | ((k == 1 && (a.ext & 16u)) ? 0u : FM_B);
+                         ((k == L.kn && (a.ext & 32u)) ? 0u : FM_T) | ((k == 1 && (a.ext & 16u)) ? 0u : FM_B) |
+                         ((parts && pC > -1) ? FM_SOLID : 0u) |           /* the particle factors are gathered from this bit of the cell and its neighbours */
+                         ((parts && (pC > -1 || pW > -1 || pS > -1 || pB > -1 || a.phase[C + 1] > -1 || a.phase[C + st.cs1b] > -1 ||
+                                     a.phase[C + st.cs2b] > -1)) ? FM_NEAR : 0u);
       const long long g = pidx(L, i, j, k);
       d.fmask[g] = (u8)m;
-      if (parts) {
-        const unsigned pm = (pC > -1 ? PM_C : 0u) | (a.phase[C + 1] > -1 ? PM_E : 0u) | (pW > -1 ? PM_W : 0u) |
-                            (a.phase[C + st.cs1b] > -1 ? PM_N : 0u) | (pS > -1 ? PM_S : 0u) |
-                            (a.phase[C + st.cs2b] > -1 ? PM_T : 0u) | (pB > -1 ? PM_B : 0u);
-        d.pmask[g] = (u8)pm;
-      }
 #define BB_PUSHM(F, COND, II, JJ, KK) if (COND) { const NbrFace &nf = d.halo.f[F]; if (nf.fmask) { nf.fmask[pidx(nf.L, II, JJ, KK)] = (u8)m; pushed = true; } }
       BB_PUSHM(0, i == L.in, 0, j, k)  BB_PUSHM(1, i == 1, nf.L.in + 1, j, k)
       BB_PUSHM(2, j == L.jn, i, 0, k)  BB_PUSHM(3, j == 1, i, nf.L.jn + 1, k)

@@ -1,7 +1,7 @@
 /* bbpcg_internal.h -- device-side data layout shared by the kernels and the host driver.
  *
  * PRIVATE PADDED LAYOUT ("P-layout") of the solver's own vectors (r, p0, p1, x) and byte
- * masks.  Same logical extent as the reference's ghosted Gcc grid -- (in+2)(jn+2)(kn+2), one
+ * mask.  Same logical extent as the reference's ghosted Gcc grid -- (in+2)(jn+2)(kn+2), one
  * ghost layer, interior 1..n (src/domain.c:1262-1289) -- but every x-row is padded so that
  * interior cell i = 1 starts on a 128-byte boundary:
  *
@@ -32,8 +32,16 @@
 #define FM_S 8u
 #define FM_T 16u
 #define FM_B 32u
-#define FM_DEAD 64u                /* ghost cell behind an external wall: z := 0 */
-/* particle mask bits (pmask), src/solver_kernel.cu:683-695 */
+/* A mask byte with NO flag bit set marks a DEAD cell -- a ghost behind an external wall (the arena is zero-filled and nobody
+ * writes those): its Jacobi entry is 0, so z = p = 0 there.  (A real cell whose six faces are all walls, M = 0, would be
+ * 1/0 in the reference; it gets 0 here.) */
+#define FM_NEAR 64u                /* the cell or one of its six neighbours lies inside a particle: only then does a kernel
+                                      gather the particle factors; the all-ones test of the fast path (0x3f) excludes it for free */
+#define FM_SOLID 128u              /* phase > -1: the cell lies inside a particle (src/solver_kernel.cu:683-695).  The particle factors
+                                      of a cell are gathered from this bit of the cell and of its six neighbours in the halo'd mask
+                                      tile -- no second mask array, no second stream (a separate 1-byte pmask tile cost the search
+                                      kernel 12 %: one more TMA request per plane) */
+/* particle factors of one cell, as gathered by the kernels: solid bit of the cell and of its neighbours */
 #define PM_C 1u                    /* phase[C] > -1 (solid) */
 #define PM_E 2u
 #define PM_W 4u
@@ -71,7 +79,7 @@ static inline Layout make_layout(int in, int jn, int kn)
  * function of (in,jn,kn), so a peer can address a neighbour's arrays from its dimensions. */
 struct ArenaMap {
   size_t r, p0, p1, x;             /* doubles[L.n] */
-  size_t fmask, pmask;             /* bytes[L.n]   */
+  size_t fmask;                    /* bytes[L.n]   */
   size_t recv[2][6];               /* doubles, generic exchange staging (double-buffered) */
   size_t partials;                 /* doubles[4*BB_MAXBLOCKS]: up to 4 values per CTA */
   size_t gpartials;                /* doubles[4*BB_MAXGROUPS]: group sums */
@@ -94,7 +102,7 @@ static inline ArenaMap make_arena_map(const Layout &L)
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
   size_t vec = (size_t)L.n * sizeof(double);
   m.r = take(vec); m.p0 = take(vec); m.p1 = take(vec); m.x = take(vec);
-  m.fmask = take((size_t)L.n); m.pmask = take((size_t)L.n);
+  m.fmask = take((size_t)L.n);
   /* staging faces sized for the largest of the four grids (a face grid is one entry longer along its normal) */
   size_t fi = (size_t)(L.jn + 1) * (L.kn + 1), fj = (size_t)(L.in + 1) * (L.kn + 1), fk = (size_t)(L.in + 1) * (L.jn + 1);
   for (int b = 0; b < 2; b++) for (int f = 0; f < 6; f++)
@@ -158,7 +166,7 @@ struct Comm {
 struct Dev {
   Layout L;
   double *r, *P[2], *x;
-  unsigned char *fmask, *pmask;
+  unsigned char *fmask;
   double *recv[2][6];
   double *partials, *gpartials;
   unsigned *counter;

@@ -26,13 +26,13 @@ typedef unsigned char u8;
 /* ------------------------------------------------------------------------------------ */
 /* Jacobi diagonal from the 6 flag^2 bits: PP_jacobi_init, src/solver_kernel.cu:73-80.
  * invM = -1/M, M = -idx2(fE^2+fW^2) - idy2(fN^2+fS^2) - idz2(fT^2+fB^2).  128 entries:
- * masks with FM_DEAD (ghosts behind walls) give 0 so that z = p = 0 there. */
+ * masks without any flag bit (dead cells: ghosts behind walls) give 0 so that z = p = 0 there; bit 6 (FM_NEAR) is ignored. */
 __global__ void k_build_tab(double *tab, double idx2, double idy2, double idz2)
 {
   const int m = threadIdx.x;
   if (m >= 128) return;
   double v = 0.;
-  if (!(m & FM_DEAD)) {
+  if (m & 63) {
     int e = (m & FM_E) != 0, w = (m & FM_W) != 0, n = (m & FM_N) != 0, s = (m & FM_S) != 0,
         t = (m & FM_T) != 0, b = (m & FM_B) != 0;
     double M = -idx2 * (double)(e + w) - idy2 * (double)(n + s) - idz2 * (double)(t + b);
@@ -76,6 +76,14 @@ __device__ __forceinline__ double stencil_noparts(const Dev &d, unsigned m, doub
   return stencil_combine(d, __dsub_rn(flagged(m & FM_E, __dsub_rn(pE, pC)), flagged(m & FM_W, __dsub_rn(pC, pW))),
                          __dsub_rn(flagged(m & FM_N, __dsub_rn(pN, pC)), flagged(m & FM_S, __dsub_rn(pC, pS))),
                          __dsub_rn(flagged(m & FM_T, __dsub_rn(pT, pC)), flagged(m & FM_B, __dsub_rn(pC, pB))));
+}
+
+/* the particle factors of cell g (P-layout offset) from the solid bits of the cell and of its six neighbours */
+__device__ __forceinline__ unsigned pm_of_neighbours(const u8 *__restrict__ fmask, long long g, const Layout &L)
+{
+  return ((fmask[g] & FM_SOLID) ? PM_C : 0u) | ((fmask[g + 1] & FM_SOLID) ? PM_E : 0u) | ((fmask[g - 1] & FM_SOLID) ? PM_W : 0u) |
+         ((fmask[g + L.px] & FM_SOLID) ? PM_N : 0u) | ((fmask[g - L.px] & FM_SOLID) ? PM_S : 0u) |
+         ((fmask[g + L.ps] & FM_SOLID) ? PM_T : 0u) | ((fmask[g - L.ps] & FM_SOLID) ? PM_B : 0u);
 }
 
 /* with particle masking: src/solver_kernel.cu:683-707.  The reference multiplies the centre value by pf{x,y,z} (1 in a
@@ -652,14 +660,14 @@ __global__ void __launch_bounds__(NT) k_masks(const Dev d, FaceStrides st, const
       unsigned m = (e_ * e_ ? FM_E : 0u) | (w_ * w_ ? FM_W : 0u) | (n_ * n_ ? FM_N : 0u) | (s_ * s_ ? FM_S : 0u) |
                    (t_ * t_ ? FM_T : 0u) | (b_ * b_ ? FM_B : 0u);
       const long long g = pidx(L, i, j, k);
-      d.fmask[g] = (u8)m;
       if (phase) {
         const long long C = i + (long long)j * st.cs1b + (long long)k * st.cs2b;
-        unsigned pm = (phase[C] > -1 ? PM_C : 0u) | (phase[C + 1] > -1 ? PM_E : 0u) | (phase[C - 1] > -1 ? PM_W : 0u) |
-                      (phase[C + st.cs1b] > -1 ? PM_N : 0u) | (phase[C - st.cs1b] > -1 ? PM_S : 0u) |
-                      (phase[C + st.cs2b] > -1 ? PM_T : 0u) | (phase[C - st.cs2b] > -1 ? PM_B : 0u);
-        d.pmask[g] = (u8)pm;
+        const bool solid = phase[C] > -1;
+        if (solid) m |= FM_SOLID;
+        if (solid || phase[C + 1] > -1 || phase[C - 1] > -1 || phase[C + st.cs1b] > -1 || phase[C - st.cs1b] > -1 ||
+            phase[C + st.cs2b] > -1 || phase[C - st.cs2b] > -1) m |= FM_NEAR;
       }
+      d.fmask[g] = (u8)m;
       /* neighbours need my boundary masks to form z in their ghost copies of my cells */
 #define BB_PUSHM(F, COND, II, JJ, KK) if (COND) { const NbrFace &nf = d.halo.f[F]; if (nf.fmask) { nf.fmask[pidx(nf.L, II, JJ, KK)] = (u8)m; pushed = true; } }
       BB_PUSHM(0, i == L.in, 0, j, k)  BB_PUSHM(1, i == 1, nf.L.in + 1, j, k)
@@ -787,7 +795,7 @@ __global__ void __launch_bounds__(NT) k_spmv_s3b(const Dev d, const double *__re
       const long long g = pidx(L, i, j, k);
       const unsigned m = d.fmask[g];
       double v;
-      if (PARTS) v = stencil_parts(d, m, d.pmask[g], src[C], src[C + 1], src[C - 1], src[C + s1b], src[C - s1b], src[C + s2b], src[C - s2b]);
+      if (PARTS) v = stencil_parts(d, m, pm_of_neighbours(d.fmask, g, L), src[C], src[C + 1], src[C - 1], src[C + s1b], src[C - s1b], src[C + s2b], src[C - s2b]);
       else v = stencil_noparts(d, m, src[C], src[C + 1], src[C - 1], src[C + s1b], src[C - s1b], src[C + s2b], src[C - s2b]);
       Ap[(i - 1) + (long long)(j - 1) * s1 + (long long)(k - 1) * s2] = v;
     }

@@ -32,9 +32,8 @@ struct ResidGeom {
   static constexpr int a128(int v) { return (v + 127) / 128 * 128; }
   static constexpr int RT = a128(HXP * HYMAX * 8);     /* halo'd p tile */
   static constexpr int MT = a128(MXP * HYMAX);
-  static constexpr int PMT = PARTS ? a128(TX * BB_TYMAX) : 0;
   static constexpr int ROT = TX * BB_TYMAX * 8;        /* owned r tile */
-  static constexpr int STAGE = MT + PMT + ROT;
+  static constexpr int STAGE = MT + ROT;
   static constexpr int D = DD, NMS = D + 2, NPS = D + 2; /* a stage stays valid for the iteration after its arrival */
   static constexpr int NO = 2;
   static constexpr int OFF_STAGE = NPS * RT;
@@ -64,16 +63,13 @@ __device__ __forceinline__ void resid_issue(const Dev &d, const SearchMaps &tm, 
   const int ms = c.g % G::NMS, ps = c.g % G::NPS;
   const unsigned bar = bar0 + 8 * ms;
   const unsigned st = sS + ms * G::STAGE;
-  const bool inner = pi >= 1 && pi <= L.kn;
   unsigned bytes = HXP * hy * 8 + G::MXP * hy;
-  if (PARTS && inner) bytes += TX * ty;
   const bool owned = !REFRESH && pi >= k0 && pi <= k1;
   if (owned) bytes += TX * ty * 8;
   tma::mbar_expect_tx(bar, bytes);
-  if (owned) tma::load3d(st + G::MT + G::PMT, &tm.ro, BB_XOFF + 1 + bx * TX, j0, pi, bar);
+  if (owned) tma::load3d(st + G::MT, &tm.ro, BB_XOFF + 1 + bx * TX, j0, pi, bar);
   tma::load3d(sP + ps * G::RT, REFRESH ? &tm.xh : &tm.p[(q + 1) & 1], x0, y0, pi, bar);   /* p of the iteration in flight (ghosts current) / x */
   tma::load3d(st, &tm.fm, x0 - G::MX0, y0, pi, bar);
-  if (PARTS && inner) tma::load3d(st + G::MT, &tm.pm, BB_XOFF + 1 + bx * TX, j0, pi, bar);
 }
 
 /* the plane loop of ONE item; see search_item (bbpcg_search_tma.cuh) for the roles of g, pc and queue */
@@ -118,8 +114,9 @@ __device__ __forceinline__ double resid_item(const Dev &d, const SearchMaps &tm,
   const bool consumer = tid < BB_PRODUCER;              /* warp-uniform; the producer warp only issues loads */
 
   double2 pB[NO], pC[NO], bn[NO];                       /* bn: refresh form, b of the NEXT plane to be computed */
+  unsigned mBm[NO];                                     /* PARTS: the item's mask bytes one plane below the one being computed */
 #pragma unroll
-  for (int o = 0; o < NO; o++) { pB[o] = make_double2(0., 0.); pC[o] = make_double2(0., 0.); bn[o] = make_double2(0., 0.); }
+  for (int o = 0; o < NO; o++) { pB[o] = make_double2(0., 0.); pC[o] = make_double2(0., 0.); bn[o] = make_double2(0., 0.); mBm[o] = 0; }
 
   double dot = 0.;
   for (int lp = 0; lp < nplanes; lp++, g++) {
@@ -150,11 +147,16 @@ __device__ __forceinline__ double resid_item(const Dev &d, const SearchMaps &tm,
 
     /* ---- plane kc = pi-1: q = -A p from registers + the previous ring slot; r -= alpha q; (r, z) ---- */
     const int kc = pi - 1;
+    if (PARTS && lp == 1) {                             /* kc = k0 - 1, the halo plane below the first computed one: remember its solid bits */
+      const unsigned char *Mb = smem + G::OFF_STAGE + ((g - 1) % G::NMS) * G::STAGE;
+#pragma unroll
+      for (int o = 0; o < NO; o++) if (own[o]) mBm[o] = *reinterpret_cast<const unsigned short *>(Mb + rowo[o] * G::MXP + G::MX0 + cA);
+    }
     if (kc >= k0) {
       const double *Pc = reinterpret_cast<const double *>(smem + ((g - 1) % G::NPS) * G::RT);
       const unsigned char *Mc = smem + G::OFF_STAGE + ((g - 1) % G::NMS) * G::STAGE;        /* mask, pmask, r of plane kc */
-      const unsigned char *PMc = Mc + G::MT;
-      const double *Rc = reinterpret_cast<const double *>(Mc + G::MT + G::PMT);
+      const unsigned char *Mtop = smem + G::OFF_STAGE + (g % G::NMS) * G::STAGE;           /* mask of plane kc + 1 (this step's arrival) */
+      const double *Rc = reinterpret_cast<const double *>(Mc + G::MT);
       double *r_pl = r + (long long)kc * L.ps;
 #pragma unroll
       for (int o = 0; o < NO; o++) {
@@ -165,12 +167,18 @@ __device__ __forceinline__ double resid_item(const Dev &d, const SearchMaps &tm,
         const double pW = Pc[so - 1], pE = Pc[so + 2];
         const unsigned m = *reinterpret_cast<const unsigned short *>(Mc + rowo[o] * G::MXP + G::MX0 + cA);
         unsigned pm = 0;
-        if (PARTS) pm = *reinterpret_cast<const unsigned short *>(PMc + (rowo[o] - 1) * TX + 2 * col2);
+        if (PARTS) {
+          if (m & ((FM_NEAR << 8) | FM_NEAR)) {                          /* rare: a particle in the 7-point neighbourhood of one of the two cells */
+            const unsigned mt = *reinterpret_cast<const unsigned short *>(Mtop + rowo[o] * G::MXP + G::MX0 + cA);
+            pm = gather_pm_inplane(Mc + rowo[o] * G::MXP + G::MX0 + cA, G::MXP, m) | pm_planes(mt, mBm[o]);
+          }
+          mBm[o] = m;                                                    /* plane kc is the next step's plane below */
+        }
         double2 rc;
         if (REFRESH) rc = bc[o];
         else rc = *reinterpret_cast<const double2 *>(Rc + (rowo[o] - 1) * TX + 2 * col2);
         double q0, q1, c0 = c63, c1 = c63;
-        const bool plain = XFULL && __all_sync(0xffffffffu, m == BB_FULLMASK2 && (!PARTS || pm == 0u));
+        const bool plain = XFULL && __all_sync(0xffffffffu, m == BB_FULLMASK2);
         if (plain) {
           q0 = stencil_plain(d, pC[o].x, pC[o].y, pW, pN.x, pS.x, pT[o].x, pB[o].x);
           q1 = stencil_plain(d, pC[o].y, pE, pC[o].x, pN.y, pS.y, pT[o].y, pB[o].y);

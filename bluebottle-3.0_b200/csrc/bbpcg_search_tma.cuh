@@ -11,7 +11,7 @@
  * All plane inputs arrive through TMA (cp.async.bulk.tensor.3d, SASS UTMALDG) into a shared-memory ring, issued D planes
  * ahead by one thread and awaited on mbarriers, so DRAM latency is covered without any register staging:
  *     P ring (D+2 slots): halo'd p_prev tile (TX+4) x (ty+2); converted IN PLACE to p_new
- *     per stage (D+1) : halo'd r tile, mask tile, owned x tile, [pmask tile], and -- PULL model -- the r values of
+ *     per stage (D+1) : halo'd r tile, mask tile, owned x tile, and -- PULL model -- the r values of
  *                       ghost cells straight from the NEIGHBOUR's r array (peer memory over NVLink or
  *                       this block itself for a periodic self-wrap): one row per y-ghost, one run of
  *                       ty+2 values from the neighbour's compact x-face buffer per x-ghost, the whole
@@ -35,7 +35,7 @@
 #include "bbpcg_kernels.cuh"
 
 struct SearchMaps {
-  CUtensorMap r, p[2], fm, pm;       /* this block: halo'd f64 tiles, halo'd u8 mask tile, owned u8 pmask tile */
+  CUtensorMap r, p[2], fm;           /* this block: halo'd f64 tiles, halo'd u8 mask tile */
   CUtensorMap xo, ro;                /* owned (TX x ty) f64 tiles of x and r */
   CUtensorMap xh;                    /* halo'd tile of x (refresh form of k_resid_tma) */
   CUtensorMap nb[6];                 /* neighbours' r: E,W = (ty+2)-run box on the 2-D compact face buffer, N,S = row box, T,B = tile box */
@@ -90,9 +90,8 @@ struct SearchGeom {
   static constexpr int GYS = a128(HXP * 8), GY = 2 * GYS;      /* two y-ghost rows */
   static constexpr int GXN = HYMAX + 2;                /* x-ghost run: ty+2 values + 1 (a TMA box must START on a 16-byte boundary, so the run starts at the even j below y0), even */
   static constexpr int GXS = a128(GXN * 8), GX = 2 * GXS;      /* two x-ghost columns: contiguous runs from the neighbour's face buffer */
-  static constexpr int PMT = PARTS ? a128(TX * BB_TYMAX) : 0;
   static constexpr int XT = TX * BB_TYMAX * 8;         /* owned x tile */
-  static constexpr int STAGE = RT + MT + GY + GX + PMT + XT;
+  static constexpr int STAGE = RT + MT + GY + GX + XT;
   static constexpr int D = DD, NRS = DD + 1, NPS = DD + 2;   /* planes in flight, r/mask stages, p-ring slots */
   static constexpr int NO = 2;                         /* owned double2 items per thread: tile rows rg+1, rg+5 */
   static constexpr int OFF_STAGE = NPS * RT;
@@ -102,7 +101,25 @@ struct SearchGeom {
   static_assert(D <= NRS, "the done-drain loop indexes barriers 0..D-1");
 };
 
-#define BB_FULLMASK2 0x3f3fu        /* both cells of a double2 have all six flags set, neither is dead */
+#define BB_FULLMASK2 0x3f3fu        /* both cells of a double2 have all six flags set and no particle nearby (FM_NEAR, FM_SOLID clear) */
+
+/* Particle factors (PM_* bits, low byte = element 0, high byte = element 1 of a double2 item) from the solid bits of the
+ * halo'd mask tile.  mp -> the item's two mask bytes inside the tile, pitch = row pitch, m2 = those two bytes. */
+__device__ __forceinline__ unsigned gather_pm_inplane(const unsigned char *mp, int pitch, unsigned m2)
+{
+  const unsigned wl = *reinterpret_cast<const unsigned short *>(mp - 2);        /* columns -2, -1 */
+  const unsigned er = *reinterpret_cast<const unsigned short *>(mp + 2);        /* columns +2, +3 */
+  const unsigned n2 = *reinterpret_cast<const unsigned short *>(mp + pitch), s2 = *reinterpret_cast<const unsigned short *>(mp - pitch);
+  const unsigned c0 = (m2 >> 7) & 1u, c1 = (m2 >> 15) & 1u;
+  const unsigned e0 = ((c1 ? PM_E : 0u) | ((wl >> 15) & 1u ? PM_W : 0u) | ((n2 >> 7) & 1u ? PM_N : 0u) | ((s2 >> 7) & 1u ? PM_S : 0u) | (c0 ? PM_C : 0u));
+  const unsigned e1 = (((er >> 7) & 1u ? PM_E : 0u) | (c0 ? PM_W : 0u) | ((n2 >> 15) & 1u ? PM_N : 0u) | ((s2 >> 15) & 1u ? PM_S : 0u) | (c1 ? PM_C : 0u));
+  return e0 | (e1 << 8);
+}
+/* ... and of the same two cells one plane up (mt) and one plane down (mb) */
+__device__ __forceinline__ unsigned pm_planes(unsigned mt, unsigned mb)
+{
+  return ((mt >> 7) & 1u ? PM_T : 0u) | ((mb >> 7) & 1u ? PM_B : 0u) | ((mt >> 15) & 1u ? (PM_T << 8) : 0u) | ((mb >> 15) & 1u ? (PM_B << 8) : 0u);
+}
 
 /* ---- the TMA producer: lane 0 of the 9th warp ------------------------------------------------------------------
  * Its cursor (item, plane) runs D planes ahead of the consumers in the FLATTENED sequence of this CTA's items, so the
@@ -146,12 +163,11 @@ __device__ __forceinline__ void search_issue(const Dev &d, const SearchMaps &tm,
     if (gy1) bytes += HXP * 8;
     if (gx0) bytes += G::GXN * 8;
     if (gx1) bytes += G::GXN * 8;
-    if (PARTS) bytes += TX * ty;
   }
   const bool owned = pi >= k0 && pi <= k1;
   if (owned) bytes += TX * ty * 8;
   tma::mbar_expect_tx(bar, bytes);
-  if (owned) tma::load3d(st + G::RT + G::MT + G::GY + G::GX + G::PMT, &tm.xo, BB_XOFF + 1 + bx * TX, j0, pi, bar);
+  if (owned) tma::load3d(st + G::RT + G::MT + G::GY + G::GX, &tm.xo, BB_XOFF + 1 + bx * TX, j0, pi, bar);
   tma::load3d(sP + ps * G::RT, &tm.p[q & 1], x0, y0, pi, bar);
   tma::load3d(st + G::RT, &tm.fm, x0 - G::MX0, y0, pi, bar);
   if (pi == 0 && d.halo.f[5].r) tma::load3d(st, &tm.nb[5], x0, y0, d.halo.f[5].L.kn, bar);          /* B neighbour's top plane    */
@@ -162,7 +178,6 @@ __device__ __forceinline__ void search_issue(const Dev &d, const SearchMaps &tm,
     if (gy1) tma::load3d(st + G::RT + G::MT + G::GYS, &tm.nb[2], x0, 1, pi, bar);
     if (gx0) tma::load2d(st + G::RT + G::MT + G::GY, &tm.nb[1], y0 & ~1, pi, bar);          /* W neighbour's E face, j = (y0 & ~1) .. */
     if (gx1) tma::load2d(st + G::RT + G::MT + G::GY + G::GXS, &tm.nb[0], y0 & ~1, pi, bar); /* E neighbour's W face                  */
-    if (PARTS) tma::load3d(st + G::RT + G::MT + G::GY + G::GX, &tm.pm, BB_XOFF + 1 + bx * TX, j0, pi, bar);
   }
 }
 
@@ -247,9 +262,9 @@ __device__ __forceinline__ double search_item(const Dev &d, const SearchMaps &tm
 
   /* register pipeline of the owned cells: p(kc-1), p(kc), masks of kc */
   double2 pB[NO], pC[NO];
-  unsigned mC[NO], pmC[NO];
+  unsigned mC[NO], pmC[NO], mBm[NO];                    /* masks of plane kc, its in-plane particle factors, masks of plane kc-1 */
 #pragma unroll
-  for (int o = 0; o < NO; o++) { pB[o] = make_double2(0., 0.); pC[o] = make_double2(0., 0.); mC[o] = 0; pmC[o] = 0; }
+  for (int o = 0; o < NO; o++) { pB[o] = make_double2(0., 0.); pC[o] = make_double2(0., 0.); mC[o] = 0; pmC[o] = 0; mBm[o] = 0; }
   /* element offsets of this thread's items inside a plane of the P-layout arrays */
   unsigned goff[NO];
 #pragma unroll
@@ -274,8 +289,7 @@ __device__ __forceinline__ double search_item(const Dev &d, const SearchMaps &tm
     const unsigned char *Mt = St + G::RT;
     const double *GYt = reinterpret_cast<const double *>(St + G::RT + G::MT);
     const double *GXt = reinterpret_cast<const double *>(St + G::RT + G::MT + G::GY);
-    const unsigned char *PMt = St + G::RT + G::MT + G::GY + G::GX;
-    const double *Xt = reinterpret_cast<const double *>(St + G::RT + G::MT + G::GY + G::GX + G::PMT);
+    const double *Xt = reinterpret_cast<const double *>(St + G::RT + G::MT + G::GY + G::GX);
     double *pnew_pl = pnew + (long long)pi * L.ps;
     double *x_pl = x + (long long)pi * L.ps;
 
@@ -296,7 +310,7 @@ __device__ __forceinline__ double search_item(const Dev &d, const SearchMaps &tm
           if (e0gx) r2.x = GXt[G::GXS / 8 + gxsh + row];
           if (e1gx) r2.y = GXt[G::GXS / 8 + gxsh + row];
         }
-        if (!e1ok) m2 = (m2 & 0x00ffu) | (FM_DEAD << 8);
+        if (!e1ok) m2 &= 0x00ffu;                                          /* no such cell: dead */
       }
       double c0 = c63, c1 = c63;
       if (!(XFULL && __all_sync(0xffffffffu, m2 == BB_FULLMASK2))) { c0 = tab[m2 & 127u]; c1 = tab[(m2 >> 8) & 127u]; }
@@ -314,7 +328,7 @@ __device__ __forceinline__ double search_item(const Dev &d, const SearchMaps &tm
           pnew_pl[goff[o]] = pn.x; x_pl[goff[o]] = x0n;
           if (e1gx) pnew_pl[goff[o] + 1] = pn.y;                           /* the E ghost's p is kept current */
         } else pnew_pl[goff[o]] = pn.x;                                    /* element 0 IS the E ghost */
-        if (PARTS) pmT[o] = *reinterpret_cast<const unsigned short *>(PMt + (row - 1) * TX + 2 * col2);
+        if (PARTS && (m2 & ((FM_NEAR << 8) | FM_NEAR))) pmT[o] = gather_pm_inplane(Mt + row * G::MXP + G::MX0 + cA, G::MXP, m2);   /* rare */
       } else if (plane_ghost) {                                            /* z-ghost copy of p kept current */
         if (XFULL || e1own) stg128(pnew_pl + goff[o], pn.x, pn.y);
         else if (e0own) pnew_pl[goff[o]] = pn.x;
@@ -327,7 +341,7 @@ __device__ __forceinline__ double search_item(const Dev &d, const SearchMaps &tm
       const double2 p2 = *reinterpret_cast<const double2 *>(Pt + so);
       unsigned m2 = *reinterpret_cast<const unsigned short *>(Mt + hrow * G::MXP + G::MX0 + cA);
       if (hgy && !plane_ghost) r2 = *reinterpret_cast<const double2 *>(GYt + hgyoff + cA);
-      if (!XFULL && !e1ok) m2 = (m2 & 0x00ffu) | (FM_DEAD << 8);
+      if (!XFULL && !e1ok) m2 &= 0x00ffu;
       double2 pn;
       pn.x = __fma_rn(beta, p2.x, __dmul_rn(r2.x, tab[m2 & 127u]));
       pn.y = __fma_rn(beta, p2.y, __dmul_rn(r2.y, tab[(m2 >> 8) & 127u]));
@@ -358,12 +372,12 @@ __device__ __forceinline__ double search_item(const Dev &d, const SearchMaps &tm
         const double pW = Pc[so - 1], pE = Pc[so + 2];
         const unsigned m = mC[o];
         double q0, q1;
-        bool plain = XFULL && __all_sync(0xffffffffu, m == BB_FULLMASK2 && (!PARTS || pmC[o] == 0u));
+        bool plain = XFULL && __all_sync(0xffffffffu, m == BB_FULLMASK2);      /* all six flags set, no particle in the 7-point neighbourhood (FM_NEAR clear) */
         if (plain) {
           q0 = stencil_plain(d, pC[o].x, pC[o].y, pW, pN.x, pS.x, pT[o].x, pB[o].x);
           q1 = stencil_plain(d, pC[o].y, pE, pC[o].x, pN.y, pS.y, pT[o].y, pB[o].y);
         } else if (PARTS) {
-          const unsigned pm = pmC[o];
+          const unsigned pm = pmC[o] | pm_planes(mT[o], mBm[o]);
           q0 = stencil_parts(d, m & 255u, pm & 255u, pC[o].x, pC[o].y, pW, pN.x, pS.x, pT[o].x, pB[o].x);
           q1 = stencil_parts(d, m >> 8, pm >> 8, pC[o].y, pE, pC[o].x, pN.y, pS.y, pT[o].y, pB[o].y);
         } else {
@@ -375,7 +389,7 @@ __device__ __forceinline__ double search_item(const Dev &d, const SearchMaps &tm
       }
     }
 #pragma unroll
-    for (int o = 0; o < NO; o++) { pB[o] = pC[o]; pC[o] = pT[o]; mC[o] = mT[o]; if (PARTS) pmC[o] = pmT[o]; }
+    for (int o = 0; o < NO; o++) { pB[o] = pC[o]; pC[o] = pT[o]; if (PARTS) { mBm[o] = mC[o]; pmC[o] = pmT[o]; } mC[o] = mT[o]; }
     tma::fence_proxy_async();
     }                                 /* consumer */
     __syncthreads();

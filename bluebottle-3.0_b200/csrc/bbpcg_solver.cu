@@ -77,6 +77,7 @@ struct bbpcg_solver {
   int plan_ty, plan_nbx, plan_nby, plan_nbz, plan_kc;
   int pdl;                          /* programmatic dependent launch of the two iteration kernels: 0 off, 1 on, 2 auto */
   int guided, guided_pct, chunk_min; /* z-chunk plan of small blocks: decreasing chunk lengths (make_plan) */
+  int epilogue_tiled, epi_chunk;    /* 1: the 16^3-brick epilogue kernel instead of the streaming pair; planes per chunk of the pair */
   int tma_warp;                     /* 1 (default): a dedicated producer warp issues the iteration kernels' TMA loads; 0: thread 0 does */
   int rhs_tiled;                    /* PP_rhs through shared-memory transposes (default) or the row-walking kernel */
   int shared_device;                /* some peer rank lives on this same GPU (single-process harness, or two processes on one GPU) */
@@ -104,7 +105,7 @@ static void point_dev_at_arena(bbpcg_solver *s)
   const ArenaMap &m = s->amap;
   d.r = (double *)(a + m.r); d.P[0] = (double *)(a + m.p0); d.P[1] = (double *)(a + m.p1);
   d.x = (double *)(a + m.x);
-  d.fmask = (u8 *)(a + m.fmask); d.pmask = (u8 *)(a + m.pmask);
+  d.fmask = (u8 *)(a + m.fmask);
   for (int b = 0; b < 2; b++) for (int f = 0; f < 6; f++) d.recv[b][f] = (double *)(a + m.recv[b][f]);
   d.partials = (double *)(a + m.partials); d.gpartials = (double *)(a + m.gpartials); d.counter = (unsigned *)(a + m.counter);
   d.sc = (Scal *)(a + m.scal); d.history = (double *)(a + m.history);
@@ -172,7 +173,6 @@ static int build_search_maps(bbpcg_solver *s, int ty)
   if (!rc) rc = make_map(&M->p[0], d.P[0], d.L, false, G::HXP, hy);
   if (!rc) rc = make_map(&M->p[1], d.P[1], d.L, false, G::HXP, hy);
   if (!rc) rc = make_map(&M->fm, d.fmask, d.L, true, G::MXP, hy);
-  if (!rc) rc = make_map(&M->pm, d.pmask, d.L, true, G::TX, ty);
   if (!rc) rc = make_map(&M->xo, d.x, d.L, false, G::TX, ty);
   if (!rc) rc = make_map(&M->ro, d.r, d.L, false, G::TX, ty);
   if (!rc) rc = make_map(&M->xh, d.x, d.L, false, G::HXP, hy);
@@ -238,7 +238,7 @@ static int create_impl(bbpcg_solver *s, const dom_struct *dom_rank, const dom_st
   }
   CU(cudaMemset(s->arena, 0, s->amap.total));
   point_dev_at_arena(s);
-  CU(cudaMemset(d.fmask, FM_DEAD, (size_t)d.L.n));          /* ghosts behind walls stay dead forever */
+  /* the zero-filled mask array marks every cell dead; ghosts behind walls are never written and stay so */
   d.idx2 = 1. / (dom_rank->dx * dom_rank->dx); d.idy2 = 1. / (dom_rank->dy * dom_rank->dy); d.idz2 = 1. / (dom_rank->dz * dom_rank->dz);
   d.dx2_6 = (dom_rank->dx * dom_rank->dx) / 6.; d.dy2_6 = (dom_rank->dy * dom_rank->dy) / 6.; d.dz2_6 = (dom_rank->dz * dom_rank->dz) / 6.;
   s->fst.us1b = dom_rank->Gfx.s1b; s->fst.us2b = dom_rank->Gfx.s2b;
@@ -573,6 +573,7 @@ static int preload_kernels()
   PL(k_solv_sum); PL(k_solv_apply); PL(k_bc_star);
   PL(k_cage_reset); PL(k_cage<false>); PL(k_cage<true>); PL(k_cage_flags<256>);
   PL(k_bc_p); PL(k_sub_mean);
+  PL(k_epi_uwp<true, true>); PL(k_epi_uwp<true, false>); PL(k_epi_uwp<false, true>); PL(k_epi_v);
   PL(k_epilogue<true, true>, EPI_SMEM); PL(k_epilogue<true, false>, EPI_SMEM); PL(k_epilogue<false, true>, EPI_SMEM);
 #undef PL
   return rc;
@@ -814,12 +815,27 @@ extern "C" int bbpcg_epilogue(bbpcg_solver *s, const bbpcg_epilogue_args *a, dou
   e.ddx = 1. / d.dx; e.ddy = 1. / d.dy; e.ddz = 1. / d.dz;
   e.dt_rho = a->dt / a->rho_f;
   e.nti = (L.in + EPI_T - 1) / EPI_T; e.ntj = (L.jn + EPI_T - 1) / EPI_T; e.ntk = (L.kn + EPI_T - 1) / EPI_T;
-  const long long ntiles = (long long)e.nti * e.ntj * e.ntk;
-  const int grid = clampi(ntiles, 1, BB_MAXBLOCKS);
-  if (project && update) k_epilogue<true, true><<<grid, 256, EPI_SMEM, s->stream>>>(s->dev, s->fst, e);
-  else if (project) k_epilogue<true, false><<<grid, 256, EPI_SMEM, s->stream>>>(s->dev, s->fst, e);
-  else k_epilogue<false, true><<<grid, 256, EPI_SMEM, s->stream>>>(s->dev, s->fst, e);
-  s->launches++;
+  if (s->epilogue_tiled) {            /* the 16^3-brick kernel (kept selectable; the streaming pair below is the default) */
+    const long long ntiles = (long long)e.nti * e.ntj * e.ntk;
+    const int grid = clampi(ntiles, 1, BB_MAXBLOCKS);
+    if (project && update) k_epilogue<true, true><<<grid, 256, EPI_SMEM, s->stream>>>(s->dev, s->fst, e);
+    else if (project) k_epilogue<true, false><<<grid, 256, EPI_SMEM, s->stream>>>(s->dev, s->fst, e);
+    else k_epilogue<false, true><<<grid, 256, EPI_SMEM, s->stream>>>(s->dev, s->fst, e);
+    s->launches++;
+  } else {
+    EpiPlan pl;
+    pl.nti = (L.in + EA_T - 1) / EA_T; pl.ntj = (L.jn + EA_T - 1) / EA_T; pl.ntk = (L.kn + EA_T - 1) / EA_T;
+    /* chunks of ~32 planes / faces: enough items for every resident CTA, one extra phi plane per chunk (3 %) */
+    pl.kc = s->epi_chunk > 0 ? s->epi_chunk : 32; pl.nzc = (L.kn + pl.kc - 1) / pl.kc;
+    pl.jc = pl.kc; pl.njc = (L.jn + 1 + pl.jc - 1) / pl.jc;
+    const long long itemsA = (long long)pl.nti * pl.ntj * pl.nzc, itemsB = (long long)pl.ntk * pl.nti * pl.njc;
+    const int gridA = clampi(itemsA, 1, s->sm_count * 3), gridB = clampi(itemsB, 1, s->sm_count * 4);
+    if (project && update) k_epi_uwp<true, true><<<gridA, 256, 0, s->stream>>>(s->dev, s->fst, e, pl);
+    else if (project) k_epi_uwp<true, false><<<gridA, 256, 0, s->stream>>>(s->dev, s->fst, e, pl);
+    else k_epi_uwp<false, true><<<gridA, 256, 0, s->stream>>>(s->dev, s->fst, e, pl);
+    s->launches++;
+    if (project) { k_epi_v<<<gridB, 256, 0, s->stream>>>(s->dev, s->fst, e, pl); s->launches++; }
+  }
   if (update) {
     const long long nrows = (long long)L.jn * L.kn;
     k_sub_mean<<<clampi(nrows, 1, s->sm_count * 16), 256, 0, s->stream>>>(s->dev, a->p, s->fst.cs1b, s->fst.cs2b, (double)s->DOM.xn * (double)s->DOM.yn * (double)s->DOM.zn);
@@ -1110,6 +1126,8 @@ extern "C" int bbpcg_set_option(bbpcg_solver *s, const char *key, long long valu
   else if (!strcmp(key, "pdl")) s->pdl = clampi(value, 0, 2);
   else if (!strcmp(key, "rhs_tiled")) s->rhs_tiled = value != 0;
   else if (!strcmp(key, "tma_warp")) s->tma_warp = value != 0;
+  else if (!strcmp(key, "epilogue_tiled")) s->epilogue_tiled = value != 0;
+  else if (!strcmp(key, "epi_chunk")) s->epi_chunk = clampi(value, 0, 4096);
   else if (!strcmp(key, "guided")) { s->guided = value != 0; s->plan_ok = 0; }
   else if (!strcmp(key, "guided_pct")) { s->guided_pct = clampi(value, 10, 400); s->plan_ok = 0; }
   else if (!strcmp(key, "chunk_min")) { s->chunk_min = clampi(value, 2, 1024); s->plan_ok = 0; }

@@ -159,7 +159,7 @@ def test_plan_of_the_benchmarked_block_shapes():
         if many:
             assert items >= 7 * slots and kc == 24 and nbz == -(-cells[2] // kc)
         else:
-            assert kc > cells[2] // nbz and nbz >= 2          # guided: the first chunk is the longest
+            assert kc >= -(-cells[2] // nbz) and (nbz >= 2 or kc == cells[2])     # guided: the first chunk is the longest
         s.set_option("ty", 7); s.set_option("kc", 16)
         assert s.info("search_ty") == 7 and s.info("search_kc") == 16 and s.info("search_nbz") == -(-cells[2] // 16)
         s.close()
