@@ -189,12 +189,12 @@ __global__ void __launch_bounds__(256, 3) k_epilogue(const __grid_constant__ Dev
  * run on the reference's ghosted pitches (5 sectors fetched for 4 used), the brick is refilled 12-14 dependent DRAM round
  * trips per tile, and ncu showed 1.29 x the algorithmic bytes at 52 % of peak (profiles/r01h_epilogue_ncu_full.md).
  *
- *   k_epi_uwp  tile 32 (i) x 32 (j), marching k: per plane ONE batch of loads (phi row tile, w*, flag_w, p0, phase with lanes
- *              along i; u*, flag_u with lanes along j), phi staged in a 9 KB tile so that the u lanes (along j) read
- *              phi(i) - phi(i-1) transposed; w uses phi(k-1) kept in registers; p and its partial sum from the same phi.
- *              Every global access is a 256-byte run (128 for the int arrays).
+ *   k_epi_uwp  tile 32 (i) x 32 (j), marching k: every plane arrives through cp.async (phi row tile, w*, flag_w, p0, phase with
+ *              lanes along i; u*, flag_u with lanes along j) one plane ahead of the computation; the u lanes (along j) read
+ *              phi(i) - phi(i-1) across the staged tile; w uses phi(k-1) kept in registers; p and its partial sum from the
+ *              same phi.  Every global access is a 256-byte run (128 for the int arrays).
  *   k_epi_v    tile 32 (k) x 32 (i), marching j: phi rows along i for 32 planes, transposed through shared memory to the
- *              k-fastest Gfy layout; the previous j plane stays in shared memory (three buffers, one barrier per plane).
+ *              k-fastest Gfy layout; the previous j plane stays in shared memory (three phi buffers).
  * phi is read twice (8 B/cell more than the fused brick) but nothing is fetched in 128-byte pieces any more.
  * Same expressions as project_line above, so u, v, w, p are bit-identical to k_epilogue's. */
 #define EA_T 32
@@ -207,10 +207,29 @@ struct EpiPlan {
   int jc, njc;                         /* k_epi_v: faces per j-chunk, chunks */
 };
 
+/* Ampere-style asynchronous copies global -> shared (LDGSTS): any 4 / 8-byte alignment, so they work on the reference's
+ * ghosted pitches where TMA boxes would not; one plane is in flight while the previous one is computed, with no register
+ * staging (a register batch per plane left the loads of only ONE plane in flight per CTA and reached 3.7 TB/s). */
+__device__ __forceinline__ void cp_async8(void *dst, const void *src)
+{ asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async4(void *dst, const void *src)
+{ asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+struct EpiStageA {                     /* one k-plane of a 32 x 32 tile */
+  double phi[EA_T][EA_PA];             /* [jj][ii]: phi(i0 - 1 + ii, j0 + jj, k) */
+  double ws[EA_T][EA_T], p0[EA_T][EA_T];            /* [jj][lane i] */
+  double us[EA_T + 1][EA_T];           /* [face f][lane j] */
+  int fw[EA_T][EA_T], ph[EA_T][EA_T], fu[EA_T + 1][EA_T];
+};
+#define EPI_SMEM_A (2 * (int)sizeof(EpiStageA))
+
 template <bool PROJECT, bool UPDATE_P>
-__global__ void __launch_bounds__(256, 3) k_epi_uwp(const __grid_constant__ Dev d, const FaceStrides st, const EpiArgs a, const EpiPlan pl)
+__global__ void __launch_bounds__(256, 2) k_epi_uwp(const __grid_constant__ Dev d, const FaceStrides st, const EpiArgs a, const EpiPlan pl)
 {
-  __shared__ double sphi[2][EA_T][EA_PA];                  /* [k & 1][jj][ii]: phi(i0 - 1 + ii, j0 + jj, k) */
+  extern __shared__ __align__(16) unsigned char epi_smem[];
+  EpiStageA *stg = reinterpret_cast<EpiStageA *>(epi_smem);
   const int in = d.L.in, jn = d.L.jn, kn = d.L.kn;
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const long long ntile = (long long)pl.nti * pl.ntj, nitems = ntile * pl.nzc;
@@ -224,34 +243,25 @@ __global__ void __launch_bounds__(256, 3) k_epi_uwp(const __grid_constant__ Dev 
     const bool close_i = i0 + ni - 1 == in;                /* this tile also owns the closing face i = in + 1 (project_u loops _is.._ie) */
     const int nfi = ni + (close_i ? 1 : 0);
     const int klast = k1 + ((PROJECT && k1 == kn) ? 1 : 0);   /* ... and the last chunk the closing face k = kn + 1 of w */
-    /* phi one plane below, at this thread's cells (rows jj = wp + 8 r, column lane) */
-    double pprev[4];
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const int jj = wp + 8 * r;
-      pprev[r] = (PROJECT && lane < ni && jj < nj) ? __ldg(a.phi + (i0 + lane) + (long long)(j0 + jj) * st.cs1b + (long long)(k0 - 1) * st.cs2b) : 0.;
-    }
-    for (int k = k0; k <= klast; k++) {
-      const int buf = k & 1;
-      const bool cells = k <= k1;                          /* k = kn + 1: only the closing w face */
-      /* ---- one batch of loads ---- */
-      double pc[4], ws[4], p0v[4], ph_halo[4], us[5];
-      int fw[4], phv[4], fu[5];
+    /* all copies of plane k into stage k & 1 (every thread issues its share; consumers read them after the wait + barrier) */
+    auto issue = [&](int k) {
+      EpiStageA &S = stg[k & 1];
+      const bool cells = k <= k1;
 #pragma unroll
       for (int r = 0; r < 4; r++) {
         const int jj = wp + 8 * r;
         if (lane < ni && jj < nj) {
           const long long C = (i0 + lane) + (long long)(j0 + jj) * st.cs1b + (long long)k * st.cs2b;
-          pc[r] = __ldg(a.phi + C);
+          cp_async8(&S.phi[jj][lane + 1], a.phi + C);
           if (PROJECT) {
             const long long F = (i0 + lane) + (long long)(j0 + jj) * st.ws1b + (long long)k * st.ws2b;
-            ws[r] = __ldg(a.w_star + F); fw[r] = __ldg(a.flag_w + F);
+            cp_async8(&S.ws[jj][lane], a.w_star + F); cp_async4(&S.fw[jj][lane], a.flag_w + F);
           }
-          if (UPDATE_P && cells) { p0v[r] = __ldg(a.p0 + C); phv[r] = __ldg(a.phase + C); }
+          if (UPDATE_P && cells) { cp_async8(&S.p0[jj][lane], a.p0 + C); cp_async4(&S.ph[jj][lane], a.phase + C); }
         }
         /* the two halo columns of the row: lane 0 -> i0 - 1, lane 1 -> i0 + ni (needed only for the closing face) */
         if (PROJECT && cells && jj < nj && (lane == 0 || (lane == 1 && close_i)))
-          ph_halo[r] = __ldg(a.phi + (lane == 0 ? i0 - 1 : i0 + ni) + (long long)(j0 + jj) * st.cs1b + (long long)k * st.cs2b);
+          cp_async8(&S.phi[jj][lane == 0 ? 0 : ni + 1], a.phi + (lane == 0 ? i0 - 1 : i0 + ni) + (long long)(j0 + jj) * st.cs1b + (long long)k * st.cs2b);
       }
       if (PROJECT && cells) {
 #pragma unroll
@@ -259,35 +269,43 @@ __global__ void __launch_bounds__(256, 3) k_epi_uwp(const __grid_constant__ Dev 
           const int f = wp + 8 * r;                        /* face i0 + f, lanes along j (Gfx is j-fastest) */
           if (f < nfi && lane < nj) {
             const long long U = (j0 + lane) + (long long)k * st.us1b + (long long)(i0 + f) * st.us2b;
-            us[r] = __ldg(a.u_star + U); fu[r] = __ldg(a.flag_u + U);
+            cp_async8(&S.us[f][lane], a.u_star + U); cp_async4(&S.fu[f][lane], a.flag_u + U);
           }
         }
-        /* ---- stage the phi row tile ---- */
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-          const int jj = wp + 8 * r;
-          if (lane < ni && jj < nj) sphi[buf][jj][lane + 1] = pc[r];
-          if (jj < nj && (lane == 0 || (lane == 1 && close_i))) sphi[buf][jj][lane == 0 ? 0 : ni + 1] = ph_halo[r];
-        }
       }
-      __syncthreads();      /* the only barrier of a plane: plane k + 1 fills the other buffer, plane k + 2 refills this one after the next barrier */
+      cp_async_commit();
+    };
+    issue(k0);
+    /* phi one plane below, at this thread's cells (rows jj = wp + 8 r, column lane): in flight together with the first plane */
+    double pprev[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int jj = wp + 8 * r;
+      pprev[r] = (PROJECT && lane < ni && jj < nj) ? __ldg(a.phi + (i0 + lane) + (long long)(j0 + jj) * st.cs1b + (long long)(k0 - 1) * st.cs2b) : 0.;
+    }
+    for (int k = k0; k <= klast; k++) {
+      const bool cells = k <= k1;                          /* k = kn + 1: only the closing w face */
+      if (k < klast) { issue(k + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+      __syncthreads();                                     /* plane k has landed for every thread */
+      const EpiStageA &S = stg[k & 1];
       /* ---- w and p: lanes along i ---- */
 #pragma unroll
       for (int r = 0; r < 4; r++) {
         const int jj = wp + 8 * r;
         if (lane < ni && jj < nj) {
+          const double pc = S.phi[jj][lane + 1];
           if (PROJECT) {
             const long long F = (i0 + lane) + (long long)(j0 + jj) * st.ws1b + (long long)k * st.ws2b;
-            const double gradPhi = abs(fw[r]) * a.ddz * (pc[r] - pprev[r]);                    /* bluebottle_kernel.cu:2351 */
-            a.w[F] = (ws[r] - a.dt_rho * gradPhi);                                             /* :2352 */
+            const double gradPhi = abs(S.fw[jj][lane]) * a.ddz * (pc - pprev[r]);              /* bluebottle_kernel.cu:2351 */
+            a.w[F] = (S.ws[jj][lane] - a.dt_rho * gradPhi);                                    /* :2352 */
           }
           if (UPDATE_P && cells) {
             const long long C = (i0 + lane) + (long long)(j0 + jj) * st.cs1b + (long long)k * st.cs2b;
-            const double val = (phv[r] < 0) * (p0v[r] + pc[r]);                                /* :2396 */
+            const double val = (S.ph[jj][lane] < 0) * (S.p0[jj][lane] + pc);                   /* :2396 */
             a.p[C] = val;
             psum += val;
           }
-          pprev[r] = pc[r];
+          pprev[r] = pc;
         }
       }
       /* ---- u: lanes along j, phi(i) - phi(i-1) read across the tile ---- */
@@ -297,13 +315,13 @@ __global__ void __launch_bounds__(256, 3) k_epi_uwp(const __grid_constant__ Dev 
           const int f = wp + 8 * r;
           if (f < nfi && lane < nj) {
             const long long U = (j0 + lane) + (long long)k * st.us1b + (long long)(i0 + f) * st.us2b;
-            const double gradPhi = abs(fu[r]) * a.ddx * (sphi[buf][lane][f + 1] - sphi[buf][lane][f]);   /* :2315 */
-            a.u[U] = (us[r] - a.dt_rho * gradPhi);                                                        /* :2316 */
+            const double gradPhi = abs(S.fu[f][lane]) * a.ddx * (S.phi[lane][f + 1] - S.phi[lane][f]);   /* :2315 */
+            a.u[U] = (S.us[f][lane] - a.dt_rho * gradPhi);                                                /* :2316 */
           }
         }
       }
+      __syncthreads();                                     /* stage k & 1 is free for plane k + 2 */
     }
-    __syncthreads();        /* the next item starts with either buffer */
   }
   if (UPDATE_P) {
     /* mean pressure: thrust::reduce + MPI_Allreduce of cuda_bluebottle.cu:2526-2529, kept on the device */
@@ -315,9 +333,14 @@ __global__ void __launch_bounds__(256, 3) k_epi_uwp(const __grid_constant__ Dev 
   }
 }
 
+struct EpiStageB { double vs[EA_T][EA_T]; int fv[EA_T][EA_T]; };      /* [ii][lane k] */
+struct EpiSmemB { double phi[3][EA_T][EA_PB]; EpiStageB s[2]; };     /* phi[j % 3][kk][ii]: phi(i0 + ii, j, k0 + kk) */
+#define EPI_SMEM_B ((int)sizeof(EpiSmemB))
+
 __global__ void __launch_bounds__(256, 4) k_epi_v(const __grid_constant__ Dev d, const FaceStrides st, const EpiArgs a, const EpiPlan pl)
 {
-  __shared__ double sphi[3][EA_T][EA_PB];                  /* [j % 3][kk][ii]: phi(i0 + ii, j, k0 + kk) */
+  extern __shared__ __align__(16) unsigned char epi_smem[];
+  EpiSmemB &M = *reinterpret_cast<EpiSmemB *>(epi_smem);
   const int in = d.L.in, jn = d.L.jn, kn = d.L.kn;
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const long long ntile = (long long)pl.ntk * pl.nti, nitems = ntile * pl.njc;
@@ -327,40 +350,37 @@ __global__ void __launch_bounds__(256, 4) k_epi_v(const __grid_constant__ Dev d,
     const int i0 = bi * EA_T + 1, k0 = bk * EA_T + 1;
     const int ni = min(EA_T, in - i0 + 1), nk = min(EA_T, kn - k0 + 1);
     const int f0 = jcn * pl.jc + 1, f1 = min(jn + 1, f0 + pl.jc - 1);      /* faces j = f0 .. f1 of Gfy._js.._je = 1 .. jn + 1 */
-    for (int j = f0 - 1; j <= f1; j++) {
-      const int buf = j % 3;
-      double pc[4], vs[4];
-      int fv[4];
+    auto issue = [&](int j) {
 #pragma unroll
       for (int r = 0; r < 4; r++) {
         const int kk = wp + 8 * r;                         /* phi: lanes along i, one k row per warp pass */
-        if (lane < ni && kk < nk) pc[r] = __ldg(a.phi + (i0 + lane) + (long long)j * st.cs1b + (long long)(k0 + kk) * st.cs2b);
+        if (lane < ni && kk < nk) cp_async8(&M.phi[j % 3][kk][lane], a.phi + (i0 + lane) + (long long)j * st.cs1b + (long long)(k0 + kk) * st.cs2b);
         const int ii = wp + 8 * r;                         /* v*, flag_v: lanes along k (Gfy is k-fastest), one i row per warp pass */
         if (j >= f0 && ii < ni && lane < nk) {
           const long long V = (k0 + lane) + (long long)(i0 + ii) * st.vs1b + (long long)j * st.vs2b;
-          vs[r] = __ldg(a.v_star + V); fv[r] = __ldg(a.flag_v + V);
+          cp_async8(&M.s[j & 1].vs[ii][lane], a.v_star + V); cp_async4(&M.s[j & 1].fv[ii][lane], a.flag_v + V);
         }
       }
-#pragma unroll
-      for (int r = 0; r < 4; r++) {
-        const int kk = wp + 8 * r;
-        if (lane < ni && kk < nk) sphi[buf][kk][lane] = pc[r];
-      }
-      __syncthreads();      /* one barrier per plane: plane j + 1 fills a third buffer, plane j + 2 refills the one read as "previous" here */
+      cp_async_commit();
+    };
+    issue(f0 - 1);
+    for (int j = f0 - 1; j <= f1; j++) {
+      if (j < f1) { issue(j + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+      __syncthreads();                                     /* plane j has landed */
       if (j >= f0) {
-        const int prev = (j - 1) % 3;
+        const int cur = j % 3, prev = (j - 1) % 3;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
           const int ii = wp + 8 * r;
           if (ii < ni && lane < nk) {
             const long long V = (k0 + lane) + (long long)(i0 + ii) * st.vs1b + (long long)j * st.vs2b;
-            const double gradPhi = abs(fv[r]) * a.ddy * (sphi[buf][lane][ii] - sphi[prev][lane][ii]);    /* bluebottle_kernel.cu:2333 */
-            a.v[V] = (vs[r] - a.dt_rho * gradPhi);                                                        /* :2334 */
+            const double gradPhi = abs(M.s[j & 1].fv[ii][lane]) * a.ddy * (M.phi[cur][lane][ii] - M.phi[prev][lane][ii]);   /* bluebottle_kernel.cu:2333 */
+            a.v[V] = (M.s[j & 1].vs[ii][lane] - a.dt_rho * gradPhi);                                                        /* :2334 */
           }
         }
       }
+      __syncthreads();                                     /* the v* stage and the oldest phi buffer are free for plane j + 2 */
     }
-    __syncthreads();
   }
 }
 

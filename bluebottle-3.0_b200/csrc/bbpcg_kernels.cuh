@@ -260,7 +260,7 @@ __device__ __forceinline__ void rank_allreduce(const Dev &d, double *v /* thread
     s_in[t][0] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
     s_in[t][1] = __longlong_as_double((long long)((w2 & 0xffffffffull) | (w3 << 32)));
     if (!ok) { d.sc->comm_timeout = 1; *c.host_flag = 1; }    /* sticky: the ranks now disagree, the solver object is dead */
-    fence_acq_rel_sys();             /* acquire side: peers' released data is read by LATER kernels */
+    if (release) fence_acq_rel_sys();  /* acquire side: peers' released data (r, ghost pushes) is read by LATER kernels; a plain sum needs none */
   }
   __syncthreads();
   if (threadIdx.x == 0) {

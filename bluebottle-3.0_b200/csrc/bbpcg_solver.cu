@@ -439,16 +439,13 @@ static int make_plan(bbpcg_solver *s)
   return BBPCG_OK;
 }
 
-/* PDL policy.  Measured on 2 B200s (scripts/comm_probe.py, profiles/r01e_comm_probe.jsonl): with 67 M cells per rank PDL
- * saves 22 us of 786 per iteration; with 16.7 M cells per rank (the 8-GPU share of 512^3) it COSTS 13 us of 237 in a
- * decomposed run (the early-launched CTAs of the next kernel hold SM slots while the last CTA of this one waits for its
- * peers) and gains nothing stand-alone.  auto = on, except for decomposed runs with small blocks. */
+/* PDL policy: on (option pdl 0 switches it off), except when several ranks share one GPU.  With the round-1 kernels PDL cost
+ * 13 us per iteration on decomposed 256^3 blocks (early-launched CTAs held SM slots while the last CTA waited for its
+ * peers); with the persistent kernels a dependent CTA only becomes resident when a slot frees, and decomposed runs measure
+ * the same with and without it (2 ranks x 256^3: 221.1 vs 221.4 us, profiles/r02l_comm_probe.jsonl), stand-alone 209 vs 213. */
 static bool pdl_active(const bbpcg_solver *s)
 {
-  if (s->shared_device || !s->pdl) return false;
-  if (s->pdl == 1) return true;
-  const long long cells = (long long)s->dev.L.in * s->dev.L.jn * s->dev.L.kn;
-  return !(s->nranks > 1 && cells < 24ll * 1000 * 1000);
+  return !s->shared_device && s->pdl != 0;
 }
 
 /* launch with (optionally) the programmatic-stream-serialization attribute: the kernel may be scheduled
@@ -573,7 +570,7 @@ static int preload_kernels()
   PL(k_solv_sum); PL(k_solv_apply); PL(k_bc_star);
   PL(k_cage_reset); PL(k_cage<false>); PL(k_cage<true>); PL(k_cage_flags<256>);
   PL(k_bc_p); PL(k_sub_mean);
-  PL(k_epi_uwp<true, true>); PL(k_epi_uwp<true, false>); PL(k_epi_uwp<false, true>); PL(k_epi_v);
+  PL(k_epi_uwp<true, true>, EPI_SMEM_A); PL(k_epi_uwp<true, false>, EPI_SMEM_A); PL(k_epi_uwp<false, true>, EPI_SMEM_A); PL(k_epi_v, EPI_SMEM_B);
   PL(k_epilogue<true, true>, EPI_SMEM); PL(k_epilogue<true, false>, EPI_SMEM); PL(k_epilogue<false, true>, EPI_SMEM);
 #undef PL
   return rc;
@@ -829,12 +826,12 @@ extern "C" int bbpcg_epilogue(bbpcg_solver *s, const bbpcg_epilogue_args *a, dou
     pl.kc = s->epi_chunk > 0 ? s->epi_chunk : 32; pl.nzc = (L.kn + pl.kc - 1) / pl.kc;
     pl.jc = pl.kc; pl.njc = (L.jn + 1 + pl.jc - 1) / pl.jc;
     const long long itemsA = (long long)pl.nti * pl.ntj * pl.nzc, itemsB = (long long)pl.ntk * pl.nti * pl.njc;
-    const int gridA = clampi(itemsA, 1, s->sm_count * 3), gridB = clampi(itemsB, 1, s->sm_count * 4);
-    if (project && update) k_epi_uwp<true, true><<<gridA, 256, 0, s->stream>>>(s->dev, s->fst, e, pl);
-    else if (project) k_epi_uwp<true, false><<<gridA, 256, 0, s->stream>>>(s->dev, s->fst, e, pl);
-    else k_epi_uwp<false, true><<<gridA, 256, 0, s->stream>>>(s->dev, s->fst, e, pl);
+    const int gridA = clampi(itemsA, 1, s->sm_count * 2), gridB = clampi(itemsB, 1, s->sm_count * 4);
+    if (project && update) k_epi_uwp<true, true><<<gridA, 256, EPI_SMEM_A, s->stream>>>(s->dev, s->fst, e, pl);
+    else if (project) k_epi_uwp<true, false><<<gridA, 256, EPI_SMEM_A, s->stream>>>(s->dev, s->fst, e, pl);
+    else k_epi_uwp<false, true><<<gridA, 256, EPI_SMEM_A, s->stream>>>(s->dev, s->fst, e, pl);
     s->launches++;
-    if (project) { k_epi_v<<<gridB, 256, 0, s->stream>>>(s->dev, s->fst, e, pl); s->launches++; }
+    if (project) { k_epi_v<<<gridB, 256, EPI_SMEM_B, s->stream>>>(s->dev, s->fst, e, pl); s->launches++; }
   }
   if (update) {
     const long long nrows = (long long)L.jn * L.kn;
