@@ -62,9 +62,6 @@ static inline __host__ __device__ long long pidx(const Layout &L, int i, int j, 
   return (long long)(i + BB_XOFF) + (long long)j * L.px + (long long)k * L.ps;
 }
 
-/* x-face buffers: value of (j,k) at j + k*pf, j fastest; pitch even so rows are 16-byte aligned (TMA) */
-static inline __host__ __device__ int xface_pitch(const Layout &L) { return (L.jn + 2 + 1) / 2 * 2; }
-
 static inline Layout make_layout(int in, int jn, int kn)
 {
   Layout L;
@@ -89,7 +86,6 @@ struct ArenaMap {
   size_t history;                  /* doubles[hist_cap] */
   size_t invM_tab;                 /* doubles[128]: Jacobi diagonal per mask value */
   size_t ztab;                     /* ints[BB_MAXZ + 1]: prefix offsets of the search kernel's z-chunks */
-  size_t xface[2];                 /* doubles[pf*(kn+2)]: compact copies of r on the faces i = 1 (W) and i = in (E) */
   size_t total;
 };
 
@@ -115,7 +111,6 @@ static inline ArenaMap make_arena_map(const Layout &L)
   m.history = take(sizeof(double) * BB_HIST_CAP);
   m.invM_tab = take(sizeof(double) * 128);
   m.ztab = take(sizeof(int) * (BB_MAXZ + 1));
-  for (int f = 0; f < 2; f++) m.xface[f] = take(sizeof(double) * (size_t)xface_pitch(L) * (L.kn + 2));
   m.total = off;
   return m;
 }
@@ -148,7 +143,6 @@ struct Scal {
  * same block, this rank's own) arrays.  r == NULL: external wall / no neighbour. */
 struct NbrFace {
   double *r, *x;
-  double *xf;           /* E/W neighbours only: its compact face buffer facing me (W nbr: its E face, E nbr: its W face) */
   unsigned char *fmask;
   double *recv[2];      /* neighbour's staging buffer for the OPPOSITE face (generic exchange) */
   Layout L;
@@ -174,9 +168,6 @@ struct Dev {
   double *history;
   const double *invM_tab;         /* [128], built once by k_build_tab */
   const int *ztab;                /* [nbz + 1]: z-chunk c of the search kernel owns planes ztab[c]+1 .. ztab[c+1] */
-  double *xf[2];                  /* my compact x-face copies of r: [0] i = 1 (for the W neighbour), [1] i = in (for the E neighbour);
-                                     NULL when nobody reads that face */
-  int pf;                         /* their pitch */
   double idx2, idy2, idz2;        /* 1/(dx*dx) ...  (per block, src/solver_kernel.cu:720-722) */
   double dx2_6, dy2_6, dz2_6;     /* dx*dx/6 ...    (src/solver_kernel.cu:683)                */
   Halo halo;

@@ -295,16 +295,6 @@ __device__ __forceinline__ bool push_halo(const Dev &d, int which, int i, int j,
   return any;
 }
 
-/* Every kernel that writes r also keeps the compact x-face copies current: an x neighbour (another rank over
- * NVLink, or this block itself for a periodic wrap) pulls its ghost COLUMN from there as one contiguous run of
- * j values per plane -- the column inside the P-layout array is element-strided (one 16-byte piece per row),
- * which cost 60 us per iteration of exposed NVLink time at 512^3 / 2 ranks split in x. */
-__device__ __forceinline__ void store_xface(const Dev &d, int i, int j, int k, double val)
-{
-  if (i == 1 && d.xf[0]) d.xf[0][j + (long long)k * d.pf] = val;
-  if (i == d.L.in && d.xf[1]) d.xf[1][j + (long long)k * d.pf] = val;
-}
-
 /* in-plane offset (i+XOFF) + j*px of this block -> correction for a neighbour whose pitch differs */
 __device__ __forceinline__ long long j_px_fix(const Layout &L, const Layout &N, int goff)
 {
@@ -361,13 +351,15 @@ __device__ __forceinline__ int claim_item(const Dev &d, const SearchArgs &a, int
 
 /* End of a persistent kernel: the LAST CTA to arrive adds the per-item partials in item order (bit-identical whatever CTA
  * computed which item) and re-arms the counters.  Returns true (all threads) in that CTA only; tot valid in thread 0. */
-__device__ bool items_reduce(const Dev &d, int nitems, int which, double &tot)
+__device__ bool items_reduce(const Dev &d, int nitems, int which, double &tot, bool peer_stores)
 {
   __shared__ double sh[32];
   __shared__ int s_last;
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();                                    /* this CTA's item partials (and its stores to r / p / x) before the count */
+    /* this CTA's item partials and its stores to r / p / x before the count; stores into PEER memory (the pushed ghost
+     * values of r) are released at system scope by the CTA that made them -- once per CTA of a one-wave kernel */
+    if (peer_stores) __threadfence_system(); else __threadfence();
     const unsigned t = atomicAdd(d.counter + BB_CLAIM_DONE, 1u);
     s_last = (t == gridDim.x - 1);
   }
@@ -518,7 +510,7 @@ __global__ void __launch_bounds__(NT) k_init(const Dev d, const double *__restri
       const double z = b * tab[d.fmask[g] & 127u];
       bb += b * b;  rz += b * z;
       d.r[g] = b;
-      store_xface(d, i, j, k, b);
+      if (d.any_nbr && (i == 1 || i == L.in || j == 1 || j == L.jn || k == 1 || k == L.kn)) pushed |= push_halo(d, 0, i, j, k, b);   /* ghost r of the neighbours */
     }
   }
   double v[2] = { bb, rz }, tot[2];

@@ -72,6 +72,13 @@ __device__ __forceinline__ void resid_issue(const Dev &d, const SearchMaps &tm, 
   tma::load3d(st, &tm.fm, x0 - G::MX0, y0, pi, bar);
 }
 
+/* two neighbouring ghost values into a neighbour's array: one 128-bit store when both exist (the pair starts on an even
+ * array index in every P-layout, whatever the neighbour's pitch) */
+__device__ __forceinline__ void push_pair(double *dst, double a, double b, bool both)
+{
+  if (both) stg128(dst, a, b); else *dst = a;
+}
+
 /* the plane loop of ONE item; see search_item (bbpcg_search_tma.cuh) for the roles of g, pc and queue */
 template <bool PARTS, int DD, bool REFRESH, bool XFULL>
 __device__ __forceinline__ double resid_item(const Dev &d, const SearchMaps &tm, const SearchArgs &a, unsigned char *smem, const ItemGeom &ig,
@@ -106,9 +113,24 @@ __device__ __forceinline__ double resid_item(const Dev &d, const SearchMaps &tm,
     own[o] = rowo[o] <= tyc && e0own;
     goff[o] = (unsigned)(iA + BB_XOFF) + (unsigned)(y0 + rowo[o]) * (unsigned)L.px;
   }
-  /* compact x-face copies of r (what an x neighbour pulls): only the threads on the block's first / last column */
-  const bool xf_w = d.xf[0] != nullptr && iA == 1;
-  const bool xf_e0 = d.xf[1] != nullptr && iA == L.in, xf_e1 = d.xf[1] != nullptr && iA + 1 == L.in;
+  /* PUSH model of the halo: the new r of a block-boundary cell also goes into the neighbour's ghost slot (plain stores into
+   * peer memory over NVLink, or into this block's own ghosts for a periodic self-wrap); the rank barrier at the end of
+   * the kernel orders them before the neighbour's next search kernel reads its r tile, ghosts included. */
+  const NbrFace &nE = d.halo.f[0], &nW = d.halo.f[1], &nN = d.halo.f[2], &nS = d.halo.f[3], &nT = d.halo.f[4], &nB = d.halo.f[5];
+  const bool px_w = nW.r != nullptr && iA == 1;
+  const bool px_e0 = nE.r != nullptr && iA == L.in, px_e1 = nE.r != nullptr && iA + 1 == L.in;
+  /* element offsets of the pushed x-face values inside a plane of the NEIGHBOUR's array (its pitch may differ across an x
+   * face), per item, so that a push costs one add per plane */
+  unsigned oW[NO], oE[NO];
+#pragma unroll
+  for (int o = 0; o < NO; o++) {
+    oW[o] = (unsigned)(nW.L.in + 1 + BB_XOFF) + (unsigned)(y0 + rowo[o]) * (unsigned)nW.L.px;
+    oE[o] = (unsigned)BB_XOFF + (unsigned)(y0 + rowo[o]) * (unsigned)nE.L.px;
+  }
+  /* y / z faces: CTA-uniform per item, rare on large blocks */
+  const bool ys_item = nS.r != nullptr && by == 0, yn_item = nN.r != nullptr && y0 + tyc == L.jn;
+  const bool zb_item = nB.r != nullptr && k0 == 1, zt_item = nT.r != nullptr && k1 == L.kn;
+  const bool yz_item = ys_item | yn_item | zb_item | zt_item;
 
   double *__restrict__ r = d.r;
   const bool consumer = tid < BB_PRODUCER;              /* warp-uniform; the producer warp only issues loads */
@@ -158,6 +180,7 @@ __device__ __forceinline__ double resid_item(const Dev &d, const SearchMaps &tm,
       const unsigned char *Mtop = smem + G::OFF_STAGE + (g % G::NMS) * G::STAGE;           /* mask of plane kc + 1 (this step's arrival) */
       const double *Rc = reinterpret_cast<const double *>(Mc + G::MT);
       double *r_pl = r + (long long)kc * L.ps;
+      double *nw_pl = nW.r + (long long)kc * nW.L.ps, *ne_pl = nE.r + (long long)kc * nE.L.ps;      /* uniform; only dereferenced when the neighbour exists */
 #pragma unroll
       for (int o = 0; o < NO; o++) {
         if (!own[o]) continue;                                           /* warp-uniform in the XFULL form */
@@ -194,14 +217,23 @@ __device__ __forceinline__ double resid_item(const Dev &d, const SearchMaps &tm,
         }
         const double r0 = REFRESH ? __dsub_rn(rc.x, q0) : __fma_rn(-alpha, q0, rc.x);     /* solver_kernel.cu:897 / :855 */
         dot = __fma_rn(r0, __dmul_rn(r0, c0), dot);                                       /* z = r invM, :858 */
-        if (XFULL || e1own) {
-          const double r1 = REFRESH ? __dsub_rn(rc.y, q1) : __fma_rn(-alpha, q1, rc.y);
+        const bool both = XFULL || e1own;
+        double r1 = 0.;
+        if (both) {
+          r1 = REFRESH ? __dsub_rn(rc.y, q1) : __fma_rn(-alpha, q1, rc.y);
           dot = __fma_rn(r1, __dmul_rn(r1, c1), dot);
           stg128(r_pl + goff[o], r0, r1);
-          if (xf_e1) d.xf[1][(y0 + rowo[o]) + (long long)kc * d.pf] = r1;
+          if (px_e1) ne_pl[oE[o]] = r1;
         } else r_pl[goff[o]] = r0;                                                        /* odd row end: element 1 is the E ghost */
-        if (xf_w) d.xf[0][(y0 + rowo[o]) + (long long)kc * d.pf] = r0;
-        if (xf_e0) d.xf[1][(y0 + rowo[o]) + (long long)kc * d.pf] = r0;
+        if (px_w) nw_pl[oW[o]] = r0;
+        if (px_e0) ne_pl[oE[o]] = r0;
+        if (yz_item) {                                                                    /* y / z faces: whole rows of the tile */
+          const int j = y0 + rowo[o];
+          if (ys_item && j == 1) push_pair(nS.r + (long long)kc * nS.L.ps + (unsigned)(iA + BB_XOFF) + (unsigned)(nS.L.jn + 1) * (unsigned)nS.L.px, r0, r1, both);
+          if (yn_item && j == L.jn) push_pair(nN.r + (long long)kc * nN.L.ps + (unsigned)(iA + BB_XOFF), r0, r1, both);
+          if (zb_item && kc == 1) push_pair(nB.r + (long long)(nB.L.kn + 1) * nB.L.ps + (unsigned)(iA + BB_XOFF) + (unsigned)j * (unsigned)nB.L.px, r0, r1, both);
+          if (zt_item && kc == L.kn) push_pair(nT.r + (unsigned)(iA + BB_XOFF) + (unsigned)j * (unsigned)nT.L.px, r0, r1, both);
+        }
       }
     }
 #pragma unroll
@@ -274,7 +306,7 @@ k_resid_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps tm
   pdl_launch_dependents();
   /* ---- (r,z): item partials in item order, rank all-reduce, stop test, beta (cuda_solver.cu:231-267) ---- */
   double tot[1];
-  const bool last = items_reduce(d, a.nitems, BB_CLAIM_RESID, tot[0]);
+  const bool last = items_reduce(d, a.nitems, BB_CLAIM_RESID, tot[0], d.comm.nranks > 1);   /* this CTA stored into peer memory */
   BB_STAMP(d, a, 4);
   if (last) {
     rank_allreduce(d, tot, 1, true);          /* peers pull the r written here */

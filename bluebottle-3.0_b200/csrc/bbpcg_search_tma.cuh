@@ -11,11 +11,11 @@
  * All plane inputs arrive through TMA (cp.async.bulk.tensor.3d, SASS UTMALDG) into a shared-memory ring, issued D planes
  * ahead by one thread and awaited on mbarriers, so DRAM latency is covered without any register staging:
  *     P ring (D+2 slots): halo'd p_prev tile (TX+4) x (ty+2); converted IN PLACE to p_new
- *     per stage (D+1) : halo'd r tile, mask tile, owned x tile, and -- PULL model -- the r values of
- *                       ghost cells straight from the NEIGHBOUR's r array (peer memory over NVLink or
- *                       this block itself for a periodic self-wrap): one row per y-ghost, one run of
- *                       ty+2 values from the neighbour's compact x-face buffer per x-ghost, the whole
- *                       tile for a z-ghost plane.
+ *     per stage (D+1) : halo'd r tile, mask tile, owned x tile.  The r values of the block's GHOST cells are already in
+ *                       this rank's r array: the neighbours' residual kernels (or this block itself for a periodic
+ *                       self-wrap) PUSHED them there with plain stores over NVLink, so this kernel issues no remote load
+ *                       (a pulled ghost value cost a 2-3 us NVLink round trip per plane on every boundary tile: 15 of the
+ *                       147 us of a 256^3 block in a 2 x 2 x 2 run, profiles/r02q_bench_n8_strong512.json).
  * Each thread owns the same (x,y) cells on every plane, so p(k-1), p(k), p(k+1) of its owned
  * cells stay in REGISTERS; only the N/S/E/W neighbours are read back from the P ring.  One
  * mbarrier wait + one __syncthreads per plane.  Stores (p_new, x) are 128-bit from registers.
@@ -38,7 +38,6 @@ struct SearchMaps {
   CUtensorMap r, p[2], fm;           /* this block: halo'd f64 tiles, halo'd u8 mask tile */
   CUtensorMap xo, ro;                /* owned (TX x ty) f64 tiles of x and r */
   CUtensorMap xh;                    /* halo'd tile of x (refresh form of k_resid_tma) */
-  CUtensorMap nb[6];                 /* neighbours' r: E,W = (ty+2)-run box on the 2-D compact face buffer, N,S = row box, T,B = tile box */
 };
 
 namespace tma {
@@ -87,11 +86,8 @@ struct SearchGeom {
   static constexpr int a128(int v) { return (v + 127) / 128 * 128; }
   static constexpr int RT = a128(HXP * HYMAX * 8);     /* halo'd f64 tile */
   static constexpr int MT = a128(MXP * HYMAX);         /* halo'd mask tile */
-  static constexpr int GYS = a128(HXP * 8), GY = 2 * GYS;      /* two y-ghost rows */
-  static constexpr int GXN = HYMAX + 2;                /* x-ghost run: ty+2 values + 1 (a TMA box must START on a 16-byte boundary, so the run starts at the even j below y0), even */
-  static constexpr int GXS = a128(GXN * 8), GX = 2 * GXS;      /* two x-ghost columns: contiguous runs from the neighbour's face buffer */
   static constexpr int XT = TX * BB_TYMAX * 8;         /* owned x tile */
-  static constexpr int STAGE = RT + MT + GY + GX + XT;
+  static constexpr int STAGE = RT + MT + XT;
   static constexpr int D = DD, NRS = DD + 1, NPS = DD + 2;   /* planes in flight, r/mask stages, p-ring slots */
   static constexpr int NO = 2;                         /* owned double2 items per thread: tile rows rg+1, rg+5 */
   static constexpr int OFF_STAGE = NPS * RT;
@@ -140,45 +136,24 @@ __device__ __forceinline__ void search_issue(const Dev &d, const SearchMaps &tm,
   constexpr int TX = G::TX, HXP = G::HXP;
   const Layout &L = d.L;
   const int ty = a.ty, hy = ty + 2;
-  const int bx = c.ig.bx, by = c.ig.by, k0 = c.ig.k0, k1 = c.ig.k1;
-  const int i0 = bx * TX + 1, j0 = by * ty + 1;
-  const int tyc = min(ty, L.jn - j0 + 1);
+  const int bx = c.ig.bx, k0 = c.ig.k0, k1 = c.ig.k1;
+  const int j0 = c.ig.by * ty + 1;
   const int x0 = BB_XOFF + 1 + bx * TX - 2;             /* array x index of tile column 0 */
   const int y0 = j0 - 1;
-  /* which ghost buffers this tile needs */
-  const bool gy0 = (by == 0) && d.halo.f[3].r != nullptr;                    /* row 0 = j 0, from S      */
-  const bool gy1 = (y0 + tyc + 1 == L.jn + 1) && d.halo.f[2].r != nullptr;   /* row tyc+1 = j jn+1, N    */
-  const bool gx0 = (bx == 0) && d.halo.f[1].r != nullptr;                    /* column i = 0, from W     */
-  const bool gx1 = (i0 + TX - 1 >= L.in) && d.halo.f[0].r != nullptr;        /* column i = in+1, from E  */
   const unsigned bar0 = tma::smem_u32(smem + G::OFF_BAR);
   const unsigned sP = tma::smem_u32(smem), sS = tma::smem_u32(smem + G::OFF_STAGE);
   const int pi = k0 - 1 + c.lp;
   const int rs = c.g % G::NRS, ps = c.g % G::NPS;
   const unsigned bar = bar0 + 8 * rs;
   const unsigned st = sS + rs * G::STAGE;
-  const bool inner = pi >= 1 && pi <= L.kn;
   unsigned bytes = 2 * (HXP * hy * 8) + G::MXP * hy;
-  if (inner) {
-    if (gy0) bytes += HXP * 8;
-    if (gy1) bytes += HXP * 8;
-    if (gx0) bytes += G::GXN * 8;
-    if (gx1) bytes += G::GXN * 8;
-  }
   const bool owned = pi >= k0 && pi <= k1;
   if (owned) bytes += TX * ty * 8;
   tma::mbar_expect_tx(bar, bytes);
-  if (owned) tma::load3d(st + G::RT + G::MT + G::GY + G::GX, &tm.xo, BB_XOFF + 1 + bx * TX, j0, pi, bar);
+  if (owned) tma::load3d(st + G::RT + G::MT, &tm.xo, BB_XOFF + 1 + bx * TX, j0, pi, bar);
   tma::load3d(sP + ps * G::RT, &tm.p[q & 1], x0, y0, pi, bar);
   tma::load3d(st + G::RT, &tm.fm, x0 - G::MX0, y0, pi, bar);
-  if (pi == 0 && d.halo.f[5].r) tma::load3d(st, &tm.nb[5], x0, y0, d.halo.f[5].L.kn, bar);          /* B neighbour's top plane    */
-  else if (pi == L.kn + 1 && d.halo.f[4].r) tma::load3d(st, &tm.nb[4], x0, y0, 1, bar);            /* T neighbour's bottom plane */
-  else tma::load3d(st, &tm.r, x0, y0, pi, bar);
-  if (inner) {
-    if (gy0) tma::load3d(st + G::RT + G::MT, &tm.nb[3], x0, d.halo.f[3].L.jn, pi, bar);
-    if (gy1) tma::load3d(st + G::RT + G::MT + G::GYS, &tm.nb[2], x0, 1, pi, bar);
-    if (gx0) tma::load2d(st + G::RT + G::MT + G::GY, &tm.nb[1], y0 & ~1, pi, bar);          /* W neighbour's E face, j = (y0 & ~1) .. */
-    if (gx1) tma::load2d(st + G::RT + G::MT + G::GY + G::GXS, &tm.nb[0], y0 & ~1, pi, bar); /* E neighbour's W face                  */
-  }
+  tma::load3d(st, &tm.r, x0, y0, pi, bar);              /* ghost rows / columns / planes included: the neighbours' residual kernels pushed them */
 }
 
 /* one step of the producer: issue the plane under the cursor, move on; at the end of an item claim the next one and
@@ -218,13 +193,6 @@ __device__ __forceinline__ double search_item(const Dev &d, const SearchMaps &tm
   const int tyc = min(ty, L.jn - j0 + 1);               /* owned rows of THIS tile (the last tile of a column may be short) */
   const int k0 = ig.k0, k1 = ig.k1, nplanes = ig.nplanes;
   const int y0 = j0 - 1;
-  const int gxsh = y0 & 1;                              /* the x-ghost runs start at the even j at or below y0 */
-
-  /* which ghost buffers this tile needs (uniform per CTA) */
-  const bool gy0 = (by == 0) && d.halo.f[3].r != nullptr;
-  const bool gy1 = (y0 + tyc + 1 == L.jn + 1) && d.halo.f[2].r != nullptr;
-  const bool gx0 = (bx == 0) && d.halo.f[1].r != nullptr;
-  const bool gx1 = (i0 + TX - 1 >= L.in) && d.halo.f[0].r != nullptr;
 
   const unsigned bar0 = tma::smem_u32(bars);
 
@@ -243,8 +211,6 @@ __device__ __forceinline__ double search_item(const Dev &d, const SearchMaps &tm
   for (int o = 0; o < NO; o++) { rowo[o] = rg + 1 + 4 * o; act[o] = rowo[o] <= tyc && e0ok; own[o] = rowo[o] <= tyc && e0own; }
   const int hrow = rg == 0 ? 0 : tyc + 1;
   const bool hvalid = rg < 2 && e0ok;
-  const bool hgy = hvalid && (rg == 0 ? gy0 : gy1);     /* r of this row comes from the GY buffer */
-  const int hgyoff = rg == 0 ? 0 : G::GYS / 8;
   const bool hmy = hvalid && (rg == 0 ? by == 0 : y0 + hrow == L.jn + 1);   /* a y-ghost row of the BLOCK: its p is kept current */
   /* singles: threads 0 .. 2*(tyc+2)-1 handle the W (tile column 1) and E (column TX+2) halo columns */
   const int nsr = tyc + 2;
@@ -253,7 +219,6 @@ __device__ __forceinline__ double search_item(const Dev &d, const SearchMaps &tm
   const int s_col = s_side ? TX + 2 : 1;
   const int s_i = i0 + s_col - 2, s_j = y0 + s_row;
   const bool s_ok = has_single && s_i <= L.in + 1;
-  const bool s_gx = s_ok && ((s_i == 0 && gx0) || (s_i == L.in + 1 && gx1));      /* r from the GX buffer */
   const bool s_store = s_ok && (s_i == 0 || s_i == L.in + 1) && s_j >= 1 && s_j <= L.jn;   /* x-ghost p kept current */
 
   double *__restrict__ pnew = d.P[(q + 1) & 1];
@@ -287,9 +252,7 @@ __device__ __forceinline__ double search_item(const Dev &d, const SearchMaps &tm
     const unsigned char *St = smem + G::OFF_STAGE + rs * G::STAGE;
     const double *Rt = reinterpret_cast<const double *>(St);
     const unsigned char *Mt = St + G::RT;
-    const double *GYt = reinterpret_cast<const double *>(St + G::RT + G::MT);
-    const double *GXt = reinterpret_cast<const double *>(St + G::RT + G::MT + G::GY);
-    const double *Xt = reinterpret_cast<const double *>(St + G::RT + G::MT + G::GY + G::GX);
+    const double *Xt = reinterpret_cast<const double *>(St + G::RT + G::MT);
     double *pnew_pl = pnew + (long long)pi * L.ps;
     double *x_pl = x + (long long)pi * L.ps;
 
@@ -302,16 +265,10 @@ __device__ __forceinline__ double search_item(const Dev &d, const SearchMaps &tm
       if (!act[o]) continue;                                             /* warp-uniform in the XFULL form */
       const int row = rowo[o];
       const int so = row * HXP + cA;
-      double2 r2 = *reinterpret_cast<const double2 *>(Rt + so);
+      const double2 r2 = *reinterpret_cast<const double2 *>(Rt + so);
       const double2 p2 = *reinterpret_cast<const double2 *>(Pt + so);
       unsigned m2 = *reinterpret_cast<const unsigned short *>(Mt + row * G::MXP + G::MX0 + cA);
-      if (!XFULL) {                                                      /* ragged row end: the E ghost i = in+1 sits inside the tile */
-        if (!plane_ghost && gx1) {
-          if (e0gx) r2.x = GXt[G::GXS / 8 + gxsh + row];
-          if (e1gx) r2.y = GXt[G::GXS / 8 + gxsh + row];
-        }
-        if (!e1ok) m2 &= 0x00ffu;                                          /* no such cell: dead */
-      }
+      if (!XFULL && !e1ok) m2 &= 0x00ffu;                                  /* ragged row end: no such cell -> dead */
       double c0 = c63, c1 = c63;
       if (!(XFULL && __all_sync(0xffffffffu, m2 == BB_FULLMASK2))) { c0 = tab[m2 & 127u]; c1 = tab[(m2 >> 8) & 127u]; }
       double2 pn;
@@ -337,10 +294,9 @@ __device__ __forceinline__ double search_item(const Dev &d, const SearchMaps &tm
     }
     if (hvalid) {                                                          /* the two halo rows (row groups 0 and 1) */
       const int so = hrow * HXP + cA;
-      double2 r2 = *reinterpret_cast<const double2 *>(Rt + so);
+      const double2 r2 = *reinterpret_cast<const double2 *>(Rt + so);
       const double2 p2 = *reinterpret_cast<const double2 *>(Pt + so);
       unsigned m2 = *reinterpret_cast<const unsigned short *>(Mt + hrow * G::MXP + G::MX0 + cA);
-      if (hgy && !plane_ghost) r2 = *reinterpret_cast<const double2 *>(GYt + hgyoff + cA);
       if (!XFULL && !e1ok) m2 &= 0x00ffu;
       double2 pn;
       pn.x = __fma_rn(beta, p2.x, __dmul_rn(r2.x, tab[m2 & 127u]));
@@ -353,8 +309,7 @@ __device__ __forceinline__ double search_item(const Dev &d, const SearchMaps &tm
     }
     if (s_ok) {
       const int so = s_row * HXP + s_col;
-      double rv = Rt[so];
-      if (s_gx && !plane_ghost) rv = GXt[(s_i == 0 ? 0 : G::GXS / 8) + gxsh + s_row];
+      const double rv = Rt[so];
       const double pn = __fma_rn(beta, Pt[so], __dmul_rn(rv, tab[Mt[s_row * G::MXP + G::MX0 + s_col] & 127u]));
       Pt[so] = pn;
       if (s_store && plane_owned) pnew_pl[(unsigned)(s_i + BB_XOFF) + (unsigned)s_j * (unsigned)L.px] = pn;
@@ -460,7 +415,7 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
   pdl_launch_dependents();          /* k_resid_tma may be scheduled behind our tail; it blocks in pdl_wait() until alpha is final */
   /* ---- (p,q): item partials in item order, rank all-reduce, alpha (cuda_solver.cu:204-206) ---- */
   double tot[1];
-  const bool last = items_reduce(d, a.nitems, BB_CLAIM_SEARCH, tot[0]);
+  const bool last = items_reduce(d, a.nitems, BB_CLAIM_SEARCH, tot[0], false);
   BB_STAMP(d, a, 4);
   if (last) {
     rank_allreduce(d, tot, 1, false);         /* this kernel writes nothing a peer reads */

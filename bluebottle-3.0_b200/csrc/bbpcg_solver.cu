@@ -111,7 +111,6 @@ static void point_dev_at_arena(bbpcg_solver *s)
   d.sc = (Scal *)(a + m.scal); d.history = (double *)(a + m.history);
   d.invM_tab = (const double *)(a + m.invM_tab);
   d.ztab = (const int *)(a + m.ztab);
-  d.pf = xface_pitch(d.L);
 }
 
 /* ---- TMA tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point, so the
@@ -146,20 +145,6 @@ static int make_map(CUtensorMap *m, void *base, const Layout &L, bool u8, int bx
   return BBPCG_OK;
 }
 
-/* 2-D map over a compact x-face buffer (pf x (kn+2), j fastest) with box by x 1 */
-static int make_map2(CUtensorMap *m, void *base, const Layout &L, int by)
-{
-  PFN_encodeTiled fn = encode_fn();
-  if (!fn) { bbpcg_set_error("cuTensorMapEncodeTiled is not available from this driver"); return BBPCG_ECUDA; }
-  cuuint64_t dims[2] = { (cuuint64_t)xface_pitch(L), (cuuint64_t)(L.kn + 2) };
-  cuuint64_t strides[1] = { (cuuint64_t)xface_pitch(L) * 8 };
-  cuuint32_t box[2] = { (cuuint32_t)by, 1u }, estr[2] = { 1u, 1u };
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { bbpcg_set_error("cuTensorMapEncodeTiled failed (%d) for the x-face box %d", (int)r, by); return BBPCG_ECUDA; }
-  return BBPCG_OK;
-}
-
 /* boxes follow the planned tile height ty: halo'd tiles (TX+4) x (ty+2), owned tiles TX x ty */
 static int build_search_maps(bbpcg_solver *s, int ty)
 {
@@ -176,13 +161,6 @@ static int build_search_maps(bbpcg_solver *s, int ty)
   if (!rc) rc = make_map(&M->xo, d.x, d.L, false, G::TX, ty);
   if (!rc) rc = make_map(&M->ro, d.r, d.L, false, G::TX, ty);
   if (!rc) rc = make_map(&M->xh, d.x, d.L, false, G::HXP, hy);
-  for (int f = 0; f < 6 && !rc; f++) {
-    const NbrFace &nf = d.halo.f[f];
-    if (!nf.r) { M->nb[f] = M->r; continue; }            /* never used: keeps the parameter well formed */
-    if (f < 2) rc = make_map2(&M->nb[f], nf.xf, nf.L, G::GXN);             /* fixed even run: a box starts and ends on 16-byte boundaries */
-    else if (f < 4) rc = make_map(&M->nb[f], nf.r, nf.L, false, G::HXP, 1);
-    else rc = make_map(&M->nb[f], nf.r, nf.L, false, G::HXP, hy);
-  }
   return rc;
 }
 
@@ -203,14 +181,10 @@ static void build_halo(bbpcg_solver *s, const int (*dims)[3])
     ArenaMap m = make_arena_map(L);
     nf.L = L;
     nf.r = (double *)(base + m.r); nf.x = (double *)(base + m.x); nf.fmask = (u8 *)(base + m.fmask);
-    nf.xf = f == 0 ? (double *)(base + m.xface[0]) : f == 1 ? (double *)(base + m.xface[1]) : NULL;   /* E nbr: its W face; W nbr: its E face */
     for (int b = 0; b < 2; b++) nf.recv[b] = (double *)(base + m.recv[b][opposite[f]]);
   }
   d.any_nbr = 0;
   for (int f = 0; f < 6; f++) if (d.halo.f[f].r) d.any_nbr = 1;
-  /* my own face copies exist only where somebody reads them: W face for a W neighbour, E face for an E neighbour */
-  d.xf[0] = d.halo.f[1].r ? (double *)(s->arena + s->amap.xface[0]) : NULL;
-  d.xf[1] = d.halo.f[0].r ? (double *)(s->arena + s->amap.xface[1]) : NULL;
   d.comm.rank = s->dom.rank; d.comm.nranks = s->nranks;
   if (d.comm.timeout_cycles == 0) d.comm.timeout_cycles = 1ll << 37;       /* ~70 s default: far above any start-up or I/O skew; option comm_timeout_ms (0 = wait for ever) */
   for (int p = 0; p < BB_MAXR; p++) d.comm.mbox[p] = NULL;
