@@ -85,7 +85,7 @@ struct ArenaMap {
   size_t mbox;                     /* u64[BB_NSLOT][BB_MAXR][4]: {32 data bits | 32-bit tag} words */
   size_t history;                  /* doubles[hist_cap] */
   size_t invM_tab;                 /* doubles[128]: Jacobi diagonal per mask value */
-  size_t ztab;                     /* ints[BB_MAXZ + 1]: prefix offsets of the search kernel's z-chunks */
+  size_t ztab;                     /* ints[2 * BB_MAXZ]: first and last plane of every z-chunk of the iteration kernels, in claim order */
   size_t total;
 };
 
@@ -110,7 +110,7 @@ static inline ArenaMap make_arena_map(const Layout &L)
   m.mbox = take(sizeof(unsigned long long) * BB_NSLOT * BB_MAXR * 4);
   m.history = take(sizeof(double) * BB_HIST_CAP);
   m.invM_tab = take(sizeof(double) * 128);
-  m.ztab = take(sizeof(int) * (BB_MAXZ + 1));
+  m.ztab = take(sizeof(int) * (2 * BB_MAXZ));
   m.total = off;
   return m;
 }
@@ -167,7 +167,7 @@ struct Dev {
   Scal *sc;
   double *history;
   const double *invM_tab;         /* [128], built once by k_build_tab */
-  const int *ztab;                /* [nbz + 1]: z-chunk c of the search kernel owns planes ztab[c]+1 .. ztab[c+1] */
+  const int *ztab;                /* [2 nbz]: z-chunk c of the iteration kernels owns planes ztab[2c] .. ztab[2c+1] */
   double idx2, idy2, idz2;        /* 1/(dx*dx) ...  (per block, src/solver_kernel.cu:720-722) */
   double dx2_6, dy2_6, dz2_6;     /* dx*dx/6 ...    (src/solver_kernel.cu:683)                */
   Halo halo;

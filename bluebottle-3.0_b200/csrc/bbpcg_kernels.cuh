@@ -136,6 +136,26 @@ __device__ __forceinline__ double block_sum(double v, double *sh /*[32]*/)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+/* This thread's share of a fixed-order sum over n partials written by OTHER CTAs (index i goes to thread i % blockDim.x, a
+ * thread adds its values in index order: the result depends on n and the block size only).  The loads of a batch of 8 are
+ * issued before the first add: written as `s += __ldcg(..)` in a plain loop the compiler kept ONE load in flight, i.e. one L2
+ * round trip (~0.9 us) per 288 partials on the critical path of every iteration kernel -- 2.7 us of the 4.7 us tail at 256^3
+ * (814 items, profiles/r02u_trace.json) and ~18 us per kernel at 512^3 (5632 items). */
+__device__ __forceinline__ double strided_partial_sum(const double *__restrict__ part, int n)
+{
+  constexpr int U = 8;
+  const int nt = blockDim.x;
+  double s = 0.;
+  for (int base = threadIdx.x; base < n; base += U * nt) {
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) { const int i = base + u * nt; v[u] = i < n ? __ldcg(part + i) : 0.; }
+#pragma unroll
+    for (int u = 0; u < U; u++) s += v[u];
+  }
+  return s;
+}
+
 template <int NV>
 __device__ bool grid_reduce(const Dev &d, double (&v)[NV], int bid, int nblocks, double (&tot)[NV], bool peer_stores)
 {
@@ -166,9 +186,7 @@ __device__ bool grid_reduce(const Dev &d, double (&v)[NV], int bid, int nblocks,
   __threadfence();
 #pragma unroll
   for (int n = 0; n < NV; n++) {
-    double s = 0.;
-    for (int i = threadIdx.x; i < gsize; i += blockDim.x) s += __ldcg(&d.partials[n * BB_MAXBLOCKS + grp * G + i]);
-    part[n] = block_sum<NV>(s, sh);
+    part[n] = block_sum<NV>(strided_partial_sum(d.partials + n * BB_MAXBLOCKS + grp * G, gsize), sh);
   }
   __syncthreads();
   if (ngrp == 1) {
@@ -192,9 +210,7 @@ __device__ bool grid_reduce(const Dev &d, double (&v)[NV], int bid, int nblocks,
   __threadfence();
 #pragma unroll
   for (int n = 0; n < NV; n++) {
-    double s = 0.;
-    for (int i = threadIdx.x; i < ngrp; i += blockDim.x) s += __ldcg(&d.gpartials[n * BB_MAXGROUPS + i]);
-    tot[n] = block_sum<NV>(s, sh);
+    tot[n] = block_sum<NV>(strided_partial_sum(d.gpartials + n * BB_MAXGROUPS, ngrp), sh);
   }
   if (threadIdx.x == 0) *d.counter = 0u;
   return true;
@@ -221,7 +237,8 @@ __device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned l
 __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p)
 { unsigned long long v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
 
-__device__ __forceinline__ void rank_allreduce(const Dev &d, double *v /* thread 0's values, in/out */, int nv, bool release)
+__device__ __forceinline__ void rank_allreduce(const Dev &d, double *v /* thread 0's values, in/out */, int nv, bool release,
+                                               const unsigned long long *seq_cur = nullptr /* thread 0: Scal::seq read earlier (off the critical path) */)
 {
   const Comm &c = d.comm;
   if (c.nranks <= 1) return;
@@ -229,7 +246,8 @@ __device__ __forceinline__ void rank_allreduce(const Dev &d, double *v /* thread
   __shared__ double s_in[BB_MAXR][2];
   __shared__ unsigned long long s_seq;
   if (threadIdx.x == 0) {
-    const unsigned long long seq = ++d.sc->seq;
+    const unsigned long long seq = (seq_cur ? *seq_cur : d.sc->seq) + 1ull;
+    d.sc->seq = seq;
     const unsigned long long tag = ((seq % 0xffffffffull) + 1ull) << 32;       /* never 0 */
     const unsigned long long b0 = (unsigned long long)__double_as_longlong(nv > 0 ? v[0] : 0.);
     const unsigned long long b1 = (unsigned long long)__double_as_longlong(nv > 1 ? v[1] : 0.);
@@ -304,7 +322,7 @@ __device__ __forceinline__ long long j_px_fix(const Layout &L, const Layout &N, 
 
 /* launch arguments of the two iteration kernels (bbpcg_search_tma.cuh, bbpcg_resid_tma.cuh) */
 struct SearchArgs {
-  int nbx, nby, nbz;   /* tiles in x, y; z-chunks: chunk c owns planes d.ztab[c]+1 .. d.ztab[c+1] */
+  int nbx, nby, nbz;   /* tiles in x, y; z-chunks: chunk c owns planes d.ztab[2c] .. d.ztab[2c+1] */
   int ty;              /* owned rows per tile (1..8): chosen by the host planner so that the CTA count fills the SM slots */
   const double *rhs;   /* refresh form of k_resid_tma only: the caller's right-hand side (Gcc s3b) and its strides */
   int s1b, s2b;
@@ -336,10 +354,21 @@ __device__ __forceinline__ ItemGeom decode_item(const Dev &d, const SearchArgs &
   const int t = item / a.nbx;
   g.by = t % a.nby;
   const int cz = t / a.nby;
-  g.k0 = __ldg(d.ztab + cz) + 1;                        /* host-written table: safe before pdl_wait() */
-  g.k1 = __ldg(d.ztab + cz + 1);
+  const int2 kk = __ldg(reinterpret_cast<const int2 *>(d.ztab) + cz);   /* host-written table: safe before pdl_wait() */
+  g.k0 = kk.x;
+  g.k1 = kk.y;
   g.nplanes = g.k1 - g.k0 + 3;                          /* planes k0-1 .. k1+1 */
   return g;
+}
+
+/* does the item own cells on a block face that has a neighbour (another rank, or this block itself for a periodic wrap)?
+ * The residual kernel pushes the new r of those cells into the neighbour's ghost slots. */
+__device__ __forceinline__ bool item_touches_nbr(const Dev &d, const SearchArgs &a, const ItemGeom &ig)
+{
+  const Layout &L = d.L;
+  return (d.halo.f[1].r != nullptr && ig.bx == 0) || (d.halo.f[0].r != nullptr && ig.bx == a.nbx - 1) ||
+         (d.halo.f[3].r != nullptr && ig.by == 0) || (d.halo.f[2].r != nullptr && ig.by == a.nby - 1) ||
+         (d.halo.f[5].r != nullptr && ig.k0 == 1) || (d.halo.f[4].r != nullptr && ig.k1 == L.kn);
 }
 
 /* next item of this CTA (-1: none left) */
@@ -366,9 +395,7 @@ __device__ bool items_reduce(const Dev &d, int nitems, int which, double &tot, b
   __syncthreads();
   if (!s_last) return false;
   __threadfence();
-  double s = 0.;
-  for (int i = threadIdx.x; i < nitems; i += blockDim.x) s += __ldcg(&d.partials[i]);
-  tot = block_sum<1>(s, sh);
+  tot = block_sum<1>(strided_partial_sum(d.partials, nitems), sh);
   if (threadIdx.x == 0) { d.counter[BB_CLAIM_DONE] = 0u; d.counter[which] = 0u; }
   return true;
 }
@@ -387,22 +414,36 @@ __device__ __forceinline__ unsigned bb_smid() { unsigned v; asm volatile("mov.u3
 /* ------------------------------------------------------------------------------------ */
 /* end of an iteration, run by ONE thread once the global (r,z) is known: the host logic of src/cuda_solver.cu:231-267
  * (history, stop test, NaN test, iteration bound, beta) on the device-resident scalars */
-__device__ __forceinline__ void finish_iteration(const Dev &d, double rz_new, bool refreshed)
+/* The scalars the tail of an iteration kernel needs, none of which the running kernel changes: thread 0 of every CTA reads
+ * them BEFORE it takes its ticket, so that in the last CTA no L2 round trip is left between the sum and the new alpha / beta
+ * (each dependent load of Scal cost ~0.8 us on the critical path of every iteration). */
+struct IterScal { double rz, bb, tol2, alpha; int q, fixed, max_q; unsigned long long seq; };
+__device__ __forceinline__ IterScal load_iter_scal(const Dev &d)
+{
+  const Scal *sc = d.sc;
+  IterScal p;                       /* L2 loads (ld.global.cg): never a line an earlier kernel's CTA left in this SM's L1 */
+  p.rz = __ldcg(&sc->rz); p.bb = __ldcg(&sc->bb); p.tol2 = __ldcg(&sc->tol2); p.alpha = __ldcg(&sc->alpha);
+  p.q = __ldcg(&sc->q); p.fixed = __ldcg(&sc->fixed); p.max_q = __ldcg(&sc->max_q); p.seq = __ldcg(&sc->seq);
+  return p;
+}
+
+__device__ __forceinline__ void finish_iteration(const Dev &d, double rz_new, bool refreshed, const IterScal &p)
 {
   Scal *sc = d.sc;
-  const int qn = sc->q + 1;
+  const int qn = p.q + 1;
   sc->q = qn;
   if (qn < BB_HIST_CAP) d.history[qn] = rz_new;
-  sc->alpha_x = refreshed ? 0. : sc->alpha;
-  if (sc->comm_timeout) { sc->done = 1; sc->status = BBPCG_COMM_TIMEOUT; sc->resid = sqrt(rz_new) / sqrt(sc->bb); return; }
-  if (!sc->fixed && rz_new <= sc->tol2 * sc->bb) {               /* :235 */
-    sc->done = 1; sc->status = BBPCG_CONVERGED; sc->resid = sqrt(rz_new) / sqrt(sc->bb);
-  } else if (!sc->fixed && isnan(rz_new)) {                      /* :245 */
+  sc->alpha_x = refreshed ? 0. : p.alpha;
+  /* the time-out flag is set by the all-reduce that just ran: the one load that cannot be made early (several ranks only) */
+  if (d.comm.nranks > 1 && sc->comm_timeout) { sc->done = 1; sc->status = BBPCG_COMM_TIMEOUT; sc->resid = sqrt(rz_new) / sqrt(p.bb); return; }
+  if (!p.fixed && rz_new <= p.tol2 * p.bb) {                     /* :235 */
+    sc->done = 1; sc->status = BBPCG_CONVERGED; sc->resid = sqrt(rz_new) / sqrt(p.bb);
+  } else if (!p.fixed && isnan(rz_new)) {                        /* :245 */
     sc->done = 1; sc->status = BBPCG_NAN; sc->resid = rz_new;
-  } else if (!sc->fixed && qn >= sc->max_q) {                    /* :192,:271 */
-    sc->done = 1; sc->status = BBPCG_MAXITER; sc->resid = sqrt(rz_new) / sqrt(sc->bb);
+  } else if (!p.fixed && qn >= p.max_q) {                        /* :192,:271 */
+    sc->done = 1; sc->status = BBPCG_MAXITER; sc->resid = sqrt(rz_new) / sqrt(p.bb);
   } else {
-    sc->beta = rz_new / sc->rz;                                  /* :256 */
+    sc->beta = rz_new / p.rz;                                    /* :256 */
     sc->rz = rz_new;                                             /* :267 */
   }
 }

@@ -270,14 +270,14 @@ k_resid_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps tm
   pdl_wait();
   BB_STAMP(d, a, 1);
   Scal *sc = d.sc;
-  const int q = sc->q;
+  const int q = __ldcg(&sc->q);
   int issued = 0;
   if (tid == a.producer) {
 #pragma unroll
     for (int l = 0; l < G::D; l++) if (pc.item >= 0) { producer_step(d, a, pc, queue, BB_CLAIM_RESID, [&](const ProdCursor &c) { resid_issue<PARTS, DD, REFRESH>(d, tm, a, smem, c, q); }); issued++; }
   }
-  const double alpha = sc->alpha;
-  const int done = sc->done;
+  const double alpha = __ldcg(&sc->alpha);
+  const int done = __ldcg(&sc->done);
   if (done) {                       /* a finished solve: drain the loads already issued, then leave */
     if (tid == a.producer) {
       const unsigned bar0 = tma::smem_u32(smem + G::OFF_BAR);
@@ -289,9 +289,11 @@ k_resid_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps tm
 
   int g = 0, n = 0;
   int cur = queue[0];
+  bool peer_push = false;           /* CTA-uniform: one of this CTA's items stored ghost values into a neighbour's array */
   while (cur >= 0) {
     const ItemGeom ig = decode_item(d, a, cur);
     const bool xfull = (ig.bx * G::TX + G::TX) <= d.L.in;
+    peer_push |= item_touches_nbr(d, a, ig);
     const double dot = xfull ? resid_item<PARTS, DD, REFRESH, true>(d, tm, a, smem, ig, g, pc, queue, q, alpha, c63)
                              : resid_item<PARTS, DD, REFRESH, false>(d, tm, a, smem, ig, g, pc, queue, q, alpha, c63);
     const double part = block_sum<1>(dot, sh_sum);      /* the item's (r,z) partial in the item's own slot */
@@ -306,11 +308,14 @@ k_resid_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps tm
   pdl_launch_dependents();
   /* ---- (r,z): item partials in item order, rank all-reduce, stop test, beta (cuda_solver.cu:231-267) ---- */
   double tot[1];
-  const bool last = items_reduce(d, a.nitems, BB_CLAIM_RESID, tot[0], d.comm.nranks > 1);   /* this CTA stored into peer memory */
+  IterScal isc;
+  if (threadIdx.x == 0) isc = load_iter_scal(d);      /* in flight while this CTA waits for its ticket */
+  /* system-scope release only in the CTAs that stored into PEER memory (boundary items of a decomposed run) */
+  const bool last = items_reduce(d, a.nitems, BB_CLAIM_RESID, tot[0], d.comm.nranks > 1 && peer_push);
   BB_STAMP(d, a, 4);
   if (last) {
-    rank_allreduce(d, tot, 1, true);          /* peers pull the r written here */
-    if (threadIdx.x == 0) finish_iteration(d, tot[0], REFRESH);
+    rank_allreduce(d, tot, 1, true, &isc.seq);        /* the neighbours read the ghost values pushed here after this barrier */
+    if (threadIdx.x == 0) finish_iteration(d, tot[0], REFRESH, isc);
     BB_STAMP(d, a, 5);
   }
 }

@@ -379,14 +379,14 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
   pdl_wait();
   BB_STAMP(d, a, 1);
   Scal *sc = d.sc;
-  const int q = sc->q;
+  const int q = __ldcg(&sc->q);     /* the scalars come from L2: with PDL this CTA may share an SM (and its L1) with the kernel that wrote them */
   int issued = 0;
   if (tid == a.producer) {
 #pragma unroll
     for (int l = 0; l < G::D; l++) if (pc.item >= 0) { producer_step(d, a, pc, queue, BB_CLAIM_SEARCH, [&](const ProdCursor &c) { search_issue<PARTS, DD>(d, tm, a, smem, c, q); }); issued++; }
   }
-  const int done = sc->done;
-  const double beta = sc->beta, ax = sc->alpha_x;
+  const int done = __ldcg(&sc->done);
+  const double beta = __ldcg(&sc->beta), ax = __ldcg(&sc->alpha_x);
   if (done) {                       /* a finished solve: drain the loads already issued (no item was claimed yet: an item has > D planes), then leave */
     if (tid == a.producer) {
       const unsigned bar0 = tma::smem_u32(smem + G::OFF_BAR);
@@ -415,13 +415,15 @@ k_search_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps t
   pdl_launch_dependents();          /* k_resid_tma may be scheduled behind our tail; it blocks in pdl_wait() until alpha is final */
   /* ---- (p,q): item partials in item order, rank all-reduce, alpha (cuda_solver.cu:204-206) ---- */
   double tot[1];
+  IterScal isc;
+  if (threadIdx.x == 0) isc = load_iter_scal(d);      /* rz, seq: in flight while this CTA waits for its ticket */
   const bool last = items_reduce(d, a.nitems, BB_CLAIM_SEARCH, tot[0], false);
   BB_STAMP(d, a, 4);
   if (last) {
-    rank_allreduce(d, tot, 1, false);         /* this kernel writes nothing a peer reads */
+    rank_allreduce(d, tot, 1, false, &isc.seq);       /* this kernel writes nothing a peer reads */
     if (threadIdx.x == 0) {
       d.sc->pAp = tot[0];
-      d.sc->alpha = d.sc->rz / tot[0];
+      d.sc->alpha = isc.rz / tot[0];
     }
     BB_STAMP(d, a, 5);
   }

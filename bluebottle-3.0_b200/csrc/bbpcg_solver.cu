@@ -72,7 +72,7 @@ struct bbpcg_solver {
   long long launches;
   unsigned exchange_count;
   /* tile / z-chunk plan of the two iteration kernels (device table Dev::ztab) */
-  int *h_ztab;                      /* pinned [BB_MAXZ + 1] */
+  int *h_ztab;                      /* pinned [2 * BB_MAXZ] */
   int plan_ok;                      /* the plan below, the uploaded table and the tensor maps are current */
   int plan_ty, plan_nbx, plan_nby, plan_nbz, plan_kc;
   int pdl;                          /* programmatic dependent launch of the two iteration kernels: 0 off, 1 on, 2 auto */
@@ -229,8 +229,8 @@ static int create_impl(bbpcg_solver *s, const dom_struct *dom_rank, const dom_st
   memset(s->h_poll, 0, 64);
   CU(cudaHostGetDevicePointer((void **)&d.comm.host_flag, (void *)&s->h_poll[BB_POLL_COMM], 0));
   CU(cudaHostAlloc(&s->h_scal, sizeof(Scal), cudaHostAllocDefault));
-  CU(cudaHostAlloc(&s->h_ztab, sizeof(int) * (BB_MAXZ + 1), cudaHostAllocDefault));
-  s->pdl = 2; s->rhs_tiled = 1; s->tma_warp = 1; s->guided = 1; s->guided_pct = 100; s->chunk_min = 8;
+  CU(cudaHostAlloc(&s->h_ztab, sizeof(int) * (2 * BB_MAXZ), cudaHostAllocDefault));
+  s->pdl = 2; s->rhs_tiled = 1; s->tma_warp = 1; s->guided = 1; s->guided_pct = 60; s->chunk_min = 4;
   /* single rank: neighbours are this block itself (periodic wrap) or nothing */
   s->nranks = 1;
   for (int p = 0; p < BB_MAXR; p++) { s->peer_arena[p] = NULL; s->peer_opened[p] = false; }
@@ -363,8 +363,8 @@ extern "C" int bbpcg_comm_import(bbpcg_solver *s, const void *all_blobs, int nra
  *     neighbours fetched, shorter ones re-read more halo planes);
  *   - few items (256^3 block, the 8-GPU share of 512^3): identical CTAs of a static one-wave split finished between 84 and
  *     135 us depending on the SM group they ran on, so the chunk lengths are GUIDED: every column is cut into chunks of
- *     decreasing length (the first wave takes ~cols/slots of what is left per claim, never less than `chunk_min` = 8 planes:
- *     12 already cost 35 % on a 256 x 128 x 128 block);
+ *     decreasing length (a claim takes `guided_pct` = 60 % of cols/slots of what is left, never less than `chunk_min` = 4
+ *     planes: 12 cost 35 % on a 256 x 128 x 128 block);
  *     fast SMs claim more of the short tail chunks and all CTAs finish together.
  * Tile height: 8 rows (fewest halo-row re-reads) unless option `ty` says otherwise; the kernels take any 1..8.
  * Option `kc` forces uniform chunks.  Uploads the chunk table (Dev::ztab) and rebuilds the tensor maps. */
@@ -377,9 +377,10 @@ static int make_plan(bbpcg_solver *s)
   const int kc_uniform = s->opt_kc > 0 ? s->opt_kc : 24;
   const long long nz_uniform = (L.kn + kc_uniform - 1) / kc_uniform;
   const bool uniform = s->opt_kc > 0 || !s->guided || (long long)nbx * ((L.jn + BB_TYMAX - 1) / BB_TYMAX) * nz_uniform >= 7ll * slots;
-  /* 8 rows: fewest halo-row re-reads.  In the guided regime 7 rows measured 1-3 % faster on the per-rank blocks of the 2-, 4- and
-   * 8-GPU runs (256^3: 209 vs 216 us, 512 x 256 x 256: 391 vs 400; profiles/r02k_sweep_shapes.jsonl) and within 1 % elsewhere */
-  const int best_ty = s->opt_ty > 0 ? s->opt_ty : uniform ? BB_TYMAX : 7;
+  /* 8 rows: fewest halo-row re-reads.  Guided regime, four interleaved passes per setting on one box (profiles/r02y_sweep.jsonl,
+   * medians): claims of 60 % of the even share down to 4 planes with 8 rows 220.3 us per iteration at 256^3 and 210.4 at
+   * 512 x 256 x 128, against 225.0 / 217.8 for the earlier plan (100 %, 8 planes, 7 rows); boxes differ by more than that. */
+  const int best_ty = s->opt_ty > 0 ? s->opt_ty : BB_TYMAX;
   const int cols = nbx * ((L.jn + best_ty - 1) / best_ty);
   std::vector<int> sz;
   if (uniform) {
@@ -390,7 +391,7 @@ static int make_plan(bbpcg_solver *s)
     const int kc = (L.kn + nz - 1) / nz;
     for (int r = L.kn; r > 0; r -= kc) sz.push_back(r < kc ? r : kc);
   } else {
-    const int minc = s->chunk_min > 0 ? s->chunk_min : 8;
+    const int minc = s->chunk_min > 0 ? s->chunk_min : 4;
     int r = L.kn;
     while (r > 0) {
       int c = (int)(((long long)r * cols * s->guided_pct / 100 + slots - 1) / slots);
@@ -403,9 +404,20 @@ static int make_plan(bbpcg_solver *s)
   if (sz.size() > BB_MAXZ) { bbpcg_set_error("too many z-chunks"); return BBPCG_EINVAL; }
   /* the copy source must stay valid until the copy ran: it is only rewritten after a stream sync */
   CU(cudaStreamSynchronize(s->stream));
-  s->h_ztab[0] = 0;
-  for (size_t i = 0; i < sz.size(); i++) s->h_ztab[i + 1] = s->h_ztab[i] + sz[i];
-  CU(cudaMemcpyAsync((void *)s->dev.ztab, s->h_ztab, sizeof(int) * (sz.size() + 1), cudaMemcpyHostToDevice, s->stream));
+  /* Placement of the chunks along z, in claim order: the first one ends at the top face k = kn, the second starts at the
+   * bottom face k = 1, the others fill the middle upwards.  The residual kernel pushes the new r of the block's top / bottom
+   * plane into the z neighbours' ghost planes (peer stores over NVLink when the block is split in z): claimed first, those
+   * stores are under way a whole kernel before the rank barrier releases them, instead of in front of it. */
+  {
+    const size_t n = sz.size();
+    int lo = 1;
+    for (size_t i = 0; i < n; i++) {
+      if (i == 0 && n > 1) { s->h_ztab[0] = L.kn - sz[0] + 1; s->h_ztab[1] = L.kn; continue; }
+      s->h_ztab[2 * i] = lo; s->h_ztab[2 * i + 1] = lo + sz[i] - 1;
+      lo += sz[i];
+    }
+  }
+  CU(cudaMemcpyAsync((void *)s->dev.ztab, s->h_ztab, sizeof(int) * (2 * sz.size()), cudaMemcpyHostToDevice, s->stream));
   s->plan_ty = best_ty; s->plan_nbx = nbx; s->plan_nby = (L.jn + best_ty - 1) / best_ty; s->plan_nbz = (int)sz.size(); s->plan_kc = sz[0];
   int rc = build_search_maps(s, best_ty);
   if (rc) return rc;

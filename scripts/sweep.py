@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--iters", type=int, default=100)
     ap.add_argument("--opt", action="append", default=[])
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
+    ap.add_argument("--repeat", type=int, default=1, help="passes over the whole list of settings (interleaved: box drift hits every setting alike); each line carries its pass")
     a = ap.parse_args()
     import torch
     import bbpcg
@@ -44,7 +45,8 @@ def main():
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     s.PP_cg_noparts(u, v, w, rhs, phi, fixed_iters=20)
     with open(a.out, "a") as f:
-        for combo in itertools.product(*vals) if vals else [()]:
+        combos = list(itertools.product(*vals)) if vals else [()]
+        for rep, combo in [(rep, c) for rep in range(a.repeat) for c in combos]:
             for k, x in zip(keys, combo):
                 s.set_option(k, x)
             s.PP_cg_noparts(u, v, w, rhs, phi, fixed_iters=10)
@@ -53,7 +55,7 @@ def main():
             s.set_option("kernel_timing", 0)
             r2 = s.PP_cg_noparts(u, v, w, rhs, phi, fixed_iters=a.iters)
             us = r2.ms_iter * 1e3 / a.iters
-            rec = {"cells": cells, "opts": dict(zip(keys, combo)), "us_per_iter": us, "its": 1e6 / us,
+            rec = {"cells": cells, "opts": dict(zip(keys, combo)), "pass": rep, "us_per_iter": us, "its": 1e6 / us,
                    "frac72": 72 * ncell / (us * 1e-6) / 1e9 / 6543.1,
                    "search_us": s.info("kt_search_ns") / max(s.info("kt_search_n"), 1) / 1e3,
                    "resid_us": s.info("kt_resid_ns") / max(s.info("kt_resid_n"), 1) / 1e3,

@@ -77,6 +77,10 @@ def main():
                    loop_min=float((x["loop_end"] - x["first"]).min()) / 1e3, loop_max=float((x["loop_end"] - x["first"]).max()) / 1e3,
                    first_cta_done=(x["loop_end"].min() - t0) / 1e3, last_cta_done=(x["loop_end"].max() - t0) / 1e3,
                    tail_after_last_cta=(x["end"] - x["loop_end"].max()) / 1e3,
+                   # the tail split: every CTA's ticket (barrier + fence + atomic), the last CTA's item-order sum, then the scalars
+                   ticket_median=float(np.median((x["red"] - x["loop_end"])[x["red"] > 0])) / 1e3,
+                   last_cta_reduce=(x["red"].max() - x["loop_end"].max()) / 1e3,
+                   scalars_after_reduce=(x["end"] - x["red"].max()) / 1e3,
                    total=(x["end"] - t0) / 1e3)
         rows[x["kind"]].append(row)
         prev_end = x["end"]

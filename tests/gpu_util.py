@@ -28,7 +28,7 @@ class Product:
             for s in self.solvers:
                 s.comm_import(blobs)
         for s in self.solvers:
-            s.set_option("comm_timeout_ms", 4000)
+            s.set_option("comm_timeout_ms", 30000)      # a rank thread that page-faults on a fresh box can be seconds late (seen once at 4000)
             for k, v in (options or {}).items():
                 s.set_option(k, v)
         self.dev = []
