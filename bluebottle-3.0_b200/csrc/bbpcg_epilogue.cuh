@@ -189,12 +189,12 @@ __global__ void __launch_bounds__(256, 3) k_epilogue(const __grid_constant__ Dev
  * run on the reference's ghosted pitches (5 sectors fetched for 4 used), the brick is refilled 12-14 dependent DRAM round
  * trips per tile, and ncu showed 1.29 x the algorithmic bytes at 52 % of peak (profiles/r01h_epilogue_ncu_full.md).
  *
- *   k_epi_uwp  tile 32 (i) x 32 (j), marching k: every plane arrives through cp.async (phi row tile, w*, flag_w, p0, phase with
- *              lanes along i; u*, flag_u with lanes along j) one plane ahead of the computation; the u lanes (along j) read
- *              phi(i) - phi(i-1) across the staged tile; w uses phi(k-1) kept in registers; p and its partial sum from the
- *              same phi.  Every global access is a 256-byte run (128 for the int arrays).
+ *   k_epi_uwp  tile 32 (i) x 32 (j), marching k: phi row tile, w*, flag_w, p0, phase with lanes along i; u*, flag_u with lanes
+ *              along j; the u lanes read phi(i) - phi(i-1) across the phi tile staged in shared memory; w uses phi(k-1) kept
+ *              in registers; p and its partial sum from the same phi.  Every global access is a 256-byte run (128 for ints).
  *   k_epi_v    tile 32 (k) x 32 (i), marching j: phi rows along i for 32 planes, transposed through shared memory to the
  *              k-fastest Gfy layout; the previous j plane stays in shared memory (three phi buffers).
+ * Both fetch every stream with plain coalesced loads into registers one plane ahead of its use (see the kernels).
  * phi is read twice (8 B/cell more than the fused brick) but nothing is fetched in 128-byte pieces any more.
  * Same expressions as project_line above, so u, v, w, p are bit-identical to k_epilogue's. */
 #define EA_T 32
@@ -207,29 +207,23 @@ struct EpiPlan {
   int jc, njc;                         /* k_epi_v: faces per j-chunk, chunks */
 };
 
-/* Ampere-style asynchronous copies global -> shared (LDGSTS): any 4 / 8-byte alignment, so they work on the reference's
- * ghosted pitches where TMA boxes would not; one plane is in flight while the previous one is computed, with no register
- * staging (a register batch per plane left the loads of only ONE plane in flight per CTA and reached 3.7 TB/s). */
-__device__ __forceinline__ void cp_async8(void *dst, const void *src)
-{ asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory"); }
-__device__ __forceinline__ void cp_async4(void *dst, const void *src)
-{ asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory"); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
-
-struct EpiStageA {                     /* one k-plane of a 32 x 32 tile */
-  double phi[EA_T][EA_PA];             /* [jj][ii]: phi(i0 - 1 + ii, j0 + jj, k) */
-  double ws[EA_T][EA_T], p0[EA_T][EA_T];            /* [jj][lane i] */
-  double us[EA_T + 1][EA_T];           /* [face f][lane j] */
-  int fw[EA_T][EA_T], ph[EA_T][EA_T], fu[EA_T + 1][EA_T];
-};
-#define EPI_SMEM_A (2 * (int)sizeof(EpiStageA))
+/* Every stream is fetched by plain coalesced loads (ld.global.nc) into REGISTERS one plane ahead of its use:
+ * w*, flag_w, p0, phase (lanes along i) and u*, flag_u (lanes along j) are private to the thread that loads them; only phi
+ * crosses threads (u reads it with lanes along j) and goes registers -> shared memory, two buffers, ONE barrier per plane.
+ * Order inside a plane: phi(k) to shared memory, w and p from the registers that have landed, the loads of plane k + 1 into
+ * the same registers, barrier, u, the loads of u*(k + 1): every load has a barrier and half a plane of arithmetic between
+ * issue and use without a second register set (109 registers, 2 CTAs per SM).
+ * Measured at 512^3 (profiles/r02ab_*, r02ac_*): this form 1.75 ms at 5.35 TB/s of DRAM traffic; the earlier all-cp.async
+ * form 1.87 ms (every stream a 4 / 8-byte LDGSTS: MIO-bound, two barriers per plane); a hybrid with u* by cp.async at 80
+ * registers / 3 CTAs per SM 2.25 ms (a third CTA per SM widens the working set: L2 hit rate 19 -> 13 %, +1.5 GB of DRAM
+ * reads); evict-first loads (ld.global.cs) 2.66 ms: they lose the L2 hits on the 32-byte sectors that neighbouring tiles
+ * share on the reference's ghosted pitches (+2.3 GB). */
+struct EpiSmemU { double phi[2][EA_T][EA_PA]; };                      /* phi[k & 1][jj][ii]: phi(i0 - 1 + ii, j0 + jj, k) */
 
 template <bool PROJECT, bool UPDATE_P>
 __global__ void __launch_bounds__(256, 2) k_epi_uwp(const __grid_constant__ Dev d, const FaceStrides st, const EpiArgs a, const EpiPlan pl)
 {
-  extern __shared__ __align__(16) unsigned char epi_smem[];
-  EpiStageA *stg = reinterpret_cast<EpiStageA *>(epi_smem);
+  __shared__ EpiSmemU M;
   const int in = d.L.in, jn = d.L.jn, kn = d.L.kn;
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const long long ntile = (long long)pl.nti * pl.ntj, nitems = ntile * pl.nzc;
@@ -243,84 +237,91 @@ __global__ void __launch_bounds__(256, 2) k_epi_uwp(const __grid_constant__ Dev 
     const bool close_i = i0 + ni - 1 == in;                /* this tile also owns the closing face i = in + 1 (project_u loops _is.._ie) */
     const int nfi = ni + (close_i ? 1 : 0);
     const int klast = k1 + ((PROJECT && k1 == kn) ? 1 : 0);   /* ... and the last chunk the closing face k = kn + 1 of w */
-    /* all copies of plane k into stage k & 1 (every thread issues its share; consumers read them after the wait + barrier) */
-    auto issue = [&](int k) {
-      EpiStageA &S = stg[k & 1];
-      const bool cells = k <= k1;
-#pragma unroll
-      for (int r = 0; r < 4; r++) {
-        const int jj = wp + 8 * r;
-        if (lane < ni && jj < nj) {
-          const long long C = (i0 + lane) + (long long)(j0 + jj) * st.cs1b + (long long)k * st.cs2b;
-          cp_async8(&S.phi[jj][lane + 1], a.phi + C);
-          if (PROJECT) {
-            const long long F = (i0 + lane) + (long long)(j0 + jj) * st.ws1b + (long long)k * st.ws2b;
-            cp_async8(&S.ws[jj][lane], a.w_star + F); cp_async4(&S.fw[jj][lane], a.flag_w + F);
-          }
-          if (UPDATE_P && cells) { cp_async8(&S.p0[jj][lane], a.p0 + C); cp_async4(&S.ph[jj][lane], a.phase + C); }
-        }
-        /* the two halo columns of the row: lane 0 -> i0 - 1, lane 1 -> i0 + ni (needed only for the closing face) */
-        if (PROJECT && cells && jj < nj && (lane == 0 || (lane == 1 && close_i)))
-          cp_async8(&S.phi[jj][lane == 0 ? 0 : ni + 1], a.phi + (lane == 0 ? i0 - 1 : i0 + ni) + (long long)(j0 + jj) * st.cs1b + (long long)k * st.cs2b);
-      }
-      if (PROJECT && cells) {
-#pragma unroll
-        for (int r = 0; r < 5; r++) {
-          const int f = wp + 8 * r;                        /* face i0 + f, lanes along j (Gfx is j-fastest) */
-          if (f < nfi && lane < nj) {
-            const long long U = (j0 + lane) + (long long)k * st.us1b + (long long)(i0 + f) * st.us2b;
-            cp_async8(&S.us[f][lane], a.u_star + U); cp_async4(&S.fu[f][lane], a.flag_u + U);
-          }
-        }
-      }
-      cp_async_commit();
-    };
-    issue(k0);
-    /* phi one plane below, at this thread's cells (rows jj = wp + 8 r, column lane): in flight together with the first plane */
-    double pprev[4];
+    /* role A: cell (i0 + lane, j0 + wp + 8 r): phi, w*, flag_w, p0, phase -> w, p.  role B: face i0 + wp + 8 r, j0 + lane: u*, flag_u -> u */
+    bool okA[4], okB[5];
+    long long cA[4], fA[4], uB[5];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const int jj = wp + 8 * r;
-      pprev[r] = (PROJECT && lane < ni && jj < nj) ? __ldg(a.phi + (i0 + lane) + (long long)(j0 + jj) * st.cs1b + (long long)(k0 - 1) * st.cs2b) : 0.;
+      okA[r] = lane < ni && jj < nj;
+      cA[r] = (i0 + lane) + (long long)(j0 + jj) * st.cs1b;             /* + k * cs2b */
+      fA[r] = (i0 + lane) + (long long)(j0 + jj) * st.ws1b;             /* + k * ws2b */
     }
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+      const int f = wp + 8 * r;
+      okB[r] = PROJECT && f < nfi && lane < nj;
+      uB[r] = (j0 + lane) + (long long)(i0 + f) * st.us2b;              /* + k * us1b */
+    }
+    /* the two halo columns of a row: lane 0 -> i0 - 1, lane 1 -> i0 + ni (needed only for the closing face); rows jj = wp + 8 r */
+    const bool hal = PROJECT && (lane == 0 || (lane == 1 && close_i));
+    const int hcol = lane == 0 ? 0 : ni + 1;
+    const long long hoff = (lane == 0 ? i0 - 1 : i0 + ni);
+    double pf[4], ws[4], p0[4], us[5], phh[4], pprev[4];
+    int fw[4], ph[4], fu[5];
+    auto loadA = [&](int k) {
+      const bool cells = k <= k1;
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        pf[r] = okA[r] ? __ldg(a.phi + cA[r] + (long long)k * st.cs2b) : 0.;
+        if (PROJECT) { ws[r] = okA[r] ? __ldg(a.w_star + fA[r] + (long long)k * st.ws2b) : 0.; fw[r] = okA[r] ? __ldg(a.flag_w + fA[r] + (long long)k * st.ws2b) : 0; }
+        if (UPDATE_P) { p0[r] = (okA[r] && cells) ? __ldg(a.p0 + cA[r] + (long long)k * st.cs2b) : 0.; ph[r] = (okA[r] && cells) ? __ldg(a.phase + cA[r] + (long long)k * st.cs2b) : 0; }
+        if (PROJECT) phh[r] = (hal && cells && wp + 8 * r < nj) ? __ldg(a.phi + hoff + (long long)(j0 + wp + 8 * r) * st.cs1b + (long long)k * st.cs2b) : 0.;
+      }
+    };
+    auto loadB = [&](int k) {
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+        us[r] = okB[r] ? __ldg(a.u_star + uB[r] + (long long)k * st.us1b) : 0.;
+        fu[r] = okB[r] ? __ldg(a.flag_u + uB[r] + (long long)k * st.us1b) : 0;
+      }
+    };
+    if (PROJECT) __syncthreads();                          /* the previous item's last u faces are done with the phi buffers */
+#pragma unroll
+    for (int r = 0; r < 4; r++) pprev[r] = (PROJECT && okA[r]) ? __ldg(a.phi + cA[r] + (long long)(k0 - 1) * st.cs2b) : 0.;
+    loadA(k0);
+    if (PROJECT) loadB(k0);
     for (int k = k0; k <= klast; k++) {
       const bool cells = k <= k1;                          /* k = kn + 1: only the closing w face */
-      if (k < klast) { issue(k + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
-      __syncthreads();                                     /* plane k has landed for every thread */
-      const EpiStageA &S = stg[k & 1];
-      /* ---- w and p: lanes along i ---- */
+      double (*P)[EA_PA] = M.phi[k & 1];
+      /* ---- phi(k) to shared memory; w and p: lanes along i ---- */
 #pragma unroll
       for (int r = 0; r < 4; r++) {
         const int jj = wp + 8 * r;
-        if (lane < ni && jj < nj) {
-          const double pc = S.phi[jj][lane + 1];
+        if (PROJECT && cells) {
+          if (okA[r]) P[jj][lane + 1] = pf[r];
+          if (hal && jj < nj) P[jj][hcol] = phh[r];
+        }
+        if (okA[r]) {
+          const double pc = pf[r];
           if (PROJECT) {
-            const long long F = (i0 + lane) + (long long)(j0 + jj) * st.ws1b + (long long)k * st.ws2b;
-            const double gradPhi = abs(S.fw[jj][lane]) * a.ddz * (pc - pprev[r]);              /* bluebottle_kernel.cu:2351 */
-            a.w[F] = (S.ws[jj][lane] - a.dt_rho * gradPhi);                                    /* :2352 */
+            const double gradPhi = abs(fw[r]) * a.ddz * (pc - pprev[r]);                             /* bluebottle_kernel.cu:2351 */
+            a.w[fA[r] + (long long)k * st.ws2b] = (ws[r] - a.dt_rho * gradPhi);                      /* :2352 */
           }
           if (UPDATE_P && cells) {
-            const long long C = (i0 + lane) + (long long)(j0 + jj) * st.cs1b + (long long)k * st.cs2b;
-            const double val = (S.ph[jj][lane] < 0) * (S.p0[jj][lane] + pc);                   /* :2396 */
-            a.p[C] = val;
+            const double val = (ph[r] < 0) * (p0[r] + pc);                                           /* :2396 */
+            a.p[cA[r] + (long long)k * st.cs2b] = val;
             psum += val;
           }
           pprev[r] = pc;
         }
       }
-      /* ---- u: lanes along j, phi(i) - phi(i-1) read across the tile ---- */
-      if (PROJECT && cells) {
+      if (k < klast) loadA(k + 1);                         /* in flight across the barrier and the u faces of plane k */
+      if (PROJECT) {
+        __syncthreads();                                   /* phi(k) visible; every thread is past the u faces of plane k - 1 (they read the other buffer) */
+        if (cells) {
+          /* ---- u: lanes along j, phi(i) - phi(i-1) read across the tile ---- */
 #pragma unroll
-        for (int r = 0; r < 5; r++) {
-          const int f = wp + 8 * r;
-          if (f < nfi && lane < nj) {
-            const long long U = (j0 + lane) + (long long)k * st.us1b + (long long)(i0 + f) * st.us2b;
-            const double gradPhi = abs(S.fu[f][lane]) * a.ddx * (S.phi[lane][f + 1] - S.phi[lane][f]);   /* :2315 */
-            a.u[U] = (S.us[f][lane] - a.dt_rho * gradPhi);                                                /* :2316 */
+          for (int r = 0; r < 5; r++) {
+            if (okB[r]) {
+              const int f = wp + 8 * r;
+              const double gradPhi = abs(fu[r]) * a.ddx * (P[lane][f + 1] - P[lane][f]);             /* :2315 */
+              a.u[uB[r] + (long long)k * st.us1b] = (us[r] - a.dt_rho * gradPhi);                    /* :2316 */
+            }
           }
+          if (k < k1) loadB(k + 1);
         }
       }
-      __syncthreads();                                     /* stage k & 1 is free for plane k + 2 */
     }
   }
   if (UPDATE_P) {
@@ -333,14 +334,17 @@ __global__ void __launch_bounds__(256, 2) k_epi_uwp(const __grid_constant__ Dev 
   }
 }
 
-struct EpiStageB { double vs[EA_T][EA_T]; int fv[EA_T][EA_T]; };      /* [ii][lane k] */
-struct EpiSmemB { double phi[3][EA_T][EA_PB]; EpiStageB s[2]; };     /* phi[j % 3][kk][ii]: phi(i0 + ii, j, k0 + kk) */
-#define EPI_SMEM_B ((int)sizeof(EpiSmemB))
+/* Every stream is fetched by plain coalesced loads into REGISTERS one face ahead of the computation (v*, flag_v and the v
+ * written are private to a thread; only phi crosses threads -- it is loaded with lanes along i and read with lanes along k --
+ * and goes registers -> shared memory, three buffers, ONE barrier per face).  0.67 ms at 512^3 = 6.03 TB/s of DRAM traffic
+ * (profiles/r02ab_*); the earlier cp.async form issued 12 LDGSTS of 4 / 8 bytes per thread and face and stalled on the MIO
+ * queue (mio_throttle 10.3 warps per issue, 1.02 ms, profiles/r02o_epilogue_ncu_full.md). */
+struct EpiSmemV { double phi[3][EA_T][EA_PB]; };                      /* phi[j % 3][kk][ii]: phi(i0 + ii, j, k0 + kk) */
+#define EPI_SMEM_V ((int)sizeof(EpiSmemV))
 
-__global__ void __launch_bounds__(256, 4) k_epi_v(const __grid_constant__ Dev d, const FaceStrides st, const EpiArgs a, const EpiPlan pl)
+__global__ void __launch_bounds__(256, 3) k_epi_v(const __grid_constant__ Dev d, const FaceStrides st, const EpiArgs a, const EpiPlan pl)
 {
-  extern __shared__ __align__(16) unsigned char epi_smem[];
-  EpiSmemB &M = *reinterpret_cast<EpiSmemB *>(epi_smem);
+  __shared__ EpiSmemV M;
   const int in = d.L.in, jn = d.L.jn, kn = d.L.kn;
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const long long ntile = (long long)pl.ntk * pl.nti, nitems = ntile * pl.njc;
@@ -350,36 +354,56 @@ __global__ void __launch_bounds__(256, 4) k_epi_v(const __grid_constant__ Dev d,
     const int i0 = bi * EA_T + 1, k0 = bk * EA_T + 1;
     const int ni = min(EA_T, in - i0 + 1), nk = min(EA_T, kn - k0 + 1);
     const int f0 = jcn * pl.jc + 1, f1 = min(jn + 1, f0 + pl.jc - 1);      /* faces j = f0 .. f1 of Gfy._js.._je = 1 .. jn + 1 */
-    auto issue = [&](int j) {
+    /* this thread's four phi cells (k row wp + 8 r, i column lane) and four v faces (i row wp + 8 r, k column lane) */
+    bool okp[4], okv[4];
+    long long cp[4], cv[4];
 #pragma unroll
-      for (int r = 0; r < 4; r++) {
-        const int kk = wp + 8 * r;                         /* phi: lanes along i, one k row per warp pass */
-        if (lane < ni && kk < nk) cp_async8(&M.phi[j % 3][kk][lane], a.phi + (i0 + lane) + (long long)j * st.cs1b + (long long)(k0 + kk) * st.cs2b);
-        const int ii = wp + 8 * r;                         /* v*, flag_v: lanes along k (Gfy is k-fastest), one i row per warp pass */
-        if (j >= f0 && ii < ni && lane < nk) {
-          const long long V = (k0 + lane) + (long long)(i0 + ii) * st.vs1b + (long long)j * st.vs2b;
-          cp_async8(&M.s[j & 1].vs[ii][lane], a.v_star + V); cp_async4(&M.s[j & 1].fv[ii][lane], a.flag_v + V);
-        }
+    for (int r = 0; r < 4; r++) {
+      const int rr = wp + 8 * r;
+      okp[r] = lane < ni && rr < nk;
+      okv[r] = rr < ni && lane < nk;
+      cp[r] = (i0 + lane) + (long long)(k0 + rr) * st.cs2b;             /* + j * cs1b */
+      cv[r] = (k0 + lane) + (long long)(i0 + rr) * st.vs1b;             /* + j * vs2b */
+    }
+    double pf[4], vs[4];
+    int fv[4];
+    __syncthreads();                                       /* the previous item's last face is computed: its phi buffers are free */
+#pragma unroll
+    for (int r = 0; r < 4; r++) if (okp[r]) M.phi[(f0 - 1) % 3][wp + 8 * r][lane] = __ldg(a.phi + cp[r] + (long long)(f0 - 1) * st.cs1b);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      pf[r] = okp[r] ? __ldg(a.phi + cp[r] + (long long)f0 * st.cs1b) : 0.;
+      vs[r] = okv[r] ? __ldg(a.v_star + cv[r] + (long long)f0 * st.vs2b) : 0.;
+      fv[r] = okv[r] ? __ldg(a.flag_v + cv[r] + (long long)f0 * st.vs2b) : 0;
+    }
+    for (int j = f0; j <= f1; j++) {
+      const int cur = j % 3, prev = (j + 2) % 3;
+      double cvs[4];
+      int cfv[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++) {                         /* face j has landed: phi to its buffer, v* / flag_v to the working set */
+        if (okp[r]) M.phi[cur][wp + 8 * r][lane] = pf[r];
+        cvs[r] = vs[r]; cfv[r] = fv[r];
       }
-      cp_async_commit();
-    };
-    issue(f0 - 1);
-    for (int j = f0 - 1; j <= f1; j++) {
-      if (j < f1) { issue(j + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
-      __syncthreads();                                     /* plane j has landed */
-      if (j >= f0) {
-        const int cur = j % 3, prev = (j - 1) % 3;
+      if (j < f1) {                                         /* face j + 1: in flight during the barrier and the computation of face j */
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-          const int ii = wp + 8 * r;
-          if (ii < ni && lane < nk) {
-            const long long V = (k0 + lane) + (long long)(i0 + ii) * st.vs1b + (long long)j * st.vs2b;
-            const double gradPhi = abs(M.s[j & 1].fv[ii][lane]) * a.ddy * (M.phi[cur][lane][ii] - M.phi[prev][lane][ii]);   /* bluebottle_kernel.cu:2333 */
-            a.v[V] = (M.s[j & 1].vs[ii][lane] - a.dt_rho * gradPhi);                                                        /* :2334 */
-          }
+          pf[r] = okp[r] ? __ldg(a.phi + cp[r] + (long long)(j + 1) * st.cs1b) : 0.;
+          vs[r] = okv[r] ? __ldg(a.v_star + cv[r] + (long long)(j + 1) * st.vs2b) : 0.;
+          fv[r] = okv[r] ? __ldg(a.flag_v + cv[r] + (long long)(j + 1) * st.vs2b) : 0;
         }
       }
-      __syncthreads();                                     /* the v* stage and the oldest phi buffer are free for plane j + 2 */
+      /* one barrier per face: phi(j) is visible, and every thread has finished face j - 1 (which read the buffer that
+       * face j + 1 will overwrite after the NEXT barrier's predecessor, i.e. not before all threads passed this one) */
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        if (okv[r]) {
+          const int ii = wp + 8 * r;
+          const double gradPhi = abs(cfv[r]) * a.ddy * (M.phi[cur][lane][ii] - M.phi[prev][lane][ii]);   /* bluebottle_kernel.cu:2333 */
+          a.v[cv[r] + (long long)j * st.vs2b] = (cvs[r] - a.dt_rho * gradPhi);                              /* :2334 */
+        }
+      }
     }
   }
 }

@@ -556,7 +556,7 @@ static int preload_kernels()
   PL(k_solv_sum); PL(k_solv_apply); PL(k_bc_star);
   PL(k_cage_reset); PL(k_cage<false>); PL(k_cage<true>); PL(k_cage_flags<256>);
   PL(k_bc_p); PL(k_sub_mean);
-  PL(k_epi_uwp<true, true>, EPI_SMEM_A); PL(k_epi_uwp<true, false>, EPI_SMEM_A); PL(k_epi_uwp<false, true>, EPI_SMEM_A); PL(k_epi_v, EPI_SMEM_B);
+  PL(k_epi_uwp<true, true>); PL(k_epi_uwp<true, false>); PL(k_epi_uwp<false, true>); PL(k_epi_v);
   PL(k_epilogue<true, true>, EPI_SMEM); PL(k_epilogue<true, false>, EPI_SMEM); PL(k_epilogue<false, true>, EPI_SMEM);
 #undef PL
   return rc;
@@ -812,12 +812,12 @@ extern "C" int bbpcg_epilogue(bbpcg_solver *s, const bbpcg_epilogue_args *a, dou
     pl.kc = s->epi_chunk > 0 ? s->epi_chunk : 32; pl.nzc = (L.kn + pl.kc - 1) / pl.kc;
     pl.jc = pl.kc; pl.njc = (L.jn + 1 + pl.jc - 1) / pl.jc;
     const long long itemsA = (long long)pl.nti * pl.ntj * pl.nzc, itemsB = (long long)pl.ntk * pl.nti * pl.njc;
-    const int gridA = clampi(itemsA, 1, s->sm_count * 2), gridB = clampi(itemsB, 1, s->sm_count * 4);
-    if (project && update) k_epi_uwp<true, true><<<gridA, 256, EPI_SMEM_A, s->stream>>>(s->dev, s->fst, e, pl);
-    else if (project) k_epi_uwp<true, false><<<gridA, 256, EPI_SMEM_A, s->stream>>>(s->dev, s->fst, e, pl);
-    else k_epi_uwp<false, true><<<gridA, 256, EPI_SMEM_A, s->stream>>>(s->dev, s->fst, e, pl);
+    const int gridA = clampi(itemsA, 1, s->sm_count * 2), gridB = clampi(itemsB, 1, s->sm_count * 3);   /* 109 / 72 registers */
+    if (project && update) k_epi_uwp<true, true><<<gridA, 256, 0, s->stream>>>(s->dev, s->fst, e, pl);
+    else if (project) k_epi_uwp<true, false><<<gridA, 256, 0, s->stream>>>(s->dev, s->fst, e, pl);
+    else k_epi_uwp<false, true><<<gridA, 256, 0, s->stream>>>(s->dev, s->fst, e, pl);
     s->launches++;
-    if (project) { k_epi_v<<<gridB, 256, EPI_SMEM_B, s->stream>>>(s->dev, s->fst, e, pl); s->launches++; }
+    if (project) { k_epi_v<<<gridB, 256, 0, s->stream>>>(s->dev, s->fst, e, pl); s->launches++; }
   }
   if (update) {
     const long long nrows = (long long)L.jn * L.kn;

@@ -50,16 +50,20 @@ def _check_against_oracle(case, p):
         assert _close(dev["p"].cpu().numpy()[INNER], case.o.array(r, ob.P)[INNER], P_TOL), r
 
 
+EPI_FORMS = {0: {"epilogue_tiled": 0},      # the plane-marching pair k_epi_uwp + k_epi_v (default)
+             1: {"epilogue_tiled": 1}}      # the 16^3-brick kernel k_epilogue
+
+
 @pytest.mark.parametrize("tiled", [0, 1])
 @pytest.mark.parametrize("cells,bc,nparts", [((32, 28, 36), "cavity", 0), ((32, 28, 36), "duct", 0), ((32, 28, 36), "periodic", 0),
                                              ((33, 17, 9), "box", 0), ((16, 16, 16), "channel", 0), ((40, 40, 40), "sedimentation", 3),
                                              ((70, 33, 45), "box", 0), ((64, 96, 65), "duct", 0)])
 def test_epilogue_three_way(cells, bc, nparts, tiled):
-    """tiled = 0: the plane-marching pair k_epi_uwp + k_epi_v (default); 1: the 16^3-brick kernel k_epilogue"""
+    """both forms of the epilogue (EPI_FORMS) against the oracle and the reference's kernels"""
     case = Case(cells, bc=bc, nparts=nparts, radius=2.5)
     case.seed_epilogue(23)
     ein = case.epilogue_inputs(0)
-    p = _product(case, options={"epilogue_tiled": tiled, "epi_chunk": 0 if cells[0] != 64 else 24})
+    p = _product(case, options=dict(EPI_FORMS[tiled], epi_chunk=0 if cells[0] != 64 else 24))
     _fused(p)
     case.o.epilogue(1.0, 1e-3)
     _check_against_oracle(case, p)
@@ -104,13 +108,14 @@ def test_epilogue_streaming_pair_equals_the_brick_kernel():
     case.seed_epilogue(29)
     outs = []
     for tiled in (0, 1):
-        p = _product(case, options={"epilogue_tiled": tiled})
+        p = _product(case, options=EPI_FORMS[tiled])
         _fused(p)
         outs.append({k: p.dev[0][k].cpu().numpy().copy() for k in ("u", "v", "w", "p")})
         p.close()
-    for k in ("u", "v", "w"):
-        assert np.array_equal(outs[0][k][INNER], outs[1][k][INNER]), k
-    assert np.abs(outs[0]["p"][INNER] - outs[1]["p"][INNER]).max() <= 1e-13 * np.abs(outs[1]["p"][INNER]).max()
+    for o in outs[1:]:
+        for k in ("u", "v", "w"):
+            assert np.array_equal(outs[0][k][INNER], o[k][INNER]), k
+        assert np.abs(outs[0]["p"][INNER] - o["p"][INNER]).max() <= 1e-13 * np.abs(o["p"][INNER]).max()
 
 
 def test_epilogue_halves_equal_the_fused_call():
