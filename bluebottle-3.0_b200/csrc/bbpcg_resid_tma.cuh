@@ -79,6 +79,18 @@ __device__ __forceinline__ void push_pair(double *dst, double a, double b, bool 
   if (both) stg128(dst, a, b); else *dst = a;
 }
 
+/* the new r of cells on a y / z face of the block into the neighbour's ghost row / plane (push model, see resid_item);
+ * faces: bit 0 S, 1 N, 2 B, 3 T -- the faces this ITEM touches that have a neighbour */
+__device__ __noinline__ void push_yz_faces(const Dev &d, int faces, int iA, int j, int kc, double r0, double r1, bool both)
+{
+  const Layout &L = d.L;
+  const NbrFace &nN = d.halo.f[2], &nS = d.halo.f[3], &nT = d.halo.f[4], &nB = d.halo.f[5];
+  if ((faces & 1) && j == 1) push_pair(nS.r + (long long)kc * nS.L.ps + (unsigned)(iA + BB_XOFF) + (unsigned)(nS.L.jn + 1) * (unsigned)nS.L.px, r0, r1, both);
+  if ((faces & 2) && j == L.jn) push_pair(nN.r + (long long)kc * nN.L.ps + (unsigned)(iA + BB_XOFF), r0, r1, both);
+  if ((faces & 4) && kc == 1) push_pair(nB.r + (long long)(nB.L.kn + 1) * nB.L.ps + (unsigned)(iA + BB_XOFF) + (unsigned)j * (unsigned)nB.L.px, r0, r1, both);
+  if ((faces & 8) && kc == L.kn) push_pair(nT.r + (unsigned)(iA + BB_XOFF) + (unsigned)j * (unsigned)nT.L.px, r0, r1, both);
+}
+
 /* the plane loop of ONE item; see search_item (bbpcg_search_tma.cuh) for the roles of g, pc and queue */
 template <bool PARTS, int DD, bool REFRESH, bool XFULL>
 __device__ __forceinline__ double resid_item(const Dev &d, const SearchMaps &tm, const SearchArgs &a, unsigned char *smem, const ItemGeom &ig,
@@ -227,13 +239,10 @@ __device__ __forceinline__ double resid_item(const Dev &d, const SearchMaps &tm,
         } else r_pl[goff[o]] = r0;                                                        /* odd row end: element 1 is the E ghost */
         if (px_w) nw_pl[oW[o]] = r0;
         if (px_e0) ne_pl[oE[o]] = r0;
-        if (yz_item) {                                                                    /* y / z faces: whole rows of the tile */
-          const int j = y0 + rowo[o];
-          if (ys_item && j == 1) push_pair(nS.r + (long long)kc * nS.L.ps + (unsigned)(iA + BB_XOFF) + (unsigned)(nS.L.jn + 1) * (unsigned)nS.L.px, r0, r1, both);
-          if (yn_item && j == L.jn) push_pair(nN.r + (long long)kc * nN.L.ps + (unsigned)(iA + BB_XOFF), r0, r1, both);
-          if (zb_item && kc == 1) push_pair(nB.r + (long long)(nB.L.kn + 1) * nB.L.ps + (unsigned)(iA + BB_XOFF) + (unsigned)j * (unsigned)nB.L.px, r0, r1, both);
-          if (zt_item && kc == L.kn) push_pair(nT.r + (unsigned)(iA + BB_XOFF) + (unsigned)j * (unsigned)nT.L.px, r0, r1, both);
-        }
+        /* y / z faces: whole rows of the tile, rare on large blocks -- behind a CALL, so that none of the address arithmetic is
+         * speculated into the plane loop (inlined, it cost every plane of every item ~80 instructions per warp: +30 % on the
+         * kernel, 534 -> 572 us at 512^3 under the power cap; profiles/r02ae_512_ncu_full.md vs r02p_512_ncu_full.md) */
+        if (yz_item) push_yz_faces(d, (ys_item ? 1 : 0) | (yn_item ? 2 : 0) | (zb_item ? 4 : 0) | (zt_item ? 8 : 0), iA, y0 + rowo[o], kc, r0, r1, both);
       }
     }
 #pragma unroll

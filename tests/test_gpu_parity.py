@@ -145,7 +145,7 @@ def test_zchunk_plans(opts):
 
 
 def test_plan_of_the_benchmarked_block_shapes():
-    """the planner's tile / z-chunk choice for the benchmarked block shapes: 8-row tiles (7 for small blocks), ONE wave of resident
+    """the planner's tile / z-chunk choice for the benchmarked block shapes: 8-row tiles, ONE wave of resident
     CTAs (2 per SM) claiming the work items; uniform ~24-plane chunks when there are many items, chunks of DECREASING length
     (never below chunk_min) for the small blocks of an 8-GPU run"""
     import bbpcg
@@ -155,7 +155,7 @@ def test_plan_of_the_benchmarked_block_shapes():
         s = bbpcg.PoissonSolver(dec, 0)
         slots = 2 * s.info("sm_count")
         grid, items, ty, kc, nbz = s.info("search_grid"), s.info("search_items"), s.info("search_ty"), s.info("search_kc"), s.info("search_nbz")
-        assert ty == (8 if many else 7) and items == (cells[0] // 128) * -(-cells[1] // ty) * nbz and grid == min(items, slots)
+        assert ty == 8 and items == (cells[0] // 128) * -(-cells[1] // ty) * nbz and grid == min(items, slots)
         if many:
             assert items >= 7 * slots and kc == 24 and nbz == -(-cells[2] // kc)
         else:
