@@ -193,6 +193,10 @@ __device__ __forceinline__ double resid_item(const Dev &d, const SearchMaps &tm,
       const double *Rc = reinterpret_cast<const double *>(Mc + G::MT);
       double *r_pl = r + (long long)kc * L.ps;
       double *nw_pl = nW.r + (long long)kc * nW.L.ps, *ne_pl = nE.r + (long long)kc * nE.L.ps;      /* uniform; only dereferenced when the neighbour exists */
+      /* y / z faces that THIS PLANE of the item pushes (CTA-uniform): a y-boundary tile on every plane, a z-boundary chunk on
+       * its one boundary plane only -- gated per item, the top and bottom chunks (half the volume of a 128-plane block under
+       * the guided plan) paid the call on every plane */
+      const int yz_faces = yz_item ? ((ys_item ? 1 : 0) | (yn_item ? 2 : 0) | ((zb_item && kc == 1) ? 4 : 0) | ((zt_item && kc == L.kn) ? 8 : 0)) : 0;
 #pragma unroll
       for (int o = 0; o < NO; o++) {
         if (!own[o]) continue;                                           /* warp-uniform in the XFULL form */
@@ -242,7 +246,7 @@ __device__ __forceinline__ double resid_item(const Dev &d, const SearchMaps &tm,
         /* y / z faces: whole rows of the tile, rare on large blocks -- behind a CALL, so that none of the address arithmetic is
          * speculated into the plane loop (inlined, it cost every plane of every item ~80 instructions per warp: +30 % on the
          * kernel, 534 -> 572 us at 512^3 under the power cap; profiles/r02ae_512_ncu_full.md vs r02p_512_ncu_full.md) */
-        if (yz_item) push_yz_faces(d, (ys_item ? 1 : 0) | (yn_item ? 2 : 0) | (zb_item ? 4 : 0) | (zt_item ? 8 : 0), iA, y0 + rowo[o], kc, r0, r1, both);
+        if (yz_faces) push_yz_faces(d, yz_faces, iA, y0 + rowo[o], kc, r0, r1, both);
       }
     }
 #pragma unroll
