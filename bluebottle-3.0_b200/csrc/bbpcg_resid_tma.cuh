@@ -92,7 +92,7 @@ __device__ __noinline__ void push_yz_faces(const Dev &d, int faces, int iA, int 
 }
 
 /* the plane loop of ONE item; see search_item (bbpcg_search_tma.cuh) for the roles of g, pc and queue */
-template <bool PARTS, int DD, bool REFRESH, bool XFULL>
+template <bool PARTS, int DD, bool REFRESH, bool XFULL, bool XPUSH>
 __device__ __forceinline__ double resid_item(const Dev &d, const SearchMaps &tm, const SearchArgs &a, unsigned char *smem, const ItemGeom &ig,
                                              int &g, ProdCursor &pc, int *queue, int q, double alpha, double c63)
 {
@@ -129,8 +129,12 @@ __device__ __forceinline__ double resid_item(const Dev &d, const SearchMaps &tm,
    * peer memory over NVLink, or into this block's own ghosts for a periodic self-wrap); the rank barrier at the end of
    * the kernel orders them before the neighbour's next search kernel reads its r tile, ghosts included. */
   const NbrFace &nE = d.halo.f[0], &nW = d.halo.f[1], &nN = d.halo.f[2], &nS = d.halo.f[3], &nT = d.halo.f[4], &nB = d.halo.f[5];
-  const bool px_w = nW.r != nullptr && iA == 1;
-  const bool px_e0 = nE.r != nullptr && iA == L.in, px_e1 = nE.r != nullptr && iA + 1 == L.in;
+  /* XPUSH: the item owns a column on an x face that has a neighbour (CTA-uniform, chosen by the caller).  The other form
+   * carries no x-push code at all: as predicated stores in the one plane loop their address arithmetic cost every warp of
+   * every item ~30 instructions per plane; behind a call (divergent: one lane per row) they cost more still -- 520 -> 569 us
+   * at 512^3 (profiles/r02ak_sweep_x_pushes_behind_call_rejected.jsonl). */
+  const bool px_w = XPUSH && nW.r != nullptr && iA == 1;
+  const bool px_e0 = XPUSH && nE.r != nullptr && iA == L.in, px_e1 = XPUSH && nE.r != nullptr && iA + 1 == L.in;
   /* element offsets of the pushed x-face values inside a plane of the NEIGHBOUR's array (its pitch may differ across an x
    * face), per item, so that a push costs one add per plane */
   unsigned oW[NO], oE[NO];
@@ -239,10 +243,10 @@ __device__ __forceinline__ double resid_item(const Dev &d, const SearchMaps &tm,
           r1 = REFRESH ? __dsub_rn(rc.y, q1) : __fma_rn(-alpha, q1, rc.y);
           dot = __fma_rn(r1, __dmul_rn(r1, c1), dot);
           stg128(r_pl + goff[o], r0, r1);
-          if (px_e1) ne_pl[oE[o]] = r1;
+          if (XPUSH && px_e1) ne_pl[oE[o]] = r1;
         } else r_pl[goff[o]] = r0;                                                        /* odd row end: element 1 is the E ghost */
-        if (px_w) nw_pl[oW[o]] = r0;
-        if (px_e0) ne_pl[oE[o]] = r0;
+        if (XPUSH && px_w) nw_pl[oW[o]] = r0;
+        if (XPUSH && px_e0) ne_pl[oE[o]] = r0;
         /* y / z faces: whole rows of the tile, rare on large blocks -- behind a CALL, so that none of the address arithmetic is
          * speculated into the plane loop (inlined, it cost every plane of every item ~80 instructions per warp: +30 % on the
          * kernel, 534 -> 572 us at 512^3 under the power cap; profiles/r02ae_512_ncu_full.md vs r02p_512_ncu_full.md) */
@@ -307,8 +311,10 @@ k_resid_tma(const __grid_constant__ Dev d, const __grid_constant__ SearchMaps tm
     const ItemGeom ig = decode_item(d, a, cur);
     const bool xfull = (ig.bx * G::TX + G::TX) <= d.L.in;
     peer_push |= item_touches_nbr(d, a, ig);
-    const double dot = xfull ? resid_item<PARTS, DD, REFRESH, true>(d, tm, a, smem, ig, g, pc, queue, q, alpha, c63)
-                             : resid_item<PARTS, DD, REFRESH, false>(d, tm, a, smem, ig, g, pc, queue, q, alpha, c63);
+    const bool xpush = (d.halo.f[1].r != nullptr && ig.bx == 0) || (d.halo.f[0].r != nullptr && ig.bx == a.nbx - 1);
+    const double dot = xfull ? (xpush ? resid_item<PARTS, DD, REFRESH, true, true>(d, tm, a, smem, ig, g, pc, queue, q, alpha, c63)
+                                      : resid_item<PARTS, DD, REFRESH, true, false>(d, tm, a, smem, ig, g, pc, queue, q, alpha, c63))
+                             : resid_item<PARTS, DD, REFRESH, false, true>(d, tm, a, smem, ig, g, pc, queue, q, alpha, c63);
     const double part = block_sum<1>(dot, sh_sum);      /* the item's (r,z) partial in the item's own slot */
     if (tid == 0) d.partials[cur] = part;
     n++;
