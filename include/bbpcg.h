@@ -267,7 +267,16 @@ int  bbpcg_rhs(bbpcg_solver *s, const real *u_star, const real *v_star, const re
 /* Ap (s3, ghost-free, device) = -A * src (Gcc s3b, device, ghosts as given) */
 int  bbpcg_spmv(bbpcg_solver *s, const real *src_s3b, real *Ap_s3, int use_phase);
 
-/* tuning / introspection */
+/* tuning / introspection.  Options (defaults are the measured best; none changes a result beyond the summation order of the
+ * dot products, which stays deterministic for a given setting):
+ *   comm_timeout_ms  spin limit of the in-kernel rank barriers (default ~70 000; <= 0: wait for ever, like MPI)
+ *   ty, kc           tile height (1..8, 0 = automatic) and uniform z-chunk length (0 = automatic) of the iteration kernels
+ *   guided, guided_pct, chunk_min   decreasing z-chunk lengths for small blocks (1, 60 % of the even share, >= 4 planes)
+ *   pdl              programmatic dependent launch of the iteration kernels (on unless several ranks share one GPU)
+ *   epilogue_tiled   1: the 16^3-brick epilogue kernel instead of the plane-marching pair;  epi_chunk: planes per chunk (32)
+ *   rhs_tiled, tma_warp, stream_blocks, check_every   see csrc/bbpcg_solver.cu
+ *   kernel_timing    1: CUDA events around every iteration kernel (bbpcg_get_info kt_*_ns / kt_*_n; switches PDL off)
+ * Info keys: pitch, sm_count, nranks, tile_tx, search_ty, search_grid, search_items, search_kc, search_nbz, pdl, comm_timeout. */
 int  bbpcg_set_option(bbpcg_solver *s, const char *key, long long value);
 long long bbpcg_get_info(bbpcg_solver *s, const char *key);
 const char *bbpcg_last_error(void);
