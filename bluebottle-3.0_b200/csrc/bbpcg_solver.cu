@@ -83,7 +83,8 @@ struct bbpcg_solver {
   int shared_device;                /* some peer rank lives on this same GPU (single-process harness, or two processes on one GPU) */
   unsigned char uuid[16];
   SearchMaps maps;                  /* tensor maps of the iteration kernels for the planned tile height */
-  int kernel_timing;
+  int kernel_timing;                /* 0 off, 1 every iteration, n > 1: the first n iterations of a solve (the others keep PDL) */
+  int kt_now;                       /* the iteration being enqueued is instrumented: no PDL attribute on its launches */
   cudaEvent_t *kev;                 /* [2*BB_KT_CAP+1] */
   double kt_search_ms, kt_resid_ms, kt_refresh_ms;
   int kt_search_n, kt_resid_n, kt_refresh_n;
@@ -446,7 +447,7 @@ static cudaError_t launch_k(bbpcg_solver *s, void (*kernel)(KArgs...), dim3 grid
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = (pdl && pdl_active(s) && !s->kernel_timing) ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = (pdl && pdl_active(s) && !s->kt_now) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
@@ -948,9 +949,12 @@ extern "C" int bbpcg_prologue(bbpcg_solver *s, real *u_star, real *v_star, real 
 }
 
 /* ---- the solve ----------------------------------------------------------------------------- */
+static int kt_limit(const bbpcg_solver *s) { return s->kernel_timing > 1 && s->kernel_timing < BB_KT_CAP ? s->kernel_timing : BB_KT_CAP; }
+
 static int enqueue_iteration(bbpcg_solver *s, int it, bool parts, const real *rhs)
 {
-  const bool kt = s->kernel_timing && it <= BB_KT_CAP;
+  const bool kt = s->kernel_timing && it <= kt_limit(s);
+  s->kt_now = kt;
   if (kt && it == 1) CU(cudaEventRecord(s->kev[0], s->stream));
   int rc = launch_search(s, parts);
   if (rc) return rc;
@@ -961,6 +965,7 @@ static int enqueue_iteration(bbpcg_solver *s, int it, bool parts, const real *rh
   } else rc = launch_resid(s, parts, NULL);
   if (rc) return rc;
   if (kt) CU(cudaEventRecord(s->kev[2 * it], s->stream));
+  s->kt_now = 0;
   return BBPCG_OK;
 }
 
@@ -1042,7 +1047,7 @@ extern "C" int bbpcg_solve(bbpcg_solver *s, const bbpcg_solve_args *a, bbpcg_res
   const Scal &sc = *s->h_scal;
   if (s->kernel_timing) {
     s->kt_search_ms = s->kt_resid_ms = s->kt_refresh_ms = 0.; s->kt_search_n = s->kt_resid_n = s->kt_refresh_n = 0;
-    for (int i = 1; i <= sc.q && i <= BB_KT_CAP && i <= it; i++) {
+    for (int i = 1; i <= sc.q && i <= kt_limit(s) && i <= it; i++) {
       float a = 0.f, b = 0.f;
       cudaEventElapsedTime(&a, s->kev[2 * i - 2], s->kev[2 * i - 1]);
       cudaEventElapsedTime(&b, s->kev[2 * i - 1], s->kev[2 * i]);
@@ -1124,7 +1129,7 @@ extern "C" int bbpcg_set_option(bbpcg_solver *s, const char *key, long long valu
     s->h_poll[BB_POLL_COMM] = 0;
   }
   else if (!strcmp(key, "kernel_timing")) {
-    s->kernel_timing = value != 0;
+    s->kernel_timing = (int)clampi(value, 0, BB_KT_CAP);
     if (s->kernel_timing && !s->kev) {
       CU(cudaSetDevice(s->device));
       s->kev = (cudaEvent_t *)calloc(2 * BB_KT_CAP + 1, sizeof(cudaEvent_t));
