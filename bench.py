@@ -510,7 +510,7 @@ def run_bbpcg(args):
     if not args.no_parity:
         parity = parity_against_reference(args, w, cells, extent, dom, phi, niter_last, dev)
 
-    # ---- exposed communication (N > 1): the same per-rank block solved stand-alone (no peers: no halo pull
+    # ---- exposed communication (N > 1): the same per-rank block solved stand-alone (no peers: no halo push
     # over NVLink, no cross-rank all-reduce wait), same kernels, fixed iteration count ----------------------
     comm = None
     if w.size > 1 and not args.no_comm_split:

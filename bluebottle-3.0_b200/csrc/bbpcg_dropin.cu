@@ -87,10 +87,10 @@ extern "C" void cuda_PP_init_jacobi_preconditioner(void)
 }
 
 /* The reference's eight wall-clock segments (src/cuda_solver.cu:372-390) do not exist as separate steps here: an iteration
- * is two fused kernels with the reductions, the all-reduces and the halo pull inside them.  The columns are filled with
+ * is two fused kernels with the reductions, the all-reduces and the halo push inside them.  The columns are filled with
  * what can be measured (CUDA events around every launch, option kernel_timing):
- *   spmv  <- k_search_tma  (PP_update_search + SpMV + (p,Ap) + its all-reduce + the halo pull of the NEXT search direction)
- *   up1   <- k_resid_tma   (PP_update_soln_resid + (r,z) + its all-reduce), incl. the every-50th refresh pair
+ *   spmv  <- k_search_tma  (PP_update_search + SpMV + (p,Ap) + its all-reduce)
+ *   up1   <- k_resid_tma   (PP_update_soln_resid + the halo push of r + (r,z) + its all-reduce), incl. the every-50th refresh pair
  *   ip1, ar1, ip2, ar2, up2, mpi <- 0 (fused into the two above) */
 struct timed_segments { real spmv, up1; };
 

@@ -228,7 +228,7 @@ __device__ bool grid_reduce(const Dev &d, double (&v)[NV], int bid, int nblocks,
  * carry the current tag.  One NVLink one-way latency per all-reduce instead of
  * store / fence.sys / flag / spin / fence.sys.
  *
- * release = true: this kernel wrote data that PEERS will read after the barrier (r in the pull
+ * release = true: this kernel wrote data that PEERS will read after the barrier (r in the former pull
  * model, ghost pushes): thread 0 -- which has observed every CTA's device-scope release through
  * the counter -- issues the one system-scope fence before anything is signalled. */
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
