@@ -95,7 +95,7 @@ SYMBOLS = [
     "bb_recorder_PP_init", "bb_recorder_PP", "bb_recorder_PP_init_timed", "bb_recorder_PP_timed",
     "bbpcg_create", "bbpcg_destroy", "bbpcg_comm_export", "bbpcg_comm_import", "bbpcg_set_coefficients",
     "bbpcg_solve", "bbpcg_solve_host", "bbpcg_history", "bbpcg_exchange_Gcc", "bbpcg_rhs", "bbpcg_spmv",
-    "bbpcg_set_option", "bbpcg_get_info", "bbpcg_last_error", "bbpcg_version",
+    "bbpcg_set_option", "bbpcg_plan_zchunks", "bbpcg_get_info", "bbpcg_last_error", "bbpcg_version",
     "bbpcg_dom_BC_p", "bbpcg_epilogue", "bbpcg_exchange", "bbpcg_solvability", "bbpcg_dom_BC_star", "bbpcg_prologue", "bbpcg_build_cages",
 ]
 DROPIN_SYMBOLS = ["cuda_PP_init_jacobi_preconditioner", "cuda_PP_cg", "cuda_PP_cg_noparts", "cuda_PP_cg_timed",
@@ -129,6 +129,7 @@ def load_library():
     lib.bb_recorder_PP_init_timed.argtypes = [C.c_char_p, C.c_char_p]
     lib.bb_recorder_PP.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]
     lib.bb_recorder_PP_timed.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, dp]
+    lib.bbpcg_plan_zchunks.argtypes = [C.c_int] * 9 + [ip, C.c_int, ip]
     lib.bbpcg_create.argtypes = [C.POINTER(vp), D, D, C.POINTER(PressureBC), C.c_int]
     lib.bbpcg_destroy.argtypes = [vp]
     lib.bbpcg_destroy.restype = None

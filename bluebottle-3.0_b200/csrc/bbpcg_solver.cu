@@ -369,58 +369,70 @@ extern "C" int bbpcg_comm_import(bbpcg_solver *s, const void *all_blobs, int nra
  *     fast SMs claim more of the short tail chunks and all CTAs finish together.
  * Tile height: 8 rows (fewest halo-row re-reads) unless option `ty` says otherwise; the kernels take any 1..8.
  * Option `kc` forces uniform chunks.  Uploads the chunk table (Dev::ztab) and rebuilds the tensor maps. */
-static int make_plan(bbpcg_solver *s)
+/* The planner proper: pure host arithmetic, exported so that the CPU tests can hold it to its contract on any block shape
+ * (every plane 1..kn in exactly one chunk, chunk lengths >= 1, boundary chunks first) without a GPU.
+ * ztab[2c], ztab[2c+1] = first and last plane of chunk c in CLAIM order; plan[5] = { ty, nbx, nby, nbz, planes of chunk 0 }. */
+extern "C" int bbpcg_plan_zchunks(int in, int jn, int kn, int slots, int opt_ty, int opt_kc, int guided, int guided_pct, int chunk_min,
+                                  int *ztab, int ztab_cap, int *plan)
 {
-  if (s->plan_ok) return BBPCG_OK;
-  const Layout &L = s->dev.L;
-  const int slots = s->sm_count * 2;
-  const int nbx = (L.in + 127) / 128;
-  const int kc_uniform = s->opt_kc > 0 ? s->opt_kc : 24;
-  const long long nz_uniform = (L.kn + kc_uniform - 1) / kc_uniform;
-  const bool uniform = s->opt_kc > 0 || !s->guided || (long long)nbx * ((L.jn + BB_TYMAX - 1) / BB_TYMAX) * nz_uniform >= 7ll * slots;
+  if (in < 1 || jn < 1 || kn < 1 || slots < 1 || !ztab || !plan) { bbpcg_set_error("bbpcg_plan_zchunks: bad argument"); return BBPCG_EINVAL; }
+  const int nbx = (in + 127) / 128;
+  const int kc_uniform = opt_kc > 0 ? opt_kc : 24;
+  const long long nz_uniform = (kn + kc_uniform - 1) / kc_uniform;
+  const bool uniform = opt_kc > 0 || !guided || (long long)nbx * ((jn + BB_TYMAX - 1) / BB_TYMAX) * nz_uniform >= 7ll * slots;
   /* 8 rows: fewest halo-row re-reads.  Guided regime, four interleaved passes per setting on one box (profiles/r02y_sweep.jsonl,
    * medians): claims of 60 % of the even share down to 4 planes with 8 rows 220.3 us per iteration at 256^3 and 210.4 at
    * 512 x 256 x 128, against 225.0 / 217.8 for the earlier plan (100 %, 8 planes, 7 rows); boxes differ by more than that. */
-  const int best_ty = s->opt_ty > 0 ? s->opt_ty : BB_TYMAX;
-  const int cols = nbx * ((L.jn + best_ty - 1) / best_ty);
+  const int best_ty = opt_ty > 0 ? (opt_ty < BB_TYMAX ? opt_ty : BB_TYMAX) : BB_TYMAX;
+  const int cols = nbx * ((jn + best_ty - 1) / best_ty);
   std::vector<int> sz;
   if (uniform) {
-    int nz = (int)nz_uniform;
-    if (nz > BB_MAXZ) nz = BB_MAXZ;
+    int nz = (int)(nz_uniform > BB_MAXZ ? BB_MAXZ : nz_uniform);
     if ((long long)cols * nz > BB_MAXBLOCKS) nz = BB_MAXBLOCKS / cols;       /* the shortest chunks the reduction workspace allows */
     if (nz < 1) { bbpcg_set_error("grid too large for the reduction workspace"); return BBPCG_EINVAL; }
-    const int kc = (L.kn + nz - 1) / nz;
-    for (int r = L.kn; r > 0; r -= kc) sz.push_back(r < kc ? r : kc);
+    const int kc = (kn + nz - 1) / nz;
+    for (int r = kn; r > 0; r -= kc) sz.push_back(r < kc ? r : kc);
   } else {
-    const int minc = s->chunk_min > 0 ? s->chunk_min : 4;
-    int r = L.kn;
+    const int minc = chunk_min > 0 ? chunk_min : 4;
+    const int pct = guided_pct > 0 ? guided_pct : 60;
+    int r = kn;
     while (r > 0) {
-      int c = (int)(((long long)r * cols * s->guided_pct / 100 + slots - 1) / slots);
+      int c = (int)(((long long)r * cols * pct / 100 + slots - 1) / slots);
       if (c < minc) c = minc;
       if (c > r || r - c < (minc + 1) / 2) c = r;
       sz.push_back(c);
       r -= c;
     }
   }
-  if (sz.size() > BB_MAXZ) { bbpcg_set_error("too many z-chunks"); return BBPCG_EINVAL; }
-  /* the copy source must stay valid until the copy ran: it is only rewritten after a stream sync */
-  CU(cudaStreamSynchronize(s->stream));
+  if (sz.size() > BB_MAXZ || 2 * sz.size() > (size_t)ztab_cap) { bbpcg_set_error("too many z-chunks"); return BBPCG_EINVAL; }
+  if ((long long)cols * (long long)sz.size() > BB_MAXBLOCKS) { bbpcg_set_error("grid too large for the reduction workspace"); return BBPCG_EINVAL; }
   /* Placement of the chunks along z, in claim order: the first one ends at the top face k = kn, the second starts at the
    * bottom face k = 1, the others fill the middle upwards.  The residual kernel pushes the new r of the block's top / bottom
    * plane into the z neighbours' ghost planes (peer stores over NVLink when the block is split in z): claimed first, those
    * stores are under way a whole kernel before the rank barrier releases them, instead of in front of it. */
-  {
-    const size_t n = sz.size();
-    int lo = 1;
-    for (size_t i = 0; i < n; i++) {
-      if (i == 0 && n > 1) { s->h_ztab[0] = L.kn - sz[0] + 1; s->h_ztab[1] = L.kn; continue; }
-      s->h_ztab[2 * i] = lo; s->h_ztab[2 * i + 1] = lo + sz[i] - 1;
-      lo += sz[i];
-    }
+  const size_t n = sz.size();
+  int lo = 1;
+  for (size_t i = 0; i < n; i++) {
+    if (i == 0 && n > 1) { ztab[0] = kn - sz[0] + 1; ztab[1] = kn; continue; }
+    ztab[2 * i] = lo; ztab[2 * i + 1] = lo + sz[i] - 1;
+    lo += sz[i];
   }
-  CU(cudaMemcpyAsync((void *)s->dev.ztab, s->h_ztab, sizeof(int) * (2 * sz.size()), cudaMemcpyHostToDevice, s->stream));
-  s->plan_ty = best_ty; s->plan_nbx = nbx; s->plan_nby = (L.jn + best_ty - 1) / best_ty; s->plan_nbz = (int)sz.size(); s->plan_kc = sz[0];
-  int rc = build_search_maps(s, best_ty);
+  plan[0] = best_ty; plan[1] = nbx; plan[2] = (jn + best_ty - 1) / best_ty; plan[3] = (int)n; plan[4] = sz[0];
+  return BBPCG_OK;
+}
+
+static int make_plan(bbpcg_solver *s)
+{
+  if (s->plan_ok) return BBPCG_OK;
+  const Layout &L = s->dev.L;
+  /* the copy source must stay valid until the copy ran: it is only rewritten after a stream sync */
+  CU(cudaStreamSynchronize(s->stream));
+  int plan[5];
+  int rc = bbpcg_plan_zchunks(L.in, L.jn, L.kn, s->sm_count * 2, s->opt_ty, s->opt_kc, s->guided, s->guided_pct, s->chunk_min, s->h_ztab, 2 * BB_MAXZ, plan);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync((void *)s->dev.ztab, s->h_ztab, sizeof(int) * (2 * plan[3]), cudaMemcpyHostToDevice, s->stream));
+  s->plan_ty = plan[0]; s->plan_nbx = plan[1]; s->plan_nby = plan[2]; s->plan_nbz = plan[3]; s->plan_kc = plan[4];
+  rc = build_search_maps(s, s->plan_ty);
   if (rc) return rc;
   s->plan_ok = 1;
   return BBPCG_OK;

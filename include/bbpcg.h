@@ -278,6 +278,11 @@ int  bbpcg_spmv(bbpcg_solver *s, const real *src_s3b, real *Ap_s3, int use_phase
  *   kernel_timing    1: CUDA events around every iteration kernel (bbpcg_get_info kt_*_ns / kt_*_n; switches PDL off)
  * Info keys: pitch, sm_count, nranks, tile_tx, search_ty, search_grid, search_items, search_kc, search_nbz, pdl, comm_timeout. */
 int  bbpcg_set_option(bbpcg_solver *s, const char *key, long long value);
+/* the tile / z-chunk planner of the iteration kernels as a pure host function (no GPU needed; CPU tests hold it to its
+ * contract): ztab[2c], ztab[2c+1] = first / last plane of chunk c in claim order, plan[5] = { ty, nbx, nby, nbz, planes of
+ * chunk 0 }; slots = resident CTAs (2 per SM); the other arguments are the options of the same names (0 = default) */
+int  bbpcg_plan_zchunks(int in, int jn, int kn, int slots, int opt_ty, int opt_kc, int guided, int guided_pct, int chunk_min,
+                        int *ztab, int ztab_cap, int *plan);
 long long bbpcg_get_info(bbpcg_solver *s, const char *key);
 const char *bbpcg_last_error(void);
 const char *bbpcg_version(void);
