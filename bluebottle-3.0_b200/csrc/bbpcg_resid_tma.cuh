@@ -80,7 +80,8 @@ __device__ __forceinline__ void push_pair(double *dst, double a, double b, bool 
 }
 
 /* the new r of cells on a y / z face of the block into the neighbour's ghost row / plane (push model, see resid_item);
- * faces: bit 0 S, 1 N, 2 B, 3 T -- the faces this ITEM touches that have a neighbour */
+ * faces: bit 0 S, 1 N, 2 B, 3 T -- the faces with a neighbour that THIS PLANE of the item touches (CTA-uniform).  Behind a
+ * call on purpose: inlined, the address arithmetic of the four stores was speculated into the plane loop of every item. */
 __device__ __noinline__ void push_yz_faces(const Dev &d, int faces, int iA, int j, int kc, double r0, double r1, bool both)
 {
   const Layout &L = d.L;
